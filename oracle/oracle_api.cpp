@@ -1,0 +1,39 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+#include "oracle.h"
+
+#include <omp.h>
+#include <cstring>
+
+using namespace hlsl;
+
+// Clear_Float / Clear_Uint (reference: Shaders/Source/Clear_Float.cs.hlsl, Clear_Uint.cs.hlsl): zero the whole texture
+static void ClearTexture(Tex& t)
+{
+    for (int y = 0; y < t.h; y++) memset(t.at(0, y + t.yoff), 0, size_t(t.w) * t.bpp());
+}
+
+extern "C" int oracle_dispatch(const char* shaderName, const void* constants, int constantsSize, const OracleTexture* textures, int texturesNum, int gridW, int gridH)
+{
+    Tex tex[32];
+    if (texturesNum > 32) return -1;
+    for (int i = 0; i < texturesNum; i++)
+    {
+        tex[i].data = (uint8_t*)textures[i].data;
+        tex[i].w = textures[i].width;
+        tex[i].h = textures[i].height;
+        tex[i].pitch = textures[i].pitchBytes;
+        tex[i].fmt = textures[i].format;
+        tex[i].yoff = textures[i].firstRow;
+    }
+    if (!strncmp(shaderName, "Clear_", 6))
+    {
+        ClearTexture(tex[0]);
+        return 0;
+    }
+    if (!strncmp(shaderName, "REBLUR_", 7)) return oracle_reblur_dispatch(shaderName, constants, constantsSize, tex, texturesNum, gridW, gridH);
+    if (!strncmp(shaderName, "SIGMA_", 6)) return oracle_sigma_dispatch(shaderName, constants, constantsSize, tex, texturesNum, gridW, gridH);
+    if (!strncmp(shaderName, "RELAX_", 6)) return oracle_relax_dispatch(shaderName, constants, constantsSize, tex, texturesNum, gridW, gridH);
+    return -1;
+}
+
+extern "C" int oracle_num_threads() { return omp_get_max_threads(); }

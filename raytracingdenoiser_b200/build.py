@@ -1,0 +1,104 @@
+"""Builds the two native libraries in-tree (they travel to the GPU box with the snapshot):
+
+  raytracingdenoiser_b200/libnrd_b200.so   product: scheduler (C++) + CUDA executor + sm_100a kernels (nvcc cross-compiles here)
+  oracle/liboracle.so                      test infrastructure: CPU restatement of the reference shaders (g++, OpenMP)
+
+Usage: python -m raytracingdenoiser_b200.build [--force]
+"""
+import concurrent.futures
+import hashlib
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "raytracingdenoiser_b200")
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "build")
+LIB = os.path.join(PKG, "libnrd_b200.so")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+              "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
+CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra"]
+# -ffp-contract=off: the oracle evaluates a*b+c with two roundings, like the "pinned" arithmetic of the kernels
+ORACLE_FLAGS = ["-std=c++17", "-O3", "-mavx2", "-mfma", "-mf16c", "-ffp-contract=off", "-fopenmp", "-fPIC", "-Wall", "-Wextra", "-shared"]
+
+
+def _sources():
+    out = []
+    for d in (CSRC, os.path.join(CSRC, "device")):
+        for f in sorted(os.listdir(d)):
+            if f.endswith(".cpp") or f.endswith(".cu"):
+                out.append(os.path.join(d, f))
+    return out
+
+
+def _headers_digest():
+    h = hashlib.sha1()
+    for d in (CSRC, os.path.join(CSRC, "device"), os.path.join(ROOT, "include")):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".h", ".cuh")):
+                h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
+def _compile(src, obj, stamp):
+    if src.endswith(".cu"):
+        cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    else:
+        cmd = ["g++"] + CXX_FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("compile failed: %s\n%s%s" % (" ".join(cmd), r.stdout, r.stderr))
+    open(stamp, "w").write("ok")
+    return r.stderr
+
+
+def build_product(force=False):
+    os.makedirs(OBJ, exist_ok=True)
+    digest = _headers_digest()
+    objs, jobs = [], []
+    for src in _sources():
+        key = hashlib.sha1((digest + open(src, "rb").read().decode("utf-8", "replace") + " ".join(NVCC_FLAGS + CXX_FLAGS)).encode()).hexdigest()[:16]
+        base = os.path.basename(src).replace(".", "_")
+        obj = os.path.join(OBJ, base + ".o")
+        stamp = os.path.join(OBJ, base + "." + key + ".stamp")
+        objs.append(obj)
+        if force or not (os.path.exists(obj) and os.path.exists(stamp)):
+            for f in os.listdir(OBJ):
+                if f.startswith(base + ".") and f.endswith(".stamp"):
+                    os.remove(os.path.join(OBJ, f))
+            jobs.append((src, obj, stamp))
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for fut in [ex.submit(_compile, *j) for j in jobs]:
+                fut.result()
+    if jobs or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed: %s\n%s%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return LIB
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in sorted(os.listdir(ORACLE_DIR)) if f.endswith(".cpp")]
+    deps = srcs + [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".h")]
+    if not force and os.path.exists(ORACLE_LIB) and all(os.path.getmtime(ORACLE_LIB) >= os.path.getmtime(d) for d in deps):
+        return ORACLE_LIB
+    cmd = ["g++"] + ORACLE_FLAGS + ["-o", ORACLE_LIB] + srcs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n%s%s" % (r.stdout, r.stderr))
+    return ORACLE_LIB
+
+
+def build_all(force=False):
+    return build_product(force), build_oracle(force)
+
+
+if __name__ == "__main__":
+    print(build_all("--force" in sys.argv))

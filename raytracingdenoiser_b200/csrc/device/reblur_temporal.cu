@@ -1,0 +1,1090 @@
+// REBLUR temporal passes on sm_100a: TemporalAccumulation, HistoryFix, TemporalStabilization.
+// Semantics: reference Shaders/Include/REBLUR_TemporalAccumulation.hlsli:11-931, REBLUR_HistoryFix.hlsli:11-463,
+// REBLUR_TemporalStabilization.hlsli:11-367 with helpers from Common.hlsli / REBLUR_Common.hlsli (cited inline), default
+// switches (CatRom on, STF on, SPECULAR_MOTION_V2, antilag mode 2), checkerboard OFF, no history-confidence /
+// disocclusion-mix / base-colour inputs.  Reprojection footprints are selected with pinned arithmetic (common.cuh).
+#include "reblur_math.cuh"
+#include "launch.h"
+
+namespace nrdb200
+{
+using namespace rb;
+
+// ---------------------------------------------------------------------------------------------
+// software samplers (clamp-to-edge), matching D3D addressing
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ f4 FetchClamped4(const Surf& s, int x, int y) { return LoadRGBA16F(s, clampi(x, 0, s.w - 1), clampi(y, 0, s.h - 1)); }
+__device__ __forceinline__ float FetchClamped1(const Surf& s, int x, int y) { return LoadR16F(s, clampi(x, 0, s.w - 1), clampi(y, 0, s.h - 1)); }
+
+__device__ __forceinline__ f4 SampleLinear4(const Surf& s, float u, float v)
+{
+    float px = u * (float)s.w - 0.5f, py = v * (float)s.h - 0.5f;
+    float fx = floorf(px), fy = floorf(py);
+    float wx = px - fx, wy = py - fy;
+    int x0 = (int)fx, y0 = (int)fy;
+    f4 a = lerp4(FetchClamped4(s, x0, y0), FetchClamped4(s, x0 + 1, y0), wx);
+    f4 b = lerp4(FetchClamped4(s, x0, y0 + 1), FetchClamped4(s, x0 + 1, y0 + 1), wx);
+    return lerp4(a, b, wy);
+}
+__device__ __forceinline__ float SampleLinear1(const Surf& s, float u, float v)
+{
+    float px = u * (float)s.w - 0.5f, py = v * (float)s.h - 0.5f;
+    float fx = floorf(px), fy = floorf(py);
+    float wx = px - fx, wy = py - fy;
+    int x0 = (int)fx, y0 = (int)fy;
+    float a = lerpf(FetchClamped1(s, x0, y0), FetchClamped1(s, x0 + 1, y0), wx);
+    float b = lerpf(FetchClamped1(s, x0, y0 + 1), FetchClamped1(s, x0 + 1, y0 + 1), wx);
+    return lerpf(a, b, wy);
+}
+
+// bilinear footprint: origin = floor(uv * size - 0.5), weights = frac   (pinned)
+struct Bilinear
+{
+    float ox, oy, wx, wy;
+};
+__device__ __forceinline__ Bilinear GetBilinear(f2 uv, const float* size)
+{
+    float tx = __fadd_rn(__fmul_rn(uv.x, size[0]), -0.5f), ty = __fadd_rn(__fmul_rn(uv.y, size[1]), -0.5f);
+    Bilinear b;
+    b.ox = floorf(tx);
+    b.oy = floorf(ty);
+    b.wx = __fadd_rn(tx, -b.ox);
+    b.wy = __fadd_rn(ty, -b.oy);
+    return b;
+}
+__device__ __forceinline__ float ApplyBilinear(float s00, float s10, float s01, float s11, const Bilinear& f)
+{
+    return lerpf(lerpf(s00, s10, f.wx), lerpf(s01, s11, f.wx), f.wy);
+}
+__device__ __forceinline__ f4 CustomWeights(const Bilinear& f, f4 cw)
+{
+    float ox = 1.0f - f.wx, oy = 1.0f - f.wy;
+    return mk4(cw.x * (ox * oy), cw.y * (f.wx * oy), cw.z * (ox * f.wy), cw.w * (f.wx * f.wy));
+}
+__device__ __forceinline__ float ApplyCustomWeights(float s00, float s10, float s01, float s11, f4 w)
+{
+    float sum = w.x + w.y + w.z + w.w;
+    float r = s00 * w.x + s10 * w.y + s01 * w.z + s11 * w.w;
+    return sum < 0.0001f ? 0.0f : r / sum;
+}
+__device__ __forceinline__ f4 InScreenBilinear(const Bilinear& f, const float* size) // Common.hlsli:287-295
+{
+    float x0 = (f.ox >= 0.0f && f.ox < size[0]) ? 1.0f : 0.0f, x1 = (f.ox + 1.0f >= 0.0f && f.ox + 1.0f < size[0]) ? 1.0f : 0.0f;
+    float y0 = (f.oy >= 0.0f && f.oy < size[1]) ? 1.0f : 0.0f, y1 = (f.oy + 1.0f >= 0.0f && f.oy + 1.0f < size[1]) ? 1.0f : 0.0f;
+    return mk4(x0 * y0, x1 * y0, x0 * y1, x1 * y1);
+}
+
+// CatRom-12 (no corners) through 5 bilinear taps with fallback to the custom-weight bilinear footprint
+// (Common.hlsli:602-656).  HasFast: additionally resolve a scalar texture with the custom weights (4 loads).
+struct CatRomSetup
+{
+    float u01x, u01y, u01z, u01w, u23x, u23y, u23z, u23w, u4x, u4y;
+    f4 w;
+    float w4, sum;
+    int bx, by;
+};
+__device__ __forceinline__ CatRomSetup SetupCatRom(f2 samplePos, const float* invSize, f4 customWeights, bool useBicubic)
+{
+    CatRomSetup s;
+    float cx = floorf(samplePos.x - 0.5f) + 0.5f, cy = floorf(samplePos.y - 0.5f) + 0.5f;
+    float fx = saturate(samplePos.x - cx), fy = saturate(samplePos.y - cy);
+    const float S = 0.5f;
+    float w0x = fx * (fx * (-S * fx + 2.0f * S) - S), w0y = fy * (fy * (-S * fy + 2.0f * S) - S);
+    float w1x = fx * (fx * ((2.0f - S) * fx - (3.0f - S))) + 1.0f, w1y = fy * (fy * ((2.0f - S) * fy - (3.0f - S))) + 1.0f;
+    float w2x = fx * (fx * (-(2.0f - S) * fx + (3.0f - 2.0f * S)) + S), w2y = fy * (fy * (-(2.0f - S) * fy + (3.0f - 2.0f * S)) + S);
+    float w3x = fx * (fx * (S * fx - S)), w3y = fy * (fy * (S * fy - S));
+    float w12x = w1x + w2x, w12y = w1y + w2y;
+    float tcx = w2x / w12x, tcy = w2y / w12y;
+    f4 w = mk4(w12x * w0y, w0x * w12y, w12x * w12y, w3x * w12y);
+    float w4 = w12x * w3y;
+    s.w = useBicubic ? w : customWeights;
+    s.w4 = useBicubic ? w4 : 0.0f;
+    s.sum = s.w.x + s.w.y + s.w.z + s.w.w + s.w4;
+    if (useBicubic)
+    {
+        s.u01x = cx + tcx; s.u01y = cy - 1.0f; s.u01z = cx - 1.0f; s.u01w = cy + tcy;
+        s.u23x = cx + tcx; s.u23y = cy + tcy;  s.u23z = cx + 2.0f; s.u23w = cy + tcy;
+        s.u4x = cx + tcx;  s.u4y = cy + 2.0f;
+    }
+    else
+    {
+        s.u01x = cx;        s.u01y = cy;        s.u01z = cx + 1.0f; s.u01w = cy;
+        s.u23x = cx;        s.u23y = cy + 1.0f; s.u23z = cx + 1.0f; s.u23w = cy + 1.0f;
+        s.u4x = cx + fx;    s.u4y = cy + fy;
+    }
+    s.u01x *= invSize[0]; s.u01y *= invSize[1]; s.u01z *= invSize[0]; s.u01w *= invSize[1];
+    s.u23x *= invSize[0]; s.u23y *= invSize[1]; s.u23z *= invSize[0]; s.u23w *= invSize[1];
+    s.u4x *= invSize[0];  s.u4y *= invSize[1];
+    s.bx = (int)cx;
+    s.by = (int)cy;
+    return s;
+}
+__device__ __forceinline__ f4 ResolveCatRom4(const CatRomSetup& s, const Surf& tex)
+{
+    f4 color = SampleLinear4(tex, s.u01x, s.u01y) * s.w.x;
+    color = color + SampleLinear4(tex, s.u01z, s.u01w) * s.w.y;
+    color = color + SampleLinear4(tex, s.u23x, s.u23y) * s.w.z;
+    color = color + SampleLinear4(tex, s.u23z, s.u23w) * s.w.w;
+    if (s.w4 != 0.0f) color = color + SampleLinear4(tex, s.u4x, s.u4y) * s.w4;
+    return s.sum < 0.0001f ? mk4(0.0f) : color * (1.0f / s.sum);
+}
+__device__ __forceinline__ float ResolveCatRom1(const CatRomSetup& s, const Surf& tex)
+{
+    float color = SampleLinear1(tex, s.u01x, s.u01y) * s.w.x;
+    color += SampleLinear1(tex, s.u01z, s.u01w) * s.w.y;
+    color += SampleLinear1(tex, s.u23x, s.u23y) * s.w.z;
+    color += SampleLinear1(tex, s.u23z, s.u23w) * s.w.w;
+    if (s.w4 != 0.0f) color += SampleLinear1(tex, s.u4x, s.u4y) * s.w4;
+    return s.sum < 0.0001f ? 0.0f : color / s.sum;
+}
+// tex.Load(origin + offset) * customWeights, out-of-bounds loads return 0
+__device__ __forceinline__ float LoadOrZero1(const Surf& s, int x, int y) { return Inside(s, x, y) ? LoadR16F(s, x, y) : 0.0f; }
+__device__ __forceinline__ float ResolveBilinearCustom1(const CatRomSetup& s, const Surf& tex, f4 cw)
+{
+    float v = LoadOrZero1(tex, s.bx, s.by) * cw.x + LoadOrZero1(tex, s.bx + 1, s.by) * cw.y + LoadOrZero1(tex, s.bx, s.by + 1) * cw.z +
+              LoadOrZero1(tex, s.bx + 1, s.by + 1) * cw.w;
+    float sum = cw.x + cw.y + cw.z + cw.w;
+    return sum < 0.0001f ? 0.0f : v / sum;
+}
+
+// thin-lens virtual position (Common.hlsli:404-461, NRD_USE_SPECULAR_MOTION_V2 = 1)
+__device__ __forceinline__ f3 GetXvirtual(float hitDist, float curvature, f3 X, f3 Xprev, f3 N, f3 V, float roughness)
+{
+    f4 D = SpecularDominantDirection(N, V, roughness);
+    f3 ray = xyz(D) * hitDist;
+    f3 T, B;
+    GetBasis(N, T, B);
+    float Oz = -dot(N, ray);
+    float Ox = dot(T, ray), Oy = dot(B, ray);
+    float mag = 1.0f / (2.0f * curvature * Oz - 1.0f);
+    float f = length(X) * (1.0f - fabsf(dot(N, V))) * fmaxf(curvature, 0.0f);
+    mag *= 1.0f / (1.0f + f);
+    float lenI = sqrtf(Ox * Ox + Oy * Oy + Oz * Oz) * fabsf(mag);
+    f3 Iw = V * lenI;
+    float closeness = saturate(length(Iw) / (hitDist + kEps));
+    f3 origin = lerp3(Xprev, X, closeness * D.w);
+    return origin - Iw * D.w;
+}
+
+__device__ __forceinline__ float EncodingAwareNormalWeight(f3 Ncurr, f3 Nprev, float maxAngle, float curvatureAngle, float thresholdAngle) // Common.hlsli:578-590
+{
+    float angle = AcosApprox(dot(Ncurr, Nprev));
+    return SmoothStep01(1.0f - (angle - curvatureAngle - thresholdAngle) / maxAngle);
+}
+
+__device__ __forceinline__ unsigned LoadPackedNrOrZero(const Surf& s, int x, int y) { return Inside(s, x, y) ? LoadU32(s, x, y) : 0u; }
+
+// Sequence::Bayer4x4 (frozen: standard 4x4 ordered-dither matrix, see oracle/mathlib.h)
+__constant__ unsigned kBayer4x4[16] = {0, 8, 2, 10, 12, 4, 14, 6, 3, 11, 1, 9, 15, 7, 13, 5};
+
+// =============================================================================================
+// Temporal accumulation
+// =============================================================================================
+struct TaArgs
+{
+    ReblurConstants c;
+    Surf tiles, nr, z, mv, prevZ, prevNr, prevInternal;
+    Surf inDiff, inSpec, histDiff, histSpec, histDiffFast, histSpecFast, prevHitDist, inHitDist;
+    Surf outDiff, outSpec, outDiffFast, outSpecFast, outHitDist, outData1, outData2;
+    int rowBegin, rowEnd;
+};
+
+template <bool DIFF, bool SPEC>
+__global__ void __launch_bounds__(128) ReblurTemporalAccumulationKernel(const __grid_constant__ TaArgs a)
+{
+    const ReblurConstants& c = a.c;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = a.rowBegin + blockIdx.y * 4 + threadIdx.y;
+    const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
+    if (x > maxX || y > maxY || y >= a.rowEnd) return;
+    if (LoadU8(a.tiles, x >> 4, y >> 4) != 0) return;
+    const float viewZ = fabsf(LoadR32F(a.z, x, y) * c.gViewZScale);
+    if (viewZ > c.gDenoisingRange) return;
+
+    const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
+    const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
+    const f3 X = PinnedRotate(c.gViewToWorld, Xv);
+
+    // 3x3 neighbourhood: averaged normal (2x2 corner), roughness moments, min hit distance for tracking
+    f3 Navg = mk3(0.0f);
+    f3 n10 = mk3(0.0f), n01 = mk3(0.0f);
+    float hitDistForTracking = kInf, roughnessM1 = 0.0f, roughnessM2 = 0.0f;
+#pragma unroll
+    for (int j = 0; j <= 2; j++)
+#pragma unroll
+        for (int i = 0; i <= 2; i++)
+        {
+            int px = clampi(x + i - 1, 0, maxX), py = clampi(y + j - 1, 0, maxY);
+            Guide g = DecodeGuide(LoadU32(a.nr, px, py));
+            if (i < 2 && j < 2) Navg = Navg + g.N;
+            if (i == 2 && j == 1) n10 = g.N;
+            if (i == 1 && j == 2) n01 = g.N;
+            if (SPEC)
+            {
+                float h = c.gSpecPrepassBlurRadius == 0.0f ? LoadRGBA16F(a.inSpec, px, py).w : LoadR16F(a.inHitDist, px, py);
+                hitDistForTracking = fminf(hitDistForTracking, h == 0.0f ? kInf : h);
+                float r2 = g.roughness * g.roughness;
+                roughnessM1 += r2;
+                roughnessM2 += r2 * r2;
+            }
+        }
+    Navg = Navg * 0.25f;
+
+    const Guide g0 = DecodeGuide(LoadU32(a.nr, x, y));
+    const f3 N = g0.N;
+    const float roughness = g0.roughness, materialID = g0.materialID;
+
+    float roughnessModified = 0.0f, roughnessSigma = 0.0f, hitDistNormalization = 0.0f;
+    RngHash rng;
+    if (SPEC)
+    {
+        float l = length(Navg);
+        float kappa = saturate(1.0f - l * l) / fmaxf(l * (3.0f - l * l), 1e-15f);
+        roughnessModified = Sqrt01(roughness * roughness + kappa);
+        roughnessM1 *= 1.0f / 9.0f;
+        roughnessM2 *= 1.0f / 9.0f;
+        roughnessSigma = GetStdDev(roughnessM1, roughnessM2);
+        rng.Initialize(x, y, c.gFrameIndex);
+        hitDistForTracking = hitDistForTracking == kInf ? 0.0f : hitDistForTracking;
+        hitDistNormalization = HitDistNormalization(viewZ, c.gHitDistParams, roughness);
+        hitDistForTracking *= c.gSpecPrepassBlurRadius == 0.0f ? hitDistNormalization : 1.0f;
+        StoreR16F(a.outHitDist, x, y, hitDistForTracking);
+    }
+
+    // previous position and surface-motion uv
+    const f4 mvRaw = LoadRGBA16F(a.mv, x, y);
+    f3 mv = mk3(__fmul_rn(mvRaw.x, c.gMvScale[0]), __fmul_rn(mvRaw.y, c.gMvScale[1]), __fmul_rn(mvRaw.z, c.gMvScale[2]));
+    f3 Xprev = X;
+    f2 smbPixelUv = mk2(__fadd_rn(pixelUv.x, mv.x), __fadd_rn(pixelUv.y, mv.y));
+    const f3 camDelta = mk3(c.gCameraDelta[0], c.gCameraDelta[1], c.gCameraDelta[2]);
+    if (c.gMvScale[3] == 0.0f)
+    {
+        if (c.gMvScale[2] == 0.0f) mv.z = __fadd_rn(PinnedRow(c.gWorldToViewPrev, 2, X.x, X.y, X.z), -viewZ);
+        float viewZprev = __fadd_rn(viewZ, mv.z);
+        f3 Xvprevlocal = ReconstructViewPosition(smbPixelUv, c.gFrustumPrev, viewZprev, c.gOrthoMode);
+        f3 r = PinnedRotateInverse(c.gWorldToViewPrev, Xvprevlocal);
+        Xprev = mk3(__fadd_rn(r.x, camDelta.x), __fadd_rn(r.y, camDelta.y), __fadd_rn(r.z, camDelta.z));
+    }
+    else
+    {
+        Xprev = mk3(__fadd_rn(X.x, mv.x), __fadd_rn(X.y, mv.y), __fadd_rn(X.z, mv.z));
+        smbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xprev);
+    }
+
+    // previous viewZ / internal data in the 4x4 CatRom footprint (12 texels, corners unused) around the bilinear origin b
+    const Bilinear smbF = GetBilinear(smbPixelUv, c.gRectSizePrev);
+    const int bx = (int)smbF.ox, by = (int)smbF.oy;
+    const int W1 = a.prevZ.w - 1, H1 = a.prevZ.h - 1;
+    // index [row][col] with row/col in 0..3 <-> texel (bx - 1 + col, by - 1 + row)
+    float pz[4][4];
+    unsigned pid[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            if ((r == 0 || r == 3) && (q == 0 || q == 3)) continue;
+            int tx = clampi(bx - 1 + q, 0, W1), ty = clampi(by - 1 + r, 0, H1);
+            pz[r][q] = fabsf(LoadR32F(a.prevZ, tx, ty) * c.gViewZScale);
+            pid[r][q] = LoadU16(a.prevInternal, tx, ty);
+        }
+
+    // previous normal averaged over the valid part of the 2x2 footprint
+    f3 smbNavg;
+    {
+        int px = (int)fmaxf(smbF.ox, 0.0f), py = (int)fmaxf(smbF.oy, 0.0f); // uint2(origin): float -> uint saturates at 0
+        float w00 = pz[1][1] < c.gDenoisingRange ? 1.0f : 0.0f, w10 = pz[1][2] < c.gDenoisingRange ? 1.0f : 0.0f;
+        float w01 = pz[2][1] < c.gDenoisingRange ? 1.0f : 0.0f, w11 = pz[2][2] < c.gDenoisingRange ? 1.0f : 0.0f;
+        f3 s = DecodeGuide(LoadPackedNrOrZero(a.prevNr, px, py)).N * w00;
+        s = s + DecodeGuide(LoadPackedNrOrZero(a.prevNr, px + 1, py)).N * w10;
+        s = s + DecodeGuide(LoadPackedNrOrZero(a.prevNr, px, py + 1)).N * w01;
+        s = s + DecodeGuide(LoadPackedNrOrZero(a.prevNr, px + 1, py + 1)).N * w11;
+        float sum = w00 + w10 + w01 + w11;
+        smbNavg = Rotate(c.gWorldPrevToWorld, s * (1.0f / (sum == 0.0f ? 1.0f : sum)));
+    }
+
+    // parallax in pixels (both definitions, Common.hlsli:319-332)
+    const f2 rectSize = mk2(c.gRectSize[0], c.gRectSize[1]);
+    const f2 uvPrevOfXprevPlusDelta = GetScreenUv(c.gWorldToClipPrev, Xprev + camDelta);
+    f2 d1 = (uvPrevOfXprevPlusDelta - (c.gOrthoMode == 0.0f ? smbPixelUv : pixelUv)) * rectSize;
+    f2 d2 = (GetScreenUv(c.gWorldToClip, Xprev - camDelta) - (c.gOrthoMode == 0.0f ? pixelUv : smbPixelUv)) * rectSize;
+    const float smbParallaxInPixels1 = length(d1), smbParallaxInPixels2 = length(d2);
+    const float smbParallaxInPixelsMax = fmaxf(smbParallaxInPixels1, smbParallaxInPixels2);
+    const float smbParallaxInPixelsMin = fminf(smbParallaxInPixels1, smbParallaxInPixels2);
+
+    // disocclusion threshold
+    const float pixelSize = c.gUnproject * lerpf(viewZ, 1.0f, fabsf(c.gOrthoMode));
+    const float frustumSize = c.gMinRectDimMulUnproject * lerpf(viewZ, 1.0f, fabsf(c.gOrthoMode));
+    float disocclusionThresholdMix = 0.0f;
+    if (materialID == c.gStrandMaterialID) disocclusionThresholdMix = pixelSize / (pixelSize + c.gStrandThickness);
+    float disocclusionThreshold = lerpf(c.gDisocclusionThreshold, c.gDisocclusionThresholdAlternate, disocclusionThresholdMix);
+    const float smallParallax = LinearStep(0.25f, 0.0f, smbParallaxInPixelsMax);
+    disocclusionThreshold += 0.05f * smallParallax;
+
+    const f3 V = c.gOrthoMode == 0.0f ? normalize(-X) : mk3(c.gViewVectorWorld[0], c.gViewVectorWorld[1], c.gViewVectorWorld[2]);
+    const float NoV = fabsf(dot(N, V));
+    const float NoVstrict = lerpf(NoV, 1.0f, saturate(smbParallaxInPixelsMax / 30.0f));
+    const float almostZeroAngle = 0.0174524064f; // cos(89 deg)
+    float thrBase = frustumSize * saturate(disocclusionThreshold / fmaxf(0.01f, NoVstrict));
+    thrBase *= dot(smbNavg, Navg) > almostZeroAngle - 0.25f * smallParallax ? 1.0f : 0.0f;
+    const f4 inScreen = InScreenBilinear(smbF, c.gRectSizePrev);
+    const f4 smbThr = mk4(thrBase * inScreen.x - kEps, thrBase * inScreen.y - kEps, thrBase * inScreen.z - kEps, thrBase * inScreen.w - kEps);
+
+    // per-texel occlusion: plane distance against the quadrant's threshold, then material ID
+    const float XvprevZ = PinnedRow(c.gWorldToViewPrev, 2, Xprev.x, Xprev.y, Xprev.z);
+    const float minMaterial = fminf(c.gSpecMinMaterial, c.gDiffMinMaterial);
+    const float centerMat = fmaxf(materialID, minMaterial);
+    float occ[4][4];
+    float occSum = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            if ((r == 0 || r == 3) && (q == 0 || q == 3)) continue;
+            // quadrant (gather 0..3) of this texel decides which of the four thresholds applies
+            float thr = r < 2 ? (q < 2 ? smbThr.x : smbThr.y) : (q < 2 ? smbThr.z : smbThr.w);
+            float o = fabsf(pz[r][q] - XvprevZ) <= thr ? 1.0f : 0.0f;
+            float m = UnpackInternalData(pid[r][q]).z;
+            o *= centerMat == fmaxf(m, minMaterial) ? 1.0f : 0.0f;
+            occ[r][q] = o;
+            occSum += o;
+        }
+    const f4 smbOcclusion = mk4(occ[1][1], occ[1][2], occ[2][1], occ[2][2]);
+    const f4 smbOcclusionWeights = CustomWeights(smbF, smbOcclusion);
+    const bool smbAllowCatRom = occSum > 11.5f;
+    float fbits = smbOcclusion.x + smbOcclusion.y * 2.0f + smbOcclusion.z * 4.0f + smbOcclusion.w * 8.0f;
+
+    const f3 id00 = UnpackInternalData(pid[1][1]), id10 = UnpackInternalData(pid[1][2]), id01 = UnpackInternalData(pid[2][1]), id11 = UnpackInternalData(pid[2][2]);
+    float diffAccumSpeed = ApplyCustomWeights(id00.x, id10.x, id01.x, id11.x, smbOcclusionWeights);
+    float smbSpecAccumSpeed = ApplyCustomWeights(id00.y, id10.y, id01.y, id11.y, smbOcclusionWeights);
+
+    // footprint quality
+    const f3 smbVprev = c.gOrthoMode == 0.0f ? normalize(camDelta - Xprev) : mk3(c.gViewVectorWorldPrev[0], c.gViewVectorWorldPrev[1], c.gViewVectorWorldPrev[2]);
+    const float NoVprev = fabsf(dot(N, smbVprev));
+    float sizeQuality = (NoVprev + 1e-3f) / (NoV + 1e-3f);
+    sizeQuality *= sizeQuality;
+    sizeQuality = lerpf(0.1f, 1.0f, saturate(sizeQuality));
+    float smbFootprintQuality = Sqrt01(ApplyBilinear(smbOcclusion.x, smbOcclusion.y, smbOcclusion.z, smbOcclusion.w, smbF)) * sizeQuality;
+
+    const f2 smbSamplePos = mk2(saturate(smbPixelUv.x) * c.gRectSizePrev[0], saturate(smbPixelUv.y) * c.gRectSizePrev[1]);
+
+    float specAccumSpeed = 0.0f, curvature = 0.0f, virtualHistoryAmount = 0.0f;
+    if (SPEC)
+    {
+        smbSpecAccumSpeed *= lerpf(smbFootprintQuality, 1.0f, 1.0f / (1.0f + smbSpecAccumSpeed));
+        smbSpecAccumSpeed = fminf(smbSpecAccumSpeed, c.gMaxAccumulatedFrameNum);
+        const f4 spec = LoadRGBA16F(a.inSpec, x, y);
+
+        // curvature along the predicted motion (REBLUR_TemporalAccumulation.hlsli:364-447)
+        {
+            f2 uvForZeroParallax = c.gOrthoMode == 0.0f ? smbPixelUv : pixelUv;
+            f2 deltaUv = (uvForZeroParallax - uvPrevOfXprevPlusDelta) * rectSize;
+            float invP = 1.0f / fmaxf(smbParallaxInPixels1, 1.0f / 256.0f);
+            deltaUv = deltaUv * invP;
+
+            f3 x10, x01;
+            {
+                f2 uv = mk2(pixelUv.x + c.gRectSizeInv[0], pixelUv.y);
+                f3 xw = Rotate(c.gViewToWorld, ReconstructViewPosition(uv, c.gFrustum, 1.0f, c.gOrthoMode));
+                f3 v = c.gOrthoMode == 0.0f ? normalize(-xw) : mk3(c.gViewVectorWorld[0], c.gViewVectorWorld[1], c.gViewVectorWorld[2]);
+                f3 o = c.gOrthoMode == 0.0f ? mk3(0.0f) : xw;
+                x10 = o + v * (dot(X - o, N) / dot(N, v));
+            }
+            {
+                f2 uv = mk2(pixelUv.x, pixelUv.y + c.gRectSizeInv[1]);
+                f3 xw = Rotate(c.gViewToWorld, ReconstructViewPosition(uv, c.gFrustum, 1.0f, c.gOrthoMode));
+                f3 v = c.gOrthoMode == 0.0f ? normalize(-xw) : mk3(c.gViewVectorWorld[0], c.gViewVectorWorld[1], c.gViewVectorWorld[2]);
+                f3 o = c.gOrthoMode == 0.0f ? mk3(0.0f) : xw;
+                x01 = o + v * (dot(X - o, N) / dot(N, v));
+            }
+            f2 w = mk2(fabsf(deltaUv.x) + 1.0f / 256.0f, fabsf(deltaUv.y) + 1.0f / 256.0f);
+            float ws = 1.0f / (w.x + w.y);
+            w = w * ws;
+            f3 xm = x10 * w.x + x01 * w.y;
+            f3 n = normalize(n10 * w.x + n01 * w.y);
+
+            // high parallax: replace the 1-pixel edge by a longer one along the motion
+            float deltaUvLenFixed = smbParallaxInPixelsMin;
+            float bayerValue = (float)((kBayer4x4[(y & 3) * 4 + (x & 3)] + c.gFrameIndex) & 15u) / 16.0f;
+            deltaUvLenFixed *= 1.0f + c.gFramerateScale * bayerValue;
+            // pinned: the snapped uv selects a texel
+            float mu = __fadd_rn(pixelUv.x, __fmul_rn(__fmul_rn(deltaUvLenFixed, deltaUv.x), c.gRectSizeInv[0]));
+            float mvv = __fadd_rn(pixelUv.y, __fmul_rn(__fmul_rn(deltaUvLenFixed, deltaUv.y), c.gRectSizeInv[1]));
+            float fx = floorf(__fmul_rn(mu, c.gRectSize[0])), fy = floorf(__fmul_rn(mvv, c.gRectSize[1]));
+            int ix = (int)fx, iy = (int)fy;
+            if (deltaUvLenFixed > 1.0f && (unsigned)ix <= (unsigned)maxX && (unsigned)iy <= (unsigned)maxY)
+            {
+                f2 motionUvHigh = mk2(__fmul_rn(__fadd_rn(fx, 0.5f), c.gRectSizeInv[0]), __fmul_rn(__fadd_rn(fy, 0.5f), c.gRectSizeInv[1]));
+                float zHigh = fabsf(LoadR32F(a.z, ix, iy) * c.gViewZScale);
+                f3 xHigh = Rotate(c.gViewToWorld, ReconstructViewPosition(motionUvHigh, c.gFrustum, zHigh, c.gOrthoMode));
+                f3 nHigh = DecodeGuide(LoadU32(a.nr, ix, iy)).N;
+                float zError = fabsf(zHigh - viewZ) / fmaxf(zHigh, viewZ);
+                if (zError < 0.1f)
+                {
+                    n = nHigh;
+                    xm = xHigh;
+                }
+            }
+            f3 edge = xm - X;
+            curvature = dot(n - N, edge) * PositiveRcp(dot(edge, edge));
+        }
+
+        // virtual motion
+        const f3 Xvirtual = GetXvirtual(hitDistForTracking, curvature, X, Xprev, N, V, roughness);
+        const float XvirtualLength = length(Xvirtual);
+        f2 vmbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xvirtual);
+        if (materialID == c.gCameraAttachedReflectionMaterialID) vmbPixelUv = smbPixelUv;
+        f2 vmbDelta = vmbPixelUv - smbPixelUv;
+        const float vmbPixelsTraveled = length(vmbDelta * rectSize);
+
+        const Bilinear vmbF = GetBilinear(vmbPixelUv, c.gRectSizePrev);
+        const int vx = (int)vmbF.ox, vy = (int)vmbF.oy;
+        // 2x2 footprint fetches (clamped, like Gather with a clamp sampler)
+        const int vx0 = clampi(vx, 0, W1), vx1 = clampi(vx + 1, 0, W1), vy0 = clampi(vy, 0, H1), vy1 = clampi(vy + 1, 0, H1);
+        f2 rrp = RelaxedRoughnessWeightParams(roughness * roughness, c.gRoughnessFraction, 0.003f);
+        f4 vmbRoughness = mk4(DecodeGuide(LoadU32(a.prevNr, vx0, vy0)).roughness, DecodeGuide(LoadU32(a.prevNr, vx1, vy0)).roughness,
+                              DecodeGuide(LoadU32(a.prevNr, vx0, vy1)).roughness, DecodeGuide(LoadU32(a.prevNr, vx1, vy1)).roughness);
+        const float jf = SmoothStep(1.0f, 0.0f, smbParallaxInPixelsMax);
+        f4 roughnessWeight;
+        roughnessWeight.x = lerpf(jf, 1.0f, NonExpWeightWithSigma(vmbRoughness.x * vmbRoughness.x, rrp.x, rrp.y, roughnessSigma));
+        roughnessWeight.y = lerpf(jf, 1.0f, NonExpWeightWithSigma(vmbRoughness.y * vmbRoughness.y, rrp.x, rrp.y, roughnessSigma));
+        roughnessWeight.z = lerpf(jf, 1.0f, NonExpWeightWithSigma(vmbRoughness.z * vmbRoughness.z, rrp.x, rrp.y, roughnessSigma));
+        roughnessWeight.w = lerpf(jf, 1.0f, NonExpWeightWithSigma(vmbRoughness.w * vmbRoughness.w, rrp.x, rrp.y, roughnessSigma));
+        float virtualHistoryRoughnessBasedConfidence = ApplyBilinear(roughnessWeight.x, roughnessWeight.y, roughnessWeight.z, roughnessWeight.w, vmbF);
+
+        // stochastic bilinear pick of the previous normal (STF): one of the 4 footprint texels, point sampled with clamp
+        auto stochasticNr = [&](f2 uv) {
+            Bilinear f = GetBilinear(uv, c.gRectSizePrev);
+            float r0 = rng.GetFloat(), r1 = rng.GetFloat();
+            float ox = f.ox + (f.wx >= r0 ? 1.0f : 0.0f), oy = f.oy + (f.wy >= r1 ? 1.0f : 0.0f);
+            // (origin + 0.5) / size * resolutionScale -> nearest texel = origin, clamped to the texture
+            int tx = (int)floorf((ox + 0.5f) / c.gRectSizePrev[0] * c.gResolutionScalePrev[0] * (float)a.prevNr.w);
+            int ty = (int)floorf((oy + 0.5f) / c.gRectSizePrev[1] * c.gResolutionScalePrev[1] * (float)a.prevNr.h);
+            return DecodeGuide(LoadU32(a.prevNr, clampi(tx, 0, W1), clampi(ty, 0, H1)));
+        };
+        const Guide vmbGuide = stochasticNr(vmbPixelUv);
+        const f3 vmbN = Rotate(c.gWorldPrevToWorld, vmbGuide.N);
+        const float Dfactor = SpecularDominantFactor(NoV, roughness);
+        float virtualHistoryNormalBasedConfidence = 1.0f / (1.0f + 0.5f * Dfactor * saturate(length(N - vmbN) - kNormalEncodingError) * vmbPixelsTraveled);
+
+        if (smbFootprintQuality == 0.0f) smbNavg = vmbN;
+
+        // virtual-motion disocclusion: plane distance, roughness, material
+        f4 vmbOcclusion;
+        {
+            float thr = disocclusionThreshold * frustumSize * lerpf(0.25f, 1.0f, NoV);
+            thr *= dot(vmbN, N) > almostZeroAngle ? 1.0f : 0.0f;
+            thr *= dot(vmbN, smbNavg) > almostZeroAngle ? 1.0f : 0.0f;
+            f4 inS = InScreenBilinear(vmbF, c.gRectSizePrev);
+            f4 vmbThr = mk4(thr * inS.x - kEps, thr * inS.y - kEps, thr * inS.z - kEps, thr * inS.w - kEps);
+            f4 vmbViewZ = mk4(fabsf(LoadR32F(a.prevZ, vx0, vy0) * c.gViewZScale), fabsf(LoadR32F(a.prevZ, vx1, vy0) * c.gViewZScale),
+                              fabsf(LoadR32F(a.prevZ, vx0, vy1) * c.gViewZScale), fabsf(LoadR32F(a.prevZ, vx1, vy1) * c.gViewZScale));
+            f3 vmbVv = ReconstructViewPosition(vmbPixelUv, c.gFrustumPrev, 1.0f, 0.0f);
+            f3 vmbV = RotateInverse(c.gWorldToViewPrev, vmbVv);
+            float NoXcurr = dot(N, Xprev - camDelta);
+            float nxy = N.x * vmbV.x + N.y * vmbV.y, nz = N.z * vmbV.z;
+            auto planeDist = [&](float z) { return fabsf(nxy * (c.gOrthoMode == 0.0f ? z : c.gOrthoMode) + nz * z - NoXcurr); };
+            vmbOcclusion.x = (planeDist(vmbViewZ.x) <= vmbThr.x ? 1.0f : 0.0f) * (roughnessWeight.x >= 0.5f ? 1.0f : 0.0f);
+            vmbOcclusion.y = (planeDist(vmbViewZ.y) <= vmbThr.y ? 1.0f : 0.0f) * (roughnessWeight.y >= 0.5f ? 1.0f : 0.0f);
+            vmbOcclusion.z = (planeDist(vmbViewZ.z) <= vmbThr.z ? 1.0f : 0.0f) * (roughnessWeight.z >= 0.5f ? 1.0f : 0.0f);
+            vmbOcclusion.w = (planeDist(vmbViewZ.w) <= vmbThr.w ? 1.0f : 0.0f) * (roughnessWeight.w >= 0.5f ? 1.0f : 0.0f);
+        }
+        const f3 v00 = UnpackInternalData(LoadU16(a.prevInternal, vx0, vy0)), v10 = UnpackInternalData(LoadU16(a.prevInternal, vx1, vy0));
+        const f3 v01 = UnpackInternalData(LoadU16(a.prevInternal, vx0, vy1)), v11 = UnpackInternalData(LoadU16(a.prevInternal, vx1, vy1));
+        {
+            float cm = fmaxf(materialID, c.gSpecMinMaterial);
+            vmbOcclusion.x *= cm == fmaxf(v00.z, c.gSpecMinMaterial) ? 1.0f : 0.0f;
+            vmbOcclusion.y *= cm == fmaxf(v10.z, c.gSpecMinMaterial) ? 1.0f : 0.0f;
+            vmbOcclusion.z *= cm == fmaxf(v01.z, c.gSpecMinMaterial) ? 1.0f : 0.0f;
+            vmbOcclusion.w *= cm == fmaxf(v11.z, c.gSpecMinMaterial) ? 1.0f : 0.0f;
+        }
+        fbits += vmbOcclusion.x * 16.0f + vmbOcclusion.y * 32.0f + vmbOcclusion.z * 64.0f + vmbOcclusion.w * 128.0f;
+
+        const f4 vmbOcclusionWeights = CustomWeights(vmbF, vmbOcclusion);
+        float vmbSpecAccumSpeed = ApplyCustomWeights(v00.y, v10.y, v01.y, v11.y, vmbOcclusionWeights);
+        float vmbFootprintQuality = Sqrt01(ApplyBilinear(vmbOcclusion.x, vmbOcclusion.y, vmbOcclusion.z, vmbOcclusion.w, vmbF));
+        vmbSpecAccumSpeed *= lerpf(vmbFootprintQuality, 1.0f, 1.0f / (1.0f + vmbSpecAccumSpeed));
+        const bool vmbAllowCatRom = (vmbOcclusion.x + vmbOcclusion.y + vmbOcclusion.z + vmbOcclusion.w > 3.5f) && smbAllowCatRom;
+
+        // how far (in angle) the virtual motion may have travelled
+        float curvatureAngleTan = pixelSize * fabsf(curvature) * fmaxf(vmbPixelsTraveled / fmaxf(NoV, 0.01f), 1.0f) * 2.0f;
+        const float curvatureAngle = atanf(curvatureAngleTan);
+        const float lobeTanHalfAngle = LobeTanHalfAngle(roughnessModified, kLobeVolume / (1.0f + vmbSpecAccumSpeed));
+        const float lobeHalfAngle = fmaxf(atanf(lobeTanHalfAngle), kNormalEncodingError);
+        float normalWeight = EncodingAwareNormalWeight(N, vmbN, lobeHalfAngle, curvatureAngle, kNormalEncodingError);
+        normalWeight = lerpf(SmoothStep(1.0f, 0.0f, vmbPixelsTraveled), 1.0f, normalWeight);
+        virtualHistoryNormalBasedConfidence = fminf(virtualHistoryNormalBasedConfidence, normalWeight);
+
+        virtualHistoryAmount = SmoothStep(0.05f, 0.95f, Dfactor) * virtualHistoryNormalBasedConfidence;
+
+        // virtual parallax difference against the previous frame's hit distance
+        float virtualHistoryParallaxBasedConfidence;
+        {
+            float hitDistForTrackingPrev = SampleLinear1(a.prevHitDist, vmbPixelUv.x * c.gResolutionScalePrev[0], vmbPixelUv.y * c.gResolutionScalePrev[1]);
+            f3 XvirtualPrev = GetXvirtual(hitDistForTrackingPrev, curvature, X, Xprev, N, V, roughness);
+            f2 vmbPixelUvPrev = GetScreenUv(c.gWorldToClipPrev, XvirtualPrev);
+            if (materialID == c.gCameraAttachedReflectionMaterialID) vmbPixelUvPrev = smbPixelUv;
+            float pixelSizeAtXvirtual = c.gUnproject * lerpf(XvirtualLength, 1.0f, fabsf(c.gOrthoMode));
+            float r = (lobeTanHalfAngle + curvatureAngle) * fminf(hitDistForTracking, hitDistForTrackingPrev) / pixelSizeAtXvirtual;
+            float d = length((vmbPixelUvPrev - vmbPixelUv) * rectSize);
+            r = fmaxf(r, 0.1f);
+            virtualHistoryParallaxBasedConfidence = LinearStep(r, 0.0f, d);
+        }
+
+        // prev-prev normal & roughness test, one tap further along the virtual motion
+        {
+            float stepBetweenTaps = fminf(vmbPixelsTraveled * c.gFramerateScale, 2.0f) + vmbPixelsTraveled;
+            float invLen = rsqrtf(dot(vmbDelta, vmbDelta));
+            f2 dir = mk2(vmbDelta.x * invLen / c.gRectSizePrev[0], vmbDelta.y * invLen / c.gRectSizePrev[1]);
+            f2 rrp2 = RelaxedRoughnessWeightParams(vmbGuide.roughness * vmbGuide.roughness, c.gRoughnessFraction, 0.003f);
+            f2 uvPrev = mk2(vmbPixelUv.x + dir.x * stepBetweenTaps, vmbPixelUv.y + dir.y * stepBetweenTaps);
+            Guide gp = stochasticNr(uvPrev);
+            float wn = EncodingAwareNormalWeight(vmbGuide.N, gp.N, lobeHalfAngle, curvatureAngle * (1.0f + stepBetweenTaps), kNormalEncodingError);
+            float wr = NonExpWeightWithSigma(gp.roughness * gp.roughness, rrp2.x, rrp2.y, roughnessSigma);
+            float k = saturate(stepBetweenTaps);
+            wn = lerpf(1.0f, wn, k);
+            wr = lerpf(1.0f, wr, k);
+            bool inS = uvPrev.x > 0.0f && uvPrev.y > 0.0f && uvPrev.x < 1.0f && uvPrev.y < 1.0f;
+            if (!inS) { wn = 1.0f; wr = 1.0f; }
+            virtualHistoryNormalBasedConfidence = fminf(virtualHistoryNormalBasedConfidence, wn);
+            virtualHistoryRoughnessBasedConfidence = fminf(virtualHistoryRoughnessBasedConfidence, wr);
+        }
+
+        const float virtualHistoryConfidenceForSmbRelaxation = virtualHistoryNormalBasedConfidence * virtualHistoryRoughnessBasedConfidence;
+        const float virtualHistoryConfidence = virtualHistoryConfidenceForSmbRelaxation * virtualHistoryParallaxBasedConfidence;
+        virtualHistoryAmount *= virtualHistoryRoughnessBasedConfidence;
+
+        // surface-motion history
+        const CatRomSetup smbSetup = SetupCatRom(smbSamplePos, c.gResourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
+        f4 smbSpecHistory = ResolveCatRom4(smbSetup, a.histSpec);
+        const float smbSpecFastHistory = ResolveBilinearCustom1(smbSetup, a.histSpecFast, smbOcclusionWeights);
+
+        float surfaceHistoryConfidence;
+        {
+            float ang = atanf(smbParallaxInPixelsMax * pixelSize / length(X));
+            float nonLinearAccumSpeed = 1.0f / (1.0f + smbSpecAccumSpeed);
+            float h = lerpf(smbSpecHistory.w, spec.w, nonLinearAccumSpeed) * hitDistNormalization;
+            float tana0 = LobeTanHalfAngle(roughnessModified, kLobeVolume);
+            tana0 *= lerpf(NoV, 1.0f, roughnessModified);
+            tana0 *= nonLinearAccumSpeed;
+            tana0 /= saturate(h / frustumSize) + kEps;
+            float a0 = fmaxf(atanf(tana0), kNormalEncodingError);
+            float f = LinearStep(a0, 0.0f, ang);
+            surfaceHistoryConfidence = Pow01(f, 4.0f);
+        }
+
+        f2 maxResponsiveFrameNum;
+        {
+            float responsiveFactor = SmoothStep01((roughness + kEps) / (c.gResponsiveAccumulationRoughnessThreshold + kEps));
+            float smc = SpecMagicCurve(roughnessModified);
+            float fx = dot(N, normalize(smbNavg)), fy = dot(N, vmbN);
+            float e = lerpf(32.0f, 1.0f, smc) * (1.0f - responsiveFactor), k = lerpf(smc, 1.0f, responsiveFactor);
+            fx = k * Pow01(fx, e);
+            fy = k * Pow01(fy, e);
+            maxResponsiveFrameNum = mk2(fmaxf(c.gMaxAccumulatedFrameNum * fx, c.gHistoryFixFrameNum), fmaxf(c.gMaxAccumulatedFrameNum * fy, c.gHistoryFixFrameNum));
+        }
+
+        float smbMaxFrameNum = fminf(c.gMaxAccumulatedFrameNum * surfaceHistoryConfidence, maxResponsiveFrameNum.x);
+        float smbBoostedMaxFrameNum = fmaxf(smbMaxFrameNum, c.gHistoryFixFrameNum * (1.0f - virtualHistoryConfidenceForSmbRelaxation));
+        float smbSpecAccumSpeedBoosted = fminf(smbSpecAccumSpeed, smbBoostedMaxFrameNum);
+        float vmbMaxFrameNum = fminf(c.gMaxAccumulatedFrameNum * virtualHistoryConfidence, maxResponsiveFrameNum.y);
+        smbSpecAccumSpeed = fminf(smbSpecAccumSpeed, smbMaxFrameNum);
+        vmbSpecAccumSpeed = fminf(vmbSpecAccumSpeed, vmbMaxFrameNum);
+
+        float magic = vmbSpecAccumSpeed > smbSpecAccumSpeed ? 8.0f : 0.5f;
+        virtualHistoryAmount *= 1.0f + (vmbSpecAccumSpeed - smbSpecAccumSpeed) / (magic * fmaxf(vmbSpecAccumSpeed, smbSpecAccumSpeed) + 1.0f);
+        virtualHistoryAmount = saturate(virtualHistoryAmount);
+
+        // virtual-motion history
+        const f2 vmbSamplePos = mk2(saturate(vmbPixelUv.x) * c.gRectSizePrev[0], saturate(vmbPixelUv.y) * c.gRectSizePrev[1]);
+        const CatRomSetup vmbSetup = SetupCatRom(vmbSamplePos, c.gResourceSizeInvPrev, vmbOcclusionWeights, vmbAllowCatRom);
+        f4 vmbSpecHistory = ResolveCatRom4(vmbSetup, a.histSpec);
+        const float vmbSpecFastHistory = ResolveBilinearCustom1(vmbSetup, a.histSpecFast, vmbOcclusionWeights);
+
+        smbSpecHistory = ClampNegativeToZero(smbSpecHistory);
+        vmbSpecHistory = ClampNegativeToZero(vmbSpecHistory);
+
+        const float smbNl = 1.0f / (1.0f + smbSpecAccumSpeed), vmbNl = 1.0f / (1.0f + vmbSpecAccumSpeed);
+        const float minHitNl = 1.0f / (1.0f + 0.5f * SpecMagicCurve(roughnessModified) * c.gMaxAccumulatedFrameNum);
+        f4 smbSpec = lerp4(smbSpecHistory, spec, smbNl);
+        smbSpec.w = lerpf(smbSpecHistory.w, spec.w, fmaxf(smbNl, minHitNl));
+        f4 vmbSpec = lerp4(vmbSpecHistory, spec, vmbNl);
+        vmbSpec.w = lerpf(vmbSpecHistory.w, spec.w, fmaxf(vmbNl, minHitNl));
+        f4 specResult = lerp4(smbSpec, vmbSpec, virtualHistoryAmount);
+        specAccumSpeed = lerpf(smbSpecAccumSpeedBoosted, vmbSpecAccumSpeed, virtualHistoryAmount);
+        const f4 specHistory = lerp4(smbSpecHistory, vmbSpecHistory, virtualHistoryAmount);
+
+        // firefly suppressor
+        const float specMaxRelativeIntensity = c.gFireflySuppressorMinRelativeScale + 38.0f / (specAccumSpeed + 1.0f);
+        float specAntifireflyFactor = specAccumSpeed * c.gMaxBlurRadius * 0.1f;
+        specAntifireflyFactor /= 1.0f + specAntifireflyFactor;
+        float specLumaClamped = fminf(specResult.x, specHistory.x * specMaxRelativeIntensity);
+        specLumaClamped = lerpf(specResult.x, specLumaClamped, specAntifireflyFactor);
+        specResult = ChangeLuma(specResult, specLumaClamped);
+        StoreRGBA16F(a.outSpec, x, y, specResult);
+
+        // fast history
+        float smbFastNl = fmaxf(1.0f - surfaceHistoryConfidence, 1.0f / (1.0f + fminf(smbSpecAccumSpeed, c.gMaxFastAccumulatedFrameNum)));
+        float vmbFastNl = fmaxf(1.0f - virtualHistoryConfidence, 1.0f / (1.0f + fminf(vmbSpecAccumSpeed, c.gMaxFastAccumulatedFrameNum)));
+        float smbSpecFast = lerpf(smbSpecFastHistory, spec.x, smbFastNl), vmbSpecFast = lerpf(vmbSpecFastHistory, spec.x, vmbFastNl);
+        float specFastResult = lerpf(smbSpecFast, vmbSpecFast, virtualHistoryAmount);
+        float specFastClamped = fminf(specFastResult, specHistory.x * specMaxRelativeIntensity * 4.0f);
+        specFastResult = lerpf(specFastResult, specFastClamped, specAntifireflyFactor);
+        StoreR16F(a.outSpecFast, x, y, specFastResult);
+    }
+
+    // Data2 is R32_UINT when there is a specular signal, R8_UINT (only the 4 surface-motion bits are non-zero) otherwise
+    if (SPEC) StoreU32(a.outData2, x, y, PackData2(fbits, curvature, virtualHistoryAmount));
+    else StoreU8(a.outData2, x, y, min(PackData2(fbits, curvature, virtualHistoryAmount), 255u));
+
+    if (DIFF)
+    {
+        diffAccumSpeed *= lerpf(smbFootprintQuality, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
+        diffAccumSpeed = fminf(diffAccumSpeed, c.gMaxAccumulatedFrameNum);
+        const f4 diff = LoadRGBA16F(a.inDiff, x, y);
+
+        const CatRomSetup smbSetup = SetupCatRom(smbSamplePos, c.gResourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
+        f4 smbDiffHistory = ClampNegativeToZero(ResolveCatRom4(smbSetup, a.histDiff));
+        const float smbDiffFastHistory = ResolveBilinearCustom1(smbSetup, a.histDiffFast, smbOcclusionWeights);
+
+        const float nl = 1.0f / (1.0f + diffAccumSpeed);
+        const float minHitNl = 1.0f / (1.0f + 0.5f * SpecMagicCurve(1.0f) * c.gMaxAccumulatedFrameNum);
+        f4 diffResult = lerp4(smbDiffHistory, diff, nl);
+        diffResult.w = lerpf(smbDiffHistory.w, diff.w, fmaxf(nl, minHitNl));
+
+        const float diffMaxRelativeIntensity = c.gFireflySuppressorMinRelativeScale + 38.0f / (diffAccumSpeed + 1.0f);
+        float diffAntifireflyFactor = diffAccumSpeed * c.gMaxBlurRadius * 0.1f;
+        diffAntifireflyFactor /= 1.0f + diffAntifireflyFactor;
+        float diffLumaClamped = fminf(diffResult.x, smbDiffHistory.x * diffMaxRelativeIntensity);
+        diffLumaClamped = lerpf(diffResult.x, diffLumaClamped, diffAntifireflyFactor);
+        diffResult = ChangeLuma(diffResult, diffLumaClamped);
+        StoreRGBA16F(a.outDiff, x, y, diffResult);
+
+        float fastNl = 1.0f / (1.0f + fminf(diffAccumSpeed, c.gMaxFastAccumulatedFrameNum));
+        float diffFastResult = lerpf(smbDiffFastHistory, diff.x, fastNl);
+        float diffFastClamped = fminf(diffFastResult, smbDiffHistory.x * diffMaxRelativeIntensity * 4.0f);
+        diffFastResult = lerpf(diffFastResult, diffFastClamped, diffAntifireflyFactor);
+        StoreR16F(a.outDiffFast, x, y, diffFastResult);
+    }
+    else
+        diffAccumSpeed = 0.0f;
+
+    // PackData1
+    if (DIFF && SPEC) StoreRG8Unorm(a.outData1, x, y, mk2(__fdiv_rn(diffAccumSpeed, kMaxAccum), __fdiv_rn(specAccumSpeed, kMaxAccum)));
+    else StoreR8Unorm(a.outData1, x, y, __fdiv_rn(DIFF ? diffAccumSpeed : specAccumSpeed, kMaxAccum));
+}
+
+// =============================================================================================
+// History fix
+// =============================================================================================
+struct HfArgs
+{
+    ReblurConstants c;
+    Surf tiles, nr, data1, z, inDiff, inSpec, inDiffFast, inSpecFast, outDiff, outSpec, outDiffFast, outSpecFast;
+    int rowBegin, rowEnd;
+};
+
+template <bool BOTH> __device__ __forceinline__ f2 LoadFrames(const Surf& s, int x, int y)
+{
+    if (BOTH)
+    {
+        f2 d = LoadRG8Unorm(s, x, y);
+        return mk2(d.x * kMaxAccum, d.y * kMaxAccum);
+    }
+    float d = LoadR8Unorm(s, x, y) * kMaxAccum;
+    return mk2(d, d);
+}
+
+template <bool IS_SPEC, bool BOTH>
+__device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, const Surf& inSig, const Surf& inFast, const Surf& outSig, const Surf& outFast,
+                                                 float viewZ, const Guide& g0, f3 Nv, f3 Xv, f2 pixelUv, float frustumSize, float fn, float strideBase)
+{
+    const ReblurConstants& c = a.c;
+    const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
+    const float roughness = g0.roughness;
+    const float minMaterial = IS_SPEC ? c.gSpecMinMaterial : c.gDiffMinMaterial;
+    f4 sig = LoadRGBA16F(inSig, x, y);
+    const float smc = SpecMagicCurve(roughness);
+    float stride = strideBase * (fn < c.gHistoryFixFrameNum ? 1.0f : 0.0f);
+    if (IS_SPEC) stride *= lerpf(0.5f, 1.0f, smc);
+    stride = floorf(stride);
+
+    if (stride != 0.0f)
+    {
+        const int stridei = (int)(stride + 0.5f);
+        const float nl = 1.0f / (1.0f + fn);
+        const float r = IS_SPEC ? roughness : 1.0f;
+        const float normalParam = NormalWeightParam(nl, c.gLobeAngleFraction, r);
+        const float geoA = 1.0f / (c.gPlaneDistSensitivity * frustumSize), geoB = -dot(Nv, Xv) * geoA;
+        const f2 rrp = RelaxedRoughnessWeightParams(roughness * roughness, sqrtf(c.gRoughnessFraction));
+        const float hitDistScale = HitDistNormalization(viewZ, c.gHitDistParams, r);
+        const float hitDist = sig.w * hitDistScale;
+        const float hitDistFactor = saturate(hitDist / frustumSize);
+        const f2 hp = HitDistanceWeightParams(hitDistFactor, nl, IS_SPEC ? smc : SpecMagicCurve(1.0f));
+        float sum = 1.0f + fn;
+        sig = sig * sum;
+        for (int j = -2; j <= 2; j++)
+            for (int i = -2; i <= 2; i++)
+            {
+                if ((i == 0 && j == 0) || (abs(i) + abs(j) == 4)) continue;
+                // uv for the in-screen test / view position is NOT clamped, the texel is
+                float u = __fadd_rn(pixelUv.x, __fmul_rn(__fmul_rn((float)i, stride), c.gRectSizeInv[0]));
+                float v = __fadd_rn(pixelUv.y, __fmul_rn(__fmul_rn((float)j, stride), c.gRectSizeInv[1]));
+                int px = clampi(x + i * stridei, 0, maxX), py = clampi(y + j * stridei, 0, maxY);
+                float zs = fabsf(LoadR32F(a.z, px, py) * c.gViewZScale);
+                Guide gs = DecodeGuide(LoadU32(a.nr, px, py));
+                f3 Xvs = ReconstructViewPosition(mk2(u, v), c.gFrustum, zs, c.gOrthoMode);
+                float w = (u > 0.0f && v > 0.0f && u < 1.0f && v < 1.0f) ? 1.0f : 0.0f;
+                w *= NonExpWeight(dot(Nv, Xvs), geoA, geoB);
+                w *= fmaxf(g0.materialID, minMaterial) == fmaxf(gs.materialID, minMaterial) ? 1.0f : 0.0f;
+                w *= ExpWeight(AcosApprox(dot(gs.N, g0.N)), normalParam, 0.0f);
+                if (IS_SPEC) w *= ExpWeight(gs.roughness * gs.roughness, rrp.x, rrp.y);
+                f2 fr = LoadFrames<BOTH>(a.data1, px, py);
+                w *= 1.0f + (IS_SPEC ? fr.y : fr.x);
+                if (w != 0.0f)
+                {
+                    f4 sv = LoadRGBA16F(inSig, px, py);
+                    float hs = sv.w * hitDistScale;
+                    w *= ExpWeight(saturate(hs / frustumSize), hp.x, hp.y);
+                    if (IS_SPEC)
+                    {
+                        float d = fabsf(hitDist - hs) / (fmaxf(hitDist, hs) + 0.001f);
+                        float b = LinearStep(0.03f, 0.05f, roughness);
+                        w *= SmoothStep(0.2f + b, 0.05f + b, d);
+                    }
+                    sum += w;
+                    sig = sig + sv * w;
+                }
+            }
+        sig = sig * PositiveRcp(sum);
+    }
+
+    // 5x5 moments of the fast history (clamped reads)
+    float center = LoadR16F(inFast, x, y);
+    float m1 = 0.0f, m2 = 0.0f;
+#pragma unroll
+    for (int j = -2; j <= 2; j++)
+#pragma unroll
+        for (int i = -2; i <= 2; i++)
+        {
+            float d = LoadR16F(inFast, clampi(x + i, 0, maxX), clampi(y + j, 0, maxY));
+            m1 += d;
+            m2 += d * d;
+        }
+    float f = saturate(fn / (c.gHistoryFixFrameNum + kEps));
+    if (IS_SPEC) f = lerpf(1.0f, f, smc);
+    StoreR16F(outFast, x, y, lerpf(sig.x, center, f));
+
+    float luma = sig.x;
+    if (c.gAntiFirefly != 0.0f)
+    {
+        float am1 = 0.0f, am2 = 0.0f;
+        for (int j = -4; j <= 4; j++)
+            for (int i = -4; i <= 4; i++)
+            {
+                if (abs(i) <= 1 && abs(j) <= 1) continue;
+                float d = LoadR16F(inFast, clampi(x + i, 0, maxX), clampi(y + j, 0, maxY));
+                am1 += d;
+                am2 += d * d;
+            }
+        am1 *= 1.0f / 72.0f;
+        am2 *= 1.0f / 72.0f;
+        float sigma = GetStdDev(am1, am2) * 2.0f;
+        luma = clampf(luma, am1 - sigma, am1 + sigma);
+    }
+    m1 *= 1.0f / 25.0f;
+    m2 *= 1.0f / 25.0f;
+    float sigma = GetStdDev(m1, m2) * 2.0f;
+    float lumaClamped = clampf(luma, m1 - sigma, m1 + sigma);
+    luma = lerpf(lumaClamped, luma, 1.0f / (1.0f + (c.gMaxFastAccumulatedFrameNum < c.gMaxAccumulatedFrameNum ? 1.0f : 0.0f) * fn * 2.0f));
+    StoreRGBA16F(outSig, x, y, ChangeLuma(sig, luma));
+}
+
+template <bool DIFF, bool SPEC>
+__global__ void __launch_bounds__(256) ReblurHistoryFixKernel(const __grid_constant__ HfArgs a)
+{
+    const ReblurConstants& c = a.c;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
+    if (x > c.gRectSizeMinusOne[0] || y > c.gRectSizeMinusOne[1] || y >= a.rowEnd) return;
+    if (LoadU8(a.tiles, x >> 4, y >> 4) != 0) return;
+    const float viewZ = fabsf(LoadR32F(a.z, x, y) * c.gViewZScale);
+    if (viewZ > c.gDenoisingRange) return;
+
+    const Guide g0 = DecodeGuide(LoadU32(a.nr, x, y));
+    const float frustumSize = c.gMinRectDimMulUnproject * lerpf(viewZ, 1.0f, fabsf(c.gOrthoMode));
+    const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
+    const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
+    const f3 Nv = RotateInverse(c.gViewToWorld, g0.N);
+    const f2 frameNum = LoadFrames<DIFF && SPEC>(a.data1, x, y);
+    const f2 stride = mk2(__fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.x)), __fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.y)));
+
+    if (DIFF) HistoryFixSignal<false, DIFF && SPEC>(a, x, y, a.inDiff, a.inDiffFast, a.outDiff, a.outDiffFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.x, stride.x);
+    if (SPEC) HistoryFixSignal<true, DIFF && SPEC>(a, x, y, a.inSpec, a.inSpecFast, a.outSpec, a.outSpecFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.y, stride.y);
+}
+
+// =============================================================================================
+// Temporal stabilization
+// =============================================================================================
+struct TsArgs
+{
+    ReblurConstants c;
+    Surf tiles, nr, z, data1, data2, inDiff, inSpec, histDiffStab, histSpecStab, hitDist, mv;
+    Surf outInternal, outDiff, outSpec, outDiffStab, outSpecStab;
+    int rowBegin, rowEnd;
+};
+
+__device__ __forceinline__ float Antilag(const ReblurConstants& c, float history, float avg, float sigma, float accumSpeed) // REBLUR_Common.hlsli:244-274, mode 2
+{
+    float s = sigma * c.gAntilagParams[0];
+    float magic = c.gAntilagParams[1] * c.gFramerateScale * c.gFramerateScale;
+    float hc = clampf(history, avg - s, avg + s);
+    float d = fabsf(history - hc) / (fmaxf(history, hc) + kEps);
+    return 1.0f / (1.0f + d * accumSpeed / magic);
+}
+
+// 3x3 luma statistics of a YCoCg signal (clamped reads)
+__device__ __forceinline__ void LumaStats3x3(const Surf& s, int x, int y, int maxX, int maxY, float& luma, float& m1, float& m2, float& mn, float& mx)
+{
+    m1 = 0.0f; m2 = 0.0f; mn = kInf; mx = -kInf; luma = 0.0f;
+#pragma unroll
+    for (int j = -1; j <= 1; j++)
+#pragma unroll
+        for (int i = -1; i <= 1; i++)
+        {
+            float d = LoadRGBA16F(s, clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)).x;
+            m1 += d;
+            m2 += d * d;
+            if (i == 0 && j == 0) luma = d;
+            else { mn = fminf(mn, d); mx = fmaxf(mx, d); }
+        }
+    m1 *= 1.0f / 9.0f;
+    m2 *= 1.0f / 9.0f;
+}
+
+template <bool DIFF, bool SPEC>
+__global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const __grid_constant__ TsArgs a)
+{
+    const ReblurConstants& c = a.c;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
+    const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
+    if (x > maxX || y > maxY || y >= a.rowEnd) return;
+    if (LoadU8(a.tiles, x >> 4, y >> 4) != 0) return;
+    const float viewZ = fabsf(LoadR32F(a.z, x, y) * c.gViewZScale);
+    if (viewZ > c.gDenoisingRange) return;
+
+    const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
+    const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
+    const f3 X = PinnedRotate(c.gViewToWorld, Xv);
+
+    const f4 mvRaw = LoadRGBA16F(a.mv, x, y);
+    f3 mv = mk3(__fmul_rn(mvRaw.x, c.gMvScale[0]), __fmul_rn(mvRaw.y, c.gMvScale[1]), __fmul_rn(mvRaw.z, c.gMvScale[2]));
+    f3 Xprev = X;
+    f2 smbPixelUv = mk2(__fadd_rn(pixelUv.x, mv.x), __fadd_rn(pixelUv.y, mv.y));
+    if (c.gMvScale[3] == 0.0f)
+    {
+        if (c.gMvScale[2] == 0.0f) mv.z = __fadd_rn(PinnedRow(c.gWorldToViewPrev, 2, X.x, X.y, X.z), -viewZ);
+        float viewZprev = __fadd_rn(viewZ, mv.z);
+        f3 Xvprevlocal = ReconstructViewPosition(smbPixelUv, c.gFrustumPrev, viewZprev, c.gOrthoMode);
+        f3 r = PinnedRotateInverse(c.gWorldToViewPrev, Xvprevlocal);
+        Xprev = mk3(__fadd_rn(r.x, c.gCameraDelta[0]), __fadd_rn(r.y, c.gCameraDelta[1]), __fadd_rn(r.z, c.gCameraDelta[2]));
+    }
+    else
+    {
+        Xprev = mk3(__fadd_rn(X.x, mv.x), __fadd_rn(X.y, mv.y), __fadd_rn(X.z, mv.z));
+        smbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xprev);
+    }
+
+    const Guide g0 = DecodeGuide(LoadU32(a.nr, x, y));
+    f2 data1 = LoadFrames<DIFF && SPEC>(a.data1, x, y);
+    const unsigned d2 = SPEC ? LoadU32(a.data2, x, y) : LoadU8(a.data2, x, y);
+    const unsigned bits = d2 & 0xFFu;
+    const float virtualHistoryAmount = (float)((d2 >> 8) & 0xFFu) / 255.0f;
+    const float curvature = __half2float(__ushort_as_half((unsigned short)(d2 >> 16)));
+
+    const Bilinear smbF = GetBilinear(smbPixelUv, c.gRectSizePrev);
+    const f4 smbOcclusion = mk4((bits & 1u) ? 1.0f : 0.0f, (bits & 2u) ? 1.0f : 0.0f, (bits & 4u) ? 1.0f : 0.0f, (bits & 8u) ? 1.0f : 0.0f);
+    const f4 smbOcclusionWeights = CustomWeights(smbF, smbOcclusion);
+    const bool smbAllowCatRom = (bits & 15u) == 15u;
+    const float smbFootprintQuality = Sqrt01(ApplyBilinear(smbOcclusion.x, smbOcclusion.y, smbOcclusion.z, smbOcclusion.w, smbF));
+    const f2 smbSamplePos = mk2(saturate(smbPixelUv.x) * c.gRectSizePrev[0], saturate(smbPixelUv.y) * c.gRectSizePrev[1]);
+    const CatRomSetup smbSetup = SetupCatRom(smbSamplePos, c.gResourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
+
+    if (DIFF)
+    {
+        float luma, m1, m2, mn, mx;
+        LumaStats3x3(a.inDiff, x, y, maxX, maxY, luma, m1, m2, mn, mx);
+        const float sigma = GetStdDev(m1, m2);
+        if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
+        float history = fmaxf(ResolveCatRom1(smbSetup, a.histDiffStab), 0.0f);
+        const float antilag = Antilag(c, history, m1, sigma, smbFootprintQuality * data1.x);
+        const float tw = smbFootprintQuality * (data1.x / (1.0f + data1.x));
+        float historyWeight = tw * antilag;
+        historyWeight *= pixelUv.x >= c.gSplitScreen ? 1.0f : 0.0f;
+        historyWeight *= smbPixelUv.x >= c.gSplitScreenPrev ? 1.0f : 0.0f;
+        const float k = sigma * (1.0f + 3.0f * c.gFramerateScale * tw);
+        history = clampf(history, m1 - k, m1 + k);
+        const float stabilized = lerpf(luma, history, fminf(historyWeight, c.gStabilizationStrength));
+        StoreRGBA16F(a.outDiff, x, y, ChangeLuma(LoadRGBA16F(a.inDiff, x, y), stabilized));
+        StoreR16F(a.outDiffStab, x, y, stabilized);
+        data1.x += 1.0f;
+        data1.x = lerpf(fminf(data1.x, c.gHistoryFixFrameNum), data1.x, antilag);
+    }
+
+    if (SPEC)
+    {
+        float luma, m1, m2, mn, mx;
+        LumaStats3x3(a.inSpec, x, y, maxX, maxY, luma, m1, m2, mn, mx);
+        const float sigma = GetStdDev(m1, m2);
+        if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
+
+        f4 spec = LoadRGBA16F(a.inSpec, x, y);
+        float hitDistForTracking = spec.w * HitDistNormalization(viewZ, c.gHitDistParams, g0.roughness);
+        if (c.gSpecPrepassBlurRadius != 0.0f) hitDistForTracking = fminf(hitDistForTracking, LoadR16F(a.hitDist, x, y));
+
+        const f3 V = c.gOrthoMode == 0.0f ? normalize(-X) : mk3(c.gViewVectorWorld[0], c.gViewVectorWorld[1], c.gViewVectorWorld[2]);
+        const f3 Xvirtual = GetXvirtual(hitDistForTracking, curvature, X, Xprev, g0.N, V, g0.roughness);
+        f2 vmbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xvirtual);
+        if (g0.materialID == c.gCameraAttachedReflectionMaterialID) vmbPixelUv = pixelUv;
+
+        float smbHistory = ResolveCatRom1(smbSetup, a.histSpecStab);
+
+        const Bilinear vmbF = GetBilinear(vmbPixelUv, c.gRectSizePrev);
+        const f4 vmbOcclusion = mk4((bits & 16u) ? 1.0f : 0.0f, (bits & 32u) ? 1.0f : 0.0f, (bits & 64u) ? 1.0f : 0.0f, (bits & 128u) ? 1.0f : 0.0f);
+        const f4 vmbOcclusionWeights = CustomWeights(vmbF, vmbOcclusion);
+        const bool vmbAllowCatRom = (bits & 240u) == 240u;
+        const float vmbFootprintQuality = Sqrt01(ApplyBilinear(vmbOcclusion.x, vmbOcclusion.y, vmbOcclusion.z, vmbOcclusion.w, vmbF));
+        const f2 vmbSamplePos = mk2(saturate(vmbPixelUv.x) * c.gRectSizePrev[0], saturate(vmbPixelUv.y) * c.gRectSizePrev[1]);
+        const CatRomSetup vmbSetup = SetupCatRom(vmbSamplePos, c.gResourceSizeInvPrev, vmbOcclusionWeights, vmbAllowCatRom);
+        float vmbHistory = ResolveCatRom1(vmbSetup, a.histSpecStab);
+
+        smbHistory = fmaxf(smbHistory, 0.0f);
+        vmbHistory = fmaxf(vmbHistory, 0.0f);
+        float history = lerpf(smbHistory, vmbHistory, virtualHistoryAmount);
+
+        const float footprintQuality = lerpf(smbFootprintQuality, vmbFootprintQuality, virtualHistoryAmount);
+        const float antilag = Antilag(c, history, m1, sigma, footprintQuality * data1.y);
+        const float tw = footprintQuality * (data1.y / (1.0f + data1.y));
+        float historyWeight = tw * antilag;
+        historyWeight *= pixelUv.x >= c.gSplitScreen ? 1.0f : 0.0f;
+        historyWeight *= virtualHistoryAmount != 1.0f ? (smbPixelUv.x >= c.gSplitScreenPrev ? 1.0f : 0.0f) : 1.0f;
+        historyWeight *= virtualHistoryAmount != 0.0f ? (vmbPixelUv.x >= c.gSplitScreenPrev ? 1.0f : 0.0f) : 1.0f;
+
+        const float responsiveFactor = SmoothStep01((g0.roughness + kEps) / (c.gResponsiveAccumulationRoughnessThreshold + kEps));
+        const float smc = SpecMagicCurve(g0.roughness);
+        const float acceleration = lerpf(smc, 1.0f, 0.5f + responsiveFactor * 0.5f);
+        historyWeight *= g0.materialID == c.gStrandMaterialID ? 0.5f : acceleration;
+
+        const float k = sigma * (1.0f + 3.0f * c.gFramerateScale * tw);
+        history = clampf(history, m1 - k, m1 + k);
+        const float stabilized = lerpf(luma, history, fminf(historyWeight, c.gStabilizationStrength));
+        StoreRGBA16F(a.outSpec, x, y, ChangeLuma(spec, stabilized));
+        StoreR16F(a.outSpecStab, x, y, stabilized);
+        data1.y += 1.0f;
+        data1.y = lerpf(fminf(data1.y, c.gHistoryFixFrameNum), data1.y, antilag);
+    }
+
+    StoreU16(a.outInternal, x, y, PackInternalData(data1.x, data1.y, g0.materialID));
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+template <bool DIFF, bool SPEC> static cudaError_t LaunchTa(const PassLaunch& p)
+{
+    TaArgs a;
+    a.c = *(const ReblurConstants*)p.constants;
+    int k = 0;
+    a.tiles = p.tex[k++]; a.nr = p.tex[k++]; a.z = p.tex[k++]; a.mv = p.tex[k++];
+    a.prevZ = p.tex[k++]; a.prevNr = p.tex[k++]; a.prevInternal = p.tex[k++];
+    k++;               // gIn_DisocclusionThresholdMix (dummy: the executor rejects isDisocclusionThresholdMixAvailable)
+    if (DIFF) k++;     // gIn_DiffConfidence (dummy)
+    if (SPEC) k++;     // gIn_SpecConfidence (dummy)
+    if (DIFF) a.inDiff = p.tex[k++];
+    if (SPEC) a.inSpec = p.tex[k++];
+    if (DIFF && SPEC) { a.histDiff = p.tex[k++]; a.histSpec = p.tex[k++]; a.histDiffFast = p.tex[k++]; a.histSpecFast = p.tex[k++]; }
+    else if (DIFF) { a.histDiff = p.tex[k++]; a.histDiffFast = p.tex[k++]; }
+    else { a.histSpec = p.tex[k++]; a.histSpecFast = p.tex[k++]; }
+    if (SPEC) { a.prevHitDist = p.tex[k++]; a.inHitDist = p.tex[k++]; }
+    if (DIFF) a.outDiff = p.tex[k++];
+    if (SPEC) a.outSpec = p.tex[k++];
+    if (DIFF) a.outDiffFast = p.tex[k++];
+    if (SPEC) { a.outSpecFast = p.tex[k++]; a.outHitDist = p.tex[k++]; }
+    a.outData1 = p.tex[k++];
+    a.outData2 = p.tex[k++];
+    a.rowBegin = p.rowBegin;
+    a.rowEnd = p.rowEnd;
+    const int W = (int)a.c.gRectSize[0];
+    dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 3) / 4), block(32, 4);
+    ReblurTemporalAccumulationKernel<DIFF, SPEC><<<grid, block, 0, p.stream>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t LaunchReblurTemporalAccumulation(const PassLaunch& p, int signal)
+{
+    if (signal == 0) return LaunchTa<true, false>(p);
+    if (signal == 1) return LaunchTa<false, true>(p);
+    return LaunchTa<true, true>(p);
+}
+
+template <bool DIFF, bool SPEC> static cudaError_t LaunchHf(const PassLaunch& p)
+{
+    HfArgs a;
+    a.c = *(const ReblurConstants*)p.constants;
+    int k = 0;
+    a.tiles = p.tex[k++]; a.nr = p.tex[k++]; a.data1 = p.tex[k++]; a.z = p.tex[k++];
+    if (DIFF) a.inDiff = p.tex[k++];
+    if (SPEC) a.inSpec = p.tex[k++];
+    if (DIFF) a.inDiffFast = p.tex[k++];
+    if (SPEC) a.inSpecFast = p.tex[k++];
+    if (DIFF) a.outDiff = p.tex[k++];
+    if (SPEC) a.outSpec = p.tex[k++];
+    if (DIFF) a.outDiffFast = p.tex[k++];
+    if (SPEC) a.outSpecFast = p.tex[k++];
+    a.rowBegin = p.rowBegin;
+    a.rowEnd = p.rowEnd;
+    const int W = (int)a.c.gRectSize[0];
+    dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
+    ReblurHistoryFixKernel<DIFF, SPEC><<<grid, block, 0, p.stream>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t LaunchReblurHistoryFix(const PassLaunch& p, int signal)
+{
+    if (signal == 0) return LaunchHf<true, false>(p);
+    if (signal == 1) return LaunchHf<false, true>(p);
+    return LaunchHf<true, true>(p);
+}
+
+template <bool DIFF, bool SPEC> static cudaError_t LaunchTs(const PassLaunch& p)
+{
+    TsArgs a;
+    a.c = *(const ReblurConstants*)p.constants;
+    int k = 0;
+    a.tiles = p.tex[k++]; a.nr = p.tex[k++];
+    if (SPEC) k++; // gIn_BaseColor_Metalness (dummy)
+    a.z = p.tex[k++]; a.data1 = p.tex[k++]; a.data2 = p.tex[k++];
+    if (DIFF) a.inDiff = p.tex[k++];
+    if (SPEC) a.inSpec = p.tex[k++];
+    if (DIFF) a.histDiffStab = p.tex[k++];
+    if (SPEC) { a.histSpecStab = p.tex[k++]; a.hitDist = p.tex[k++]; }
+    a.mv = p.tex[k++];
+    a.outInternal = p.tex[k++];
+    if (DIFF) a.outDiff = p.tex[k++];
+    if (SPEC) a.outSpec = p.tex[k++];
+    if (DIFF) a.outDiffStab = p.tex[k++];
+    if (SPEC) a.outSpecStab = p.tex[k++];
+    a.rowBegin = p.rowBegin;
+    a.rowEnd = p.rowEnd;
+    const int W = (int)a.c.gRectSize[0];
+    dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
+    ReblurTemporalStabilizationKernel<DIFF, SPEC><<<grid, block, 0, p.stream>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t LaunchReblurTemporalStabilization(const PassLaunch& p, int signal)
+{
+    if (signal == 0) return LaunchTs<true, false>(p);
+    if (signal == 1) return LaunchTs<false, true>(p);
+    return LaunchTs<true, true>(p);
+}
+} // namespace nrdb200

@@ -1,0 +1,145 @@
+"""Test infrastructure: a CPU "RHI" that executes the product scheduler's DispatchDesc[] on the oracle (oracle/liboracle.so).
+
+It plays the role of the application / integration layer of the reference: it creates the pool textures the InstanceDesc
+asks for (as numpy arrays), binds resources in DispatchDesc order and runs each dispatch through `oracle_dispatch`.
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from raytracingdenoiser_b200 import nrd
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ORACLE_PATH = os.path.join(_ROOT, "oracle", "liboracle.so")
+
+
+class OracleTexture(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pitchBytes", C.c_int32), ("format", C.c_int32), ("firstRow", C.c_int32)]
+
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(_ORACLE_PATH):
+            from raytracingdenoiser_b200 import build
+            build.build_oracle()
+        _oracle = C.CDLL(_ORACLE_PATH)
+        _oracle.oracle_dispatch.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(OracleTexture), C.c_int, C.c_int, C.c_int]
+        _oracle.oracle_dispatch.restype = C.c_int
+        _oracle.oracle_num_threads.restype = C.c_int
+    return _oracle
+
+
+_NP = {nrd.Format.R8_UNORM: (np.uint8, 1), nrd.Format.R8_UINT: (np.uint8, 1), nrd.Format.RG8_UNORM: (np.uint8, 2), nrd.Format.RGBA8_UNORM: (np.uint8, 4),
+       nrd.Format.R16_UINT: (np.uint16, 1), nrd.Format.R16_SFLOAT: (np.float16, 1), nrd.Format.RGBA16_SFLOAT: (np.float16, 4), nrd.Format.R32_UINT: (np.uint32, 1),
+       nrd.Format.R32_SFLOAT: (np.float32, 1), nrd.Format.R10_G10_B10_A2_UNORM: (np.uint32, 1)}
+
+
+def alloc(fmt, w, h):
+    dt, ch = _NP[nrd.Format(fmt)]
+    return np.zeros((h, w, ch) if ch > 1 else (h, w), dtype=dt)
+
+
+class CpuDenoiser(object):
+    """Mirror of harness.GpuDenoiser on the CPU: same scheduler (the product's), oracle passes, numpy textures."""
+
+    def __init__(self, denoiser, width, height, identifier=0, settings=None, user_formats=None, instance=None):
+        from raytracingdenoiser_b200 import harness
+        self.width, self.height, self.identifier = width, height, identifier
+        self.instance = instance or nrd.Instance([(identifier, denoiser)])
+        if settings is not None and instance is None:
+            self.instance.set_denoiser_settings(identifier, settings)
+        desc = self.instance.get_instance_desc()
+        self.permanent = [alloc(f, (width + ds - 1) // ds, (height + ds - 1) // ds) for f, ds in desc["permanentPool"]]
+        self.transient = [alloc(f, (width + ds - 1) // ds, (height + ds - 1) // ds) for f, ds in desc["transientPool"]]
+        self.formats = {"permanent": [f for f, _ in desc["permanentPool"]], "transient": [f for f, _ in desc["transientPool"]]}
+        self.user = {}
+        self.user_fmt = {}
+        for name in harness.DENOISER_RESOURCES[denoiser]:
+            fmt = harness.USER_FORMATS[name][0]
+            self.user[name] = alloc(fmt, width, height)
+            self.user_fmt[name] = fmt
+
+    def resolve(self, rtype, index):
+        if rtype == nrd.ResourceType.PERMANENT_POOL:
+            return self.permanent[index], self.formats["permanent"][index]
+        if rtype == nrd.ResourceType.TRANSIENT_POOL:
+            return self.transient[index], self.formats["transient"][index]
+        name = nrd.ResourceType(rtype).name
+        return self.user[name], self.user_fmt[name]
+
+    def set_inputs(self, frame):
+        for name, arr in self.user.items():
+            if name.startswith("IN_"):
+                src = frame[name]
+                src = src.cpu().numpy() if hasattr(src, "cpu") else np.asarray(src)
+                arr[...] = src.view(arr.dtype).reshape(arr.shape)
+
+    def run_dispatch(self, d):
+        lib = oracle_lib()
+        texs = (OracleTexture * len(d.resources))()
+        keep = []
+        for i, (_, rtype, index) in enumerate(d.resources):
+            arr, fmt = self.resolve(rtype, index)
+            keep.append(arr)
+            texs[i].data = arr.ctypes.data
+            texs[i].height, texs[i].width = arr.shape[0], arr.shape[1]
+            texs[i].pitchBytes = arr.strides[0]
+            texs[i].format = int(fmt)
+            texs[i].firstRow = 0
+        buf = C.create_string_buffer(d.constants, len(d.constants)) if d.constants else None
+        r = lib.oracle_dispatch(d.shaderFileName.encode(), buf, len(d.constants), texs, len(d.resources), d.gridWidth, d.gridHeight)
+        if r != 0:
+            raise RuntimeError("oracle_dispatch(%s) failed with %d" % (d.shaderFileName, r))
+
+    def denoise(self, common_settings, on_dispatch=None):
+        self.instance.set_common_settings(common_settings)
+        dispatches = self.instance.get_compute_dispatches([self.identifier])
+        for i, d in enumerate(dispatches):
+            if on_dispatch:
+                on_dispatch(i, d, "before")
+            self.run_dispatch(d)
+            if on_dispatch:
+                on_dispatch(i, d, "after")
+        return dispatches
+
+
+def compare(a, b, fmt, rel=1e-3, abs_tol=1e-4):
+    """Per-channel parity metric of SURVEY.md 8(d): returns (fraction of texels within tolerance, worst excess factor)."""
+    fmt = nrd.Format(fmt)
+    if fmt in (nrd.Format.RGBA16_SFLOAT, nrd.Format.R16_SFLOAT, nrd.Format.R32_SFLOAT):
+        x, y = a.astype(np.float64), b.astype(np.float64)
+        x = np.nan_to_num(x, nan=1e30, posinf=1e30, neginf=-1e30)
+        y = np.nan_to_num(y, nan=1e30, posinf=1e30, neginf=-1e30)
+        tol = rel * np.maximum(np.abs(x), np.abs(y)) + abs_tol
+        err = np.abs(x - y)
+        ok = err <= tol
+        if ok.ndim == 3:
+            ok_px = ok.all(axis=2)
+        else:
+            ok_px = ok
+        worst = float((err / tol).max()) if err.size else 0.0
+        return float(ok_px.mean()), worst
+    if fmt == nrd.Format.R10_G10_B10_A2_UNORM:
+        d = np.zeros(a.shape, dtype=np.int64)
+        for shift, mask in ((0, 1023), (10, 1023), (20, 1023), (30, 3)):
+            d = np.maximum(d, np.abs(((a.astype(np.int64) >> shift) & mask) - ((b.astype(np.int64) >> shift) & mask)))
+        return float((d <= 1).mean()), float(d.max())
+    if fmt == nrd.Format.R16_UINT:  # REBLUR internal data: 6 + 6 + 4 bits
+        d = np.zeros(a.shape, dtype=np.int64)
+        for shift, mask in ((0, 63), (6, 63), (12, 15)):
+            d = np.maximum(d, np.abs(((a.astype(np.int64) >> shift) & mask) - ((b.astype(np.int64) >> shift) & mask)))
+        return float((d <= 1).mean()), float(d.max())
+    if fmt == nrd.Format.R32_UINT:
+        same = a == b
+        return float(same.mean()), float((~same).sum())
+    d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+    ok = d <= 1
+    if ok.ndim == 3:
+        ok = ok.all(axis=2)
+    return float(ok.mean()), float(d.max())
