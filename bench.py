@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Mpixels/s of REBLUR_DIFFUSE_SPECULAR at 3840x2160 (BASELINE.json metric), one frame per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--width 3840 --height 2160]
+
+value     whole chain, inputs already resident in HBM (each frame's inputs are separate 265 MB buffers, i.e. larger than
+          the 126 MB L2, so no flush is needed between steps), CUDA events on the launching stream, max over ranks.
+e2e       the same metric through the C-ABI with HOST buffers: pinned host -> H2D -> nrdCudaDenoise -> D2H inside the timed region.
+roofline  Blur + PostBlur (the north-star kernels): algorithmic bytes (92 B/px) / measured CUDA-event time,
+          against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference   the CPU restatement of the reference shaders (oracle/, OpenMP over all host cores) on a
+          bounded sample of the same frames.  It is a reported baseline; the oracle is never on the product path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+ALGO_BYTES_PER_PIXEL = {  # SURVEY.md Appendix A, REBLUR_DIFFUSE_SPECULAR defaults
+    "Classify tiles": 4, "Pre-pass": 42, "Temporal accumulation": 94, "History fix": 50, "Blur": 46, "Post-blur": 46, "Temporal stabilization": 66,
+}
+FALLBACK_HBM_GBS = 6650.0
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi SM clock / throttle-reason sampler running beside the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.reasons, self.max_mhz, self.proc = index, [], set(), None, None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        s = sorted(self.samples)
+        # median of the upper half: samples taken while the GPU was busy
+        busy = s[len(s) // 2:] if s else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def generate_frames(width, height, count, device):
+    from raytracingdenoiser_b200 import scene
+    sc = scene.Scene(width, height, device=device)
+    return [sc.frame(f) for f in range(count)]
+
+
+def run_cpu_reference(width, height, frames, steps, warmup):
+    """Times the oracle chain (all host threads) on `frames`; returns (Mpx/s, ms per step, threads)."""
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd
+    cpu = orr.CpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, width, height)
+    host = [{k: (v.cpu() if hasattr(v, "cpu") else v) for k, v in fr.items()} for fr in frames]
+    times = []
+    for i in range(warmup + steps):
+        fr = host[i % len(host)]
+        cs = harness.make_common_settings(fr, width, height, i)
+        cpu.set_inputs(fr)
+        t0 = time.perf_counter()
+        cpu.denoise(cs)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return width * height * len(times) / total / 1e6, 1e3 * total / len(times), orr.oracle_lib().oracle_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+    from raytracingdenoiser_b200 import build
+    build.build_all()
+    from raytracingdenoiser_b200 import harness, nrd
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W, H, K, Wm = args.width, args.height, args.steps, max(args.warmup, 3)
+    workload = "REBLUR_DIFFUSE_SPECULAR %dx%d, %d-frame synthetic sequence with motion vectors, default settings" % (W, H, K + Wm)
+    base = {"metric": "Mpixels/s REBLUR_DIFFUSE_SPECULAR @4K", "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": K, "warmup": Wm, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "l2": "per-frame inputs are distinct 265 MB buffers (> 126 MB L2), no flush needed"}}
+
+    # ------------------------------------------------------------------ reference arm: CPU restatement on host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        gen_dev = "cuda" if torch.cuda.is_available() else "cpu"
+        nframes = min(K + Wm, 6)
+        frames = generate_frames(W, H, nframes, gen_dev)
+        mpx, ms, threads = run_cpu_reference(W, H, frames, K, Wm)
+        out = dict(base)
+        out.update({"impl": "reference", "value": mpx, "ms_per_step": ms, "gpu_launches": 0,
+                    "cpu_baseline": {"value": mpx, "unit": "Mpixels/s", "cores": threads, "kind": "port",
+                                     "sample": "%d timed frames of the %dx%d sequence (inputs cycle over %d generated frames)" % (K, W, H, nframes)},
+                    "e2e": {"value": mpx, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(out))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    frames = generate_frames(W, H, K + Wm, dev)
+    gpu = harness.GpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, device=local_rank)
+    stream = torch.cuda.current_stream(dev)
+    in_names = [n for n in gpu.tex if n.startswith("IN_")]
+
+    def bind(fr):
+        # inputs are device resident: bind this frame's own buffers (what an application's ring of G-buffers looks like)
+        for n in in_names:
+            t = fr[n]
+            fmt = harness.USER_FORMATS[n][0]
+            gpu.ctx.set_user_texture(getattr(nrd.ResourceType, n), t.data_ptr(), t.stride(0) * t.element_size(), fmt)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    # IN_MV is bound as a storage texture by the chain (frame 0 clears it): keep pristine copies out of the way
+    mv0 = frames[0]["IN_MV"].clone()
+    for i in range(Wm):
+        bind(frames[i])
+        gpu.denoise(harness.make_common_settings(frames[i], W, H, i))
+        if i == 0:
+            frames[0]["IN_MV"].copy_(mv0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = nrd.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(Wm, Wm + K):
+        bind(frames[i])
+        gpu.denoise(harness.make_common_settings(frames[i], W, H, i))
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = nrd.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = W * H * K / (ms_total * 1e-3) / 1e6
+
+    # ---- per-pass breakdown with CUDA events around every dispatch (separate run, not part of `value`)
+    per_pass = {}
+    pipelines = gpu.instance.get_instance_desc()["pipelines"]
+    import ctypes as C
+    reps = min(K, 8)
+    for i in range(Wm + K - reps, Wm + K):
+        bind(frames[i])
+        gpu.instance.set_common_settings(harness.make_common_settings(frames[i], W, H, i + K))
+        r, raw, n = gpu.instance.get_compute_dispatches_raw([gpu.identifier])
+        evs = []
+        for j in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            gpu.ctx.execute_raw(C.byref(raw[j]), stream.cuda_stream)
+            b.record(stream)
+            evs.append((raw[j].name.decode().split(" - ")[-1], a, b))
+        torch.cuda.synchronize(dev)
+        for name, a, b in evs:
+            per_pass.setdefault(name, []).append(a.elapsed_time(b))
+    pass_ms = {k: sum(v) / len(v) for k, v in per_pass.items()}
+    peak, peak_kind = measured_peaks()
+    blur_ms = pass_ms.get("Blur", 0.0) + pass_ms.get("Post-blur", 0.0)
+    algo_bytes = (ALGO_BYTES_PER_PIXEL["Blur"] + ALGO_BYTES_PER_PIXEL["Post-blur"]) * W * H
+    achieved = algo_bytes / (blur_ms * 1e-3) / 1e9 if blur_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "REBLUR Blur + PostBlur (2 launches)", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch_pair": algo_bytes,
+                "per_pass_ms": pass_ms,
+                "per_pass_frac": {k: (ALGO_BYTES_PER_PIXEL[k] * W * H / (v * 1e-3) / 1e9 / peak) for k, v in pass_ms.items() if k in ALGO_BYTES_PER_PIXEL and v > 0}}
+
+    # ---- end to end with host buffers: pinned host -> H2D -> denoise -> D2H of both outputs, every step
+    nhost = min(K + Wm, 8)
+    host_frames = [{n: frames[i][n].cpu().pin_memory() for n in in_names} for i in range(nhost)]
+    for n in in_names:  # back to the context's own input textures
+        t = gpu.tex[n]
+        gpu.ctx.set_user_texture(getattr(nrd.ResourceType, n), t.data_ptr(), t.stride(0) * t.element_size(), harness.USER_FORMATS[n][0])
+    host_out = {n: torch.empty_like(t, device="cpu").pin_memory() for n, t in gpu.outputs().items()}
+    h2d = sum(t.numel() * t.element_size() for t in host_frames[0].values())
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+
+    def e2e_step(i):
+        hf = host_frames[i % nhost]
+        for n in in_names:
+            gpu.tex[n].copy_(hf[n], non_blocking=True)
+        gpu.denoise(harness.make_common_settings(frames[i % len(frames)], W, H, i + 2 * K))
+        for n, t in gpu.outputs().items():
+            host_out[n].copy_(t, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(K):
+        e2e_step(3 + i)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms_e2e = max(e0.elapsed_time(e1), wall * 1e3)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e = {"value": W * H * K / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    out = dict(base)
+    out.update({"value": value, "ms_per_step": ms_total / K, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e})
+
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        sample_frames = 2
+        mpx, ms, threads = run_cpu_reference(W, H, frames[Wm:Wm + 3], sample_frames, 1)
+        out["cpu_baseline"] = {"value": mpx, "unit": "Mpixels/s", "cores": threads, "kind": "port",
+                               "sample": "%d timed frames (+1 warm-up) of the same %dx%d sequence on the host cores" % (sample_frames, W, H)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -195,7 +195,7 @@ struct PassLaunch
 {
     const void* constants; // host pointer to the dispatch's constant block
     uint32_t constantsSize;
-    Surf tex[24];          // bindings in DispatchDesc order
+    Surf tex[32];          // bindings in DispatchDesc order
     uint32_t texNum;
     int gridW, gridH;      // DispatchDesc grid (reference thread-group counts)
     int rowBegin, rowEnd;  // rows this launch must produce, in the pass's own pixel units

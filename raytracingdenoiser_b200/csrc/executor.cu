@@ -246,7 +246,7 @@ NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d
     p.gridW = d->gridWidth;
     p.gridH = d->gridHeight;
     p.stream = (cudaStream_t)stream;
-    if (d->resourcesNum > 24) return Result::FAILURE;
+    if (d->resourcesNum > 32) return Fail(ctx, Result::FAILURE, "too many resources in one dispatch");
     for (uint32_t i = 0; i < d->resourcesNum; i++)
     {
         const ResourceDesc& r = d->resources[i];

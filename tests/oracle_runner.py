@@ -109,9 +109,21 @@ class CpuDenoiser(object):
         return dispatches
 
 
-def compare(a, b, fmt, rel=1e-3, abs_tol=1e-4):
+def compare(a, b, fmt, rel=1e-3, abs_tol=1e-4, layout=None):
     """Per-channel parity metric of SURVEY.md 8(d): returns (fraction of texels within tolerance, worst excess factor)."""
     fmt = nrd.Format(fmt)
+    if layout == "reblur_data2":
+        # REBLUR PackData2 (REBLUR_Common.hlsli:59-70): bits 0-7 occlusion flags (exact), 8-15 virtual history amount
+        # (UNORM8, 1 LSB), 16-31 curvature as FP16 (relative tolerance)
+        a64, b64 = a.astype(np.int64), b.astype(np.int64)
+        ok = (a64 & 0xFF) == (b64 & 0xFF)
+        ok &= np.abs(((a64 >> 8) & 0xFF) - ((b64 >> 8) & 0xFF)) <= 1
+        ca = ((a64 >> 16) & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+        cb = ((b64 >> 16) & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+        ca, cb = np.nan_to_num(ca, nan=1e30, posinf=1e30, neginf=-1e30), np.nan_to_num(cb, nan=1e30, posinf=1e30, neginf=-1e30)
+        err, tol = np.abs(ca - cb), 2e-3 * np.maximum(np.abs(ca), np.abs(cb)) + abs_tol
+        ok &= err <= tol
+        return float(ok.mean()), float((err / tol).max())
     if fmt in (nrd.Format.RGBA16_SFLOAT, nrd.Format.R16_SFLOAT, nrd.Format.R32_SFLOAT):
         x, y = a.astype(np.float64), b.astype(np.float64)
         x = np.nan_to_num(x, nan=1e30, posinf=1e30, neginf=-1e30)

@@ -1,0 +1,104 @@
+"""Shared machinery of the GPU parity tests: run the oracle and the CUDA executor side by side on one nrd.Instance.
+
+per-pass parity ("hard gate"): before every dispatch the CUDA context's textures are overwritten with the
+oracle's state, the SAME DispatchDesc is executed by both, and every texture the pass writes is compared.
+sequence parity ("statistical gate"): both executors run the whole chain on their own state for N frames.
+"""
+import ctypes as C
+
+import numpy as np
+
+import oracle_runner as orr
+from raytracingdenoiser_b200 import harness, nrd, scene
+
+# tolerance of north_star: 1e-3 relative (+1e-4 absolute floor); >= 99.9 % of texels, none worse than 10x
+REL, ABS, MIN_FRACTION, MAX_EXCESS = 1e-3, 1e-4, 0.999, 10.0
+
+
+class SideBySide(object):
+    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0):
+        import torch
+        self.denoiser, self.w, self.h, self.identifier = denoiser, width, height, identifier
+        self.cpu = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, settings=settings)
+        self.instance = self.cpu.instance
+        self.ctx = nrd.CudaContext(self.instance, width, height, device=device)
+        self.torch = torch
+        self.dev_user = {}
+        for name in harness.DENOISER_RESOURCES[denoiser]:
+            fmt, dtype, ch = harness.USER_FORMATS[name]
+            t = torch.zeros((height, width, ch) if ch > 1 else (height, width), dtype=dtype, device="cuda:%d" % device)
+            self.dev_user[name] = t
+            self.ctx.set_user_texture(getattr(nrd.ResourceType, name), t.data_ptr(), t.stride(0) * t.element_size(), fmt)
+        self.scene = scene.Scene(width, height)
+        self.report = []
+
+    def _sync_to_gpu(self, d):
+        for _, rtype, index in d.resources:
+            arr, _ = self.cpu.resolve(rtype, index)
+            self.ctx.upload(rtype, index, np.ascontiguousarray(arr))
+
+    def _compare_outputs(self, frame, d):
+        for dtype_, rtype, index in d.resources:
+            if dtype_ != nrd.DescriptorType.STORAGE_TEXTURE:
+                continue
+            ref, fmt = self.cpu.resolve(rtype, index)
+            got = np.empty_like(ref)
+            self.ctx.download(rtype, index, got)
+            layout = "reblur_data2" if ("REBLUR" in d.shaderFileName and "TemporalAccumulation" in d.shaderFileName and fmt == nrd.Format.R32_UINT) else None
+            frac, worst = orr.compare(ref, got, fmt, REL, ABS, layout=layout)
+            self.report.append({"frame": frame, "pass": d.name, "shader": d.shaderFileName, "resource": "%s[%d]" % (nrd.ResourceType(rtype).name, index),
+                                "format": nrd.Format(fmt).name, "fraction": frac, "worst": worst})
+
+    def run_per_pass(self, frames, first_frame=0):
+        """Hard gate.  Returns the list of per-(frame, pass, output) comparison records."""
+        for f in range(first_frame, first_frame + frames):
+            fr = self.scene.frame(f, harness.radiance_mode(self.denoiser))
+            self.cpu.set_inputs(fr)
+            cs = harness.make_common_settings(fr, self.w, self.h, f)
+            self.instance.set_common_settings(cs)
+            r, raw, n = self.instance.get_compute_dispatches_raw([self.identifier])
+            assert r == nrd.Result.SUCCESS
+            pipelines = self.instance.get_instance_desc()["pipelines"]
+            for i in range(n):
+                d = nrd.Dispatch(raw[i], pipelines)
+                self._sync_to_gpu(d)
+                self.ctx.execute_raw(C.byref(raw[i]))
+                self.torch.cuda.synchronize()
+                self.cpu.run_dispatch(d)
+                self._compare_outputs(f, d)
+            if f == first_frame:
+                self.cpu.set_inputs(fr)  # the frame-0 clears also zero IN_MV (reference quirk), restore it
+        return self.report
+
+    def failures(self):
+        return [r for r in self.report if r["fraction"] < MIN_FRACTION]
+
+
+def run_sequence(denoiser, width, height, frames, settings=None, device=0):
+    """Statistical gate: independent end-to-end runs; returns {output name: (fraction within tolerance, PSNR dB)}."""
+    import torch
+    sc = scene.Scene(width, height)
+    cpu = orr.CpuDenoiser(denoiser, width, height, settings=settings)
+    gpu = harness.GpuDenoiser(denoiser, width, height, device=device, settings=settings)
+    for f in range(frames):
+        fr = sc.frame(f, harness.radiance_mode(denoiser))
+        cs = harness.make_common_settings(fr, width, height, f)
+        cpu.set_inputs(fr)
+        cpu.denoise(cs)
+        gpu.set_inputs(fr)
+        gpu.denoise(cs)
+        if f == 0:
+            cpu.set_inputs(fr)
+    torch.cuda.synchronize()
+    out = {}
+    for name, t in gpu.outputs().items():
+        ref = cpu.user[name]
+        got = t.cpu().numpy().view(ref.dtype).reshape(ref.shape)
+        frac, _ = orr.compare(ref, got, cpu.user_fmt[name], REL, ABS)
+        a, b = ref.astype(np.float64), got.astype(np.float64)
+        mse = float(((a - b) ** 2).mean())
+        peak = float(max(np.abs(a).max(), 1e-6))
+        psnr = 10.0 * np.log10(peak * peak / mse) if mse > 0 else 200.0
+        out[name] = (frac, psnr)
+    gpu.destroy()
+    return out

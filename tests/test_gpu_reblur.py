@@ -1,0 +1,53 @@
+"""GPU parity of the REBLUR kernels against the oracle, through the C-ABI (nrdCudaExecuteDispatch / nrdCudaDenoise)."""
+import json
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _dump(name, report):
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, name), "w") as f:
+        json.dump(report, f, indent=1)
+
+
+@pytest.mark.parametrize("denoiser_name,width,height,frames", [
+    ("REBLUR_DIFFUSE_SPECULAR", 250, 141, 6),   # ragged size: partial tiles and groups on both axes
+    ("REBLUR_DIFFUSE", 256, 144, 4),
+    ("REBLUR_SPECULAR", 256, 144, 4),
+])
+def test_reblur_per_pass_parity(denoiser_name, width, height, frames):
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    sbs = parity.SideBySide(getattr(nrd.Denoiser, denoiser_name), width, height)
+    report = sbs.run_per_pass(frames)
+    _dump("parity_%s.json" % denoiser_name, report)
+    bad = sbs.failures()
+    assert not bad, "per-pass parity failures (fraction within 1e-3 rel + 1e-4 abs < %.4f):\n%s" % (
+        parity.MIN_FRACTION, "\n".join("f%d %s %s %s frac=%.5f worst=%.1f" % (r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["worst"]) for r in bad[:40]))
+
+
+def test_reblur_spatial_only_config():
+    """BASELINE config 2: REBLUR_DIFFUSE with temporal accumulation off (Blur + PostBlur_NoTemporalStabilization)."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    s = nrd.ReblurSettings(maxAccumulatedFrameNum=0, maxFastAccumulatedFrameNum=0, maxStabilizedFrameNum=0, historyFixFrameNum=0, diffusePrepassBlurRadius=0.0)
+    sbs = parity.SideBySide(nrd.Denoiser.REBLUR_DIFFUSE, 480, 270, settings=s)
+    report = sbs.run_per_pass(2)
+    names = {r["shader"] for r in report}
+    assert "REBLUR_Diffuse_PostBlur_NoTemporalStabilization.cs" in names and "REBLUR_Diffuse_PrePass.cs" not in names
+    _dump("parity_spatial_only.json", report)
+    assert not sbs.failures(), sbs.failures()[:10]
+
+
+def test_reblur_sequence_parity():
+    """Statistical gate: 12 independent frames end to end; >= 99 % of texels within tolerance, PSNR >= 60 dB."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    res = parity.run_sequence(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, 320, 180, 12)
+    _dump("sequence_reblur.json", res)
+    for name, (frac, psnr) in res.items():
+        assert frac >= 0.99 and psnr >= 60.0, (name, frac, psnr)
