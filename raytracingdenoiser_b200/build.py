@@ -21,7 +21,7 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-              "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
+              "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra"]
 # -ffp-contract=off: the oracle evaluates a*b+c with two roundings, like the "pinned" arithmetic of the kernels
 ORACLE_FLAGS = ["-std=c++17", "-O3", "-mavx2", "-mfma", "-mf16c", "-ffp-contract=off", "-fopenmp", "-fPIC", "-Wall", "-Wextra", "-shared"]

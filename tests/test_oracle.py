@@ -1,0 +1,97 @@
+"""Oracle tests (no GPU): the CPU restatement against its committed golden vectors and against properties the filter
+chain must have (sky untouched, energy preserved, variance reduced, history length grows, determinism)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_runner as orr
+from raytracingdenoiser_b200 import harness, nrd, scene
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLDEN)
+
+
+def _cases():
+    import make_golden
+    return make_golden.CASES
+
+
+@pytest.mark.parametrize("name", ["reblur_diffuse_specular_96x64", "sigma_shadow_96x64", "relax_diffuse_specular_96x64"])
+def test_oracle_reproduces_golden_vectors(name):
+    import make_golden
+    path = os.path.join(GOLDEN, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("golden vector not generated yet")
+    den, w, h, frames = make_golden.CASES[name]
+    out = make_golden.run_case(den, w, h, frames)
+    ref = np.load(path)
+    for k in ref.files:
+        # the oracle is plain IEEE arithmetic + libm; allow 1 ulp of the storage format for libm differences between hosts
+        frac, worst = orr.compare(ref[k], out[k], orr.CpuDenoiser(getattr(nrd.Denoiser, den), 16, 16).user_fmt[k], rel=1e-3, abs_tol=1e-4)
+        assert frac >= 0.9995, (k, frac, worst)
+
+
+def test_reblur_chain_properties():
+    W, H, N = 160, 90, 8
+    sc = scene.Scene(W, H)
+    cpu = orr.CpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H)
+    for f in range(N):
+        fr = sc.frame(f)
+        cpu.set_inputs(fr)
+        cpu.denoise(harness.make_common_settings(fr, W, H, f))
+        if f == 0:
+            cpu.set_inputs(fr)
+    z = cpu.user["IN_VIEWZ"]
+    sky = z > 5e5
+    out = cpu.user["OUT_DIFF_RADIANCE_HITDIST"].astype(np.float32)
+    noisy = cpu.user["IN_DIFF_RADIANCE_HITDIST"].astype(np.float32)
+    assert sky.any() and (~sky).any()
+    assert not np.isnan(out).any()
+    # luminance (Y of YCoCg) is preserved on average and its pixel-to-pixel variation is reduced
+    m_in, m_out = noisy[~sky][:, 0].mean(), out[~sky][:, 0].mean()
+    assert abs(m_in - m_out) / m_in < 0.08, (m_in, m_out)
+    hf = lambda a: np.abs(np.diff(a[..., 0], axis=1))[~sky[:, 1:] & ~sky[:, :-1]].mean()
+    assert hf(out) < 0.35 * hf(noisy)
+    # history length: internal data (6 bits per signal) grows by about one frame per frame on static-ish surfaces
+    internal = cpu.permanent[2]
+    diff_frames = (internal & 63)[~sky]
+    assert np.median(diff_frames) >= N - 2
+    # PREV_VIEWZ (written by Blur) is the current viewZ wherever the tile is not all-sky
+    prev_z = cpu.permanent[0]
+    assert np.array_equal(prev_z[~sky], z[~sky])
+
+
+def test_oracle_is_deterministic():
+    W, H = 64, 48
+    sc = scene.Scene(W, H)
+    outs = []
+    for _ in range(2):
+        cpu = orr.CpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H)
+        for f in range(3):
+            fr = sc.frame(f)
+            cpu.set_inputs(fr)
+            cpu.denoise(harness.make_common_settings(fr, W, H, f))
+            if f == 0:
+                cpu.set_inputs(fr)
+        outs.append(cpu.user["OUT_SPEC_RADIANCE_HITDIST"].copy())
+    assert np.array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16))
+
+
+def test_scene_encodings():
+    sc = scene.Scene(64, 48)
+    fr = sc.frame(2)
+    nr = fr["IN_NORMAL_ROUGHNESS"].numpy().view(np.uint32)
+    z = fr["IN_VIEWZ"].numpy()
+    assert fr["IN_MV"].dtype.__str__() == "torch.float16" and fr["IN_MV"].shape == (48, 64, 4)
+    assert ((nr >> 30) <= 3).all() and (z > 0).all()
+    # decode the oct-packed normals of surface pixels: unit length after normalisation, facing the camera half-space mostly
+    p = np.stack([(nr & 1023) / 1023.0, ((nr >> 10) & 1023) / 1023.0], -1) * 2 - 1
+    n = np.concatenate([p, 1 - np.abs(p).sum(-1, keepdims=True)], -1)
+    t = np.clip(-n[..., 2], 0, 1)
+    n[..., 0] -= t * np.where(n[..., 0] >= 0, 1, -1)
+    n[..., 1] -= t * np.where(n[..., 1] >= 0, 1, -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    ground = (z < 5e5) & (np.abs(n[..., 1] - 1.0) < 0.01)
+    assert ground.mean() > 0.1
