@@ -91,9 +91,10 @@ inline float step(float a, float x) { return x >= a ? 1.0f : 0.0f; }
 inline float rcp(float x) { return 1.0f / x; }
 inline float rsqrt(float x) { return 1.0f / std::sqrt(x); }
 inline float frac(float x) { return x - std::floor(x); }
-inline float clamp(float x, float a, float b) { return std::min(std::max(x, a), b); }
-inline float min(float a, float b) { return std::min(a, b); }
-inline float max(float a, float b) { return std::max(a, b); }
+// D3D min/max: if one operand is NaN the other one is returned (IEEE minNum / maxNum), clamp = min(max(x, a), b)
+inline float min(float a, float b) { return std::fmin(a, b); }
+inline float max(float a, float b) { return std::fmax(a, b); }
+inline float clamp(float x, float a, float b) { return std::fmin(std::fmax(x, a), b); }
 inline float abs(float a) { return std::fabs(a); }
 inline float sqrt(float a) { return std::sqrt(a); }
 inline float floor(float a) { return std::floor(a); }
