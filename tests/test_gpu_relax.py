@@ -1,0 +1,75 @@
+"""GPU parity of the RELAX_DIFFUSE_SPECULAR kernels against the oracle (oracle/relax.cpp)."""
+import json
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _dump(name, report):
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, name), "w") as f:
+        json.dump(report, f, indent=1)
+
+
+@pytest.mark.parametrize("width,height,frames", [(640, 360, 4), (250, 141, 6)])
+def test_relax_per_pass_parity(width, height, frames):
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    sbs = parity.SideBySide(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, width, height)
+    report = sbs.run_per_pass(frames)
+    _dump("parity_RELAX_%dx%d.json" % (width, height), report)
+    bad = sbs.failures()
+    assert not bad, "\n".join("f%d %s %s %s frac=%.5f worst=%.1f" % (r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["worst"]) for r in bad[:40])
+
+
+def test_relax_settings_variants_per_pass():
+    """Non-default settings: 3 A-trous iterations (odd/even binding variants), anti-lag off, roughness edge stopping off."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    s = nrd.RelaxSettings()
+    s.atrousIterationNum = 3
+    s.enableRoughnessEdgeStopping = False
+    s.historyFixFrameNum = 2
+    s.diffusePrepassBlurRadius = 0.0
+    s.enableAntiFirefly = False
+    sbs = parity.SideBySide(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, 320, 180, settings=s)
+    report = sbs.run_per_pass(4)
+    _dump("parity_RELAX_variant.json", report)
+    bad = sbs.failures()
+    assert not bad, "\n".join("f%d %s %s %s frac=%.5f worst=%.1f" % (r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["worst"]) for r in bad[:40])
+
+
+def test_relax_sequence_parity():
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    res = parity.run_sequence(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, 320, 180, 12)
+    _dump("sequence_relax.json", res)
+    for name, (frac, psnr) in res.items():
+        assert frac >= 0.99 and psnr >= 60.0, (name, frac, psnr)
+
+
+def test_relax_against_golden_vector():
+    """Committed fixture (oracle output, tests/golden/make_golden.py): the GPU path alone must reproduce it."""
+    import numpy as np
+    import torch
+    import make_golden_path  # noqa: F401
+    import make_golden
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    den, w, h, frames = make_golden.CASES["relax_diffuse_specular_96x64"]
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "relax_diffuse_specular_96x64.npz"))
+    d = getattr(nrd.Denoiser, den)
+    gpu = harness.GpuDenoiser(d, w, h)
+    sc = scene.Scene(w, h)
+    for f in range(frames):
+        fr = sc.frame(f, harness.radiance_mode(d))
+        gpu.set_inputs(fr)
+        gpu.denoise(harness.make_common_settings(fr, w, h, f))
+    torch.cuda.synchronize()
+    for name, t in gpu.outputs().items():
+        got = t.cpu().numpy().view(ref[name].dtype).reshape(ref[name].shape)
+        frac, _ = orr.compare(ref[name], got, nrd.Format.RGBA16_SFLOAT, 1e-3, 1e-4)
+        assert frac >= 0.99, (name, frac)
