@@ -332,10 +332,13 @@ NRD_API const char* NRD_CALL GetDenoiserString(Denoiser denoiser);
 // (reference: Integration/NRDIntegration.h:81-131, NRDIntegration.hpp:292-363 pool creation,
 // :516-623 Denoise, :625-803 Dispatch).  Plain pointers and sizes only.
 //
-// A context holds one horizontal strip [stripY0, stripY1) of the frame (the whole frame on one
-// GPU) plus `haloRows` ghost rows above and below; every texture (pool or user) is a pitched
-// HBM surface covering rows [stripY0-halo, stripY1+halo) clipped to the frame.  Kernels address
-// texels in full-frame coordinates.
+// One GPU: a context holds the whole frame; pool textures are allocated by the context, IN_*/OUT_* textures are the
+// application's own device pointers (nrdCudaSetUserTexture).
+// Several GPUs (one process per GPU): the frame is cut into horizontal strips of `stripHeight` rows (a multiple of 16, the
+// same on every rank; rank r owns rows [r*stripHeight, min((r+1)*stripHeight, height)) ).  A context then holds only its
+// strip of every texture -- pools AND user textures, all carved from one arena that is exported with CUDA IPC -- and the
+// kernels load rows of other strips directly from the owner's HBM over NVLink (no halo copies, no recomputation); a
+// device-side flag barrier separates the passes.  Kernels address texels in full-frame coordinates in both modes.
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 typedef struct NrdCudaContext NrdCudaContext;
@@ -344,7 +347,7 @@ typedef struct NrdCudaContextDesc
 {
     uint16_t resourceWidth, resourceHeight;   // full-frame texture size (== CommonSettings::resourceSize)
     uint16_t stripY0, stripY1;                // rows owned by this context; {0, resourceHeight} for one GPU
-    uint16_t haloRows;                        // ghost rows kept above/below the strip (0 for one GPU)
+    uint16_t stripHeight;                     // 0 = one GPU; else rows per rank (multiple of 16), stripY0 = rank * stripHeight
     int32_t device;                           // CUDA device ordinal
 } NrdCudaContextDesc;
 
@@ -375,6 +378,27 @@ NRD_API nrd::Result nrdCudaDenoise(NrdCudaContext* context, const nrd::Identifie
 // physically present in the context are transferred.  Used to checkpoint / restore the permanent pool and by the tests.
 NRD_API nrd::Result nrdCudaUploadTexture(NrdCudaContext* context, uint32_t resourceType, uint32_t indexInPool, const void* hostPtr, size_t hostPitchBytes);
 NRD_API nrd::Result nrdCudaDownloadTexture(NrdCudaContext* context, uint32_t resourceType, uint32_t indexInPool, void* hostPtr, size_t hostPitchBytes);
+// Asynchronous 2D copy (cudaMemcpyDefault: pinned host or device memory) between an application buffer holding the rows
+// physically present in the context (`ptr` addresses texel (0, firstRow)) and a texture of the context.
+NRD_API nrd::Result nrdCudaCopyTexture(NrdCudaContext* context, uint32_t resourceType, uint32_t indexInPool, void* ptr, size_t pitchBytes, int32_t toContext, void* stream);
+
+// ---- multi-GPU (strip mode) ----
+#define NRD_CUDA_IPC_HANDLE_SIZE 64
+// The arena of a strip-mode context and its CUDA IPC handle (NRD_CUDA_IPC_HANDLE_SIZE bytes).
+NRD_API nrd::Result nrdCudaGetArena(NrdCudaContext* context, void** devicePtr, size_t* bytes);
+NRD_API nrd::Result nrdCudaGetIpcHandle(NrdCudaContext* context, void* handleOut);
+// Connects the strips: `ipcHandles` = worldSize handles in rank order (entry `rank` is ignored), as gathered with
+// torch.distributed / MPI; alternatively `arenas` = worldSize arena pointers that are already addressable from this
+// context's device (contexts of one process).  Exactly one of the two is non-null.
+NRD_API nrd::Result nrdCudaConnectPeers(NrdCudaContext* context, uint32_t rank, uint32_t worldSize, const void* ipcHandles, void* const* arenas);
+
+// Enqueues one inter-GPU barrier on `stream` (no-op on one GPU).  nrdCudaDenoise starts with one -- the input strips the
+// peers wrote on their streams are complete before the first pass reads them -- and nrdCudaExecuteDispatch ends with one;
+// applications that walk the dispatch list themselves call this once per frame before the first dispatch.
+NRD_API nrd::Result nrdCudaBarrier(NrdCudaContext* context, void* stream);
+// cudaStreamSynchronize + check that no inter-GPU barrier timed out (a peer that died or fell out of step).
+NRD_API nrd::Result nrdCudaSynchronize(NrdCudaContext* context, void* stream);
+
 // Last CUDA error string seen by the executor ("" if none).
 NRD_API const char* nrdCudaGetLastError(NrdCudaContext* context);
 // Total kernels launched by this library in the process (for bench.py's gpu_launches).

@@ -15,17 +15,36 @@ namespace nrdb200
 // ---------------------------------------------------------------------------------------------
 // Surfaces
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU: the frame is cut into horizontal strips of `stripRows` rows (uniform, whole 16-row tiles), one per GPU.
+// Every context carves its surfaces out of one arena with the same layout, so the address of a texel owned by GPU o is
+// the local address plus (arena of o - local arena): a load of a row outside the local strip goes straight to the
+// owner's HBM over NVLink.  Stores are always local.  The deltas live in constant memory, one table per context slot.
+constexpr int kMaxPeers = 8;
+constexpr int kMaxPeerSlots = 4;
+static __constant__ long long g_peerDelta[kMaxPeerSlots * kMaxPeers];
+static inline cudaError_t SetPeerTableThisTU(int slot, const long long* delta)
+{
+    return cudaMemcpyToSymbol(g_peerDelta, delta, sizeof(long long) * kMaxPeers, sizeof(long long) * kMaxPeers * (size_t)slot);
+}
+
 struct Surf
 {
-    uint8_t* base; // address of texel (0, y0)
-    int pitch;     // bytes per row
-    int w, h;      // full (virtual) texture size
-    int y0, y1;    // rows physically present: [y0, y1)
+    uint8_t* base;       // address of texel (0, y0)
+    int pitch;           // bytes per row
+    int w, h;            // full (virtual) texture size
+    int y0, y1;          // rows physically present: [y0, y1)
+    unsigned stripRows;  // rows per strip in this texture's own units; 0 = whole frame is local
+    unsigned stripMagic; // floor(2^32 / stripRows) + 1: owner(y) = umulhi(y, magic), exact for y, stripRows < 65536
+    int peerSlot;
+    int pad_;
 };
 
 template <class T> __device__ __forceinline__ const T* TexelPtr(const Surf& s, int x, int y)
 {
-    return reinterpret_cast<const T*>(s.base + (size_t)(y - s.y0) * s.pitch) + x;
+    if (s.stripRows == 0) return reinterpret_cast<const T*>(s.base + (size_t)(y - s.y0) * s.pitch) + x;
+    const unsigned owner = __umulhi((unsigned)y, s.stripMagic);
+    const uint8_t* row = s.base + g_peerDelta[s.peerSlot * kMaxPeers + owner] + (size_t)((unsigned)y - owner * s.stripRows) * s.pitch;
+    return reinterpret_cast<const T*>(row) + x;
 }
 template <class T> __device__ __forceinline__ T* TexelPtrRW(const Surf& s, int x, int y)
 {

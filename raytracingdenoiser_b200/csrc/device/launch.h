@@ -16,4 +16,10 @@ cudaError_t LaunchReblurTemporalStabilization(const PassLaunch& p, int signal);
 
 cudaError_t LaunchSigma(const PassLaunch& p, const char* shaderName);
 cudaError_t LaunchRelax(const PassLaunch& p, const char* shaderName);
+
+// peer address table of one context slot, replicated into the constant memory of every kernel translation unit
+cudaError_t SetPeerTableReblurSpatial(int slot, const long long* delta);
+cudaError_t SetPeerTableReblurTemporal(int slot, const long long* delta);
+cudaError_t SetPeerTableSigma(int slot, const long long* delta);
+cudaError_t SetPeerTableRelax(int slot, const long long* delta);
 } // namespace nrdb200

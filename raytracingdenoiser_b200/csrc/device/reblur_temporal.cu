@@ -1087,4 +1087,6 @@ cudaError_t LaunchReblurTemporalStabilization(const PassLaunch& p, int signal)
     if (signal == 1) return LaunchTs<false, true>(p);
     return LaunchTs<true, true>(p);
 }
+
+cudaError_t SetPeerTableReblurTemporal(int slot, const long long* delta) { return SetPeerTableThisTU(slot, delta); }
 } // namespace nrdb200

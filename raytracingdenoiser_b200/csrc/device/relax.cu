@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(256) RelaxClassifyTilesKernel(const __grid_con
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.tilesW * a.tilesH) return;
     int tx = warp % a.tilesW, ty = warp / a.tilesW;
+    if (ty < a.tiles.y0 || ty >= a.tiles.y1) return; // tile rows of another strip
     bool allSky = true;
 #pragma unroll
     for (int k = 0; k < 8; k++)
@@ -1277,4 +1278,6 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         return cudaErrorNotSupported;
     return cudaGetLastError();
 }
+
+cudaError_t SetPeerTableRelax(int slot, const long long* delta) { return SetPeerTableThisTU(slot, delta); }
 } // namespace nrdb200

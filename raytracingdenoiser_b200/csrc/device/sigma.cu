@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(256) SigmaClassifyTilesKernel(const __grid_con
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.tilesW * a.tilesH) return;
     const int tx = warp % a.tilesW, ty = warp / a.tilesW;
+    if (ty < a.tiles.y0 || ty >= a.tiles.y1) return; // tile rows of another strip
     int nLit = 0, nUmbra = 0, nInf = 0;
     float maxRadius = 0.0f;
 #pragma unroll
@@ -124,7 +125,7 @@ struct SigmaSmoothArgs
 __global__ void __launch_bounds__(256) SigmaSmoothTilesKernel(const __grid_constant__ SigmaSmoothArgs a)
 {
     const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
-    if (!Inside(a.smoothed, x, y)) return;
+    if (!Inside(a.smoothed, x, y) || y < a.smoothed.y0 || y >= a.smoothed.y1) return;
     f4 center = UnpackRGBA8(LoadU32(a.tiles, x, y));
     float k = 1.01f / (center.y + 0.01f);
     float blurry = 0.0f, sum = 0.0f;
@@ -502,4 +503,6 @@ cudaError_t LaunchSigma(const PassLaunch& p, const char* shader)
         return cudaErrorNotSupported;
     return cudaGetLastError();
 }
+
+cudaError_t SetPeerTableSigma(int slot, const long long* delta) { return SetPeerTableThisTU(slot, delta); }
 } // namespace nrdb200

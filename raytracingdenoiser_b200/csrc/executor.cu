@@ -2,6 +2,11 @@
 // Takes the role of the reference's optional NRI integration layer (Integration/NRDIntegration.hpp: pool creation
 // :292-363, Denoise :516-623, Dispatch :625-803).  Stream order replaces the SRV/UAV barriers (:667-704); constants
 // travel as __grid_constant__ kernel parameters instead of a constant-buffer ring (:721-749).
+//
+// Multi-GPU (strip mode, see include/nrd_b200.h): every texture of a context is a strip of `stripHeight` rows carved from
+// one arena; arenas are exchanged with CUDA IPC and the kernels read foreign rows straight from the owner (common.cuh
+// TexelPtr).  Between two passes every rank signals all its peers and waits for all of them (StripBarrierKernel): a pass
+// may read what any rank wrote in the previous pass and may overwrite what any rank read in it.
 #include "../../include/nrd_b200.h"
 #include "device/launch.h"
 #include "scheduler.h"
@@ -9,6 +14,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,6 +24,11 @@ using namespace nrdb200;
 namespace
 {
 std::atomic<uint64_t> g_launchCount{0};
+std::mutex g_slotMutex;
+bool g_slotUsed[kMaxPeerSlots] = {};
+
+constexpr size_t kArenaHeader = 256;           // barrier flags: kMaxPeers x u32 (slot s = last epoch signalled by rank s), then the error word
+constexpr long long kBarrierTimeoutCycles = 4000000000ll; // ~2 s: a missing peer turns into an error instead of a hung GPU
 
 uint32_t BytesPerTexel(Format f)
 {
@@ -33,59 +44,81 @@ struct Texture
     size_t pitch = 0;
     Format format = Format::R8_UNORM;
     uint16_t width = 0, height = 0; // virtual size
-    uint16_t firstRow = 0, rows = 0;
+    uint16_t firstRow = 0, rows = 0; // rows that hold data
+    uint16_t allocRows = 0;          // rows reserved in the arena (uniform strip height in strip mode)
+    uint16_t downsample = 1;
     bool owned = false;
 };
+
+// user textures the supported denoisers consume, with the one format the kernels are written for
+bool ExpectedUserFormat(ResourceType type, Format& expected)
+{
+    switch (type)
+    {
+        case ResourceType::IN_MV: expected = Format::RGBA16_SFLOAT; return true;
+        case ResourceType::IN_NORMAL_ROUGHNESS: expected = Format::R10_G10_B10_A2_UNORM; return true;
+        case ResourceType::IN_VIEWZ: expected = Format::R32_SFLOAT; return true;
+        case ResourceType::IN_DIFF_RADIANCE_HITDIST:
+        case ResourceType::IN_SPEC_RADIANCE_HITDIST:
+        case ResourceType::OUT_DIFF_RADIANCE_HITDIST:
+        case ResourceType::OUT_SPEC_RADIANCE_HITDIST: expected = Format::RGBA16_SFLOAT; return true;
+        case ResourceType::IN_PENUMBRA: expected = Format::R16_SFLOAT; return true;
+        case ResourceType::OUT_SHADOW_TRANSLUCENCY: expected = Format::R8_UNORM; return true;
+        default: return false;
+    }
+}
 } // namespace
 
 struct NrdCudaContext
 {
     Instance* instance = nullptr;
     NrdCudaContextDesc desc{};
+    uint8_t* arena = nullptr;
+    size_t arenaBytes = 0;
     std::vector<Texture> permanent, transient;
     Texture user[(size_t)ResourceType::MAX_NUM];
+    // strip mode
+    uint32_t rank = 0, world = 1;
+    int peerSlot = -1;
+    bool connected = false;
+    void* peerArena[kMaxPeers] = {};
+    bool peerOpened[kMaxPeers] = {};
+    long long peerDelta[kMaxPeers] = {};
+    uint32_t epoch = 0;
     std::string lastError;
 };
 
 namespace
 {
-// kernel the pool clears map to (reference: Clear_Float.cs / Clear_Uint.cs -- both write zeros)
 Result Fail(NrdCudaContext* ctx, Result r, const std::string& msg)
 {
     if (ctx) ctx->lastError = msg;
     return r;
 }
 
-void StripRows(const NrdCudaContextDesc& d, uint16_t downsample, uint16_t virtualHeight, uint16_t& first, uint16_t& rows)
+bool StripMode(const NrdCudaContext* ctx) { return ctx->desc.stripHeight != 0; }
+
+// rows [first, first + rows) of a texture with `downsample` that belong to the context
+void OwnedRows(const NrdCudaContextDesc& d, uint16_t downsample, uint16_t virtualHeight, uint16_t& first, uint16_t& rows)
 {
-    int y0 = (int)d.stripY0 - (int)d.haloRows, y1 = (int)d.stripY1 + (int)d.haloRows;
-    if (y0 < 0) y0 = 0;
-    if (y1 > (int)d.resourceHeight) y1 = d.resourceHeight;
-    int f = y0 / downsample, l = (y1 + downsample - 1) / downsample;
+    int f = d.stripY0 / downsample, l = (d.stripY1 + downsample - 1) / downsample;
     if (l > (int)virtualHeight) l = virtualHeight;
+    if (f > l) f = l;
     first = (uint16_t)f;
     rows = (uint16_t)(l - f);
 }
 
-Result AllocatePool(NrdCudaContext* ctx, const TextureDesc* descs, uint32_t n, std::vector<Texture>& out)
+void DescribeTexture(const NrdCudaContext* ctx, Format format, uint16_t downsample, Texture& t)
 {
-    out.resize(n);
-    for (uint32_t i = 0; i < n; i++)
-    {
-        Texture& t = out[i];
-        const uint16_t ds = descs[i].downsampleFactor;
-        t.format = descs[i].format;
-        t.width = uint16_t((ctx->desc.resourceWidth + ds - 1) / ds);
-        t.height = uint16_t((ctx->desc.resourceHeight + ds - 1) / ds);
-        StripRows(ctx->desc, ds, t.height, t.firstRow, t.rows);
-        size_t rowBytes = (size_t)t.width * BytesPerTexel(t.format);
-        t.pitch = (rowBytes + 255) & ~(size_t)255; // 256-B aligned rows: 128-bit vector access and TMA-legal strides
-        cudaError_t e = cudaMalloc(&t.ptr, t.pitch * t.rows);
-        if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-        cudaMemset(t.ptr, 0, t.pitch * t.rows);
-        t.owned = true;
-    }
-    return Result::SUCCESS;
+    t.format = format;
+    t.downsample = downsample;
+    t.width = uint16_t((ctx->desc.resourceWidth + downsample - 1) / downsample);
+    t.height = uint16_t((ctx->desc.resourceHeight + downsample - 1) / downsample);
+    OwnedRows(ctx->desc, downsample, t.height, t.firstRow, t.rows);
+    t.allocRows = StripMode(ctx) ? uint16_t(ctx->desc.stripHeight / downsample) : t.rows;
+    size_t rowBytes = (size_t)t.width * BytesPerTexel(format);
+    t.pitch = (rowBytes + 255) & ~(size_t)255; // 256-B aligned rows: 128-bit vector access and TMA-legal strides
+    t.owned = true;
 }
 
 const Texture* Resolve(NrdCudaContext* ctx, ResourceType type, uint32_t index)
@@ -96,15 +129,21 @@ const Texture* Resolve(NrdCudaContext* ctx, ResourceType type, uint32_t index)
     return nullptr;
 }
 
-Surf ToSurf(const Texture& t)
+Surf ToSurf(const NrdCudaContext* ctx, const Texture& t)
 {
-    Surf s;
+    Surf s{};
     s.base = (uint8_t*)t.ptr;
     s.pitch = (int)t.pitch;
     s.w = t.width;
     s.h = t.height;
     s.y0 = t.firstRow;
     s.y1 = t.firstRow + t.rows;
+    if (StripMode(ctx) && ctx->world > 1)
+    {
+        s.stripRows = ctx->desc.stripHeight / t.downsample;
+        s.stripMagic = (unsigned)(0x100000000ull / s.stripRows) + 1u;
+        s.peerSlot = ctx->peerSlot;
+    }
     return s;
 }
 
@@ -120,6 +159,14 @@ bool ParseReblur(const char* name, int& signal, const char*& pass)
     pass = p;
     return true;
 }
+
+struct BarrierArgs
+{
+    unsigned* flags; // local arena header
+    long long delta[kMaxPeers];
+    unsigned rank, world, epoch;
+    long long timeout;
+};
 } // namespace
 
 namespace nrdb200
@@ -137,6 +184,7 @@ cudaError_t LaunchClear(const PassLaunch& p)
 {
     const Surf& s = p.tex[0];
     size_t bytes = (size_t)s.pitch * (size_t)(s.y1 - s.y0);
+    if (bytes == 0) return cudaSuccess;
     if ((s.pitch & 15) != 0 || ((uintptr_t)s.base & 15) != 0) return cudaMemsetAsync(s.base, 0, bytes, p.stream); // user textures with odd pitch
     size_t n16 = bytes / 16;
     int blocks = (int)((n16 + 255) / 256);
@@ -145,14 +193,63 @@ cudaError_t LaunchClear(const PassLaunch& p)
     ClearKernel<<<blocks, 256, 0, p.stream>>>((uint4*)s.base, n16);
     return cudaGetLastError();
 }
+
+// All-to-all flag barrier over NVLink: lane t tells rank t "I finished epoch e" (a store into t's arena header) and then
+// waits until rank t has told us the same.  Everything the previous kernel wrote is visible device-wide when this kernel
+// starts (stream order); the system-scope fences order it against the flag for the remote readers.
+__global__ void StripBarrierKernel(const __grid_constant__ BarrierArgs a)
+{
+    const unsigned t = threadIdx.x;
+    if (t >= a.world) return;
+    __threadfence_system();
+    volatile unsigned* remote = (volatile unsigned*)((uint8_t*)a.flags + a.delta[t]) + a.rank;
+    *remote = a.epoch;
+    volatile unsigned* mine = a.flags + t;
+    const long long start = clock64();
+    while ((int)(*mine - a.epoch) < 0)
+    {
+        if (clock64() - start > a.timeout)
+        {
+            a.flags[kMaxPeers] = a.epoch; // error word
+            break;
+        }
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
 } // namespace nrdb200
+
+namespace
+{
+Result Barrier(NrdCudaContext* ctx, cudaStream_t stream)
+{
+    if (!StripMode(ctx) || ctx->world <= 1) return Result::SUCCESS;
+    BarrierArgs a{};
+    a.flags = (unsigned*)ctx->arena;
+    for (uint32_t i = 0; i < ctx->world; i++) a.delta[i] = ctx->peerDelta[i];
+    a.rank = ctx->rank;
+    a.world = ctx->world;
+    a.epoch = ++ctx->epoch;
+    a.timeout = kBarrierTimeoutCycles;
+    StripBarrierKernel<<<1, 32, 0, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, std::string("strip barrier: ") + cudaGetErrorString(e));
+}
+} // namespace
 
 extern "C" {
 
 NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc* desc, NrdCudaContext** out)
 {
     if (!instance || !desc || !out) return Result::INVALID_ARGUMENT;
-    if (!desc->resourceWidth || !desc->resourceHeight || desc->stripY1 <= desc->stripY0 || desc->stripY1 > desc->resourceHeight) return Result::INVALID_ARGUMENT;
+    if (!desc->resourceWidth || !desc->resourceHeight || desc->stripY1 < desc->stripY0 || desc->stripY1 > desc->resourceHeight) return Result::INVALID_ARGUMENT;
+    if (desc->stripHeight == 0 && (desc->stripY0 != 0 || desc->stripY1 != desc->resourceHeight)) return Result::INVALID_ARGUMENT;
+    if (desc->stripHeight != 0)
+    {
+        // uniform strips of whole 16-row tiles; the last ranks may own fewer (or no) rows
+        if (desc->stripHeight % 16 != 0 || desc->stripY0 % desc->stripHeight != 0 || desc->stripY1 - desc->stripY0 > desc->stripHeight) return Result::INVALID_ARGUMENT;
+        if (desc->stripY1 != desc->resourceHeight && desc->stripY1 - desc->stripY0 != desc->stripHeight) return Result::INVALID_ARGUMENT;
+    }
     int deviceCount = 0;
     if (cudaGetDeviceCount(&deviceCount) != cudaSuccess || deviceCount == 0) return Result::FAILURE; // no silent CPU path: fail loudly
     if (cudaSetDevice(desc->device) != cudaSuccess) return Result::FAILURE;
@@ -161,13 +258,43 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
     ctx->instance = instance;
     ctx->desc = *desc;
     const InstanceDesc& id = GetInstanceDesc(*instance);
-    Result r = AllocatePool(ctx, id.permanentPool, id.permanentPoolSize, ctx->permanent);
-    if (r == Result::SUCCESS) r = AllocatePool(ctx, id.transientPool, id.transientPoolSize, ctx->transient);
-    if (r != Result::SUCCESS)
+    ctx->permanent.resize(id.permanentPoolSize);
+    ctx->transient.resize(id.transientPoolSize);
+    for (uint32_t i = 0; i < id.permanentPoolSize; i++) DescribeTexture(ctx, id.permanentPool[i].format, id.permanentPool[i].downsampleFactor, ctx->permanent[i]);
+    for (uint32_t i = 0; i < id.transientPoolSize; i++) DescribeTexture(ctx, id.transientPool[i].format, id.transientPool[i].downsampleFactor, ctx->transient[i]);
+    if (StripMode(ctx))
     {
-        nrdCudaDestroyContext(ctx);
-        return r;
+        // foreign device pointers cannot be reached by the peers: the strips of the IN_* / OUT_* textures live in the arena too
+        for (uint32_t t = 0; t < (uint32_t)ResourceType::MAX_NUM; t++)
+        {
+            Format f;
+            if (ExpectedUserFormat((ResourceType)t, f)) DescribeTexture(ctx, f, 1, ctx->user[t]);
+        }
     }
+    // one arena, identical layout on every rank
+    size_t offset = kArenaHeader;
+    auto place = [&](Texture& t) {
+        if (!t.owned) return;
+        t.ptr = (void*)offset;
+        offset += (t.pitch * t.allocRows + 255) & ~(size_t)255;
+    };
+    for (Texture& t : ctx->permanent) place(t);
+    for (Texture& t : ctx->transient) place(t);
+    for (Texture& t : ctx->user) place(t);
+    ctx->arenaBytes = offset;
+    cudaError_t e = cudaMalloc((void**)&ctx->arena, ctx->arenaBytes);
+    if (e != cudaSuccess)
+    {
+        delete ctx;
+        return Result::FAILURE;
+    }
+    cudaMemset(ctx->arena, 0, ctx->arenaBytes);
+    auto rebase = [&](Texture& t) {
+        if (t.owned) t.ptr = ctx->arena + (size_t)t.ptr;
+    };
+    for (Texture& t : ctx->permanent) rebase(t);
+    for (Texture& t : ctx->transient) rebase(t);
+    for (Texture& t : ctx->user) rebase(t);
     *out = ctx;
     return Result::SUCCESS;
 }
@@ -175,38 +302,35 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
 NRD_API void nrdCudaDestroyContext(NrdCudaContext* ctx)
 {
     if (!ctx) return;
-    for (Texture& t : ctx->permanent)
-        if (t.owned) cudaFree(t.ptr);
-    for (Texture& t : ctx->transient)
-        if (t.owned) cudaFree(t.ptr);
+    cudaSetDevice(ctx->desc.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kMaxPeers; i++)
+        if (ctx->peerOpened[i]) cudaIpcCloseMemHandle(ctx->peerArena[i]);
+    if (ctx->peerSlot >= 0)
+    {
+        std::lock_guard<std::mutex> lock(g_slotMutex);
+        g_slotUsed[ctx->peerSlot] = false;
+    }
+    if (ctx->arena) cudaFree(ctx->arena);
     delete ctx;
 }
 
 NRD_API Result nrdCudaSetUserTexture(NrdCudaContext* ctx, uint32_t resourceType, void* devicePtr, size_t pitchBytes, uint32_t format)
 {
     if (!ctx || resourceType >= (uint32_t)ResourceType::TRANSIENT_POOL || format >= (uint32_t)Format::MAX_NUM) return Result::INVALID_ARGUMENT;
+    if (StripMode(ctx)) return Fail(ctx, Result::UNSUPPORTED, "strip mode: user textures live in the context's arena, fill them through nrdCudaGetTexture / nrdCudaCopyTexture");
     Format expected;
-    switch ((ResourceType)resourceType)
-    {
-        case ResourceType::IN_MV: expected = Format::RGBA16_SFLOAT; break;
-        case ResourceType::IN_NORMAL_ROUGHNESS: expected = Format::R10_G10_B10_A2_UNORM; break;
-        case ResourceType::IN_VIEWZ: expected = Format::R32_SFLOAT; break;
-        case ResourceType::IN_DIFF_RADIANCE_HITDIST:
-        case ResourceType::IN_SPEC_RADIANCE_HITDIST:
-        case ResourceType::OUT_DIFF_RADIANCE_HITDIST:
-        case ResourceType::OUT_SPEC_RADIANCE_HITDIST: expected = Format::RGBA16_SFLOAT; break;
-        case ResourceType::IN_PENUMBRA: expected = Format::R16_SFLOAT; break;
-        case ResourceType::OUT_SHADOW_TRANSLUCENCY: expected = Format::R8_UNORM; break;
-        default: return Fail(ctx, Result::UNSUPPORTED, "resource type not consumed by the supported denoisers");
-    }
+    if (!ExpectedUserFormat((ResourceType)resourceType, expected)) return Fail(ctx, Result::UNSUPPORTED, "resource type not consumed by the supported denoisers");
     if ((Format)format != expected) return Fail(ctx, Result::UNSUPPORTED, "unsupported format for this resource type (see nrd_b200.h)");
     Texture& t = ctx->user[resourceType];
     t.ptr = devicePtr;
     t.pitch = pitchBytes;
     t.format = (Format)format;
+    t.downsample = 1;
     t.width = ctx->desc.resourceWidth;
     t.height = ctx->desc.resourceHeight;
-    StripRows(ctx->desc, 1, t.height, t.firstRow, t.rows);
+    OwnedRows(ctx->desc, 1, t.height, t.firstRow, t.rows);
+    t.allocRows = t.rows;
     t.owned = false;
     return Result::SUCCESS;
 }
@@ -226,6 +350,65 @@ NRD_API Result nrdCudaGetTexture(NrdCudaContext* ctx, uint32_t resourceType, uin
     return Result::SUCCESS;
 }
 
+NRD_API Result nrdCudaGetArena(NrdCudaContext* ctx, void** devicePtr, size_t* bytes)
+{
+    if (!ctx || !devicePtr || !bytes) return Result::INVALID_ARGUMENT;
+    *devicePtr = ctx->arena;
+    *bytes = ctx->arenaBytes;
+    return Result::SUCCESS;
+}
+
+NRD_API Result nrdCudaGetIpcHandle(NrdCudaContext* ctx, void* handleOut)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == NRD_CUDA_IPC_HANDLE_SIZE, "IPC handle size");
+    if (!ctx || !handleOut) return Result::INVALID_ARGUMENT;
+    if (!StripMode(ctx)) return Fail(ctx, Result::UNSUPPORTED, "not a strip-mode context");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ctx->arena);
+    if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    memcpy(handleOut, &h, sizeof(h));
+    return Result::SUCCESS;
+}
+
+NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t worldSize, const void* ipcHandles, void* const* arenas)
+{
+    if (!ctx || worldSize == 0 || worldSize > (uint32_t)kMaxPeers || rank >= worldSize || (!ipcHandles == !arenas)) return Result::INVALID_ARGUMENT;
+    if (!StripMode(ctx)) return Fail(ctx, Result::UNSUPPORTED, "not a strip-mode context");
+    if (ctx->connected) return Fail(ctx, Result::FAILURE, "peers already connected");
+    if ((uint32_t)ctx->desc.stripY0 != rank * (uint32_t)ctx->desc.stripHeight) return Fail(ctx, Result::INVALID_ARGUMENT, "stripY0 must be rank * stripHeight");
+    if (worldSize * (uint32_t)ctx->desc.stripHeight < ctx->desc.resourceHeight) return Fail(ctx, Result::INVALID_ARGUMENT, "the strips do not cover the frame");
+    cudaSetDevice(ctx->desc.device);
+    for (uint32_t i = 0; i < worldSize; i++)
+    {
+        if (i == rank) { ctx->peerArena[i] = ctx->arena; continue; }
+        if (arenas) ctx->peerArena[i] = arenas[i];
+        else
+        {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const uint8_t*)ipcHandles + (size_t)i * sizeof(h), sizeof(h));
+            cudaError_t e = cudaIpcOpenMemHandle(&ctx->peerArena[i], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            ctx->peerOpened[i] = true;
+        }
+    }
+    for (uint32_t i = 0; i < (uint32_t)kMaxPeers; i++) ctx->peerDelta[i] = i < worldSize ? (long long)((uint8_t*)ctx->peerArena[i] - ctx->arena) : 0;
+    {
+        std::lock_guard<std::mutex> lock(g_slotMutex);
+        for (int s = 0; s < kMaxPeerSlots && ctx->peerSlot < 0; s++)
+            if (!g_slotUsed[s]) { g_slotUsed[s] = true; ctx->peerSlot = s; }
+    }
+    if (ctx->peerSlot < 0) return Fail(ctx, Result::FAILURE, "too many strip-mode contexts in one process");
+    cudaError_t e = SetPeerTableReblurSpatial(ctx->peerSlot, ctx->peerDelta);
+    if (e == cudaSuccess) e = SetPeerTableReblurTemporal(ctx->peerSlot, ctx->peerDelta);
+    if (e == cudaSuccess) e = SetPeerTableSigma(ctx->peerSlot, ctx->peerDelta);
+    if (e == cudaSuccess) e = SetPeerTableRelax(ctx->peerSlot, ctx->peerDelta);
+    if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("peer table: ") + cudaGetErrorString(e));
+    ctx->rank = rank;
+    ctx->world = worldSize;
+    ctx->connected = true;
+    return Result::SUCCESS;
+}
+
 NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d, void* stream)
 {
     if (!ctx || !d) return Result::INVALID_ARGUMENT;
@@ -238,6 +421,8 @@ NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d
         return Fail(ctx, Result::UNSUPPORTED, "dynamic resolution (rectSize != resourceSize) is not implemented by the CUDA executor");
     if (cs.isHistoryConfidenceAvailable || cs.isDisocclusionThresholdMixAvailable || cs.isBaseColorMetalnessAvailable)
         return Fail(ctx, Result::UNSUPPORTED, "confidence / disocclusion-mix / base-colour inputs are not implemented by the CUDA executor");
+    if (StripMode(ctx) && !ctx->connected && (ctx->desc.stripY0 != 0 || ctx->desc.stripY1 != ctx->desc.resourceHeight))
+        return Fail(ctx, Result::FAILURE, "strip-mode context used before nrdCudaConnectPeers");
 
     PassLaunch p{};
     p.constants = d->constantBufferData;
@@ -252,18 +437,17 @@ NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d
         const ResourceDesc& r = d->resources[i];
         const Texture* t = Resolve(ctx, r.type, r.indexInPool);
         if (!t) return Fail(ctx, Result::INVALID_ARGUMENT, std::string("unbound resource ") + GetResourceTypeString(r.type) + " for " + d->name);
-        p.tex[i] = ToSurf(*t);
+        p.tex[i] = ToSurf(ctx, *t);
     }
-    // rows to produce: the context's strip plus halo (full frame on one GPU)
-    uint16_t first, rows;
-    StripRows(ctx->desc, 1, ctx->desc.resourceHeight, first, rows);
-    p.rowBegin = first;
-    p.rowEnd = first + rows;
+    // rows to produce: the context's strip (the full frame on one GPU)
+    p.rowBegin = ctx->desc.stripY0;
+    p.rowEnd = ctx->desc.stripY1;
 
     cudaError_t e = cudaErrorNotSupported;
     int signal = 0;
     const char* pass = nullptr;
     if (!strncmp(shader, "Clear_", 6)) e = LaunchClear(p);
+    else if (p.rowEnd <= p.rowBegin) e = cudaSuccess; // a rank without rows still takes part in the barriers
     else if (!strcmp(shader, "REBLUR_ClassifyTiles.cs")) e = LaunchReblurClassifyTiles(p);
     else if (ParseReblur(shader, signal, pass))
     {
@@ -281,7 +465,7 @@ NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d
     if (e == cudaErrorNotSupported) return Fail(ctx, Result::UNSUPPORTED, std::string("no CUDA kernel for pass ") + shader);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string(shader) + ": " + cudaGetErrorString(e));
     g_launchCount.fetch_add(1, std::memory_order_relaxed);
-    return Result::SUCCESS;
+    return Barrier(ctx, p.stream);
 }
 
 NRD_API Result nrdCudaDenoise(NrdCudaContext* ctx, const Identifier* identifiers, uint32_t identifiersNum, void* stream, uint32_t* launches)
@@ -290,6 +474,8 @@ NRD_API Result nrdCudaDenoise(NrdCudaContext* ctx, const Identifier* identifiers
     const DispatchDesc* dispatches = nullptr;
     uint32_t n = 0;
     Result r = GetComputeDispatches(*ctx->instance, identifiers, identifiersNum, dispatches, n);
+    if (r != Result::SUCCESS) return r;
+    r = Barrier(ctx, (cudaStream_t)stream); // the peers' input strips of this frame are complete
     if (r != Result::SUCCESS) return r;
     for (uint32_t i = 0; i < n; i++)
     {
@@ -305,6 +491,7 @@ NRD_API Result nrdCudaUploadTexture(NrdCudaContext* ctx, uint32_t resourceType, 
     if (!ctx || !hostPtr) return Result::INVALID_ARGUMENT;
     const Texture* t = Resolve(ctx, (ResourceType)resourceType, indexInPool);
     if (!t) return Result::INVALID_ARGUMENT;
+    if (!t->rows) return Result::SUCCESS;
     cudaError_t e = cudaMemcpy2D(t->ptr, t->pitch, hostPtr, hostPitchBytes, (size_t)t->width * BytesPerTexel(t->format), t->rows, cudaMemcpyHostToDevice);
     return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, cudaGetErrorString(e));
 }
@@ -314,8 +501,42 @@ NRD_API Result nrdCudaDownloadTexture(NrdCudaContext* ctx, uint32_t resourceType
     if (!ctx || !hostPtr) return Result::INVALID_ARGUMENT;
     const Texture* t = Resolve(ctx, (ResourceType)resourceType, indexInPool);
     if (!t) return Result::INVALID_ARGUMENT;
+    if (!t->rows) return Result::SUCCESS;
     cudaError_t e = cudaMemcpy2D(hostPtr, hostPitchBytes, t->ptr, t->pitch, (size_t)t->width * BytesPerTexel(t->format), t->rows, cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, cudaGetErrorString(e));
+}
+
+NRD_API Result nrdCudaCopyTexture(NrdCudaContext* ctx, uint32_t resourceType, uint32_t indexInPool, void* ptr, size_t pitchBytes, int32_t toContext, void* stream)
+{
+    if (!ctx || !ptr) return Result::INVALID_ARGUMENT;
+    const Texture* t = Resolve(ctx, (ResourceType)resourceType, indexInPool);
+    if (!t) return Result::INVALID_ARGUMENT;
+    if (!t->rows) return Result::SUCCESS;
+    const size_t rowBytes = (size_t)t->width * BytesPerTexel(t->format);
+    cudaError_t e = toContext ? cudaMemcpy2DAsync(t->ptr, t->pitch, ptr, pitchBytes, rowBytes, t->rows, cudaMemcpyDefault, (cudaStream_t)stream)
+                              : cudaMemcpy2DAsync(ptr, pitchBytes, t->ptr, t->pitch, rowBytes, t->rows, cudaMemcpyDefault, (cudaStream_t)stream);
+    return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, cudaGetErrorString(e));
+}
+
+NRD_API Result nrdCudaBarrier(NrdCudaContext* ctx, void* stream)
+{
+    if (!ctx) return Result::INVALID_ARGUMENT;
+    return Barrier(ctx, (cudaStream_t)stream);
+}
+
+NRD_API Result nrdCudaSynchronize(NrdCudaContext* ctx, void* stream)
+{
+    if (!ctx) return Result::INVALID_ARGUMENT;
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    if (StripMode(ctx) && ctx->world > 1)
+    {
+        unsigned err = 0;
+        e = cudaMemcpy(&err, ctx->arena + sizeof(unsigned) * kMaxPeers, sizeof(err), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, cudaGetErrorString(e));
+        if (err) return Fail(ctx, Result::FAILURE, "strip barrier timed out waiting for a peer (epoch " + std::to_string(err) + ")");
+    }
+    return Result::SUCCESS;
 }
 
 NRD_API const char* nrdCudaGetLastError(NrdCudaContext* ctx) { return ctx ? ctx->lastError.c_str() : ""; }

@@ -180,7 +180,7 @@ RelaxSettings = _struct("RelaxSettings", [
 SigmaSettings = _struct("SigmaSettings", [("lightDirection", f32 * 3), ("planeDistanceSensitivity", f32), ("maxStabilizedFrameNum", u32)],
                         dict(planeDistanceSensitivity=0.02, maxStabilizedFrameNum=5))
 
-NrdCudaContextDesc = _struct("NrdCudaContextDesc", [("resourceWidth", u16), ("resourceHeight", u16), ("stripY0", u16), ("stripY1", u16), ("haloRows", u16), ("device", C.c_int32)])
+NrdCudaContextDesc = _struct("NrdCudaContextDesc", [("resourceWidth", u16), ("resourceHeight", u16), ("stripY0", u16), ("stripY1", u16), ("stripHeight", u16), ("device", C.c_int32)])
 NrdCudaTextureInfo = _struct("NrdCudaTextureInfo", [("devicePtr", C.c_void_p), ("pitchBytes", C.c_size_t), ("format", u32), ("width", u16), ("height", u16),
                                                     ("firstRow", u16), ("rowsNum", u16)])
 
@@ -223,10 +223,24 @@ _lib.nrdCudaGetLastError.argtypes = [C.c_void_p]
 _lib.nrdCudaGetLastError.restype = C.c_char_p
 _lib.nrdCudaGetLaunchCount.argtypes = []
 _lib.nrdCudaGetLaunchCount.restype = C.c_uint64
+_lib.nrdCudaCopyTexture.argtypes = [C.c_void_p, u32, u32, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]
+_lib.nrdCudaCopyTexture.restype = u32
+_lib.nrdCudaGetArena.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+_lib.nrdCudaGetArena.restype = u32
+_lib.nrdCudaGetIpcHandle.argtypes = [C.c_void_p, C.c_void_p]
+_lib.nrdCudaGetIpcHandle.restype = u32
+_lib.nrdCudaConnectPeers.argtypes = [C.c_void_p, u32, u32, C.c_void_p, C.POINTER(C.c_void_p)]
+_lib.nrdCudaConnectPeers.restype = u32
+_lib.nrdCudaBarrier.argtypes = [C.c_void_p, C.c_void_p]
+_lib.nrdCudaBarrier.restype = u32
+_lib.nrdCudaSynchronize.argtypes = [C.c_void_p, C.c_void_p]
+_lib.nrdCudaSynchronize.restype = u32
+IPC_HANDLE_SIZE = 64
 
 EXPORTED_SYMBOLS = ["CreateInstance", "DestroyInstance", "GetLibraryDesc", "GetInstanceDesc", "SetCommonSettings", "SetDenoiserSettings",
                     "GetComputeDispatches", "GetResourceTypeString", "GetDenoiserString", "nrdCudaCreateContext", "nrdCudaDestroyContext",
-                    "nrdCudaSetUserTexture", "nrdCudaGetTexture", "nrdCudaExecuteDispatch", "nrdCudaDenoise", "nrdCudaUploadTexture", "nrdCudaDownloadTexture", "nrdCudaGetLastError", "nrdCudaGetLaunchCount"]
+                    "nrdCudaSetUserTexture", "nrdCudaGetTexture", "nrdCudaExecuteDispatch", "nrdCudaDenoise", "nrdCudaUploadTexture", "nrdCudaDownloadTexture", "nrdCudaGetLastError", "nrdCudaGetLaunchCount",
+                    "nrdCudaCopyTexture", "nrdCudaGetArena", "nrdCudaGetIpcHandle", "nrdCudaConnectPeers", "nrdCudaBarrier", "nrdCudaSynchronize"]
 
 
 class NrdError(RuntimeError):
@@ -352,12 +366,15 @@ class Instance(object):
 class CudaContext(object):
     """CUDA executor for one Instance (replaces nrd::Integration).  Textures are plain device pointers + pitch."""
 
-    def __init__(self, instance, width, height, device=0, strip=None, halo_rows=0):
+    def __init__(self, instance, width, height, device=0, strip=None, strip_height=0):
+        """strip=(y0, y1), strip_height=S: strip-mode context of a multi-GPU run (see include/nrd_b200.h)."""
         desc = NrdCudaContextDesc()
         desc.resourceWidth, desc.resourceHeight = width, height
         desc.stripY0, desc.stripY1 = strip if strip else (0, height)
-        desc.haloRows = halo_rows
+        desc.stripHeight = strip_height
         desc.device = device
+        self.strip = (desc.stripY0, desc.stripY1)
+        self.strip_height = strip_height
         self.instance = instance
         self.width, self.height = width, height
         self._ctx = C.c_void_p()
@@ -397,6 +414,38 @@ class CudaContext(object):
 
     def download(self, resource_type, index_in_pool, array):
         self._check("nrdCudaDownloadTexture", _lib.nrdCudaDownloadTexture(self._ctx, int(resource_type), index_in_pool, array.ctypes.data, array.strides[0]))
+
+    def copy(self, resource_type, index_in_pool, ptr, pitch_bytes, to_context, stream=0):
+        """Async 2D copy of the rows held by the context between a device / pinned-host buffer and a texture."""
+        self._check("nrdCudaCopyTexture", _lib.nrdCudaCopyTexture(self._ctx, int(resource_type), index_in_pool, C.c_void_p(ptr), pitch_bytes, 1 if to_context else 0,
+                                                                   C.c_void_p(stream)))
+
+    def arena(self):
+        ptr, size = C.c_void_p(), C.c_size_t()
+        self._check("nrdCudaGetArena", _lib.nrdCudaGetArena(self._ctx, C.byref(ptr), C.byref(size)))
+        return ptr.value, size.value
+
+    def ipc_handle(self):
+        buf = C.create_string_buffer(IPC_HANDLE_SIZE)
+        self._check("nrdCudaGetIpcHandle", _lib.nrdCudaGetIpcHandle(self._ctx, buf))
+        return buf.raw
+
+    def connect_peers(self, rank, world_size, ipc_handles=None, arenas=None):
+        """ipc_handles: list of world_size 64-byte handles (other processes); arenas: list of arena pointers (same process)."""
+        if arenas is not None:
+            arr = (C.c_void_p * world_size)(*arenas)
+            r = _lib.nrdCudaConnectPeers(self._ctx, rank, world_size, None, arr)
+        else:
+            blob = b"".join(ipc_handles)
+            assert len(blob) == IPC_HANDLE_SIZE * world_size
+            r = _lib.nrdCudaConnectPeers(self._ctx, rank, world_size, blob, None)
+        self._check("nrdCudaConnectPeers", r)
+
+    def barrier(self, stream=0):
+        self._check("nrdCudaBarrier", _lib.nrdCudaBarrier(self._ctx, C.c_void_p(stream)))
+
+    def synchronize(self, stream=0):
+        self._check("nrdCudaSynchronize", _lib.nrdCudaSynchronize(self._ctx, C.c_void_p(stream)))
 
     def execute_raw(self, raw_dispatch_ptr, stream=0):
         self._check("nrdCudaExecuteDispatch", _lib.nrdCudaExecuteDispatch(self._ctx, raw_dispatch_ptr, C.c_void_p(stream)))

@@ -1,0 +1,79 @@
+"""Strip mode (the multi-GPU data path) on ONE GPU: the frame is cut into strips that are separate contexts of this
+process, connected through their arena pointers; every kernel then takes the owner-lookup path for rows of other strips
+and the passes are separated by the flag barrier.  The result must be bit-identical to the single-context run.
+(The cross-process CUDA-IPC variant of the same check is tests/multi_gpu_check.py, run under torchrun on 2+ GPUs.)"""
+import ctypes as C
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(denoiser_name, w, h, world, frames):
+    import torch
+    from raytracingdenoiser_b200 import harness, nrd, scene, strips
+    den = getattr(nrd.Denoiser, denoiser_name)
+    mode = harness.radiance_mode(den)
+    full = harness.GpuDenoiser(den, w, h)
+    parts = [strips.StripDenoiser(den, w, h, r, world) for r in range(world)]
+    for p in parts:
+        p.connect_local(parts)
+    streams = [torch.cuda.Stream() for _ in parts]
+    sc = scene.Scene(w, h)
+    for f in range(frames):
+        fr = sc.frame(f, mode)
+        cs = harness.make_common_settings(fr, w, h, f)
+        full.set_inputs(fr)
+        full.denoise(cs)
+        torch.cuda.synchronize()
+        lists = []
+        for p, st in zip(parts, streams):
+            p.set_inputs(fr, st)
+            lists.append(p.dispatches(cs))
+            p.ctx.barrier(st.cuda_stream)
+        n = lists[0][1]
+        assert all(m == n for _, m in lists)
+        # interleave the ranks pass by pass: each launch is asynchronous, the barrier kernels meet on the device
+        for i in range(n):
+            for p, st, (raw, _) in zip(parts, streams, lists):
+                p.ctx.execute_raw(C.byref(raw[i]), st.cuda_stream)
+        for p, st in zip(parts, streams):
+            p.synchronize(st)
+    ref = full.outputs()
+    outs = [p.read_outputs(stream=st) for p, st in zip(parts, streams)]
+    torch.cuda.synchronize()
+    for name, t in ref.items():
+        got = torch.cat([o[name] for o in outs], dim=0)
+        same = (got.view(torch.uint8) == t.view(torch.uint8))
+        assert bool(same.all()), (name, float(same.float().mean()))
+    for p in parts:
+        p.destroy()
+    full.destroy()
+
+
+@pytest.mark.parametrize("denoiser,w,h,world,frames", [
+    ("REBLUR_DIFFUSE_SPECULAR", 320, 192, 2, 4),
+    ("REBLUR_DIFFUSE_SPECULAR", 250, 141, 3, 3),
+    ("RELAX_DIFFUSE_SPECULAR", 320, 180, 2, 4),
+    ("SIGMA_SHADOW", 320, 180, 4, 3),
+])
+def test_strips_bit_identical_to_full_frame(denoiser, w, h, world, frames):
+    _run(denoiser, w, h, world, frames)
+
+
+def test_strip_context_rejects_foreign_user_pointers_and_bad_geometry():
+    import torch
+    from raytracingdenoiser_b200 import nrd
+    inst = nrd.Instance([(0, nrd.Denoiser.SIGMA_SHADOW)])
+    with pytest.raises(nrd.NrdError):
+        nrd.CudaContext(inst, 256, 128, strip=(0, 60), strip_height=60)      # not whole tiles
+    with pytest.raises(nrd.NrdError):
+        nrd.CudaContext(inst, 256, 128, strip=(16, 80), strip_height=64)     # y0 is not a multiple of the strip height
+    ctx = nrd.CudaContext(inst, 256, 128, strip=(64, 128), strip_height=64)
+    t = torch.zeros((64, 256), dtype=torch.float32, device="cuda")
+    with pytest.raises(nrd.NrdError):
+        ctx.set_user_texture(nrd.ResourceType.IN_VIEWZ, t.data_ptr(), 1024, nrd.Format.R32_SFLOAT)
+    info = ctx.get_texture(nrd.ResourceType.IN_VIEWZ)
+    assert (info.firstRow, info.rowsNum, info.width, info.height) == (64, 64, 256, 128)
+    ctx.destroy()
+    inst.destroy()

@@ -1,0 +1,71 @@
+"""Host side of the multi-GPU path.
+CPU (gloo, world_size 2): strip partition and the IPC-handle exchange.  GPU (only on boxes with >= 2 GPUs): the
+cross-process check of tests/multi_gpu_check.py under torchrun."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_partition_rows_covers_the_frame_with_whole_tiles():
+    from raytracingdenoiser_b200 import strips
+    for h in (16, 141, 720, 1080, 2160, 4320):
+        for n in (1, 2, 3, 4, 8):
+            try:
+                s, parts = strips.partition_rows(h, n)
+            except ValueError:
+                assert (h + 15) // 16 < n or ((h + 15) // 16 + n - 1) // n * (n - 1) * 16 >= h
+                continue
+            assert s % 16 == 0 and len(parts) == n
+            assert parts[0][0] == 0 and parts[-1][1] == h
+            for r, (y0, y1) in enumerate(parts):
+                assert y0 == r * s and 0 < y1 - y0 <= s
+                if r + 1 < n:
+                    assert y1 == parts[r + 1][0] and y1 - y0 == s
+    assert strips.partition_rows(2160, 8) == (272, [(r * 272, min(2160, (r + 1) * 272)) for r in range(8)])
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from raytracingdenoiser_b200 import strips
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = bytes([(rank * 37 + i) & 255 for i in range(64)])
+    got = strips.exchange_ipc_handles(mine)
+    q.put((rank, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ipc_handle_exchange_over_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 400
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [bytes([(r * 37 + i) & 255 for i in range(64)]) for r in range(2)]
+    assert res[0] == expect and res[1] == expect
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("denoiser", ["REBLUR_DIFFUSE_SPECULAR", "RELAX_DIFFUSE_SPECULAR", "SIGMA_SHADOW"])
+def test_cross_process_strips_bit_identical(denoiser):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(HERE, "multi_gpu_check.py"), denoiser, "640", "368", "4"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
