@@ -153,16 +153,32 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     frames = generate_frames(W, H, K + Wm, dev)
-    gpu = harness.GpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, W, H, device=local_rank)
     stream = torch.cuda.current_stream(dev)
-    in_names = [n for n in gpu.tex if n.startswith("IN_")]
+    den = nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR
+    in_names = [n for n in harness.DENOISER_RESOURCES[den] if n.startswith("IN_")]
+    out_names = [n for n in harness.DENOISER_RESOURCES[den] if n.startswith("OUT_")]
+    if world == 1:
+        gpu = harness.GpuDenoiser(den, W, H, device=local_rank)
+        y0, y1 = 0, H
 
-    def bind(fr):
-        # inputs are device resident: bind this frame's own buffers (what an application's ring of G-buffers looks like)
-        for n in in_names:
-            t = fr[n]
-            fmt = harness.USER_FORMATS[n][0]
-            gpu.ctx.set_user_texture(getattr(nrd.ResourceType, n), t.data_ptr(), t.stride(0) * t.element_size(), fmt)
+        def bind(fr):
+            # inputs are device resident: bind this frame's own buffers (what an application's ring of G-buffers looks like)
+            for n in in_names:
+                t = fr[n]
+                gpu.ctx.set_user_texture(getattr(nrd.ResourceType, n), t.data_ptr(), t.stride(0) * t.element_size(), harness.USER_FORMATS[n][0])
+    else:
+        # strong scaling: one strip of whole 16-row tiles per rank, foreign rows are NVLink peer loads (strips.py).  The strip
+        # textures live in the context's IPC arena, so "binding" a frame is a device-to-device copy of this rank's rows --
+        # it is inside the timed region.
+        from raytracingdenoiser_b200 import strips
+        gpu = strips.StripDenoiser(den, W, H, rank, world, device=local_rank)
+        gpu.connect()
+        y0, y1 = gpu.y0, gpu.y1
+        frames = [{k: (v[y0:y1].contiguous() if k in in_names else v) for k, v in fr.items() if k in in_names or not k.startswith("IN_")} for fr in frames]
+        torch.cuda.empty_cache()
+
+        def bind(fr):
+            gpu.set_input_strips({n: fr[n] for n in in_names}, stream)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -174,7 +190,7 @@ def main():
     for i in range(Wm):
         bind(frames[i])
         gpu.denoise(harness.make_common_settings(frames[i], W, H, i))
-        if i == 0:
+        if i == 0 and world == 1:
             frames[0]["IN_MV"].copy_(mv0)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -194,6 +210,8 @@ def main():
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+    if world > 1:
+        gpu.synchronize()  # raises if an inter-GPU barrier timed out
     value = W * H * K / (ms_total * 1e-3) / 1e6
 
     # ---- per-pass breakdown with CUDA events around every dispatch (separate run, not part of `value`)
@@ -205,11 +223,12 @@ def main():
         bind(frames[i])
         gpu.instance.set_common_settings(harness.make_common_settings(frames[i], W, H, i + K))
         r, raw, n = gpu.instance.get_compute_dispatches_raw([gpu.identifier])
+        gpu.ctx.barrier(stream.cuda_stream)
         evs = []
         for j in range(n):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            gpu.ctx.execute_raw(C.byref(raw[j]), stream.cuda_stream)
+            gpu.ctx.execute_raw(C.byref(raw[j]), stream.cuda_stream)  # N > 1: includes the wait for the slowest peer
             b.record(stream)
             evs.append((raw[j].name.decode().split(" - ")[-1], a, b))
         torch.cuda.synchronize(dev)
@@ -225,23 +244,38 @@ def main():
                 "per_pass_ms": pass_ms,
                 "per_pass_frac": {k: (ALGO_BYTES_PER_PIXEL[k] * W * H / (v * 1e-3) / 1e9 / peak) for k, v in pass_ms.items() if k in ALGO_BYTES_PER_PIXEL and v > 0}}
 
-    # ---- end to end with host buffers: pinned host -> H2D -> denoise -> D2H of both outputs, every step
+    # ---- end to end with host buffers: pinned host -> H2D -> denoise -> D2H of both outputs, every step (per rank: its strip)
     nhost = min(K + Wm, 8)
     host_frames = [{n: frames[i][n].cpu().pin_memory() for n in in_names} for i in range(nhost)]
-    for n in in_names:  # back to the context's own input textures
-        t = gpu.tex[n]
-        gpu.ctx.set_user_texture(getattr(nrd.ResourceType, n), t.data_ptr(), t.stride(0) * t.element_size(), harness.USER_FORMATS[n][0])
-    host_out = {n: torch.empty_like(t, device="cpu").pin_memory() for n, t in gpu.outputs().items()}
+    rows = y1 - y0
+    host_out = {}
+    for n in out_names:
+        fmt, dtype, ch = harness.USER_FORMATS[n]
+        host_out[n] = torch.empty((rows, W, ch) if ch > 1 else (rows, W), dtype=dtype).pin_memory()
+    if world == 1:
+        for n in in_names:  # back to the context's own input textures
+            t = gpu.tex[n]
+            gpu.ctx.set_user_texture(getattr(nrd.ResourceType, n), t.data_ptr(), t.stride(0) * t.element_size(), harness.USER_FORMATS[n][0])
     h2d = sum(t.numel() * t.element_size() for t in host_frames[0].values())
     d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+    if world > 1:
+        t = torch.tensor([float(h2d), float(d2h)], device=dev)
+        dist.all_reduce(t)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
 
     def e2e_step(i):
         hf = host_frames[i % nhost]
-        for n in in_names:
-            gpu.tex[n].copy_(hf[n], non_blocking=True)
-        gpu.denoise(harness.make_common_settings(frames[i % len(frames)], W, H, i + 2 * K))
-        for n, t in gpu.outputs().items():
-            host_out[n].copy_(t, non_blocking=True)
+        cs = harness.make_common_settings(frames[i % len(frames)], W, H, i + 2 * K)
+        if world == 1:
+            for n in in_names:
+                gpu.tex[n].copy_(hf[n], non_blocking=True)
+            gpu.denoise(cs)
+            for n, t in gpu.outputs().items():
+                host_out[n].copy_(t, non_blocking=True)
+        else:
+            gpu.set_input_strips(hf, stream)
+            gpu.denoise(cs)
+            gpu.read_outputs(out=host_out, stream=stream)
 
     for i in range(3):
         e2e_step(i)

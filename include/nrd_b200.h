@@ -337,8 +337,10 @@ NRD_API const char* NRD_CALL GetDenoiserString(Denoiser denoiser);
 // Several GPUs (one process per GPU): the frame is cut into horizontal strips of `stripHeight` rows (a multiple of 16, the
 // same on every rank; rank r owns rows [r*stripHeight, min((r+1)*stripHeight, height)) ).  A context then holds only its
 // strip of every texture -- pools AND user textures, all carved from one arena that is exported with CUDA IPC -- and the
-// kernels load rows of other strips directly from the owner's HBM over NVLink (no halo copies, no recomputation); a
-// device-side flag barrier separates the passes.  Kernels address texels in full-frame coordinates in both modes.
+// owner of a row keeps `haloRows` ghost copies of its boundary rows current in its two neighbours (bulk NVLink stores
+// after every pass that writes them); taps that land even further away are loaded directly from the owner's HBM, so the
+// result does not depend on the halo size (no recomputation, bit-identical to one GPU).  A device-side flag barrier
+// separates the passes.  Kernels address texels in full-frame coordinates in both modes.
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 typedef struct NrdCudaContext NrdCudaContext;
@@ -348,7 +350,8 @@ typedef struct NrdCudaContextDesc
     uint16_t resourceWidth, resourceHeight;   // full-frame texture size (== CommonSettings::resourceSize)
     uint16_t stripY0, stripY1;                // rows owned by this context; {0, resourceHeight} for one GPU
     uint16_t stripHeight;                     // 0 = one GPU; else rows per rank (multiple of 16), stripY0 = rank * stripHeight
-    int32_t device;                           // CUDA device ordinal
+    uint16_t haloRows;                        // strip mode: ghost rows kept above/below the strip (rounded up to 16, clamped to stripHeight)
+    int32_t device;                          // CUDA device ordinal
 } NrdCudaContextDesc;
 
 typedef struct NrdCudaTextureInfo

@@ -16,9 +16,11 @@ namespace nrdb200
 // Surfaces
 // ---------------------------------------------------------------------------------------------
 // Multi-GPU: the frame is cut into horizontal strips of `stripRows` rows (uniform, whole 16-row tiles), one per GPU.
-// Every context carves its surfaces out of one arena with the same layout, so the address of a texel owned by GPU o is
-// the local address plus (arena of o - local arena): a load of a row outside the local strip goes straight to the
-// owner's HBM over NVLink.  Stores are always local.  The deltas live in constant memory, one table per context slot.
+// Every context carves its surfaces out of one arena with the same layout; a surface holds its own strip plus `halo`
+// ghost rows above and below, which the owner of those rows refreshes after every pass that writes them (executor.cu,
+// GhostPushKernel: bulk NVLink stores).  A tap that lands outside even the ghost rows is loaded straight from the owner's
+// HBM: its address is the local address plus (arena of the owner - local arena).  Stores are always local.  The deltas live
+// in constant memory, one table per context slot.
 constexpr int kMaxPeers = 8;
 constexpr int kMaxPeerSlots = 4;
 static __constant__ long long g_peerDelta[kMaxPeerSlots * kMaxPeers];
@@ -29,26 +31,30 @@ static inline cudaError_t SetPeerTableThisTU(int slot, const long long* delta)
 
 struct Surf
 {
-    uint8_t* base;       // address of texel (0, y0)
+    uint8_t* base;       // address of texel (0, ly0)
     int pitch;           // bytes per row
     int w, h;            // full (virtual) texture size
-    int y0, y1;          // rows physically present: [y0, y1)
+    int y0, y1;          // rows owned by this context: [y0, y1)  (the whole texture on one GPU)
+    int ly0;             // first row held locally (y0 - halo in strip mode, may be negative)
+    unsigned lrows;      // rows held locally
     unsigned stripRows;  // rows per strip in this texture's own units; 0 = whole frame is local
     unsigned stripMagic; // floor(2^32 / stripRows) + 1: owner(y) = umulhi(y, magic), exact for y, stripRows < 65536
+    int halo;            // ghost rows on either side, in this texture's own units
     int peerSlot;
-    int pad_;
 };
 
 template <class T> __device__ __forceinline__ const T* TexelPtr(const Surf& s, int x, int y)
 {
-    if (s.stripRows == 0) return reinterpret_cast<const T*>(s.base + (size_t)(y - s.y0) * s.pitch) + x;
+    const int ly = y - s.ly0;
+    if ((unsigned)ly < s.lrows) return reinterpret_cast<const T*>(s.base + (size_t)ly * s.pitch) + x;
+    // rare: beyond the ghost rows (only reachable in strip mode, callers clamp y to [0, h))
     const unsigned owner = __umulhi((unsigned)y, s.stripMagic);
-    const uint8_t* row = s.base + g_peerDelta[s.peerSlot * kMaxPeers + owner] + (size_t)((unsigned)y - owner * s.stripRows) * s.pitch;
+    const uint8_t* row = s.base + g_peerDelta[s.peerSlot * kMaxPeers + owner] + (size_t)((unsigned)y - owner * s.stripRows + (unsigned)s.halo) * s.pitch;
     return reinterpret_cast<const T*>(row) + x;
 }
 template <class T> __device__ __forceinline__ T* TexelPtrRW(const Surf& s, int x, int y)
 {
-    return reinterpret_cast<T*>(s.base + (size_t)(y - s.y0) * s.pitch) + x;
+    return reinterpret_cast<T*>(s.base + (size_t)(y - s.ly0) * s.pitch) + x;
 }
 __device__ __forceinline__ bool Inside(const Surf& s, int x, int y) { return (unsigned)x < (unsigned)s.w && (unsigned)y < (unsigned)s.h; }
 

@@ -40,13 +40,15 @@ uint32_t BytesPerTexel(Format f)
 
 struct Texture
 {
-    void* ptr = nullptr; // texel (0, firstRow)
+    void* ptr = nullptr; // first row held locally: texel (0, firstRow - haloRows) in strip mode, texel (0, firstRow) otherwise
     size_t pitch = 0;
     Format format = Format::R8_UNORM;
     uint16_t width = 0, height = 0; // virtual size
     uint16_t firstRow = 0, rows = 0; // rows that hold data
-    uint16_t allocRows = 0;          // rows reserved in the arena (uniform strip height in strip mode)
+    uint16_t allocRows = 0;          // rows reserved in the arena (strip mode: uniform strip height + 2 x haloRows)
+    uint16_t haloRows = 0;           // ghost rows above and below the strip, in this texture's own rows
     uint16_t downsample = 1;
+    void* OwnPtr() const { return (uint8_t*)ptr + (size_t)haloRows * pitch; } // texel (0, firstRow)
     bool owned = false;
 };
 
@@ -85,6 +87,7 @@ struct NrdCudaContext
     bool peerOpened[kMaxPeers] = {};
     long long peerDelta[kMaxPeers] = {};
     uint32_t epoch = 0;
+    uint32_t halo = 0; // ghost rows (full-resolution rows, multiple of 16, <= stripHeight)
     std::string lastError;
 };
 
@@ -115,7 +118,8 @@ void DescribeTexture(const NrdCudaContext* ctx, Format format, uint16_t downsamp
     t.width = uint16_t((ctx->desc.resourceWidth + downsample - 1) / downsample);
     t.height = uint16_t((ctx->desc.resourceHeight + downsample - 1) / downsample);
     OwnedRows(ctx->desc, downsample, t.height, t.firstRow, t.rows);
-    t.allocRows = StripMode(ctx) ? uint16_t(ctx->desc.stripHeight / downsample) : t.rows;
+    t.haloRows = uint16_t(ctx->halo / downsample);
+    t.allocRows = StripMode(ctx) ? uint16_t(ctx->desc.stripHeight / downsample + 2 * t.haloRows) : t.rows;
     size_t rowBytes = (size_t)t.width * BytesPerTexel(format);
     t.pitch = (rowBytes + 255) & ~(size_t)255; // 256-B aligned rows: 128-bit vector access and TMA-legal strides
     t.owned = true;
@@ -138,12 +142,18 @@ Surf ToSurf(const NrdCudaContext* ctx, const Texture& t)
     s.h = t.height;
     s.y0 = t.firstRow;
     s.y1 = t.firstRow + t.rows;
+    s.ly0 = t.firstRow;
+    s.lrows = t.owned ? t.allocRows : t.rows;
     if (StripMode(ctx) && ctx->world > 1)
     {
         s.stripRows = ctx->desc.stripHeight / t.downsample;
         s.stripMagic = (unsigned)(0x100000000ull / s.stripRows) + 1u;
+        s.halo = t.haloRows;
+        s.ly0 = (int)t.firstRow - (int)t.haloRows;
         s.peerSlot = ctx->peerSlot;
     }
+    else if (StripMode(ctx))
+        s.base += (size_t)t.haloRows * t.pitch, s.lrows = t.rows; // a strip-mode context that holds the whole frame
     return s;
 }
 
@@ -167,6 +177,18 @@ struct BarrierArgs
     unsigned rank, world, epoch;
     long long timeout;
 };
+
+struct PushItem
+{
+    const uint8_t* src;
+    uint8_t* dst;
+    unsigned long long bytes;
+};
+constexpr int kMaxPushItems = 32;
+struct PushArgs
+{
+    PushItem items[kMaxPushItems];
+};
 } // namespace
 
 namespace nrdb200
@@ -183,7 +205,7 @@ __global__ void ClearKernel(uint4* p, size_t n16)
 cudaError_t LaunchClear(const PassLaunch& p)
 {
     const Surf& s = p.tex[0];
-    size_t bytes = (size_t)s.pitch * (size_t)(s.y1 - s.y0);
+    size_t bytes = (size_t)s.pitch * (size_t)s.lrows; // ghost rows included: every rank clears them itself
     if (bytes == 0) return cudaSuccess;
     if ((s.pitch & 15) != 0 || ((uintptr_t)s.base & 15) != 0) return cudaMemsetAsync(s.base, 0, bytes, p.stream); // user textures with odd pitch
     size_t n16 = bytes / 16;
@@ -217,6 +239,17 @@ __global__ void StripBarrierKernel(const __grid_constant__ BarrierArgs a)
     }
     __threadfence_system();
 }
+
+// Ghost refresh: after a pass wrote its strip of a texture, the first / last `halo` rows of the strip are stored into the
+// ghost rows of the neighbour above / below (contiguous blocks of whole pitched rows, 16-byte NVLink stores).
+__global__ void __launch_bounds__(256) GhostPushKernel(const __grid_constant__ PushArgs a)
+{
+    const PushItem& it = a.items[blockIdx.y];
+    const uint4* src = (const uint4*)it.src;
+    uint4* dst = (uint4*)it.dst;
+    const size_t n = it.bytes / 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 } // namespace nrdb200
 
 namespace
@@ -234,6 +267,52 @@ Result Barrier(NrdCudaContext* ctx, cudaStream_t stream)
     StripBarrierKernel<<<1, 32, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, std::string("strip barrier: ") + cudaGetErrorString(e));
+}
+
+// Sends the boundary rows of `textures` (arena-owned, just written by this rank) to the ghost rows of the two neighbours.
+Result PushGhosts(NrdCudaContext* ctx, const Texture* const* textures, uint32_t n, cudaStream_t stream)
+{
+    if (!StripMode(ctx) || ctx->world <= 1 || ctx->halo == 0 || n == 0) return Result::SUCCESS;
+    PushArgs a{};
+    uint32_t items = 0;
+    unsigned long long maxBytes = 0;
+    auto flush = [&]() -> Result {
+        if (!items) return Result::SUCCESS;
+        unsigned blocksX = (unsigned)((maxBytes / 16 + 256 * 8 - 1) / (256 * 8)); // ~8 x 16 B per thread
+        if (blocksX < 1) blocksX = 1;
+        if (blocksX > 148 * 4) blocksX = 148 * 4;
+        GhostPushKernel<<<dim3(blocksX, items), 256, 0, stream>>>(a);
+        cudaError_t e = cudaGetLastError();
+        items = 0;
+        maxBytes = 0;
+        return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, std::string("ghost push: ") + cudaGetErrorString(e));
+    };
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const Texture& t = *textures[i];
+        if (!t.owned || !t.rows || !t.haloRows) continue;
+        const uint32_t S = ctx->desc.stripHeight / t.downsample, H = t.haloRows;
+        uint8_t* base = (uint8_t*)t.ptr;
+        if (ctx->rank > 0)
+        {
+            // my first rows are the bottom ghost rows of the strip above: local rows [S + H, S + 2H) over there
+            const uint32_t cnt = t.rows < H ? t.rows : H;
+            a.items[items++] = {base + (size_t)H * t.pitch, base + ctx->peerDelta[ctx->rank - 1] + (size_t)(S + H) * t.pitch, (unsigned long long)cnt * t.pitch};
+            if ((unsigned long long)cnt * t.pitch > maxBytes) maxBytes = (unsigned long long)cnt * t.pitch;
+        }
+        if (ctx->rank + 1 < ctx->world && t.rows == S)
+        {
+            // my last rows are the top ghost rows of the strip below: local rows [0, H) over there
+            a.items[items++] = {base + (size_t)S * t.pitch, base + ctx->peerDelta[ctx->rank + 1], (unsigned long long)H * t.pitch};
+            if ((unsigned long long)H * t.pitch > maxBytes) maxBytes = (unsigned long long)H * t.pitch;
+        }
+        if (items + 2 > (uint32_t)kMaxPushItems)
+        {
+            Result r = flush();
+            if (r != Result::SUCCESS) return r;
+        }
+    }
+    return flush();
 }
 } // namespace
 
@@ -257,6 +336,12 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
     NrdCudaContext* ctx = new NrdCudaContext();
     ctx->instance = instance;
     ctx->desc = *desc;
+    if (desc->stripHeight != 0)
+    {
+        // ghost rows: whole tiles, at most one strip (they are refreshed by the direct neighbours only)
+        ctx->halo = ((uint32_t)desc->haloRows + 15u) / 16u * 16u;
+        if (ctx->halo > desc->stripHeight) ctx->halo = desc->stripHeight;
+    }
     const InstanceDesc& id = GetInstanceDesc(*instance);
     ctx->permanent.resize(id.permanentPoolSize);
     ctx->transient.resize(id.transientPoolSize);
@@ -340,7 +425,7 @@ NRD_API Result nrdCudaGetTexture(NrdCudaContext* ctx, uint32_t resourceType, uin
     if (!ctx || !info) return Result::INVALID_ARGUMENT;
     const Texture* t = Resolve(ctx, (ResourceType)resourceType, indexInPool);
     if (!t) return Result::INVALID_ARGUMENT;
-    info->devicePtr = t->ptr;
+    info->devicePtr = t->OwnPtr();
     info->pitchBytes = t->pitch;
     info->format = (uint32_t)t->format;
     info->width = t->width;
@@ -409,7 +494,12 @@ NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t 
     return Result::SUCCESS;
 }
 
-NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d, void* stream)
+}  // extern "C"
+
+namespace
+{
+// pushMask: bit i set = the ghost rows of resource i must be refreshed after this pass (it is read by a later pass)
+Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream, uint32_t pushMask)
 {
     if (!ctx || !d) return Result::INVALID_ARGUMENT;
     const InstanceDesc& id = GetInstanceDesc(*ctx->instance);
@@ -465,7 +555,51 @@ NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d
     if (e == cudaErrorNotSupported) return Fail(ctx, Result::UNSUPPORTED, std::string("no CUDA kernel for pass ") + shader);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string(shader) + ": " + cudaGetErrorString(e));
     g_launchCount.fetch_add(1, std::memory_order_relaxed);
+    if (strncmp(shader, "Clear_", 6) != 0 && pushMask) // clears zero the ghost rows locally
+    {
+        const Texture* list[32];
+        uint32_t n = 0;
+        for (uint32_t i = 0; i < d->resourcesNum; i++)
+            if ((pushMask >> i) & 1u) list[n++] = Resolve(ctx, d->resources[i].type, d->resources[i].indexInPool);
+        Result r = PushGhosts(ctx, list, n, p.stream);
+        if (r != Result::SUCCESS) return r;
+    }
     return Barrier(ctx, p.stream);
+}
+
+uint32_t StorageMask(const DispatchDesc* d)
+{
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < d->resourcesNum && i < 32; i++)
+        if (d->resources[i].descriptorType == DescriptorType::STORAGE_TEXTURE) m |= 1u << i;
+    return m;
+}
+
+// frame start: the IN_* strips the application just wrote are pushed to the neighbours' ghost rows, then all ranks meet
+Result FrameStart(NrdCudaContext* ctx, void* stream)
+{
+    if (StripMode(ctx) && ctx->world > 1)
+    {
+        const Texture* list[(size_t)ResourceType::MAX_NUM];
+        uint32_t n = 0;
+        for (uint32_t t = 0; t < (uint32_t)ResourceType::MAX_NUM; t++)
+        {
+            const char* name = GetResourceTypeString((ResourceType)t);
+            if (ctx->user[t].ptr && name && !strncmp(name, "IN_", 3)) list[n++] = &ctx->user[t];
+        }
+        Result r = PushGhosts(ctx, list, n, (cudaStream_t)stream);
+        if (r != Result::SUCCESS) return r;
+    }
+    return Barrier(ctx, (cudaStream_t)stream);
+}
+} // namespace
+
+extern "C" {
+
+NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d, void* stream)
+{
+    if (!ctx || !d) return Result::INVALID_ARGUMENT;
+    return ExecuteInternal(ctx, d, stream, StorageMask(d)); // no look-ahead here: refresh the ghosts of every output
 }
 
 NRD_API Result nrdCudaDenoise(NrdCudaContext* ctx, const Identifier* identifiers, uint32_t identifiersNum, void* stream, uint32_t* launches)
@@ -475,11 +609,36 @@ NRD_API Result nrdCudaDenoise(NrdCudaContext* ctx, const Identifier* identifiers
     uint32_t n = 0;
     Result r = GetComputeDispatches(*ctx->instance, identifiers, identifiersNum, dispatches, n);
     if (r != Result::SUCCESS) return r;
-    r = Barrier(ctx, (cudaStream_t)stream); // the peers' input strips of this frame are complete
+    r = FrameStart(ctx, stream);
     if (r != Result::SUCCESS) return r;
     for (uint32_t i = 0; i < n; i++)
     {
-        r = nrdCudaExecuteDispatch(ctx, &dispatches[i], stream);
+        // an output needs fresh ghost rows only if a later pass reads it before anyone overwrites it; what survives the frame
+        // may be read next frame unless it is transient
+        uint32_t mask = 0;
+        const DispatchDesc& d = dispatches[i];
+        for (uint32_t k = 0; k < d.resourcesNum && k < 32; k++)
+        {
+            const ResourceDesc& out = d.resources[k];
+            if (out.descriptorType != DescriptorType::STORAGE_TEXTURE) continue;
+            bool decided = false, needed = false;
+            for (uint32_t j = i + 1; j < n && !decided; j++)
+                for (uint32_t m = 0; m < dispatches[j].resourcesNum && !decided; m++)
+                {
+                    const ResourceDesc& use = dispatches[j].resources[m];
+                    if (use.type != out.type || use.indexInPool != out.indexInPool) continue;
+                    decided = true;
+                    needed = use.descriptorType == DescriptorType::TEXTURE;
+                    // a pass may bind a texture both ways (never in the supported chains); reading wins
+                    for (uint32_t q = m + 1; q < dispatches[j].resourcesNum; q++)
+                        if (dispatches[j].resources[q].type == out.type && dispatches[j].resources[q].indexInPool == out.indexInPool &&
+                            dispatches[j].resources[q].descriptorType == DescriptorType::TEXTURE)
+                            needed = true;
+                }
+            if (!decided) needed = out.type != ResourceType::TRANSIENT_POOL; // history, or an output a denoiser re-reads next frame (SIGMA)
+            if (needed) mask |= 1u << k;
+        }
+        r = ExecuteInternal(ctx, &d, stream, mask);
         if (r != Result::SUCCESS) return r;
     }
     if (launches) *launches = n;
@@ -492,7 +651,7 @@ NRD_API Result nrdCudaUploadTexture(NrdCudaContext* ctx, uint32_t resourceType, 
     const Texture* t = Resolve(ctx, (ResourceType)resourceType, indexInPool);
     if (!t) return Result::INVALID_ARGUMENT;
     if (!t->rows) return Result::SUCCESS;
-    cudaError_t e = cudaMemcpy2D(t->ptr, t->pitch, hostPtr, hostPitchBytes, (size_t)t->width * BytesPerTexel(t->format), t->rows, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy2D(t->OwnPtr(), t->pitch, hostPtr, hostPitchBytes, (size_t)t->width * BytesPerTexel(t->format), t->rows, cudaMemcpyHostToDevice);
     return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, cudaGetErrorString(e));
 }
 
@@ -502,7 +661,7 @@ NRD_API Result nrdCudaDownloadTexture(NrdCudaContext* ctx, uint32_t resourceType
     const Texture* t = Resolve(ctx, (ResourceType)resourceType, indexInPool);
     if (!t) return Result::INVALID_ARGUMENT;
     if (!t->rows) return Result::SUCCESS;
-    cudaError_t e = cudaMemcpy2D(hostPtr, hostPitchBytes, t->ptr, t->pitch, (size_t)t->width * BytesPerTexel(t->format), t->rows, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy2D(hostPtr, hostPitchBytes, t->OwnPtr(), t->pitch, (size_t)t->width * BytesPerTexel(t->format), t->rows, cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, cudaGetErrorString(e));
 }
 
@@ -513,15 +672,15 @@ NRD_API Result nrdCudaCopyTexture(NrdCudaContext* ctx, uint32_t resourceType, ui
     if (!t) return Result::INVALID_ARGUMENT;
     if (!t->rows) return Result::SUCCESS;
     const size_t rowBytes = (size_t)t->width * BytesPerTexel(t->format);
-    cudaError_t e = toContext ? cudaMemcpy2DAsync(t->ptr, t->pitch, ptr, pitchBytes, rowBytes, t->rows, cudaMemcpyDefault, (cudaStream_t)stream)
-                              : cudaMemcpy2DAsync(ptr, pitchBytes, t->ptr, t->pitch, rowBytes, t->rows, cudaMemcpyDefault, (cudaStream_t)stream);
+    cudaError_t e = toContext ? cudaMemcpy2DAsync(t->OwnPtr(), t->pitch, ptr, pitchBytes, rowBytes, t->rows, cudaMemcpyDefault, (cudaStream_t)stream)
+                              : cudaMemcpy2DAsync(ptr, pitchBytes, t->OwnPtr(), t->pitch, rowBytes, t->rows, cudaMemcpyDefault, (cudaStream_t)stream);
     return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, cudaGetErrorString(e));
 }
 
 NRD_API Result nrdCudaBarrier(NrdCudaContext* ctx, void* stream)
 {
     if (!ctx) return Result::INVALID_ARGUMENT;
-    return Barrier(ctx, (cudaStream_t)stream);
+    return FrameStart(ctx, stream);
 }
 
 NRD_API Result nrdCudaSynchronize(NrdCudaContext* ctx, void* stream)

@@ -180,7 +180,7 @@ RelaxSettings = _struct("RelaxSettings", [
 SigmaSettings = _struct("SigmaSettings", [("lightDirection", f32 * 3), ("planeDistanceSensitivity", f32), ("maxStabilizedFrameNum", u32)],
                         dict(planeDistanceSensitivity=0.02, maxStabilizedFrameNum=5))
 
-NrdCudaContextDesc = _struct("NrdCudaContextDesc", [("resourceWidth", u16), ("resourceHeight", u16), ("stripY0", u16), ("stripY1", u16), ("stripHeight", u16), ("device", C.c_int32)])
+NrdCudaContextDesc = _struct("NrdCudaContextDesc", [("resourceWidth", u16), ("resourceHeight", u16), ("stripY0", u16), ("stripY1", u16), ("stripHeight", u16), ("haloRows", u16), ("device", C.c_int32)])
 NrdCudaTextureInfo = _struct("NrdCudaTextureInfo", [("devicePtr", C.c_void_p), ("pitchBytes", C.c_size_t), ("format", u32), ("width", u16), ("height", u16),
                                                     ("firstRow", u16), ("rowsNum", u16)])
 
@@ -366,12 +366,13 @@ class Instance(object):
 class CudaContext(object):
     """CUDA executor for one Instance (replaces nrd::Integration).  Textures are plain device pointers + pitch."""
 
-    def __init__(self, instance, width, height, device=0, strip=None, strip_height=0):
-        """strip=(y0, y1), strip_height=S: strip-mode context of a multi-GPU run (see include/nrd_b200.h)."""
+    def __init__(self, instance, width, height, device=0, strip=None, strip_height=0, halo_rows=0):
+        """strip=(y0, y1), strip_height=S, halo_rows=H: strip-mode context of a multi-GPU run (see include/nrd_b200.h)."""
         desc = NrdCudaContextDesc()
         desc.resourceWidth, desc.resourceHeight = width, height
         desc.stripY0, desc.stripY1 = strip if strip else (0, height)
         desc.stripHeight = strip_height
+        desc.haloRows = halo_rows
         desc.device = device
         self.strip = (desc.stripY0, desc.stripY1)
         self.strip_height = strip_height

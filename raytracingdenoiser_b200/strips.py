@@ -5,11 +5,16 @@ are read by the kernels straight from the owner's HBM over NVLink (CUDA IPC mapp
 flag barrier separates the passes (csrc/executor.cu).  There is no data-path collective: torch.distributed only carries the
 64-byte IPC handles at start-up and the timing reductions of bench.py.
 """
+import os
+
 import torch
 
 from . import harness, nrd
 
 TILE = 16
+# ghost rows each strip keeps of its neighbours (refreshed by bulk NVLink stores after every pass); taps beyond them are
+# direct peer loads, so the value only trades halo traffic against the (slow) direct loads
+DEFAULT_HALO_ROWS = int(os.environ.get("NRD_B200_HALO_ROWS", "96"))
 
 
 def partition_rows(height, world_size):
@@ -38,14 +43,15 @@ def exchange_ipc_handles(local_handle, group=None):
 class StripDenoiser(object):
     """The strip of one rank: instance + strip-mode CUDA context.  IN_*/OUT_* strips live in the context's arena."""
 
-    def __init__(self, denoiser, width, height, rank, world_size, device=0, identifier=0, settings=None):
+    def __init__(self, denoiser, width, height, rank, world_size, device=0, identifier=0, settings=None, halo_rows=None):
         self.denoiser, self.width, self.height, self.identifier = denoiser, width, height, identifier
         self.rank, self.world_size = rank, world_size
         self.device = torch.device("cuda", device)
         self.strip_height, strips = partition_rows(height, world_size)
         self.y0, self.y1 = strips[rank]
         self.instance = nrd.Instance([(identifier, denoiser)])
-        self.ctx = nrd.CudaContext(self.instance, width, height, device=device, strip=(self.y0, self.y1), strip_height=self.strip_height)
+        self.ctx = nrd.CudaContext(self.instance, width, height, device=device, strip=(self.y0, self.y1), strip_height=self.strip_height,
+                                   halo_rows=DEFAULT_HALO_ROWS if halo_rows is None else halo_rows)
         if settings is not None:
             self.instance.set_denoiser_settings(identifier, settings)
         self.names = harness.DENOISER_RESOURCES[denoiser]

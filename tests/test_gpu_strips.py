@@ -9,13 +9,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(denoiser_name, w, h, world, frames):
+def _run(denoiser_name, w, h, world, frames, halo, whole_frame_call):
     import torch
     from raytracingdenoiser_b200 import harness, nrd, scene, strips
     den = getattr(nrd.Denoiser, denoiser_name)
     mode = harness.radiance_mode(den)
     full = harness.GpuDenoiser(den, w, h)
-    parts = [strips.StripDenoiser(den, w, h, r, world) for r in range(world)]
+    parts = [strips.StripDenoiser(den, w, h, r, world, halo_rows=halo) for r in range(world)]
     for p in parts:
         p.connect_local(parts)
     streams = [torch.cuda.Stream() for _ in parts]
@@ -26,17 +26,23 @@ def _run(denoiser_name, w, h, world, frames):
         full.set_inputs(fr)
         full.denoise(cs)
         torch.cuda.synchronize()
-        lists = []
-        for p, st in zip(parts, streams):
-            p.set_inputs(fr, st)
-            lists.append(p.dispatches(cs))
-            p.ctx.barrier(st.cuda_stream)
-        n = lists[0][1]
-        assert all(m == n for _, m in lists)
-        # interleave the ranks pass by pass: each launch is asynchronous, the barrier kernels meet on the device
-        for i in range(n):
-            for p, st, (raw, _) in zip(parts, streams, lists):
-                p.ctx.execute_raw(C.byref(raw[i]), st.cuda_stream)
+        if whole_frame_call:
+            # nrdCudaDenoise per rank (with the ghost look-ahead): all launches are asynchronous, the ranks meet on the device
+            for p, st in zip(parts, streams):
+                p.set_inputs(fr, st)
+                p.denoise(cs, st)
+        else:
+            lists = []
+            for p, st in zip(parts, streams):
+                p.set_inputs(fr, st)
+                lists.append(p.dispatches(cs))
+                p.ctx.barrier(st.cuda_stream)
+            n = lists[0][1]
+            assert all(m == n for _, m in lists)
+            # application-driven dispatch loop, ranks interleaved pass by pass
+            for i in range(n):
+                for p, st, (raw, _) in zip(parts, streams, lists):
+                    p.ctx.execute_raw(C.byref(raw[i]), st.cuda_stream)
         for p, st in zip(parts, streams):
             p.synchronize(st)
     ref = full.outputs()
@@ -51,14 +57,16 @@ def _run(denoiser_name, w, h, world, frames):
     full.destroy()
 
 
-@pytest.mark.parametrize("denoiser,w,h,world,frames", [
-    ("REBLUR_DIFFUSE_SPECULAR", 320, 192, 2, 4),
-    ("REBLUR_DIFFUSE_SPECULAR", 250, 141, 3, 3),
-    ("RELAX_DIFFUSE_SPECULAR", 320, 180, 2, 4),
-    ("SIGMA_SHADOW", 320, 180, 4, 3),
+@pytest.mark.parametrize("denoiser,w,h,world,frames,halo,whole_frame_call", [
+    ("REBLUR_DIFFUSE_SPECULAR", 320, 192, 2, 4, 32, True),     # ghost rows + direct peer loads beyond them
+    ("REBLUR_DIFFUSE_SPECULAR", 320, 192, 2, 3, 0, False),     # no ghost rows: every foreign tap is a direct peer load
+    ("REBLUR_DIFFUSE_SPECULAR", 250, 141, 3, 3, 96, True),     # halo clamped to the strip height (48 rows)
+    ("RELAX_DIFFUSE_SPECULAR", 320, 180, 2, 4, 16, True),
+    ("RELAX_DIFFUSE_SPECULAR", 320, 180, 3, 3, 64, False),
+    ("SIGMA_SHADOW", 320, 180, 4, 4, 16, True),
 ])
-def test_strips_bit_identical_to_full_frame(denoiser, w, h, world, frames):
-    _run(denoiser, w, h, world, frames)
+def test_strips_bit_identical_to_full_frame(denoiser, w, h, world, frames, halo, whole_frame_call):
+    _run(denoiser, w, h, world, frames, halo, whole_frame_call)
 
 
 def test_strip_context_rejects_foreign_user_pointers_and_bad_geometry():
