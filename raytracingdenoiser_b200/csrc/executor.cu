@@ -532,6 +532,12 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     // rows to produce: the context's strip (the full frame on one GPU)
     p.rowBegin = ctx->desc.stripY0;
     p.rowEnd = ctx->desc.stripY1;
+    {
+        // profiling aid (one GPU only): NRD_B200_DEBUG_ROWS="y0,y1" restricts every pass to a row range, to cost a strip in isolation
+        static const char* dbg = getenv("NRD_B200_DEBUG_ROWS");
+        int a = 0, b = 0;
+        if (dbg && !StripMode(ctx) && sscanf(dbg, "%d,%d", &a, &b) == 2 && a % 16 == 0 && b > a && b <= (int)ctx->desc.resourceHeight) p.rowBegin = a, p.rowEnd = b;
+    }
 
     cudaError_t e = cudaErrorNotSupported;
     int signal = 0;

@@ -90,7 +90,7 @@ class Scene(object):
     def camera(self, frame):
         eye = [0.6 * math.sin(frame * 0.05), 1.7 + 0.05 * math.sin(frame * 0.11), -4.0 + 0.035 * frame]
         yaw = 0.10 * math.sin(frame * 0.035)
-        pitch = -0.10
+        pitch = -0.36  # horizon at ~17 % of the frame height: most of the frame is geometry the denoiser has to process
         return look_at_lh(eye, yaw, pitch), np.array(eye, dtype=np.float32)
 
     # ---- analytic intersection of rays (origin o[...,3], direction d[...,3]) with the scene ----
