@@ -845,23 +845,32 @@ __device__ __forceinline__ float Antilag(const ReblurConstants& c, float history
 }
 
 // 3x3 luma statistics of a YCoCg signal (clamped reads)
+// 3x3 luma moments.  sigma = sqrt(|m2 - m1^2|) cancels catastrophically on flat regions (the result is rounding noise of
+// relative size ~3e-4 that then scales the clamping box), so the moments are accumulated in the oracle's order with
+// individually rounded operations: centre first, then row-major, true division by 9.
 __device__ __forceinline__ void LumaStats3x3(const Surf& s, int x, int y, int maxX, int maxY, float& luma, float& m1, float& m2, float& mn, float& mx)
 {
-    m1 = 0.0f; m2 = 0.0f; mn = kInf; mx = -kInf; luma = 0.0f;
+    luma = LoadRGBA16F(s, x, y).x;
+    m1 = luma;
+    m2 = __fmul_rn(luma, luma);
+    mn = kInf;
+    mx = -kInf;
 #pragma unroll
     for (int j = -1; j <= 1; j++)
 #pragma unroll
         for (int i = -1; i <= 1; i++)
         {
+            if (i == 0 && j == 0) continue;
             float d = LoadRGBA16F(s, clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)).x;
-            m1 += d;
-            m2 += d * d;
-            if (i == 0 && j == 0) luma = d;
-            else { mn = fminf(mn, d); mx = fmaxf(mx, d); }
+            m1 = __fadd_rn(m1, d);
+            m2 = __fadd_rn(m2, __fmul_rn(d, d));
+            mn = fminf(mn, d);
+            mx = fmaxf(mx, d);
         }
-    m1 *= 1.0f / 9.0f;
-    m2 *= 1.0f / 9.0f;
+    m1 = __fdiv_rn(m1, 9.0f);
+    m2 = __fdiv_rn(m2, 9.0f);
 }
+__device__ __forceinline__ float PinnedStdDev(float m1, float m2) { return __fsqrt_rn(fabsf(__fadd_rn(m2, -__fmul_rn(m1, m1)))); }
 
 template <bool DIFF, bool SPEC>
 __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const __grid_constant__ TsArgs a)
@@ -916,7 +925,7 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
     {
         float luma, m1, m2, mn, mx;
         LumaStats3x3(a.inDiff, x, y, maxX, maxY, luma, m1, m2, mn, mx);
-        const float sigma = GetStdDev(m1, m2);
+        const float sigma = PinnedStdDev(m1, m2);
         if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
         float history = fmaxf(ResolveCatRom1(smbSetup, a.histDiffStab), 0.0f);
         const float antilag = Antilag(c, history, m1, sigma, smbFootprintQuality * data1.x);
@@ -937,7 +946,7 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
     {
         float luma, m1, m2, mn, mx;
         LumaStats3x3(a.inSpec, x, y, maxX, maxY, luma, m1, m2, mn, mx);
-        const float sigma = GetStdDev(m1, m2);
+        const float sigma = PinnedStdDev(m1, m2);
         if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
 
         f4 spec = LoadRGBA16F(a.inSpec, x, y);

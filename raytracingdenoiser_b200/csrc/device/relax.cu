@@ -31,6 +31,7 @@ __constant__ unsigned kBayerRx[16] = {0, 8, 2, 10, 12, 4, 14, 6, 3, 11, 1, 9, 15
 typedef RelaxConstants RC;
 
 __device__ __forceinline__ float Luma(f3 c) { return 0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z; }
+__device__ __forceinline__ float PinnedLuma(f3 c) { return __fadd_rn(__fadd_rn(__fmul_rn(c.x, 0.2126f), __fmul_rn(c.y, 0.7152f)), __fmul_rn(c.z, 0.0722f)); }
 __device__ __forceinline__ f3 abs3(f3 a) { return mk3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
 __device__ __forceinline__ f3 max3(f3 a, f3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 __device__ __forceinline__ f3 min3(f3 a, f3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
@@ -854,6 +855,7 @@ __device__ __forceinline__ void ClampSignal(const RC& c, const Surf& zSurf, int 
                                             const Surf& outSlow, const Surf& outFast)
 {
     const int W = c.gRectSize[0], H = c.gRectSize[1];
+    // moments in the oracle's operation order: sigma = sqrt(m2 - m1^2) is rounding noise on flat regions (see LumaStats3x3)
     f3 m1 = mk3(0.0f), m2 = mk3(0.0f), noisyM1 = mk3(0.0f);
     float noisyM2 = 0.0f, sum = 0.0f;
 #pragma unroll 1
@@ -864,22 +866,22 @@ __device__ __forceinline__ void ClampSignal(const RC& c, const Surf& zSurf, int 
             int px = clampi(x + dx, 0, W - 1), py = clampi(y + dy, 0, H - 1);
             if (LoadR32F(zSurf, px, py) < c.gDenoisingRange)
             {
-                f3 sy = RgbToYCoCg(xyz(LoadRGBA16F(inFast, px, py)));
-                m1 = m1 + sy;
-                m2 = m2 + sy * sy;
+                f3 sy = RgbToYCoCg(xyz(LoadRGBA16F(inFast, px, py))); // exact: power-of-two coefficients
+                m1 = PinnedAdd(m1, sy);
+                m2 = PinnedAdd(m2, mk3(__fmul_rn(sy.x, sy.x), __fmul_rn(sy.y, sy.y), __fmul_rn(sy.z, sy.z)));
                 f3 n = xyz(LoadRGBA16F(inNoisy, px, py));
-                float l = Luma(n);
-                noisyM1 = noisyM1 + n;
-                noisyM2 += l * l;
+                float l = PinnedLuma(n);
+                noisyM1 = PinnedAdd(noisyM1, n);
+                noisyM2 = __fadd_rn(noisyM2, __fmul_rn(l, l));
                 sum += 1.0f;
             }
         }
-    m1 = mk3(m1.x / sum, m1.y / sum, m1.z / sum);
-    m2 = mk3(m2.x / sum, m2.y / sum, m2.z / sum);
-    noisyM1 = mk3(noisyM1.x / sum, noisyM1.y / sum, noisyM1.z / sum);
-    noisyM2 /= sum;
-    f3 var = m2 - m1 * m1;
-    f3 sigma = mk3(sqrtf(fmaxf(0.0f, var.x)), sqrtf(fmaxf(0.0f, var.y)), sqrtf(fmaxf(0.0f, var.z)));
+    m1 = mk3(__fdiv_rn(m1.x, sum), __fdiv_rn(m1.y, sum), __fdiv_rn(m1.z, sum));
+    m2 = mk3(__fdiv_rn(m2.x, sum), __fdiv_rn(m2.y, sum), __fdiv_rn(m2.z, sum));
+    noisyM1 = mk3(__fdiv_rn(noisyM1.x, sum), __fdiv_rn(noisyM1.y, sum), __fdiv_rn(noisyM1.z, sum));
+    noisyM2 = __fdiv_rn(noisyM2, sum);
+    f3 var = mk3(__fadd_rn(m2.x, -__fmul_rn(m1.x, m1.x)), __fadd_rn(m2.y, -__fmul_rn(m1.y, m1.y)), __fadd_rn(m2.z, -__fmul_rn(m1.z, m1.z)));
+    f3 sigma = mk3(__fsqrt_rn(fmaxf(0.0f, var.x)), __fsqrt_rn(fmaxf(0.0f, var.y)), __fsqrt_rn(fmaxf(0.0f, var.z)));
     f3 cmin = m1 - sigma * c.gColorBoxSigmaScale, cmax = m1 + sigma * c.gColorBoxSigmaScale;
     const f4 fastCenter = LoadRGBA16F(inFast, x, y);
     const f3 responsiveYCoCg = RgbToYCoCg(xyz(fastCenter));
@@ -920,8 +922,8 @@ __device__ __forceinline__ void ClampSignal(const RC& c, const Surf& zSurf, int 
     outR = mk4(xyz(outR) + accel, outR.w);
 
     const float slowL = Luma(xyz(slow));
-    const float noisyL = Luma(noisyM1);
-    const float temporalSigma = c.gHistoryResetTemporalSigmaScale * sqrtf(fmaxf(0.0f, noisyM2 - noisyL * noisyL));
+    const float noisyL = PinnedLuma(noisyM1);
+    const float temporalSigma = c.gHistoryResetTemporalSigmaScale * __fsqrt_rn(fmaxf(0.0f, __fadd_rn(noisyM2, -__fmul_rn(noisyL, noisyL))));
     const float spatialSigma = c.gHistoryResetSpatialSigmaScale * sigma.x;
     float resetAmount = (IS_SPEC ? 0.5f : 1.0f) * c.gHistoryResetAmount * fmaxf(0.0f, fabsf(slowL - noisyL) - spatialSigma - temporalSigma) /
                         (1.0e-6f + fmaxf(slowL, noisyL) + spatialSigma + temporalSigma);
