@@ -263,27 +263,57 @@ def main():
         dist.all_reduce(t)
         h2d, d2h = int(t[0].item()), int(t[1].item())
 
+    # Pipelined like an application would: three streams, double-buffered staging.  Step i: H2D of its inputs (copy-in stream)
+    # -> denoise + device copy of the outputs to a staging buffer (compute stream) -> D2H (copy-out stream); the H2D of step
+    # i+1 and the D2H of step i-1 overlap the denoising of step i.  Every step still moves its own inputs and results.
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    rows_shape = lambda n: ((rows, W, harness.USER_FORMATS[n][2]) if harness.USER_FORMATS[n][2] > 1 else (rows, W))
+    dev_in = [{n: torch.empty(rows_shape(n), dtype=harness.USER_FORMATS[n][1], device=dev) for n in in_names} for _ in range(2)]
+    dev_out = [{n: torch.empty(rows_shape(n), dtype=harness.USER_FORMATS[n][1], device=dev) for n in out_names} for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_comp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_step(i):
+        b = i & 1
         hf = host_frames[i % nhost]
         cs = harness.make_common_settings(frames[i % len(frames)], W, H, i + 2 * K)
-        if world == 1:
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_comp[b])  # the denoise of step i-2 no longer reads this staging set
             for n in in_names:
-                gpu.tex[n].copy_(hf[n], non_blocking=True)
+                dev_in[b][n].copy_(hf[n], non_blocking=True)
+            ev_in[b].record(s_in)
+        stream.wait_event(ev_in[b])
+        stream.wait_event(ev_out[b])      # the D2H of step i-2 has drained this output staging set
+        if world == 1:
+            bind(dev_in[b])
             gpu.denoise(cs)
             for n, t in gpu.outputs().items():
-                host_out[n].copy_(t, non_blocking=True)
+                dev_out[b][n].copy_(t, non_blocking=True)
         else:
-            gpu.set_input_strips(hf, stream)
+            gpu.set_input_strips(dev_in[b], stream)
             gpu.denoise(cs)
-            gpu.read_outputs(out=host_out, stream=stream)
+            gpu.read_outputs(out=dev_out[b], stream=stream)
+        ev_comp[b].record(stream)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_comp[b])
+            for n in out_names:
+                host_out[n].copy_(dev_out[b][n], non_blocking=True)
+            ev_out[b].record(s_out)
 
-    for i in range(3):
+    def e2e_join():
+        stream.wait_event(ev_out[0])
+        stream.wait_event(ev_out[1])
+
+    for i in range(4):
         e2e_step(i)
+    e2e_join()
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
     for i in range(K):
-        e2e_step(3 + i)
+        e2e_step(4 + i)
+    e2e_join()
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0

@@ -45,9 +45,9 @@ def _headers_digest():
     return h.hexdigest()
 
 
-def _compile(src, obj, stamp):
+def _compile(src, obj, stamp, extra):
     if src.endswith(".cu"):
-        cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
     else:
         cmd = ["g++"] + CXX_FLAGS + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -62,16 +62,22 @@ def build_product(force=False):
     digest = _headers_digest()
     objs, jobs = [], []
     for src in _sources():
-        key = hashlib.sha1((digest + open(src, "rb").read().decode("utf-8", "replace") + " ".join(NVCC_FLAGS + CXX_FLAGS)).encode()).hexdigest()[:16]
-        base = os.path.basename(src).replace(".", "_")
-        obj = os.path.join(OBJ, base + ".o")
-        stamp = os.path.join(OBJ, base + "." + key + ".stamp")
-        objs.append(obj)
-        if force or not (os.path.exists(obj) and os.path.exists(stamp)):
-            for f in os.listdir(OBJ):
-                if f.startswith(base + ".") and f.endswith(".stamp"):
-                    os.remove(os.path.join(OBJ, f))
-            jobs.append((src, obj, stamp))
+        # kernel translation units are built twice: strip (multi-GPU) addressing and plain one-GPU addressing (device/common.cuh)
+        is_kernel_tu = os.path.basename(os.path.dirname(src)) == "device" and src.endswith(".cu")
+        for suffix, extra in ((("", []), ("_single", ["-DNRD_B200_NO_STRIPS"])) if is_kernel_tu else (("", []),)):
+            key = hashlib.sha1((digest + open(src, "rb").read().decode("utf-8", "replace") + " ".join(NVCC_FLAGS + CXX_FLAGS + extra)).encode()).hexdigest()[:16]
+            base = os.path.basename(src).replace(".", "_") + suffix
+            obj = os.path.join(OBJ, base + ".o")
+            stamp = os.path.join(OBJ, base + "." + key + ".stamp")
+            objs.append(obj)
+            if force or not (os.path.exists(obj) and os.path.exists(stamp)):
+                for f in os.listdir(OBJ):
+                    if f.startswith(base + ".") and f.endswith(".stamp"):
+                        os.remove(os.path.join(OBJ, f))
+                jobs.append((src, obj, stamp, extra))
+    for f in os.listdir(OBJ):  # objects of sources that no longer exist must not be linked by accident
+        if f.endswith(".o") and os.path.join(OBJ, f) not in objs:
+            os.remove(os.path.join(OBJ, f))
     if jobs:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             for fut in [ex.submit(_compile, *j) for j in jobs]:

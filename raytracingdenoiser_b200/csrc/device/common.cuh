@@ -6,51 +6,65 @@
 // __fadd_rn, __fdiv_rn, __fsqrt_rn; never contracted to FMA) in the same operation order as the CPU oracle, so both
 // pick the same texel.  Everything else is free to use FMA contraction and fast intrinsics (results agree to ~1e-6).
 #pragma once
+// The kernels are built twice from the same sources: the one-GPU build (-DNRD_B200_NO_STRIPS, namespace nrdb200_single)
+// addresses surfaces with a plain pitch computation; the strip build (namespace nrdb200) adds the ghost-row / peer lookup
+// of the multi-GPU mode.  Keeping that lookup out of the one-GPU kernels is worth ~30 % of their run time (registers,
+// code size and a divergent branch around every load).
+#if defined(NRD_B200_NO_STRIPS)
+#define nrdb200 nrdb200_single
+#endif
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "surf.h"
+
+// Kernel launch of a pass.  With p.preloadOnly the kernel is only loaded: CUDA loads kernels lazily on first launch, and that
+// load waits for the device to go idle -- which never happens while a StripBarrierKernel of this process spins for a peer
+// whose next kernel is the one being loaded.  Strip-mode contexts therefore preload their kernels at creation.
+#define NRD_B200_LAUNCH(p, grid, block, args, ...)                              \
+    do                                                                          \
+    {                                                                           \
+        if ((p).preloadOnly)                                                    \
+        {                                                                       \
+            cudaFuncAttributes fa_;                                             \
+            cudaError_t pe_ = cudaFuncGetAttributes(&fa_, __VA_ARGS__);         \
+            if (pe_ != cudaSuccess) return pe_;                                 \
+        }                                                                       \
+        else                                                                    \
+            __VA_ARGS__<<<grid, block, 0, (p).stream>>>(args);                  \
+    } while (0)
+
 namespace nrdb200
 {
+using namespace nrdb200_abi;
 // ---------------------------------------------------------------------------------------------
-// Surfaces
+// Surfaces (surf.h)
 // ---------------------------------------------------------------------------------------------
-// Multi-GPU: the frame is cut into horizontal strips of `stripRows` rows (uniform, whole 16-row tiles), one per GPU.
-// Every context carves its surfaces out of one arena with the same layout; a surface holds its own strip plus `halo`
-// ghost rows above and below, which the owner of those rows refreshes after every pass that writes them (executor.cu,
-// GhostPushKernel: bulk NVLink stores).  A tap that lands outside even the ghost rows is loaded straight from the owner's
-// HBM: its address is the local address plus (arena of the owner - local arena).  Stores are always local.  The deltas live
-// in constant memory, one table per context slot.
-constexpr int kMaxPeers = 8;
-constexpr int kMaxPeerSlots = 4;
+#if !defined(NRD_B200_NO_STRIPS)
+// (arena of rank r) - (local arena), one table per context slot
 static __constant__ long long g_peerDelta[kMaxPeerSlots * kMaxPeers];
 static inline cudaError_t SetPeerTableThisTU(int slot, const long long* delta)
 {
     return cudaMemcpyToSymbol(g_peerDelta, delta, sizeof(long long) * kMaxPeers, sizeof(long long) * kMaxPeers * (size_t)slot);
 }
-
-struct Surf
+// rare path: the row is beyond the ghost rows, fetch it from its owner (callers clamp y to [0, h))
+// (inlined on purpose: a real call gives the kernels a stack frame, and the first launch of a kernel that needs a bigger
+// stack makes the driver wait for every running kernel -- including a spinning StripBarrierKernel of another context)
+static __device__ __forceinline__ const uint8_t* PeerRow(const Surf& s, int y)
 {
-    uint8_t* base;       // address of texel (0, ly0)
-    int pitch;           // bytes per row
-    int w, h;            // full (virtual) texture size
-    int y0, y1;          // rows owned by this context: [y0, y1)  (the whole texture on one GPU)
-    int ly0;             // first row held locally (y0 - halo in strip mode, may be negative)
-    unsigned lrows;      // rows held locally
-    unsigned stripRows;  // rows per strip in this texture's own units; 0 = whole frame is local
-    unsigned stripMagic; // floor(2^32 / stripRows) + 1: owner(y) = umulhi(y, magic), exact for y, stripRows < 65536
-    int halo;            // ghost rows on either side, in this texture's own units
-    int peerSlot;
-};
+    const unsigned owner = __umulhi((unsigned)y, s.stripMagic);
+    return s.base + g_peerDelta[s.peerSlot * kMaxPeers + owner] + (size_t)((unsigned)y - owner * s.stripRows + (unsigned)s.halo) * s.pitch;
+}
+#endif
 
 template <class T> __device__ __forceinline__ const T* TexelPtr(const Surf& s, int x, int y)
 {
     const int ly = y - s.ly0;
-    if ((unsigned)ly < s.lrows) return reinterpret_cast<const T*>(s.base + (size_t)ly * s.pitch) + x;
-    // rare: beyond the ghost rows (only reachable in strip mode, callers clamp y to [0, h))
-    const unsigned owner = __umulhi((unsigned)y, s.stripMagic);
-    const uint8_t* row = s.base + g_peerDelta[s.peerSlot * kMaxPeers + owner] + (size_t)((unsigned)y - owner * s.stripRows + (unsigned)s.halo) * s.pitch;
-    return reinterpret_cast<const T*>(row) + x;
+#if !defined(NRD_B200_NO_STRIPS)
+    if ((unsigned)ly >= s.lrows) return reinterpret_cast<const T*>(PeerRow(s, y)) + x;
+#endif
+    return reinterpret_cast<const T*>(s.base + (size_t)ly * s.pitch) + x;
 }
 template <class T> __device__ __forceinline__ T* TexelPtrRW(const Surf& s, int x, int y)
 {
@@ -215,15 +229,4 @@ struct RngHash
     }
 };
 
-// Launch bookkeeping shared with the executor
-struct PassLaunch
-{
-    const void* constants; // host pointer to the dispatch's constant block
-    uint32_t constantsSize;
-    Surf tex[32];          // bindings in DispatchDesc order
-    uint32_t texNum;
-    int gridW, gridH;      // DispatchDesc grid (reference thread-group counts)
-    int rowBegin, rowEnd;  // rows this launch must produce, in the pass's own pixel units
-    cudaStream_t stream;
-};
 } // namespace nrdb200

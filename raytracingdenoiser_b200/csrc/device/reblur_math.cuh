@@ -3,8 +3,8 @@
 // organised for the GPU: guides are decoded once, uniform work is hoisted, transcendental-heavy parameters are per pixel
 // not per tap, and texel-selecting arithmetic is pinned (see common.cuh).
 #pragma once
+#include "common.cuh" // first: selects the namespace of this build of the kernels
 #include "../constants.h"
-#include "common.cuh"
 
 namespace nrdb200
 {

@@ -2,8 +2,8 @@
 // (anti-lag), A-trous with the spatial-variance first iteration, A-trous.
 // Behaviour follows the reference's shaders (cited per kernel); arithmetic that selects a texel / footprint or that is stored
 // quantised is pinned to the oracle's operation order (oracle/relax.cpp), everything else is free to contract.
+#include "launch.h" // first: selects the namespace of this build of the kernels
 #include "../constants.h"
-#include "launch.h"
 #include "reblur_math.cuh"
 #include "samplers.cuh"
 
@@ -380,7 +380,7 @@ struct RxTaArgs
     Surf outSpec, outDiff, outSpecFast, outDiffFast, outHitDist, outLength, outConfidence;
     int rowBegin, rowEnd;
 };
-__global__ void __launch_bounds__(128) RelaxTemporalAccumulationKernel(const __grid_constant__ RxTaArgs a)
+__global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const __grid_constant__ RxTaArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 4 + threadIdx.y;
@@ -1217,7 +1217,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.z = p.tex[0]; a.tiles = p.tex[1];
         a.denoisingRange = c.gDenoisingRange; a.tilesW = p.gridW; a.tilesH = p.gridH;
         int warps = a.tilesW * a.tilesH;
-        RelaxClassifyTilesKernel<<<(warps * 32 + 255) / 256, 256, 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, (warps * 32 + 255) / 256, 256, a, RelaxClassifyTilesKernel);
     }
     else if (!strcmp(shader, "RELAX_DiffuseSpecular_PrePass.cs"))
     {
@@ -1225,7 +1225,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.c = c;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.nr = p.tex[3]; a.z = p.tex[4]; a.outSpec = p.tex[5]; a.outDiff = p.tex[6];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        RelaxPrePassKernel<<<grid, block, 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, grid, block, a, RelaxPrePassKernel);
     }
     else if (!strcmp(shader, "RELAX_DiffuseSpecular_TemporalAccumulation.cs"))
     {
@@ -1237,7 +1237,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.outSpec = p.tex[18]; a.outDiff = p.tex[19]; a.outSpecFast = p.tex[20]; a.outDiffFast = p.tex[21]; a.outHitDist = p.tex[22]; a.outLength = p.tex[23];
         a.outConfidence = p.tex[24];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        RelaxTemporalAccumulationKernel<<<dim3((W + 31) / 32, (rows + 3) / 4), dim3(32, 4), 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, dim3((W + 31) / 32, (rows + 3) / 4), dim3(32, 4), a, RelaxTemporalAccumulationKernel);
     }
     else if (!strcmp(shader, "RELAX_DiffuseSpecular_HistoryFix.cs"))
     {
@@ -1245,7 +1245,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.c = c;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.length = p.tex[3]; a.nr = p.tex[4]; a.z = p.tex[5]; a.outSpec = p.tex[6]; a.outDiff = p.tex[7];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        RelaxHistoryFixKernel<<<grid, block, 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, grid, block, a, RelaxHistoryFixKernel);
     }
     else if (!strcmp(shader, "RELAX_DiffuseSpecular_HistoryClamping.cs"))
     {
@@ -1255,7 +1255,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.length = p.tex[8];
         a.outSpec = p.tex[9]; a.outDiff = p.tex[10]; a.outSpecFast = p.tex[11]; a.outDiffFast = p.tex[12]; a.outLength = p.tex[13];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        RelaxHistoryClampingKernel<<<grid, block, 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, grid, block, a, RelaxHistoryClampingKernel);
     }
     else if (!strcmp(shader, "RELAX_DiffuseSpecular_AtrousSmem.cs") || !strcmp(shader, "RELAX_DiffuseSpecular_Atrous.cs"))
     {
@@ -1268,12 +1268,12 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         if (smem)
         {
             a.outNr = p.tex[11]; a.outMaterial = p.tex[12]; a.outZ = p.tex[13];
-            RelaxAtrousSmemKernel<<<dim3((a.z.w + 31) / 32, grid.y), block, 0, p.stream>>>(a);
+            NRD_B200_LAUNCH(p, dim3((a.z.w + 31) / 32, grid.y), block, a, RelaxAtrousSmemKernel);
         }
         else
         {
             a.outNr = a.outMaterial = a.outZ = a.z;
-            RelaxAtrousKernel<<<grid, block, 0, p.stream>>>(a);
+            NRD_B200_LAUNCH(p, grid, block, a, RelaxAtrousKernel);
         }
     }
     else
@@ -1281,5 +1281,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
     return cudaGetLastError();
 }
 
+#if !defined(NRD_B200_NO_STRIPS)
 cudaError_t SetPeerTableRelax(int slot, const long long* delta) { return SetPeerTableThisTU(slot, delta); }
+#endif
 } // namespace nrdb200

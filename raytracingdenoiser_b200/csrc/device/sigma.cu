@@ -460,21 +460,21 @@ cudaError_t LaunchSigma(const PassLaunch& p, const char* shader)
         a.viewZScale = c.gViewZScale; a.denoisingRange = c.gDenoisingRange; a.unproject = c.gUnproject; a.orthoMode = c.gOrthoMode;
         a.tilesW = p.gridW; a.tilesH = p.gridH;
         int warps = a.tilesW * a.tilesH;
-        SigmaClassifyTilesKernel<<<(warps * 32 + 255) / 256, 256, 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, (warps * 32 + 255) / 256, 256, a, SigmaClassifyTilesKernel);
     }
     else if (!strcmp(shader, "SIGMA_SmoothTiles.cs"))
     {
         SigmaSmoothArgs a;
         a.tiles = p.tex[0]; a.smoothed = p.tex[1];
         a.tilesMaxX = c.gTilesSizeMinusOne[0]; a.tilesMaxY = c.gTilesSizeMinusOne[1];
-        SigmaSmoothTilesKernel<<<dim3(p.gridW, p.gridH), dim3(16, 16), 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, dim3(p.gridW, p.gridH), dim3(16, 16), a, SigmaSmoothTilesKernel);
     }
     else if (!strcmp(shader, "SIGMA_Copy.cs"))
     {
         SigmaCopyArgs a;
         a.tiles = p.tex[0]; a.inHistory = p.tex[1]; a.inLength = p.tex[2]; a.outHistory = p.tex[3]; a.outLength = p.tex[4];
         a.w = a.inHistory.w; a.h = a.inHistory.h; a.isRectChanged = c.gIsRectChanged; a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        SigmaCopyKernel<<<dim3((a.w + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), dim3(32, 8), 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, dim3((a.w + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), dim3(32, 8), a, SigmaCopyKernel);
     }
     else if (!strcmp(shader, "SIGMA_Shadow_Blur.cs") || !strcmp(shader, "SIGMA_Shadow_PostBlur.cs"))
     {
@@ -487,8 +487,8 @@ cudaError_t LaunchSigma(const PassLaunch& p, const char* shader)
         a.outShadow = p.tex[first ? 5 : 6];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
         dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
-        if (first) SigmaBlurKernel<true><<<grid, block, 0, p.stream>>>(a);
-        else SigmaBlurKernel<false><<<grid, block, 0, p.stream>>>(a);
+        if (first) NRD_B200_LAUNCH(p, grid, block, a, SigmaBlurKernel<true>);
+        else NRD_B200_LAUNCH(p, grid, block, a, SigmaBlurKernel<false>);
     }
     else if (!strcmp(shader, "SIGMA_Shadow_TemporalStabilization.cs"))
     {
@@ -497,12 +497,14 @@ cudaError_t LaunchSigma(const PassLaunch& p, const char* shader)
         a.z = p.tex[0]; a.mv = p.tex[1]; a.penumbra = p.tex[2]; a.shadow = p.tex[3]; a.history = p.tex[4]; a.historyLength = p.tex[5]; a.tiles = p.tex[6];
         a.outShadow = p.tex[7]; a.outLength = p.tex[8];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        SigmaTemporalStabilizationKernel<<<dim3((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), dim3(32, 8), 0, p.stream>>>(a);
+        NRD_B200_LAUNCH(p, dim3((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), dim3(32, 8), a, SigmaTemporalStabilizationKernel);
     }
     else
         return cudaErrorNotSupported;
     return cudaGetLastError();
 }
 
+#if !defined(NRD_B200_NO_STRIPS)
 cudaError_t SetPeerTableSigma(int slot, const long long* delta) { return SetPeerTableThisTU(slot, delta); }
+#endif
 } // namespace nrdb200

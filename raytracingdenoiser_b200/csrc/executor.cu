@@ -9,6 +9,7 @@
 // may read what any rank wrote in the previous pass and may overwrite what any rank read in it.
 #include "../../include/nrd_b200.h"
 #include "device/launch.h"
+#include "constants.h"
 #include "scheduler.h"
 
 #include <atomic>
@@ -21,8 +22,34 @@
 using namespace nrd;
 using namespace nrdb200;
 
+NRD_B200_DECLARE_LAUNCHERS(nrdb200_single)
+namespace nrdb200
+{
+cudaError_t LaunchClear(const PassLaunch& p);
+}
+
 namespace
 {
+// the two builds of the kernels (device/common.cuh): one-GPU contexts never pay for the strip addressing
+struct Launchers
+{
+    cudaError_t (*classifyTiles)(const PassLaunch&);
+    cudaError_t (*prePass)(const PassLaunch&, int);
+    cudaError_t (*temporalAccumulation)(const PassLaunch&, int);
+    cudaError_t (*historyFix)(const PassLaunch&, int);
+    cudaError_t (*blur)(const PassLaunch&, int);
+    cudaError_t (*postBlur)(const PassLaunch&, int, bool);
+    cudaError_t (*temporalStabilization)(const PassLaunch&, int);
+    cudaError_t (*sigma)(const PassLaunch&, const char*);
+    cudaError_t (*relax)(const PassLaunch&, const char*);
+};
+const Launchers kStripLaunchers = {nrdb200::LaunchReblurClassifyTiles, nrdb200::LaunchReblurPrePass, nrdb200::LaunchReblurTemporalAccumulation,
+                                   nrdb200::LaunchReblurHistoryFix, nrdb200::LaunchReblurBlur, nrdb200::LaunchReblurPostBlur,
+                                   nrdb200::LaunchReblurTemporalStabilization, nrdb200::LaunchSigma, nrdb200::LaunchRelax};
+const Launchers kSingleLaunchers = {nrdb200_single::LaunchReblurClassifyTiles, nrdb200_single::LaunchReblurPrePass, nrdb200_single::LaunchReblurTemporalAccumulation,
+                                    nrdb200_single::LaunchReblurHistoryFix, nrdb200_single::LaunchReblurBlur, nrdb200_single::LaunchReblurPostBlur,
+                                    nrdb200_single::LaunchReblurTemporalStabilization, nrdb200_single::LaunchSigma, nrdb200_single::LaunchRelax};
+
 std::atomic<uint64_t> g_launchCount{0};
 std::mutex g_slotMutex;
 bool g_slotUsed[kMaxPeerSlots] = {};
@@ -168,6 +195,49 @@ bool ParseReblur(const char* name, int& signal, const char*& pass)
     else return false;
     pass = p;
     return true;
+}
+
+// pass (shader file name) -> kernel launcher of one build
+cudaError_t LaunchByName(const Launchers& L, const PassLaunch& p, const char* shader)
+{
+    int signal = 0;
+    const char* pass = nullptr;
+    if (!strncmp(shader, "Clear_", 6)) return p.preloadOnly ? cudaSuccess : LaunchClear(p);
+    if (p.rowEnd <= p.rowBegin) return cudaSuccess; // a rank without rows still takes part in the barriers
+    if (!strcmp(shader, "REBLUR_ClassifyTiles.cs")) return L.classifyTiles(p);
+    if (ParseReblur(shader, signal, pass))
+    {
+        if (!strcmp(pass, "PrePass.cs")) return L.prePass(p, signal);
+        if (!strcmp(pass, "TemporalAccumulation.cs")) return L.temporalAccumulation(p, signal);
+        if (!strcmp(pass, "HistoryFix.cs")) return L.historyFix(p, signal);
+        if (!strcmp(pass, "Blur.cs")) return L.blur(p, signal);
+        if (!strcmp(pass, "PostBlur.cs")) return L.postBlur(p, signal, false);
+        if (!strcmp(pass, "PostBlur_NoTemporalStabilization.cs")) return L.postBlur(p, signal, true);
+        if (!strcmp(pass, "TemporalStabilization.cs")) return L.temporalStabilization(p, signal);
+        return cudaErrorNotSupported;
+    }
+    if (!strncmp(shader, "SIGMA_", 6)) return L.sigma(p, shader);
+    if (!strncmp(shader, "RELAX_", 6)) return L.relax(p, shader);
+    return cudaErrorNotSupported;
+}
+
+// Loads every kernel the instance's pipelines map to (see NRD_B200_LAUNCH): nothing may be loaded lazily once barriers spin.
+void PreloadKernels(const NrdCudaContext* ctx, const Launchers& L)
+{
+    alignas(16) static unsigned char dummy[1024] = {}; // a zeroed constant block big enough for every denoiser
+    ((RelaxConstants*)dummy)->gDiffCheckerboard = ((RelaxConstants*)dummy)->gSpecCheckerboard = 2; // RELAX launchers reject other modes
+    const InstanceDesc& id = GetInstanceDesc(*ctx->instance);
+    for (uint32_t i = 0; i < id.pipelinesNum; i++)
+    {
+        PassLaunch p{};
+        p.constants = dummy;
+        p.constantsSize = sizeof(dummy);
+        p.gridW = p.gridH = 1;
+        p.rowBegin = 0;
+        p.rowEnd = 16;
+        p.preloadOnly = true;
+        (void)LaunchByName(L, p, id.pipelines[i].shaderFileName); // passes without a kernel are reported when they are dispatched
+    }
 }
 
 struct BarrierArgs
@@ -491,6 +561,7 @@ NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t 
     ctx->rank = rank;
     ctx->world = worldSize;
     ctx->connected = true;
+    PreloadKernels(ctx, worldSize > 1 ? kStripLaunchers : kSingleLaunchers);
     return Result::SUCCESS;
 }
 
@@ -539,24 +610,11 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         if (dbg && !StripMode(ctx) && sscanf(dbg, "%d,%d", &a, &b) == 2 && a % 16 == 0 && b > a && b <= (int)ctx->desc.resourceHeight) p.rowBegin = a, p.rowEnd = b;
     }
 
-    cudaError_t e = cudaErrorNotSupported;
-    int signal = 0;
-    const char* pass = nullptr;
-    if (!strncmp(shader, "Clear_", 6)) e = LaunchClear(p);
-    else if (p.rowEnd <= p.rowBegin) e = cudaSuccess; // a rank without rows still takes part in the barriers
-    else if (!strcmp(shader, "REBLUR_ClassifyTiles.cs")) e = LaunchReblurClassifyTiles(p);
-    else if (ParseReblur(shader, signal, pass))
-    {
-        if (!strcmp(pass, "PrePass.cs")) e = LaunchReblurPrePass(p, signal);
-        else if (!strcmp(pass, "TemporalAccumulation.cs")) e = LaunchReblurTemporalAccumulation(p, signal);
-        else if (!strcmp(pass, "HistoryFix.cs")) e = LaunchReblurHistoryFix(p, signal);
-        else if (!strcmp(pass, "Blur.cs")) e = LaunchReblurBlur(p, signal);
-        else if (!strcmp(pass, "PostBlur.cs")) e = LaunchReblurPostBlur(p, signal, false);
-        else if (!strcmp(pass, "PostBlur_NoTemporalStabilization.cs")) e = LaunchReblurPostBlur(p, signal, true);
-        else if (!strcmp(pass, "TemporalStabilization.cs")) e = LaunchReblurTemporalStabilization(p, signal);
-    }
-    else if (!strncmp(shader, "SIGMA_", 6)) e = LaunchSigma(p, shader);
-    else if (!strncmp(shader, "RELAX_", 6)) e = LaunchRelax(p, shader);
+    // NRD_B200_FORCE_STRIP_KERNELS: run a one-GPU context on the strip build of the kernels.  The two builds are compiled
+    // separately and differ in the last bits (FMA contraction); N-GPU results are bit-identical to THIS configuration.
+    const bool stripBuild = (StripMode(ctx) && ctx->world > 1) || getenv("NRD_B200_FORCE_STRIP_KERNELS") != nullptr;
+    const Launchers& L = stripBuild ? kStripLaunchers : kSingleLaunchers;
+    cudaError_t e = LaunchByName(L, p, shader);
 
     if (e == cudaErrorNotSupported) return Fail(ctx, Result::UNSUPPORTED, std::string("no CUDA kernel for pass ") + shader);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string(shader) + ": " + cudaGetErrorString(e));

@@ -14,7 +14,7 @@ import enum
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libnrd_b200.so")
+_LIB_PATH = os.environ.get("NRD_B200_LIB") or os.path.join(_HERE, "libnrd_b200.so")  # the override is for A/B kernel builds
 
 
 def _load():

@@ -14,6 +14,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 
 def main():
+    os.environ["NRD_B200_FORCE_STRIP_KERNELS"] = "1"  # rank 0's full-frame reference runs the strip build of the kernels
     import torch
     import torch.distributed as dist
     from raytracingdenoiser_b200 import harness, nrd, scene, strips
