@@ -85,6 +85,8 @@ struct CatRomSetup
     f4 w;
     float w4, sum;
     int bx, by;
+    float tcx, tcy; // position of the merged inner taps between texel bx and bx+1 (by and by+1)
+    bool bicubic;
 };
 __device__ __forceinline__ CatRomSetup SetupCatRom(f2 samplePos, const float* invSize, f4 customWeights, bool useBicubic)
 {
@@ -120,27 +122,45 @@ __device__ __forceinline__ CatRomSetup SetupCatRom(f2 samplePos, const float* in
     s.u4x *= invSize[0];  s.u4y *= invSize[1];
     s.bx = (int)cx;
     s.by = (int)cy;
+    s.tcx = tcx;
+    s.tcy = tcy;
+    s.bicubic = useBicubic;
     return s;
 }
 #ifndef NRD_B200_CATROM_INLINE
 #define NRD_B200_CATROM_INLINE __forceinline__
 #endif
+// The reference takes 5 hardware-bilinear taps; a software bilinear tap is 4 loads + 3 lerps, i.e. 20 loads for a
+// footprint of 12 distinct texels.  Here every texel is loaded once and weighted with (tap weight) x (its bilinear weight):
+// the same polynomial, summed in a different order (differences ~1e-6 relative, far inside the parity tolerance).
+// Without a valid bicubic footprint the filter degenerates to the 2x2 texels with the custom bilinear weights.
+template <class LOAD> __device__ __forceinline__ auto ResolveCatRomTexels(const CatRomSetup& s, const Surf& tex, LOAD load) -> decltype(load(tex, 0, 0))
+{
+    typedef decltype(load(tex, 0, 0)) V;
+    const int x0 = s.bx, y0 = s.by;
+    V color;
+    if (s.bicubic)
+    {
+        const float ax = 1.0f - s.tcx, bx = s.tcx, ay = 1.0f - s.tcy, by = s.tcy;
+        color = load(tex, x0, y0 - 1) * (s.w.x * ax) + load(tex, x0 + 1, y0 - 1) * (s.w.x * bx);
+        color = color + load(tex, x0 - 1, y0) * (s.w.y * ay) + load(tex, x0 - 1, y0 + 1) * (s.w.y * by);
+        color = color + load(tex, x0, y0) * (s.w.z * ax * ay) + load(tex, x0 + 1, y0) * (s.w.z * bx * ay);
+        color = color + load(tex, x0, y0 + 1) * (s.w.z * ax * by) + load(tex, x0 + 1, y0 + 1) * (s.w.z * bx * by);
+        color = color + load(tex, x0 + 2, y0) * (s.w.w * ay) + load(tex, x0 + 2, y0 + 1) * (s.w.w * by);
+        color = color + load(tex, x0, y0 + 2) * (s.w4 * ax) + load(tex, x0 + 1, y0 + 2) * (s.w4 * bx);
+    }
+    else
+        color = load(tex, x0, y0) * s.w.x + load(tex, x0 + 1, y0) * s.w.y + load(tex, x0, y0 + 1) * s.w.z + load(tex, x0 + 1, y0 + 1) * s.w.w;
+    return color;
+}
 __device__ NRD_B200_CATROM_INLINE f4 ResolveCatRom4(const CatRomSetup& s, const Surf& tex)
 {
-    f4 color = SampleLinear4(tex, s.u01x, s.u01y) * s.w.x;
-    color = color + SampleLinear4(tex, s.u01z, s.u01w) * s.w.y;
-    color = color + SampleLinear4(tex, s.u23x, s.u23y) * s.w.z;
-    color = color + SampleLinear4(tex, s.u23z, s.u23w) * s.w.w;
-    if (s.w4 != 0.0f) color = color + SampleLinear4(tex, s.u4x, s.u4y) * s.w4;
+    f4 color = ResolveCatRomTexels(s, tex, [](const Surf& t, int x, int y) { return FetchClamped4(t, x, y); });
     return s.sum < 0.0001f ? mk4(0.0f) : color * (1.0f / s.sum);
 }
 __device__ __forceinline__ float ResolveCatRom1(const CatRomSetup& s, const Surf& tex)
 {
-    float color = SampleLinear1(tex, s.u01x, s.u01y) * s.w.x;
-    color += SampleLinear1(tex, s.u01z, s.u01w) * s.w.y;
-    color += SampleLinear1(tex, s.u23x, s.u23y) * s.w.z;
-    color += SampleLinear1(tex, s.u23z, s.u23w) * s.w.w;
-    if (s.w4 != 0.0f) color += SampleLinear1(tex, s.u4x, s.u4y) * s.w4;
+    float color = ResolveCatRomTexels(s, tex, [](const Surf& t, int x, int y) { return FetchClamped1(t, x, y); });
     return s.sum < 0.0001f ? 0.0f : color / s.sum;
 }
 // tex.Load(origin + offset) * customWeights, out-of-bounds loads return 0
