@@ -58,7 +58,7 @@ __device__ __forceinline__ float NonExpWeightWithSigma(float x, float px, float 
 __device__ __forceinline__ float ExpWeight(float x, float px, float py)
 {
     float v = -3.0f * fabsf(x * px + py);
-    return __frcp_rn(v * v - v + 1.0f);
+    return __fdividef(1.0f, v * v - v + 1.0f); // a weight in (0, 1]: the 2-ulp reciprocal is enough (the IEEE one costs ~8 instructions per tap)
 }
 
 __device__ __forceinline__ float HitDistNormalization(float viewZ, const float* p, float roughness) // NRD.hlsli:520-523
