@@ -5,9 +5,14 @@
 
 value     whole chain, inputs already resident in HBM (each frame's inputs are separate 265 MB buffers, i.e. larger than
           the 126 MB L2, so no flush is needed between steps), CUDA events on the launching stream, max over ranks.
-e2e       the same metric through the C-ABI with HOST buffers: pinned host -> H2D -> nrdCudaDenoise -> D2H inside the timed region.
+          N > 1 (torchrun, one process per GPU): strong scaling of the same frames -- every rank denoises one horizontal strip
+          (raytracingdenoiser_b200/strips.py: CUDA-IPC arenas, NVLink ghost rows, device-side barriers; no collective on the
+          data path); the device-to-device copy of a rank's input strip into its IPC arena is inside the timed region.
+e2e       the same metric through the C-ABI with HOST buffers: pinned host -> H2D -> nrdCudaDenoise -> D2H of both outputs for
+          every step, pipelined over three streams with double-buffered staging (what an application would do).
 roofline  Blur + PostBlur (the north-star kernels): algorithmic bytes (92 B/px) / measured CUDA-event time,
-          against MEASURED_PEAKS.json hbm_gbs.
+          against MEASURED_PEAKS.json hbm_gbs; per_pass_frac gives the same for every pass.  At N > 1 the per-pass times of
+          rank 0 include the wait for the slowest peer.
 cpu_baseline / --impl reference   the CPU restatement of the reference shaders (oracle/, OpenMP over all host cores) on a
           bounded sample of the same frames.  It is a reported baseline; the oracle is never on the product path.
 """
@@ -240,7 +245,10 @@ def main():
     algo_bytes = (ALGO_BYTES_PER_PIXEL["Blur"] + ALGO_BYTES_PER_PIXEL["Post-blur"]) * W * H
     achieved = algo_bytes / (blur_ms * 1e-3) / 1e9 if blur_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "REBLUR Blur + PostBlur (2 launches)", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch_pair": algo_bytes,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one Blur + one PostBlur launch at 3840x2160, from the ncu --set full
+                # capture summarised in profiles/r1_reblur_ncu_summary.txt (304.9 MB + 305.6 MB); below the algorithmic bytes
+                # because sky tiles are skipped
+                "frac": achieved / peak, "traffic": 610.5e6 if (W, H, world) == (3840, 2160, 1) else None, "algorithmic_bytes_per_launch_pair": algo_bytes,
                 "per_pass_ms": pass_ms,
                 "per_pass_frac": {k: (ALGO_BYTES_PER_PIXEL[k] * W * H / (v * 1e-3) / 1e9 / peak) for k, v in pass_ms.items() if k in ALGO_BYTES_PER_PIXEL and v > 0}}
 
