@@ -350,7 +350,7 @@ typedef struct NrdCudaContextDesc
     uint16_t resourceWidth, resourceHeight;   // full-frame texture size (== CommonSettings::resourceSize)
     uint16_t stripY0, stripY1;                // rows owned by this context; {0, resourceHeight} for one GPU
     uint16_t stripHeight;                     // 0 = one GPU; else rows per rank (multiple of 16), stripY0 = rank * stripHeight
-    uint16_t haloRows;                        // strip mode: ghost rows kept above/below the strip (rounded up to 16, clamped to stripHeight)
+    uint16_t haloRows;                        // strip mode: ghost rows kept above/below the strip (rounded up to 16, at least 16, at most stripHeight)
     int32_t device;                          // CUDA device ordinal
 } NrdCudaContextDesc;
 

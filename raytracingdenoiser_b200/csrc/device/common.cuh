@@ -62,9 +62,32 @@ template <class T> __device__ __forceinline__ const T* TexelPtr(const Surf& s, i
 {
     const int ly = y - s.ly0;
 #if !defined(NRD_B200_NO_STRIPS)
-    if ((unsigned)ly >= s.lrows) return reinterpret_cast<const T*>(PeerRow(s, y)) + x;
+    if (s.stripRows != 0 && (unsigned)ly >= s.lrows) return reinterpret_cast<const T*>(PeerRow(s, y)) + x;
 #endif
     return reinterpret_cast<const T*>(s.base + (size_t)ly * s.pitch) + x;
+}
+// The owner lookup above costs a divergent branch and ~10 instructions of code around EVERY load.  Kernels avoid it where the
+// row is known to be local: Near(s) is a view of the surface whose loads skip the lookup (stripRows = 0 is a compile-time
+// constant after inlining) -- legal for the centre pixel and its fixed small neighbourhoods (the halo is >= 16 rows), and for
+// whole footprints / taps after one RowsLocal() test: `if (RowsLocal(s, y0, y1)) f(Near(s)); else f(s);`.
+__device__ __forceinline__ Surf Near(const Surf& s)
+{
+#if defined(NRD_B200_NO_STRIPS)
+    return s;
+#else
+    Surf r = s;
+    r.stripRows = 0;
+    return r;
+#endif
+}
+// rows [ya, yb] (inclusive, inside the frame) are all held by this GPU (own strip or ghost rows)
+__device__ __forceinline__ bool RowsLocal(const Surf& s, int ya, int yb)
+{
+#if defined(NRD_B200_NO_STRIPS)
+    return true;
+#else
+    return (unsigned)(ya - s.ly0) < s.lrows && (unsigned)(yb - s.ly0) < s.lrows;
+#endif
 }
 template <class T> __device__ __forceinline__ T* TexelPtrRW(const Surf& s, int x, int y)
 {

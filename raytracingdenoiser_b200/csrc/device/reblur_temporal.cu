@@ -19,6 +19,9 @@ __device__ __forceinline__ float FetchClamped1(const Surf& s, int x, int y) { re
 #ifndef NRD_B200_SAMPLER_INLINE
 #define NRD_B200_SAMPLER_INLINE __forceinline__
 #endif
+// rows [ya, yb] after clamping to the texture are local: the footprint can be read through Near(s) (common.cuh)
+__device__ __forceinline__ bool FootprintLocal(const Surf& s, int ya, int yb) { return RowsLocal(s, clampi(ya, 0, s.h - 1), clampi(yb, 0, s.h - 1)); }
+
 __device__ NRD_B200_SAMPLER_INLINE f4 SampleLinear4(const Surf& s, float u, float v)
 {
     float px = u * (float)s.w - 0.5f, py = v * (float)s.h - 0.5f;
@@ -29,15 +32,19 @@ __device__ NRD_B200_SAMPLER_INLINE f4 SampleLinear4(const Surf& s, float u, floa
     f4 b = lerp4(FetchClamped4(s, x0, y0 + 1), FetchClamped4(s, x0 + 1, y0 + 1), wx);
     return lerp4(a, b, wy);
 }
+__device__ __forceinline__ float SampleLinear1Impl(const Surf& s, int x0, int y0, float wx, float wy)
+{
+    float a = lerpf(FetchClamped1(s, x0, y0), FetchClamped1(s, x0 + 1, y0), wx);
+    float b = lerpf(FetchClamped1(s, x0, y0 + 1), FetchClamped1(s, x0 + 1, y0 + 1), wx);
+    return lerpf(a, b, wy);
+}
 __device__ __forceinline__ float SampleLinear1(const Surf& s, float u, float v)
 {
     float px = u * (float)s.w - 0.5f, py = v * (float)s.h - 0.5f;
     float fx = floorf(px), fy = floorf(py);
     float wx = px - fx, wy = py - fy;
     int x0 = (int)fx, y0 = (int)fy;
-    float a = lerpf(FetchClamped1(s, x0, y0), FetchClamped1(s, x0 + 1, y0), wx);
-    float b = lerpf(FetchClamped1(s, x0, y0 + 1), FetchClamped1(s, x0 + 1, y0 + 1), wx);
-    return lerpf(a, b, wy);
+    return FootprintLocal(s, y0, y0 + 1) ? SampleLinear1Impl(Near(s), x0, y0, wx, wy) : SampleLinear1Impl(s, x0, y0, wx, wy);
 }
 
 // bilinear footprint: origin = floor(uv * size - 0.5), weights = frac   (pinned)
@@ -155,20 +162,26 @@ template <class LOAD> __device__ __forceinline__ auto ResolveCatRomTexels(const 
 }
 __device__ NRD_B200_CATROM_INLINE f4 ResolveCatRom4(const CatRomSetup& s, const Surf& tex)
 {
-    f4 color = ResolveCatRomTexels(s, tex, [](const Surf& t, int x, int y) { return FetchClamped4(t, x, y); });
+    auto load = [](const Surf& t, int x, int y) { return FetchClamped4(t, x, y); };
+    f4 color = FootprintLocal(tex, s.by - 1, s.by + 2) ? ResolveCatRomTexels(s, Near(tex), load) : ResolveCatRomTexels(s, tex, load);
     return s.sum < 0.0001f ? mk4(0.0f) : color * (1.0f / s.sum);
 }
 __device__ __forceinline__ float ResolveCatRom1(const CatRomSetup& s, const Surf& tex)
 {
-    float color = ResolveCatRomTexels(s, tex, [](const Surf& t, int x, int y) { return FetchClamped1(t, x, y); });
+    auto load = [](const Surf& t, int x, int y) { return FetchClamped1(t, x, y); };
+    float color = FootprintLocal(tex, s.by - 1, s.by + 2) ? ResolveCatRomTexels(s, Near(tex), load) : ResolveCatRomTexels(s, tex, load);
     return s.sum < 0.0001f ? 0.0f : color / s.sum;
 }
 // tex.Load(origin + offset) * customWeights, out-of-bounds loads return 0
 __device__ __forceinline__ float LoadOrZero1(const Surf& s, int x, int y) { return Inside(s, x, y) ? LoadR16F(s, x, y) : 0.0f; }
+__device__ __forceinline__ float BilinearCustom1Sum(const CatRomSetup& s, const Surf& tex, f4 cw)
+{
+    return LoadOrZero1(tex, s.bx, s.by) * cw.x + LoadOrZero1(tex, s.bx + 1, s.by) * cw.y + LoadOrZero1(tex, s.bx, s.by + 1) * cw.z +
+           LoadOrZero1(tex, s.bx + 1, s.by + 1) * cw.w;
+}
 __device__ __forceinline__ float ResolveBilinearCustom1(const CatRomSetup& s, const Surf& tex, f4 cw)
 {
-    float v = LoadOrZero1(tex, s.bx, s.by) * cw.x + LoadOrZero1(tex, s.bx + 1, s.by) * cw.y + LoadOrZero1(tex, s.bx, s.by + 1) * cw.z +
-              LoadOrZero1(tex, s.bx + 1, s.by + 1) * cw.w;
+    float v = FootprintLocal(tex, s.by, s.by + 1) ? BilinearCustom1Sum(s, Near(tex), cw) : BilinearCustom1Sum(s, tex, cw);
     float sum = cw.x + cw.y + cw.z + cw.w;
     return sum < 0.0001f ? 0.0f : v / sum;
 }
@@ -226,8 +239,8 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
     const int y = a.rowBegin + blockIdx.y * 4 + threadIdx.y;
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
     if (x > maxX || y > maxY || y >= a.rowEnd) return;
-    if (LoadU8(a.tiles, x >> 4, y >> 4) != 0) return;
-    const float viewZ = fabsf(LoadR32F(a.z, x, y) * c.gViewZScale);
+    if (LoadU8(Near(a.tiles), x >> 4, y >> 4) != 0) return;
+    const float viewZ = fabsf(LoadR32F(Near(a.z), x, y) * c.gViewZScale);
     if (viewZ > c.gDenoisingRange) return;
 
     const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
@@ -244,13 +257,13 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         for (int i = 0; i <= 2; i++)
         {
             int px = clampi(x + i - 1, 0, maxX), py = clampi(y + j - 1, 0, maxY);
-            Guide g = DecodeGuide(LoadU32(a.nr, px, py));
+            Guide g = DecodeGuide(LoadU32(Near(a.nr), px, py));
             if (i < 2 && j < 2) Navg = Navg + g.N;
             if (i == 2 && j == 1) n10 = g.N;
             if (i == 1 && j == 2) n01 = g.N;
             if (SPEC)
             {
-                float h = c.gSpecPrepassBlurRadius == 0.0f ? LoadRGBA16F(a.inSpec, px, py).w : LoadR16F(a.inHitDist, px, py);
+                float h = c.gSpecPrepassBlurRadius == 0.0f ? LoadRGBA16F(Near(a.inSpec), px, py).w : LoadR16F(Near(a.inHitDist), px, py);
                 hitDistForTracking = fminf(hitDistForTracking, h == 0.0f ? kInf : h);
                 float r2 = g.roughness * g.roughness;
                 roughnessM1 += r2;
@@ -259,7 +272,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         }
     Navg = Navg * 0.25f;
 
-    const Guide g0 = DecodeGuide(LoadU32(a.nr, x, y));
+    const Guide g0 = DecodeGuide(LoadU32(Near(a.nr), x, y));
     const f3 N = g0.N;
     const float roughness = g0.roughness, materialID = g0.materialID;
 
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
     }
 
     // previous position and surface-motion uv
-    const f4 mvRaw = LoadRGBA16F(a.mv, x, y);
+    const f4 mvRaw = LoadRGBA16F(Near(a.mv), x, y);
     f3 mv = mk3(__fmul_rn(mvRaw.x, c.gMvScale[0]), __fmul_rn(mvRaw.y, c.gMvScale[1]), __fmul_rn(mvRaw.z, c.gMvScale[2]));
     f3 Xprev = X;
     f2 smbPixelUv = mk2(__fadd_rn(pixelUv.x, mv.x), __fadd_rn(pixelUv.y, mv.y));
@@ -307,16 +320,21 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
     // index [row][col] with row/col in 0..3 <-> texel (bx - 1 + col, by - 1 + row)
     float pz[4][4];
     unsigned pid[4][4];
+    const bool smbLocal = FootprintLocal(a.prevZ, by - 1, by + 2); // one owner test for the 28 loads of this footprint
+    auto gatherSmb = [&](const Surf& prevZ, const Surf& prevInternal) {
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+        for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-        {
-            if ((r == 0 || r == 3) && (q == 0 || q == 3)) continue;
-            int tx = clampi(bx - 1 + q, 0, W1), ty = clampi(by - 1 + r, 0, H1);
-            pz[r][q] = fabsf(LoadR32F(a.prevZ, tx, ty) * c.gViewZScale);
-            pid[r][q] = LoadU16(a.prevInternal, tx, ty);
-        }
+            for (int q = 0; q < 4; q++)
+            {
+                if ((r == 0 || r == 3) && (q == 0 || q == 3)) continue;
+                int tx = clampi(bx - 1 + q, 0, W1), ty = clampi(by - 1 + r, 0, H1);
+                pz[r][q] = fabsf(LoadR32F(prevZ, tx, ty) * c.gViewZScale);
+                pid[r][q] = LoadU16(prevInternal, tx, ty);
+            }
+    };
+    if (smbLocal) gatherSmb(Near(a.prevZ), Near(a.prevInternal));
+    else gatherSmb(a.prevZ, a.prevInternal);
 
     // previous normal averaged over the valid part of the 2x2 footprint
     f3 smbNavg;
@@ -324,10 +342,13 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         int px = (int)fmaxf(smbF.ox, 0.0f), py = (int)fmaxf(smbF.oy, 0.0f); // uint2(origin): float -> uint saturates at 0
         float w00 = pz[1][1] < c.gDenoisingRange ? 1.0f : 0.0f, w10 = pz[1][2] < c.gDenoisingRange ? 1.0f : 0.0f;
         float w01 = pz[2][1] < c.gDenoisingRange ? 1.0f : 0.0f, w11 = pz[2][2] < c.gDenoisingRange ? 1.0f : 0.0f;
-        f3 s = DecodeGuide(LoadPackedNrOrZero(a.prevNr, px, py)).N * w00;
-        s = s + DecodeGuide(LoadPackedNrOrZero(a.prevNr, px + 1, py)).N * w10;
-        s = s + DecodeGuide(LoadPackedNrOrZero(a.prevNr, px, py + 1)).N * w01;
-        s = s + DecodeGuide(LoadPackedNrOrZero(a.prevNr, px + 1, py + 1)).N * w11;
+        auto sumN = [&](const Surf& prevNr) {
+            f3 t = DecodeGuide(LoadPackedNrOrZero(prevNr, px, py)).N * w00;
+            t = t + DecodeGuide(LoadPackedNrOrZero(prevNr, px + 1, py)).N * w10;
+            t = t + DecodeGuide(LoadPackedNrOrZero(prevNr, px, py + 1)).N * w01;
+            return t + DecodeGuide(LoadPackedNrOrZero(prevNr, px + 1, py + 1)).N * w11;
+        };
+        f3 s = smbLocal ? sumN(Near(a.prevNr)) : sumN(a.prevNr);
         float sum = w00 + w10 + w01 + w11;
         smbNavg = Rotate(c.gWorldPrevToWorld, s * (1.0f / (sum == 0.0f ? 1.0f : sum)));
     }
@@ -403,7 +424,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
     {
         smbSpecAccumSpeed *= lerpf(smbFootprintQuality, 1.0f, 1.0f / (1.0f + smbSpecAccumSpeed));
         smbSpecAccumSpeed = fminf(smbSpecAccumSpeed, c.gMaxAccumulatedFrameNum);
-        const f4 spec = LoadRGBA16F(a.inSpec, x, y);
+        const f4 spec = LoadRGBA16F(Near(a.inSpec), x, y);
 
         // curvature along the predicted motion (REBLUR_TemporalAccumulation.hlsli:364-447)
         {
@@ -445,9 +466,10 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
             if (deltaUvLenFixed > 1.0f && (unsigned)ix <= (unsigned)maxX && (unsigned)iy <= (unsigned)maxY)
             {
                 f2 motionUvHigh = mk2(__fmul_rn(__fadd_rn(fx, 0.5f), c.gRectSizeInv[0]), __fmul_rn(__fadd_rn(fy, 0.5f), c.gRectSizeInv[1]));
-                float zHigh = fabsf(LoadR32F(a.z, ix, iy) * c.gViewZScale);
+                const bool tapLocal = RowsLocal(a.z, iy, iy);
+                float zHigh = fabsf((tapLocal ? LoadR32F(Near(a.z), ix, iy) : LoadR32F(a.z, ix, iy)) * c.gViewZScale);
                 f3 xHigh = Rotate(c.gViewToWorld, ReconstructViewPosition(motionUvHigh, c.gFrustum, zHigh, c.gOrthoMode));
-                f3 nHigh = DecodeGuide(LoadU32(a.nr, ix, iy)).N;
+                f3 nHigh = DecodeGuide(tapLocal ? LoadU32(Near(a.nr), ix, iy) : LoadU32(a.nr, ix, iy)).N;
                 float zError = fabsf(zHigh - viewZ) / fmaxf(zHigh, viewZ);
                 if (zError < 0.1f)
                 {
@@ -472,8 +494,18 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         // 2x2 footprint fetches (clamped, like Gather with a clamp sampler)
         const int vx0 = clampi(vx, 0, W1), vx1 = clampi(vx + 1, 0, W1), vy0 = clampi(vy, 0, H1), vy1 = clampi(vy + 1, 0, H1);
         f2 rrp = RelaxedRoughnessWeightParams(roughness * roughness, c.gRoughnessFraction, 0.003f);
-        f4 vmbRoughness = mk4(DecodeGuide(LoadU32(a.prevNr, vx0, vy0)).roughness, DecodeGuide(LoadU32(a.prevNr, vx1, vy0)).roughness,
-                              DecodeGuide(LoadU32(a.prevNr, vx0, vy1)).roughness, DecodeGuide(LoadU32(a.prevNr, vx1, vy1)).roughness);
+        const bool vmbLocal = RowsLocal(a.prevNr, vy0, vy1); // one owner test for the 12 loads of this 2x2 footprint
+        unsigned vmbNr[4];
+        float vmbZ[4];
+        unsigned vmbId[4];
+        auto gatherVmb = [&](const Surf& prevNr, const Surf& prevZ, const Surf& prevInternal) {
+            vmbNr[0] = LoadU32(prevNr, vx0, vy0); vmbNr[1] = LoadU32(prevNr, vx1, vy0); vmbNr[2] = LoadU32(prevNr, vx0, vy1); vmbNr[3] = LoadU32(prevNr, vx1, vy1);
+            vmbZ[0] = LoadR32F(prevZ, vx0, vy0); vmbZ[1] = LoadR32F(prevZ, vx1, vy0); vmbZ[2] = LoadR32F(prevZ, vx0, vy1); vmbZ[3] = LoadR32F(prevZ, vx1, vy1);
+            vmbId[0] = LoadU16(prevInternal, vx0, vy0); vmbId[1] = LoadU16(prevInternal, vx1, vy0); vmbId[2] = LoadU16(prevInternal, vx0, vy1); vmbId[3] = LoadU16(prevInternal, vx1, vy1);
+        };
+        if (vmbLocal) gatherVmb(Near(a.prevNr), Near(a.prevZ), Near(a.prevInternal));
+        else gatherVmb(a.prevNr, a.prevZ, a.prevInternal);
+        f4 vmbRoughness = mk4(DecodeGuide(vmbNr[0]).roughness, DecodeGuide(vmbNr[1]).roughness, DecodeGuide(vmbNr[2]).roughness, DecodeGuide(vmbNr[3]).roughness);
         const float jf = SmoothStep(1.0f, 0.0f, smbParallaxInPixelsMax);
         f4 roughnessWeight;
         roughnessWeight.x = lerpf(jf, 1.0f, NonExpWeightWithSigma(vmbRoughness.x * vmbRoughness.x, rrp.x, rrp.y, roughnessSigma));
@@ -507,8 +539,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
             thr *= dot(vmbN, smbNavg) > almostZeroAngle ? 1.0f : 0.0f;
             f4 inS = InScreenBilinear(vmbF, c.gRectSizePrev);
             f4 vmbThr = mk4(thr * inS.x - kEps, thr * inS.y - kEps, thr * inS.z - kEps, thr * inS.w - kEps);
-            f4 vmbViewZ = mk4(fabsf(LoadR32F(a.prevZ, vx0, vy0) * c.gViewZScale), fabsf(LoadR32F(a.prevZ, vx1, vy0) * c.gViewZScale),
-                              fabsf(LoadR32F(a.prevZ, vx0, vy1) * c.gViewZScale), fabsf(LoadR32F(a.prevZ, vx1, vy1) * c.gViewZScale));
+            f4 vmbViewZ = mk4(fabsf(vmbZ[0] * c.gViewZScale), fabsf(vmbZ[1] * c.gViewZScale), fabsf(vmbZ[2] * c.gViewZScale), fabsf(vmbZ[3] * c.gViewZScale));
             f3 vmbVv = ReconstructViewPosition(vmbPixelUv, c.gFrustumPrev, 1.0f, 0.0f);
             f3 vmbV = RotateInverse(c.gWorldToViewPrev, vmbVv);
             float NoXcurr = dot(N, Xprev - camDelta);
@@ -519,8 +550,8 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
             vmbOcclusion.z = (planeDist(vmbViewZ.z) <= vmbThr.z ? 1.0f : 0.0f) * (roughnessWeight.z >= 0.5f ? 1.0f : 0.0f);
             vmbOcclusion.w = (planeDist(vmbViewZ.w) <= vmbThr.w ? 1.0f : 0.0f) * (roughnessWeight.w >= 0.5f ? 1.0f : 0.0f);
         }
-        const f3 v00 = UnpackInternalData(LoadU16(a.prevInternal, vx0, vy0)), v10 = UnpackInternalData(LoadU16(a.prevInternal, vx1, vy0));
-        const f3 v01 = UnpackInternalData(LoadU16(a.prevInternal, vx0, vy1)), v11 = UnpackInternalData(LoadU16(a.prevInternal, vx1, vy1));
+        const f3 v00 = UnpackInternalData(vmbId[0]), v10 = UnpackInternalData(vmbId[1]);
+        const f3 v01 = UnpackInternalData(vmbId[2]), v11 = UnpackInternalData(vmbId[3]);
         {
             float cm = fmaxf(materialID, c.gSpecMinMaterial);
             vmbOcclusion.x *= cm == fmaxf(v00.z, c.gSpecMinMaterial) ? 1.0f : 0.0f;
@@ -671,7 +702,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
     {
         diffAccumSpeed *= lerpf(smbFootprintQuality, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
         diffAccumSpeed = fminf(diffAccumSpeed, c.gMaxAccumulatedFrameNum);
-        const f4 diff = LoadRGBA16F(a.inDiff, x, y);
+        const f4 diff = LoadRGBA16F(Near(a.inDiff), x, y);
 
         const CatRomSetup smbSetup = SetupCatRom(smbSamplePos, c.gResourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
         f4 smbDiffHistory = ClampNegativeToZero(ResolveCatRom4(smbSetup, a.histDiff));
@@ -733,7 +764,7 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
     const float roughness = g0.roughness;
     const float minMaterial = IS_SPEC ? c.gSpecMinMaterial : c.gDiffMinMaterial;
-    f4 sig = LoadRGBA16F(inSig, x, y);
+    f4 sig = LoadRGBA16F(Near(inSig), x, y);
     const float smc = SpecMagicCurve(roughness);
     float stride = strideBase * (fn < c.gHistoryFixFrameNum ? 1.0f : 0.0f);
     if (IS_SPEC) stride *= lerpf(0.5f, 1.0f, smc);
@@ -753,51 +784,56 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
         const f2 hp = HitDistanceWeightParams(hitDistFactor, nl, IS_SPEC ? smc : SpecMagicCurve(1.0f));
         float sum = 1.0f + fn;
         sig = sig * sum;
-        for (int j = -2; j <= 2; j++)
-            for (int i = -2; i <= 2; i++)
-            {
-                if ((i == 0 && j == 0) || (abs(i) + abs(j) == 4)) continue;
-                // uv for the in-screen test / view position is NOT clamped, the texel is
-                float u = __fadd_rn(pixelUv.x, __fmul_rn(__fmul_rn((float)i, stride), c.gRectSizeInv[0]));
-                float v = __fadd_rn(pixelUv.y, __fmul_rn(__fmul_rn((float)j, stride), c.gRectSizeInv[1]));
-                int px = clampi(x + i * stridei, 0, maxX), py = clampi(y + j * stridei, 0, maxY);
-                float zs = fabsf(LoadR32F(a.z, px, py) * c.gViewZScale);
-                Guide gs = DecodeGuide(LoadU32(a.nr, px, py));
-                f3 Xvs = ReconstructViewPosition(mk2(u, v), c.gFrustum, zs, c.gOrthoMode);
-                float w = (u > 0.0f && v > 0.0f && u < 1.0f && v < 1.0f) ? 1.0f : 0.0f;
-                w *= NonExpWeight(dot(Nv, Xvs), geoA, geoB);
-                w *= fmaxf(g0.materialID, minMaterial) == fmaxf(gs.materialID, minMaterial) ? 1.0f : 0.0f;
-                w *= ExpWeight(AcosApprox(dot(gs.N, g0.N)), normalParam, 0.0f);
-                if (IS_SPEC) w *= ExpWeight(gs.roughness * gs.roughness, rrp.x, rrp.y);
-                f2 fr = LoadFrames<BOTH>(a.data1, px, py);
-                w *= 1.0f + (IS_SPEC ? fr.y : fr.x);
-                if (w != 0.0f)
+        // the 20 taps reach +-2 strides: one owner test for all of them
+        auto taps = [&](const Surf& zS, const Surf& nrS, const Surf& data1S, const Surf& sigS) {
+            for (int j = -2; j <= 2; j++)
+                for (int i = -2; i <= 2; i++)
                 {
-                    f4 sv = LoadRGBA16F(inSig, px, py);
-                    float hs = sv.w * hitDistScale;
-                    w *= ExpWeight(saturate(hs / frustumSize), hp.x, hp.y);
-                    if (IS_SPEC)
+                    if ((i == 0 && j == 0) || (abs(i) + abs(j) == 4)) continue;
+                    // uv for the in-screen test / view position is NOT clamped, the texel is
+                    float u = __fadd_rn(pixelUv.x, __fmul_rn(__fmul_rn((float)i, stride), c.gRectSizeInv[0]));
+                    float v = __fadd_rn(pixelUv.y, __fmul_rn(__fmul_rn((float)j, stride), c.gRectSizeInv[1]));
+                    int px = clampi(x + i * stridei, 0, maxX), py = clampi(y + j * stridei, 0, maxY);
+                    float zs = fabsf(LoadR32F(zS, px, py) * c.gViewZScale);
+                    Guide gs = DecodeGuide(LoadU32(nrS, px, py));
+                    f3 Xvs = ReconstructViewPosition(mk2(u, v), c.gFrustum, zs, c.gOrthoMode);
+                    float w = (u > 0.0f && v > 0.0f && u < 1.0f && v < 1.0f) ? 1.0f : 0.0f;
+                    w *= NonExpWeight(dot(Nv, Xvs), geoA, geoB);
+                    w *= fmaxf(g0.materialID, minMaterial) == fmaxf(gs.materialID, minMaterial) ? 1.0f : 0.0f;
+                    w *= ExpWeight(AcosApprox(dot(gs.N, g0.N)), normalParam, 0.0f);
+                    if (IS_SPEC) w *= ExpWeight(gs.roughness * gs.roughness, rrp.x, rrp.y);
+                    f2 fr = LoadFrames<BOTH>(data1S, px, py);
+                    w *= 1.0f + (IS_SPEC ? fr.y : fr.x);
+                    if (w != 0.0f)
                     {
-                        float d = fabsf(hitDist - hs) / (fmaxf(hitDist, hs) + 0.001f);
-                        float b = LinearStep(0.03f, 0.05f, roughness);
-                        w *= SmoothStep(0.2f + b, 0.05f + b, d);
+                        f4 sv = LoadRGBA16F(sigS, px, py);
+                        float hs = sv.w * hitDistScale;
+                        w *= ExpWeight(saturate(hs / frustumSize), hp.x, hp.y);
+                        if (IS_SPEC)
+                        {
+                            float d = fabsf(hitDist - hs) / (fmaxf(hitDist, hs) + 0.001f);
+                            float b = LinearStep(0.03f, 0.05f, roughness);
+                            w *= SmoothStep(0.2f + b, 0.05f + b, d);
+                        }
+                        sum += w;
+                        sig = sig + sv * w;
                     }
-                    sum += w;
-                    sig = sig + sv * w;
                 }
-            }
+        };
+        if (FootprintLocal(a.z, y - 2 * stridei, y + 2 * stridei)) taps(Near(a.z), Near(a.nr), Near(a.data1), Near(inSig));
+        else taps(a.z, a.nr, a.data1, inSig);
         sig = sig * PositiveRcp(sum);
     }
 
     // 5x5 moments of the fast history (clamped reads)
-    float center = LoadR16F(inFast, x, y);
+    float center = LoadR16F(Near(inFast), x, y);
     float m1 = 0.0f, m2 = 0.0f;
 #pragma unroll
     for (int j = -2; j <= 2; j++)
 #pragma unroll
         for (int i = -2; i <= 2; i++)
         {
-            float d = LoadR16F(inFast, clampi(x + i, 0, maxX), clampi(y + j, 0, maxY));
+            float d = LoadR16F(Near(inFast), clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)); // +-2 rows: inside the ghost rows
             m1 += d;
             m2 += d * d;
         }
@@ -813,7 +849,7 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
             for (int i = -4; i <= 4; i++)
             {
                 if (abs(i) <= 1 && abs(j) <= 1) continue;
-                float d = LoadR16F(inFast, clampi(x + i, 0, maxX), clampi(y + j, 0, maxY));
+                float d = LoadR16F(Near(inFast), clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)); // +-4 rows
                 am1 += d;
                 am2 += d * d;
             }
@@ -840,16 +876,16 @@ __global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS) ReblurHistoryFixK
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
     if (x > c.gRectSizeMinusOne[0] || y > c.gRectSizeMinusOne[1] || y >= a.rowEnd) return;
-    if (LoadU8(a.tiles, x >> 4, y >> 4) != 0) return;
-    const float viewZ = fabsf(LoadR32F(a.z, x, y) * c.gViewZScale);
+    if (LoadU8(Near(a.tiles), x >> 4, y >> 4) != 0) return;
+    const float viewZ = fabsf(LoadR32F(Near(a.z), x, y) * c.gViewZScale);
     if (viewZ > c.gDenoisingRange) return;
 
-    const Guide g0 = DecodeGuide(LoadU32(a.nr, x, y));
+    const Guide g0 = DecodeGuide(LoadU32(Near(a.nr), x, y));
     const float frustumSize = c.gMinRectDimMulUnproject * lerpf(viewZ, 1.0f, fabsf(c.gOrthoMode));
     const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
     const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
     const f3 Nv = RotateInverse(c.gViewToWorld, g0.N);
-    const f2 frameNum = LoadFrames<DIFF && SPEC>(a.data1, x, y);
+    const f2 frameNum = LoadFrames<DIFF && SPEC>(Near(a.data1), x, y);
     const f2 stride = mk2(__fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.x)), __fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.y)));
 
     if (DIFF) HistoryFixSignal<false, DIFF && SPEC>(a, x, y, a.inDiff, a.inDiffFast, a.outDiff, a.outDiffFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.x, stride.x);
@@ -882,7 +918,7 @@ __device__ __forceinline__ float Antilag(const ReblurConstants& c, float history
 // individually rounded operations: centre first, then row-major, true division by 9.
 __device__ __forceinline__ void LumaStats3x3(const Surf& s, int x, int y, int maxX, int maxY, float& luma, float& m1, float& m2, float& mn, float& mx)
 {
-    luma = LoadRGBA16F(s, x, y).x;
+    luma = LoadRGBA16F(Near(s), x, y).x;
     m1 = luma;
     m2 = __fmul_rn(luma, luma);
     mn = kInf;
@@ -893,7 +929,7 @@ __device__ __forceinline__ void LumaStats3x3(const Surf& s, int x, int y, int ma
         for (int i = -1; i <= 1; i++)
         {
             if (i == 0 && j == 0) continue;
-            float d = LoadRGBA16F(s, clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)).x;
+            float d = LoadRGBA16F(Near(s), clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)).x;
             m1 = __fadd_rn(m1, d);
             m2 = __fadd_rn(m2, __fmul_rn(d, d));
             mn = fminf(mn, d);
@@ -912,15 +948,15 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
     const int y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
     if (x > maxX || y > maxY || y >= a.rowEnd) return;
-    if (LoadU8(a.tiles, x >> 4, y >> 4) != 0) return;
-    const float viewZ = fabsf(LoadR32F(a.z, x, y) * c.gViewZScale);
+    if (LoadU8(Near(a.tiles), x >> 4, y >> 4) != 0) return;
+    const float viewZ = fabsf(LoadR32F(Near(a.z), x, y) * c.gViewZScale);
     if (viewZ > c.gDenoisingRange) return;
 
     const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
     const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
     const f3 X = PinnedRotate(c.gViewToWorld, Xv);
 
-    const f4 mvRaw = LoadRGBA16F(a.mv, x, y);
+    const f4 mvRaw = LoadRGBA16F(Near(a.mv), x, y);
     f3 mv = mk3(__fmul_rn(mvRaw.x, c.gMvScale[0]), __fmul_rn(mvRaw.y, c.gMvScale[1]), __fmul_rn(mvRaw.z, c.gMvScale[2]));
     f3 Xprev = X;
     f2 smbPixelUv = mk2(__fadd_rn(pixelUv.x, mv.x), __fadd_rn(pixelUv.y, mv.y));
@@ -938,9 +974,9 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
         smbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xprev);
     }
 
-    const Guide g0 = DecodeGuide(LoadU32(a.nr, x, y));
-    f2 data1 = LoadFrames<DIFF && SPEC>(a.data1, x, y);
-    const unsigned d2 = SPEC ? LoadU32(a.data2, x, y) : LoadU8(a.data2, x, y);
+    const Guide g0 = DecodeGuide(LoadU32(Near(a.nr), x, y));
+    f2 data1 = LoadFrames<DIFF && SPEC>(Near(a.data1), x, y);
+    const unsigned d2 = SPEC ? LoadU32(Near(a.data2), x, y) : LoadU8(Near(a.data2), x, y);
     const unsigned bits = d2 & 0xFFu;
     const float virtualHistoryAmount = (float)((d2 >> 8) & 0xFFu) / 255.0f;
     const float curvature = __half2float(__ushort_as_half((unsigned short)(d2 >> 16)));
@@ -968,7 +1004,7 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
         const float k = sigma * (1.0f + 3.0f * c.gFramerateScale * tw);
         history = clampf(history, m1 - k, m1 + k);
         const float stabilized = lerpf(luma, history, fminf(historyWeight, c.gStabilizationStrength));
-        StoreRGBA16F(a.outDiff, x, y, ChangeLuma(LoadRGBA16F(a.inDiff, x, y), stabilized));
+        StoreRGBA16F(a.outDiff, x, y, ChangeLuma(LoadRGBA16F(Near(a.inDiff), x, y), stabilized));
         StoreR16F(a.outDiffStab, x, y, stabilized);
         data1.x += 1.0f;
         data1.x = lerpf(fminf(data1.x, c.gHistoryFixFrameNum), data1.x, antilag);
@@ -981,9 +1017,9 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
         const float sigma = PinnedStdDev(m1, m2);
         if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
 
-        f4 spec = LoadRGBA16F(a.inSpec, x, y);
+        f4 spec = LoadRGBA16F(Near(a.inSpec), x, y);
         float hitDistForTracking = spec.w * HitDistNormalization(viewZ, c.gHitDistParams, g0.roughness);
-        if (c.gSpecPrepassBlurRadius != 0.0f) hitDistForTracking = fminf(hitDistForTracking, LoadR16F(a.hitDist, x, y));
+        if (c.gSpecPrepassBlurRadius != 0.0f) hitDistForTracking = fminf(hitDistForTracking, LoadR16F(Near(a.hitDist), x, y));
 
         const f3 V = c.gOrthoMode == 0.0f ? normalize(-X) : mk3(c.gViewVectorWorld[0], c.gViewVectorWorld[1], c.gViewVectorWorld[2]);
         const f3 Xvirtual = GetXvirtual(hitDistForTracking, curvature, X, Xprev, g0.N, V, g0.roughness);

@@ -409,7 +409,10 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
     if (desc->stripHeight != 0)
     {
         // ghost rows: whole tiles, at most one strip (they are refreshed by the direct neighbours only)
+        // at least one tile: the kernels read the centre pixel's fixed neighbourhoods (up to +-4 rows, REBLUR history fix up to
+        // +-14) without an owner lookup (device/common.cuh Near)
         ctx->halo = ((uint32_t)desc->haloRows + 15u) / 16u * 16u;
+        if (ctx->halo < 16u) ctx->halo = 16u;
         if (ctx->halo > desc->stripHeight) ctx->halo = desc->stripHeight;
     }
     const InstanceDesc& id = GetInstanceDesc(*instance);

@@ -70,7 +70,7 @@ def _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call):
 
 @pytest.mark.parametrize("denoiser,w,h,world,frames,halo,whole_frame_call", [
     ("REBLUR_DIFFUSE_SPECULAR", 320, 192, 2, 4, 32, True),     # ghost rows + direct peer loads beyond them
-    ("REBLUR_DIFFUSE_SPECULAR", 320, 192, 2, 3, 0, False),     # no ghost rows: every foreign tap is a direct peer load
+    ("REBLUR_DIFFUSE_SPECULAR", 320, 192, 2, 3, 0, False),     # minimum halo (one tile): most foreign taps are direct peer loads
     ("REBLUR_DIFFUSE_SPECULAR", 250, 141, 3, 3, 96, True),     # halo clamped to the strip height (48 rows)
     ("RELAX_DIFFUSE_SPECULAR", 320, 180, 2, 4, 16, True),
     ("RELAX_DIFFUSE_SPECULAR", 320, 180, 3, 3, 64, False),
