@@ -176,7 +176,11 @@ def main():
         # textures live in the context's IPC arena, so "binding" a frame is a device-to-device copy of this rank's rows --
         # it is inside the timed region.
         from raytracingdenoiser_b200 import strips
-        gpu = strips.StripDenoiser(den, W, H, rank, world, device=local_rank)
+        # cost-balanced partition from the sky mask of the first frame (every rank computes the same one): tiles beyond the
+        # denoising range are skipped by every pass, so uniform strips would leave the rank that owns the sky idle
+        partition = strips.partition_rows_weighted(H, world, strips.tile_row_cost_from_viewz(frames[0]["IN_VIEWZ"]), min_rows=strips.DEFAULT_HALO_ROWS)
+        gpu = strips.StripDenoiser(den, W, H, rank, world, device=local_rank, partition=partition)
+        base["config"]["strips"] = [list(p) for p in partition[1]]
         gpu.connect()
         y0, y1 = gpu.y0, gpu.y1
         frames = [{k: (v[y0:y1].contiguous() if k in in_names else v) for k, v in fr.items() if k in in_names or not k.startswith("IN_")} for fr in frames]

@@ -349,7 +349,7 @@ typedef struct NrdCudaContextDesc
 {
     uint16_t resourceWidth, resourceHeight;   // full-frame texture size (== CommonSettings::resourceSize)
     uint16_t stripY0, stripY1;                // rows owned by this context; {0, resourceHeight} for one GPU
-    uint16_t stripHeight;                     // 0 = one GPU; else rows per rank (multiple of 16), stripY0 = rank * stripHeight
+    uint16_t stripHeight;                     // 0 = one GPU; else the rows reserved per rank (multiple of 16, >= the tallest strip)
     uint16_t haloRows;                        // strip mode: ghost rows kept above/below the strip (rounded up to 16, at least 16, at most stripHeight)
     int32_t device;                          // CUDA device ordinal
 } NrdCudaContextDesc;
@@ -392,8 +392,11 @@ NRD_API nrd::Result nrdCudaGetArena(NrdCudaContext* context, void** devicePtr, s
 NRD_API nrd::Result nrdCudaGetIpcHandle(NrdCudaContext* context, void* handleOut);
 // Connects the strips: `ipcHandles` = worldSize handles in rank order (entry `rank` is ignored), as gathered with
 // torch.distributed / MPI; alternatively `arenas` = worldSize arena pointers that are already addressable from this
-// context's device (contexts of one process).  Exactly one of the two is non-null.
-NRD_API nrd::Result nrdCudaConnectPeers(NrdCudaContext* context, uint32_t rank, uint32_t worldSize, const void* ipcHandles, void* const* arenas);
+// context's device (contexts of one process).  Exactly one of the two is non-null.  `stripStarts` (worldSize + 1 entries:
+// first row of every rank's strip, then the frame height) describes a non-uniform, e.g. cost-balanced, partition; every
+// strip starts on a multiple of 16, holds at least haloRows rows and at most stripHeight; null = uniform strips.
+NRD_API nrd::Result nrdCudaConnectPeers(NrdCudaContext* context, uint32_t rank, uint32_t worldSize, const void* ipcHandles, void* const* arenas,
+                                        const uint16_t* stripStarts);
 
 // Enqueues one inter-GPU barrier on `stream` (no-op on one GPU).  nrdCudaDenoise starts with one -- the input strips the
 // peers wrote on their streams are complete before the first pass reads them -- and nrdCudaExecuteDispatch ends with one;

@@ -42,19 +42,23 @@ using namespace nrdb200_abi;
 // Surfaces (surf.h)
 // ---------------------------------------------------------------------------------------------
 #if !defined(NRD_B200_NO_STRIPS)
-// (arena of rank r) - (local arena), one table per context slot
-static __constant__ long long g_peerDelta[kMaxPeerSlots * kMaxPeers];
-static inline cudaError_t SetPeerTableThisTU(int slot, const long long* delta)
+// strip geometry, one table per context slot (surf.h)
+static __constant__ PeerTable g_peerTable[kMaxPeerSlots];
+static inline cudaError_t SetPeerTableThisTU(int slot, const PeerTable* table)
 {
-    return cudaMemcpyToSymbol(g_peerDelta, delta, sizeof(long long) * kMaxPeers, sizeof(long long) * kMaxPeers * (size_t)slot);
+    return cudaMemcpyToSymbol(g_peerTable, table, sizeof(PeerTable), sizeof(PeerTable) * (size_t)slot);
 }
 // rare path: the row is beyond the ghost rows, fetch it from its owner (callers clamp y to [0, h))
 // (inlined on purpose: a real call gives the kernels a stack frame, and the first launch of a kernel that needs a bigger
 // stack makes the driver wait for every running kernel -- including a spinning StripBarrierKernel of another context)
 static __device__ __forceinline__ const uint8_t* PeerRow(const Surf& s, int y)
 {
-    const unsigned owner = __umulhi((unsigned)y, s.stripMagic);
-    return s.base + g_peerDelta[s.peerSlot * kMaxPeers + owner] + (size_t)((unsigned)y - owner * s.stripRows + (unsigned)s.halo) * s.pitch;
+    const PeerTable& t = g_peerTable[s.peerSlot];
+    const int yFull = y << s.rowShift;
+    int owner = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxPeers; k++) owner += yFull >= t.start[k] ? 1 : 0;
+    return s.base + t.delta[owner] + (size_t)(y - (t.start[owner] >> s.rowShift) + s.halo) * s.pitch;
 }
 #endif
 

@@ -24,9 +24,9 @@ NRD_B200_DECLARE_LAUNCHERS(nrdb200)
 namespace nrdb200
 {
 // peer address table of one context slot, replicated into the constant memory of every kernel translation unit
-cudaError_t SetPeerTableReblurSpatial(int slot, const long long* delta);
-cudaError_t SetPeerTableReblurTemporal(int slot, const long long* delta);
-cudaError_t SetPeerTableSigma(int slot, const long long* delta);
-cudaError_t SetPeerTableRelax(int slot, const long long* delta);
+cudaError_t SetPeerTableReblurSpatial(int slot, const nrdb200_abi::PeerTable* table);
+cudaError_t SetPeerTableReblurTemporal(int slot, const nrdb200_abi::PeerTable* table);
+cudaError_t SetPeerTableSigma(int slot, const nrdb200_abi::PeerTable* table);
+cudaError_t SetPeerTableRelax(int slot, const nrdb200_abi::PeerTable* table);
 } // namespace nrdb200
 #endif

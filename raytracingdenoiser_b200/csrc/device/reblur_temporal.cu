@@ -1166,6 +1166,6 @@ cudaError_t LaunchReblurTemporalStabilization(const PassLaunch& p, int signal)
 }
 
 #if !defined(NRD_B200_NO_STRIPS)
-cudaError_t SetPeerTableReblurTemporal(int slot, const long long* delta) { return SetPeerTableThisTU(slot, delta); }
+cudaError_t SetPeerTableReblurTemporal(int slot, const PeerTable* table) { return SetPeerTableThisTU(slot, table); }
 #endif
 } // namespace nrdb200

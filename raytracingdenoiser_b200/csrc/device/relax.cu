@@ -1282,6 +1282,6 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
 }
 
 #if !defined(NRD_B200_NO_STRIPS)
-cudaError_t SetPeerTableRelax(int slot, const long long* delta) { return SetPeerTableThisTU(slot, delta); }
+cudaError_t SetPeerTableRelax(int slot, const PeerTable* table) { return SetPeerTableThisTU(slot, table); }
 #endif
 } // namespace nrdb200

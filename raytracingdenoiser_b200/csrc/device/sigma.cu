@@ -505,6 +505,6 @@ cudaError_t LaunchSigma(const PassLaunch& p, const char* shader)
 }
 
 #if !defined(NRD_B200_NO_STRIPS)
-cudaError_t SetPeerTableSigma(int slot, const long long* delta) { return SetPeerTableThisTU(slot, delta); }
+cudaError_t SetPeerTableSigma(int slot, const PeerTable* table) { return SetPeerTableThisTU(slot, table); }
 #endif
 } // namespace nrdb200

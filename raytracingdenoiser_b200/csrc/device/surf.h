@@ -8,8 +8,17 @@ namespace nrdb200_abi
 constexpr int kMaxPeers = 8;
 constexpr int kMaxPeerSlots = 4;
 
-// A pitched HBM surface.  On one GPU the whole texture is local.  In strip mode (several GPUs, one horizontal strip of
-// `stripRows` rows each) a surface holds its own strip plus `halo` ghost rows above and below, which the owner of those
+// Strip geometry of one context slot: (arena of rank r) - (local arena), and the first full-resolution row of every rank's
+// strip (start[worldSize] = frame height, unused entries = INT_MAX).  Strips are whole 16-row tiles, not necessarily uniform.
+struct PeerTable
+{
+    long long delta[kMaxPeers];
+    int start[kMaxPeers + 1];
+    int pad_;
+};
+
+// A pitched HBM surface.  On one GPU the whole texture is local.  In strip mode (several GPUs, one horizontal strip
+// each) a surface holds its own strip plus `halo` ghost rows above and below, which the owner of those
 // rows refreshes after every pass that writes them (executor.cu, GhostPushKernel); a tap that lands outside even the
 // ghost rows is loaded straight from the owner's HBM: every context carves its surfaces out of one arena with the same
 // layout, so that address is the local address plus (arena of the owner - local arena).  Stores are always local.
@@ -21,8 +30,8 @@ struct Surf
     int y0, y1;          // rows owned by this context: [y0, y1)  (the whole texture on one GPU)
     int ly0;             // first row held locally (y0 - halo in strip mode, may be negative)
     unsigned lrows;      // rows held locally
-    unsigned stripRows;  // rows per strip in this texture's own units; 0 = whole frame is local
-    unsigned stripMagic; // floor(2^32 / stripRows) + 1: owner(y) = umulhi(y, magic), exact for y, stripRows < 65536
+    unsigned stripRows;  // strip mode: rows reserved per strip in this texture's own units (capacity); 0 = whole frame is local
+    unsigned rowShift;   // log2 of the texture's downsample factor: full-resolution row = y << rowShift (owner lookup)
     int halo;            // ghost rows on either side, in this texture's own units
     int peerSlot;
 };

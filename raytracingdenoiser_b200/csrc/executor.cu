@@ -113,6 +113,7 @@ struct NrdCudaContext
     void* peerArena[kMaxPeers] = {};
     bool peerOpened[kMaxPeers] = {};
     long long peerDelta[kMaxPeers] = {};
+    uint32_t stripStart[kMaxPeers + 1] = {}; // first row of every rank's strip, [world] = frame height
     uint32_t epoch = 0;
     uint32_t halo = 0; // ghost rows (full-resolution rows, multiple of 16, <= stripHeight)
     std::string lastError;
@@ -174,9 +175,10 @@ Surf ToSurf(const NrdCudaContext* ctx, const Texture& t)
     if (StripMode(ctx) && ctx->world > 1)
     {
         s.stripRows = ctx->desc.stripHeight / t.downsample;
-        s.stripMagic = (unsigned)(0x100000000ull / s.stripRows) + 1u;
+        s.rowShift = t.downsample == 16 ? 4u : 0u;
         s.halo = t.haloRows;
         s.ly0 = (int)t.firstRow - (int)t.haloRows;
+        s.lrows = (unsigned)t.rows + 2u * t.haloRows; // the rows that are kept current: a strip shorter than the reserved height leaves the tail unused
         s.peerSlot = ctx->peerSlot;
     }
     else if (StripMode(ctx))
@@ -361,20 +363,20 @@ Result PushGhosts(NrdCudaContext* ctx, const Texture* const* textures, uint32_t 
     {
         const Texture& t = *textures[i];
         if (!t.owned || !t.rows || !t.haloRows) continue;
-        const uint32_t S = ctx->desc.stripHeight / t.downsample, H = t.haloRows;
+        const uint32_t H = t.haloRows, cnt = t.rows < H ? t.rows : H; // ConnectPeers guarantees rows >= H except for the last strip
         uint8_t* base = (uint8_t*)t.ptr;
         if (ctx->rank > 0)
         {
-            // my first rows are the bottom ghost rows of the strip above: local rows [S + H, S + 2H) over there
-            const uint32_t cnt = t.rows < H ? t.rows : H;
-            a.items[items++] = {base + (size_t)H * t.pitch, base + ctx->peerDelta[ctx->rank - 1] + (size_t)(S + H) * t.pitch, (unsigned long long)cnt * t.pitch};
+            // my first rows are the bottom ghost rows of the strip above: they follow its own rows, i.e. local rows [H + rowsAbove, ...) there
+            const uint32_t rowsAbove = (ctx->stripStart[ctx->rank] - ctx->stripStart[ctx->rank - 1]) / t.downsample;
+            a.items[items++] = {base + (size_t)H * t.pitch, base + ctx->peerDelta[ctx->rank - 1] + (size_t)(H + rowsAbove) * t.pitch, (unsigned long long)cnt * t.pitch};
             if ((unsigned long long)cnt * t.pitch > maxBytes) maxBytes = (unsigned long long)cnt * t.pitch;
         }
-        if (ctx->rank + 1 < ctx->world && t.rows == S)
+        if (ctx->rank + 1 < ctx->world)
         {
-            // my last rows are the top ghost rows of the strip below: local rows [0, H) over there
-            a.items[items++] = {base + (size_t)S * t.pitch, base + ctx->peerDelta[ctx->rank + 1], (unsigned long long)H * t.pitch};
-            if ((unsigned long long)H * t.pitch > maxBytes) maxBytes = (unsigned long long)H * t.pitch;
+            // my last rows are the top ghost rows of the strip below: local rows [H - cnt, H) over there
+            a.items[items++] = {base + (size_t)(H + t.rows - cnt) * t.pitch, base + ctx->peerDelta[ctx->rank + 1] + (size_t)(H - cnt) * t.pitch, (unsigned long long)cnt * t.pitch};
+            if ((unsigned long long)cnt * t.pitch > maxBytes) maxBytes = (unsigned long long)cnt * t.pitch;
         }
         if (items + 2 > (uint32_t)kMaxPushItems)
         {
@@ -396,8 +398,8 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
     if (desc->stripHeight != 0)
     {
         // uniform strips of whole 16-row tiles; the last ranks may own fewer (or no) rows
-        if (desc->stripHeight % 16 != 0 || desc->stripY0 % desc->stripHeight != 0 || desc->stripY1 - desc->stripY0 > desc->stripHeight) return Result::INVALID_ARGUMENT;
-        if (desc->stripY1 != desc->resourceHeight && desc->stripY1 - desc->stripY0 != desc->stripHeight) return Result::INVALID_ARGUMENT;
+        if (desc->stripHeight % 16 != 0 || desc->stripY0 % 16 != 0 || desc->stripY1 - desc->stripY0 > desc->stripHeight) return Result::INVALID_ARGUMENT;
+        if (desc->stripY1 != desc->resourceHeight && desc->stripY1 % 16 != 0) return Result::INVALID_ARGUMENT;
     }
     int deviceCount = 0;
     if (cudaGetDeviceCount(&deviceCount) != cudaSuccess || deviceCount == 0) return Result::FAILURE; // no silent CPU path: fail loudly
@@ -528,13 +530,27 @@ NRD_API Result nrdCudaGetIpcHandle(NrdCudaContext* ctx, void* handleOut)
     return Result::SUCCESS;
 }
 
-NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t worldSize, const void* ipcHandles, void* const* arenas)
+NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t worldSize, const void* ipcHandles, void* const* arenas, const uint16_t* stripStarts)
 {
     if (!ctx || worldSize == 0 || worldSize > (uint32_t)kMaxPeers || rank >= worldSize || (!ipcHandles == !arenas)) return Result::INVALID_ARGUMENT;
     if (!StripMode(ctx)) return Fail(ctx, Result::UNSUPPORTED, "not a strip-mode context");
     if (ctx->connected) return Fail(ctx, Result::FAILURE, "peers already connected");
-    if ((uint32_t)ctx->desc.stripY0 != rank * (uint32_t)ctx->desc.stripHeight) return Fail(ctx, Result::INVALID_ARGUMENT, "stripY0 must be rank * stripHeight");
-    if (worldSize * (uint32_t)ctx->desc.stripHeight < ctx->desc.resourceHeight) return Fail(ctx, Result::INVALID_ARGUMENT, "the strips do not cover the frame");
+    // strip starts: given explicitly (cost-aware partition) or uniform strips of stripHeight rows
+    for (uint32_t i = 0; i <= worldSize; i++)
+    {
+        uint32_t y = stripStarts ? stripStarts[i] : i * (uint32_t)ctx->desc.stripHeight;
+        if (!stripStarts && (i == worldSize || y > ctx->desc.resourceHeight)) y = ctx->desc.resourceHeight;
+        ctx->stripStart[i] = y;
+    }
+    if (ctx->stripStart[0] != 0 || ctx->stripStart[worldSize] != ctx->desc.resourceHeight) return Fail(ctx, Result::INVALID_ARGUMENT, "the strips do not cover the frame");
+    for (uint32_t i = 0; i < worldSize; i++)
+    {
+        const uint32_t rows = ctx->stripStart[i + 1] - ctx->stripStart[i];
+        if (ctx->stripStart[i + 1] <= ctx->stripStart[i] || ctx->stripStart[i] % 16 != 0 || rows > ctx->desc.stripHeight)
+            return Fail(ctx, Result::INVALID_ARGUMENT, "every strip must start on a multiple of 16, own rows and fit stripHeight");
+        if (rows < ctx->halo && i + 1 < worldSize) return Fail(ctx, Result::INVALID_ARGUMENT, "haloRows exceeds the height of a strip (ghost rows are refreshed by the direct neighbours only)");
+    }
+    if (ctx->stripStart[rank] != ctx->desc.stripY0 || ctx->stripStart[rank + 1] != ctx->desc.stripY1) return Fail(ctx, Result::INVALID_ARGUMENT, "stripY0/stripY1 do not match the strip table");
     cudaSetDevice(ctx->desc.device);
     for (uint32_t i = 0; i < worldSize; i++)
     {
@@ -556,10 +572,14 @@ NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t 
             if (!g_slotUsed[s]) { g_slotUsed[s] = true; ctx->peerSlot = s; }
     }
     if (ctx->peerSlot < 0) return Fail(ctx, Result::FAILURE, "too many strip-mode contexts in one process");
-    cudaError_t e = SetPeerTableReblurSpatial(ctx->peerSlot, ctx->peerDelta);
-    if (e == cudaSuccess) e = SetPeerTableReblurTemporal(ctx->peerSlot, ctx->peerDelta);
-    if (e == cudaSuccess) e = SetPeerTableSigma(ctx->peerSlot, ctx->peerDelta);
-    if (e == cudaSuccess) e = SetPeerTableRelax(ctx->peerSlot, ctx->peerDelta);
+    PeerTable table{};
+    for (uint32_t i = 0; i < (uint32_t)kMaxPeers; i++) table.delta[i] = ctx->peerDelta[i];
+    for (uint32_t i = 0; i <= (uint32_t)kMaxPeers; i++) table.start[i] = i <= worldSize ? (int)ctx->stripStart[i] : 0x7fffffff;
+    if (worldSize < (uint32_t)kMaxPeers) table.start[worldSize] = 0x7fffffff; // rows >= start[world] do not exist: never counted as an owner change
+    cudaError_t e = SetPeerTableReblurSpatial(ctx->peerSlot, &table);
+    if (e == cudaSuccess) e = SetPeerTableReblurTemporal(ctx->peerSlot, &table);
+    if (e == cudaSuccess) e = SetPeerTableSigma(ctx->peerSlot, &table);
+    if (e == cudaSuccess) e = SetPeerTableRelax(ctx->peerSlot, &table);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("peer table: ") + cudaGetErrorString(e));
     ctx->rank = rank;
     ctx->world = worldSize;

@@ -229,7 +229,7 @@ _lib.nrdCudaGetArena.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.
 _lib.nrdCudaGetArena.restype = u32
 _lib.nrdCudaGetIpcHandle.argtypes = [C.c_void_p, C.c_void_p]
 _lib.nrdCudaGetIpcHandle.restype = u32
-_lib.nrdCudaConnectPeers.argtypes = [C.c_void_p, u32, u32, C.c_void_p, C.POINTER(C.c_void_p)]
+_lib.nrdCudaConnectPeers.argtypes = [C.c_void_p, u32, u32, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(u16)]
 _lib.nrdCudaConnectPeers.restype = u32
 _lib.nrdCudaBarrier.argtypes = [C.c_void_p, C.c_void_p]
 _lib.nrdCudaBarrier.restype = u32
@@ -431,15 +431,17 @@ class CudaContext(object):
         self._check("nrdCudaGetIpcHandle", _lib.nrdCudaGetIpcHandle(self._ctx, buf))
         return buf.raw
 
-    def connect_peers(self, rank, world_size, ipc_handles=None, arenas=None):
-        """ipc_handles: list of world_size 64-byte handles (other processes); arenas: list of arena pointers (same process)."""
+    def connect_peers(self, rank, world_size, ipc_handles=None, arenas=None, strip_starts=None):
+        """ipc_handles: list of world_size 64-byte handles (other processes); arenas: list of arena pointers (same process);
+        strip_starts: world_size + 1 row indices of a non-uniform partition (None = uniform strips of strip_height rows)."""
+        starts = (u16 * (world_size + 1))(*strip_starts) if strip_starts is not None else None
         if arenas is not None:
             arr = (C.c_void_p * world_size)(*arenas)
-            r = _lib.nrdCudaConnectPeers(self._ctx, rank, world_size, None, arr)
+            r = _lib.nrdCudaConnectPeers(self._ctx, rank, world_size, None, arr, starts)
         else:
             blob = b"".join(ipc_handles)
             assert len(blob) == IPC_HANDLE_SIZE * world_size
-            r = _lib.nrdCudaConnectPeers(self._ctx, rank, world_size, blob, None)
+            r = _lib.nrdCudaConnectPeers(self._ctx, rank, world_size, blob, None, starts)
         self._check("nrdCudaConnectPeers", r)
 
     def barrier(self, stream=0):

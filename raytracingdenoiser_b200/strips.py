@@ -28,6 +28,44 @@ def partition_rows(height, world_size):
     return strip_height, strips
 
 
+def partition_rows_weighted(height, world_size, tile_row_cost, min_rows=TILE):
+    """Cost-balanced strips of whole 16-row tiles.  tile_row_cost[i] = estimated cost of tile row i (e.g. its number of
+    non-sky tiles); returns (capacity, [(y0, y1)] per rank) with capacity = the tallest strip, to be passed as strip_height.
+    Greedy prefix split: strip r ends at the first tile row where the running cost reaches (r + 1) / world_size of the total,
+    subject to every strip holding at least `min_rows` rows."""
+    tiles = (height + TILE - 1) // TILE
+    cost = [float(c) for c in tile_row_cost]
+    assert len(cost) == tiles, (len(cost), tiles)
+    min_tiles = max(1, (min_rows + TILE - 1) // TILE)
+    if min_tiles * world_size > tiles:
+        raise ValueError("a %d-row frame cannot be cut into %d strips of at least %d rows" % (height, world_size, min_rows))
+    total = sum(cost) or 1.0
+    bounds, acc, t = [0], 0.0, 0
+    for r in range(world_size - 1):
+        target = total * (r + 1) / world_size
+        lo = bounds[-1] + min_tiles                          # this strip needs min_tiles rows ...
+        hi = tiles - min_tiles * (world_size - 1 - r)        # ... and so does every strip after it
+        while t < lo or (t < hi and acc + 0.5 * cost[t] < target):
+            acc += cost[t]
+            t += 1
+        bounds.append(t)
+    bounds.append(tiles)
+    strips = [(bounds[r] * TILE, min(bounds[r + 1] * TILE, height)) for r in range(world_size)]
+    capacity = max((y1 - y0 + TILE - 1) // TILE * TILE for y0, y1 in strips)
+    return capacity, strips
+
+
+def tile_row_cost_from_viewz(viewz, denoising_range=500000.0):
+    """Cost model of the partition: a 16x16 tile that is entirely beyond the denoising range is skipped by every pass
+    (ClassifyTiles), all other tiles cost about the same.  viewz: (H, W) tensor of IN_VIEWZ; returns one cost per tile row."""
+    h, w = viewz.shape
+    th, tw = (h + TILE - 1) // TILE, (w + TILE - 1) // TILE
+    pad = torch.full((th * TILE, tw * TILE), float("inf"), dtype=viewz.dtype, device=viewz.device)
+    pad[:h, :w] = viewz.abs()
+    live = (pad.view(th, TILE, tw, TILE).amin(dim=(1, 3)) <= denoising_range)
+    return (live.float().sum(dim=1) + 0.02 * tw).tolist()   # a skipped tile still costs its early-out
+
+
 def exchange_ipc_handles(local_handle, group=None):
     """all_gather of the per-rank 64-byte CUDA IPC handles (works on the gloo and the nccl backend)."""
     import torch.distributed as dist
@@ -43,11 +81,13 @@ def exchange_ipc_handles(local_handle, group=None):
 class StripDenoiser(object):
     """The strip of one rank: instance + strip-mode CUDA context.  IN_*/OUT_* strips live in the context's arena."""
 
-    def __init__(self, denoiser, width, height, rank, world_size, device=0, identifier=0, settings=None, halo_rows=None):
+    def __init__(self, denoiser, width, height, rank, world_size, device=0, identifier=0, settings=None, halo_rows=None, partition=None):
+        """partition = (capacity, [(y0, y1)] per rank) from partition_rows_weighted; default: uniform strips."""
         self.denoiser, self.width, self.height, self.identifier = denoiser, width, height, identifier
         self.rank, self.world_size = rank, world_size
         self.device = torch.device("cuda", device)
-        self.strip_height, strips = partition_rows(height, world_size)
+        self.strip_height, strips = partition if partition is not None else partition_rows(height, world_size)
+        self.strip_starts = [y0 for y0, _ in strips] + [height] if partition is not None else None
         self.y0, self.y1 = strips[rank]
         self.instance = nrd.Instance([(identifier, denoiser)])
         self.ctx = nrd.CudaContext(self.instance, width, height, device=device, strip=(self.y0, self.y1), strip_height=self.strip_height,
@@ -59,11 +99,11 @@ class StripDenoiser(object):
     def connect(self, group=None):
         """Multi-process: exchange the IPC handles over torch.distributed and map the peers' arenas."""
         handles = exchange_ipc_handles(self.ctx.ipc_handle(), group)
-        self.ctx.connect_peers(self.rank, self.world_size, ipc_handles=handles)
+        self.ctx.connect_peers(self.rank, self.world_size, ipc_handles=handles, strip_starts=self.strip_starts)
 
     def connect_local(self, all_strips):
         """Single process (tests): every strip is a context of this process on a device that can address the others."""
-        self.ctx.connect_peers(self.rank, self.world_size, arenas=[s.ctx.arena()[0] for s in all_strips])
+        self.ctx.connect_peers(self.rank, self.world_size, arenas=[s.ctx.arena()[0] for s in all_strips], strip_starts=self.strip_starts)
 
     def _stream(self, stream):
         return stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream

@@ -11,22 +11,27 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(denoiser_name, w, h, world, frames, halo, whole_frame_call):
+def _run(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted=False):
     import os
     os.environ["NRD_B200_FORCE_STRIP_KERNELS"] = "1"  # the full-frame reference runs the strip build of the kernels
     try:
-        _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call)
+        _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted)
     finally:
         del os.environ["NRD_B200_FORCE_STRIP_KERNELS"]
 
 
-def _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call):
+def _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted):
     import torch
     from raytracingdenoiser_b200 import harness, nrd, scene, strips
     den = getattr(nrd.Denoiser, denoiser_name)
     mode = harness.radiance_mode(den)
     full = harness.GpuDenoiser(den, w, h)
-    parts = [strips.StripDenoiser(den, w, h, r, world, halo_rows=halo) for r in range(world)]
+    partition = None
+    if weighted:  # cost-balanced, non-uniform strips from the sky mask of the first frame
+        cost = strips.tile_row_cost_from_viewz(scene.Scene(w, h).frame(0, mode)["IN_VIEWZ"])
+        partition = strips.partition_rows_weighted(h, world, cost, min_rows=max(halo, 16))
+        assert len(set(y1 - y0 for y0, y1 in partition[1])) > 1, partition
+    parts = [strips.StripDenoiser(den, w, h, r, world, halo_rows=halo, partition=partition) for r in range(world)]
     for p in parts:
         p.connect_local(parts)
     streams = [torch.cuda.Stream() for _ in parts]
@@ -80,6 +85,12 @@ def test_strips_bit_identical_to_full_frame(denoiser, w, h, world, frames, halo,
     _run(denoiser, w, h, world, frames, halo, whole_frame_call)
 
 
+@pytest.mark.parametrize("denoiser,w,h,world,halo", [("REBLUR_DIFFUSE_SPECULAR", 320, 192, 3, 32), ("RELAX_DIFFUSE_SPECULAR", 320, 180, 2, 16),
+                                                    ("SIGMA_SHADOW", 320, 180, 3, 16)])
+def test_cost_balanced_strips_bit_identical_to_full_frame(denoiser, w, h, world, halo):
+    _run(denoiser, w, h, world, 3, halo, True, weighted=True)
+
+
 def test_strip_context_rejects_foreign_user_pointers_and_bad_geometry():
     import torch
     from raytracingdenoiser_b200 import nrd
@@ -87,7 +98,9 @@ def test_strip_context_rejects_foreign_user_pointers_and_bad_geometry():
     with pytest.raises(nrd.NrdError):
         nrd.CudaContext(inst, 256, 128, strip=(0, 60), strip_height=60)      # not whole tiles
     with pytest.raises(nrd.NrdError):
-        nrd.CudaContext(inst, 256, 128, strip=(16, 80), strip_height=64)     # y0 is not a multiple of the strip height
+        nrd.CudaContext(inst, 256, 128, strip=(24, 88), strip_height=64)     # y0 is not a multiple of 16
+    with pytest.raises(nrd.NrdError):
+        nrd.CudaContext(inst, 256, 128, strip=(0, 96), strip_height=64)      # taller than the reserved strip height
     ctx = nrd.CudaContext(inst, 256, 128, strip=(64, 128), strip_height=64)
     t = torch.zeros((64, 256), dtype=torch.float32, device="cuda")
     with pytest.raises(nrd.NrdError):

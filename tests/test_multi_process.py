@@ -29,6 +29,22 @@ def test_partition_rows_covers_the_frame_with_whole_tiles():
     assert strips.partition_rows(2160, 8) == (272, [(r * 272, min(2160, (r + 1) * 272)) for r in range(8)])
 
 
+def test_partition_rows_weighted_balances_cost_and_respects_minimum():
+    from raytracingdenoiser_b200 import strips
+    tiles = 135                                  # 2160 rows
+    cost = [1.0] * 18 + [60.0] * (tiles - 18)    # 13 % sky on top
+    for n in (2, 4, 8):
+        cap, parts = strips.partition_rows_weighted(2160, n, cost, min_rows=96)
+        assert parts[0][0] == 0 and parts[-1][1] == 2160 and cap % 16 == 0
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert all(y0 % 16 == 0 and y1 - y0 >= 96 and y1 - y0 <= cap for y0, y1 in parts)
+        shares = [sum(cost[y0 // 16:(y1 + 15) // 16]) for y0, y1 in parts]
+        assert max(shares) <= sum(cost) / n + 2 * 60.0   # within a tile row or two of the ideal share
+        assert parts[0][1] - parts[0][0] > parts[-1][1] - parts[-1][0]   # the sky strip is taller
+    with pytest.raises(ValueError):
+        strips.partition_rows_weighted(64, 8, [1.0] * 4)
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     from raytracingdenoiser_b200 import strips
