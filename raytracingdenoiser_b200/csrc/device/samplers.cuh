@@ -40,6 +40,8 @@ struct CatRomSetup
     f4 w;
     float w4, sum;
     int bx, by;
+    float tcx, tcy; // position of the merged inner taps between texel bx and bx+1 (by and by+1)
+    bool bicubic;
 };
 __device__ __forceinline__ CatRomSetup SetupCatRom(f2 samplePos, const float* invSize, f4 customWeights, bool useBicubic)
 {
@@ -75,15 +77,30 @@ __device__ __forceinline__ CatRomSetup SetupCatRom(f2 samplePos, const float* in
     s.u4x *= invSize[0];  s.u4y *= invSize[1];
     s.bx = (int)cx;
     s.by = (int)cy;
+    s.tcx = tcx;
+    s.tcy = tcy;
+    s.bicubic = useBicubic;
     return s;
 }
+// The reference takes 5 hardware-bilinear taps; in software that is 20 texel loads for a footprint of 12 distinct texels.
+// Every texel is loaded once and weighted with (tap weight) x (its bilinear weight): the same polynomial summed in a different
+// order (~1e-6 relative).  Without a valid bicubic footprint: the 2x2 texels with the custom bilinear weights.
 __device__ __forceinline__ f4 ResolveCatRom4(const CatRomSetup& s, const Surf& tex)
 {
-    f4 color = SampleLinear4(tex, s.u01x, s.u01y) * s.w.x;
-    color = color + SampleLinear4(tex, s.u01z, s.u01w) * s.w.y;
-    color = color + SampleLinear4(tex, s.u23x, s.u23y) * s.w.z;
-    color = color + SampleLinear4(tex, s.u23z, s.u23w) * s.w.w;
-    if (s.w4 != 0.0f) color = color + SampleLinear4(tex, s.u4x, s.u4y) * s.w4;
+    const int x0 = s.bx, y0 = s.by;
+    f4 color;
+    if (s.bicubic)
+    {
+        const float ax = 1.0f - s.tcx, bx = s.tcx, ay = 1.0f - s.tcy, by = s.tcy;
+        color = FetchClamped4(tex, x0, y0 - 1) * (s.w.x * ax) + FetchClamped4(tex, x0 + 1, y0 - 1) * (s.w.x * bx);
+        color = color + FetchClamped4(tex, x0 - 1, y0) * (s.w.y * ay) + FetchClamped4(tex, x0 - 1, y0 + 1) * (s.w.y * by);
+        color = color + FetchClamped4(tex, x0, y0) * (s.w.z * ax * ay) + FetchClamped4(tex, x0 + 1, y0) * (s.w.z * bx * ay);
+        color = color + FetchClamped4(tex, x0, y0 + 1) * (s.w.z * ax * by) + FetchClamped4(tex, x0 + 1, y0 + 1) * (s.w.z * bx * by);
+        color = color + FetchClamped4(tex, x0 + 2, y0) * (s.w.w * ay) + FetchClamped4(tex, x0 + 2, y0 + 1) * (s.w.w * by);
+        color = color + FetchClamped4(tex, x0, y0 + 2) * (s.w4 * ax) + FetchClamped4(tex, x0 + 1, y0 + 2) * (s.w4 * bx);
+    }
+    else
+        color = FetchClamped4(tex, x0, y0) * s.w.x + FetchClamped4(tex, x0 + 1, y0) * s.w.y + FetchClamped4(tex, x0, y0 + 1) * s.w.z + FetchClamped4(tex, x0 + 1, y0 + 1) * s.w.w;
     return s.sum < 0.0001f ? mk4(0.0f) : color * (1.0f / s.sum);
 }
 __device__ __forceinline__ float ResolveCatRom1(const CatRomSetup& s, const Surf& tex)
