@@ -201,6 +201,12 @@ __device__ __forceinline__ f4 LoadRGBA16F(const Surf& s, int x, int y) { return 
 __device__ __forceinline__ void StoreRGBA16F(const Surf& s, int x, int y, f4 v) { *TexelPtrRW<uint2>(s, x, y) = PackHalf4(v); }
 __device__ __forceinline__ float LoadR16F(const Surf& s, int x, int y) { return __half2float(__ushort_as_half(__ldg(TexelPtr<unsigned short>(s, x, y)))); }
 __device__ __forceinline__ void StoreR16F(const Surf& s, int x, int y, float v) { *TexelPtrRW<unsigned short>(s, x, y) = __half_as_ushort(__float2half_rn(v)); }
+__device__ __forceinline__ f4 LoadRGBA32F(const Surf& s, int x, int y)
+{
+    float4 v = __ldg(TexelPtr<float4>(s, x, y));
+    return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ void StoreRGBA32F(const Surf& s, int x, int y, f4 v) { *TexelPtrRW<float4>(s, x, y) = make_float4(v.x, v.y, v.z, v.w); }
 __device__ __forceinline__ float LoadR32F(const Surf& s, int x, int y) { return __ldg(TexelPtr<float>(s, x, y)); }
 __device__ __forceinline__ void StoreR32F(const Surf& s, int x, int y, float v) { *TexelPtrRW<float>(s, x, y) = v; }
 __device__ __forceinline__ unsigned LoadU32(const Surf& s, int x, int y) { return __ldg(TexelPtr<unsigned>(s, x, y)); }

@@ -47,5 +47,10 @@ struct PassLaunch
     int rowBegin, rowEnd;  // rows this launch must produce, in the pass's own pixel units
     cudaStream_t stream;
     bool preloadOnly;      // do not launch: only make the driver load the kernel this pass maps to (see NRD_B200_LAUNCH)
+    // Decoded-guide cache (executor-owned RGBA32F surface, not part of the DispatchDesc): {N.x, N.y, N.z, raw viewZ} of the
+    // current frame's IN_NORMAL_ROUGHNESS / IN_VIEWZ.  guideMode 1 = this pass writes it (REBLUR PrePass), 2 = it is valid and
+    // may be read instead of decoding the packed normal at every tap (REBLUR Blur / PostBlur), 0 = not available.
+    Surf guide;
+    int guideMode;
 };
 } // namespace nrdb200_abi

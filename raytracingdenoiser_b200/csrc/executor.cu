@@ -106,6 +106,10 @@ struct NrdCudaContext
     size_t arenaBytes = 0;
     std::vector<Texture> permanent, transient;
     Texture user[(size_t)ResourceType::MAX_NUM];
+    // decoded-guide cache of the REBLUR spatial passes (surf.h PassLaunch::guide): written by PrePass, valid until the next
+    // frame starts (REBLUR ClassifyTiles is the first pass of every frame)
+    Texture guide;
+    bool guideValid = false;
     // strip mode
     uint32_t rank = 0, world = 1;
     int peerSlot = -1;
@@ -438,9 +442,11 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
         t.ptr = (void*)offset;
         offset += (t.pitch * t.allocRows + 255) & ~(size_t)255;
     };
+    DescribeTexture(ctx, Format::RGBA32_SFLOAT, 1, ctx->guide);
     for (Texture& t : ctx->permanent) place(t);
     for (Texture& t : ctx->transient) place(t);
     for (Texture& t : ctx->user) place(t);
+    place(ctx->guide);
     ctx->arenaBytes = offset;
     cudaError_t e = cudaMalloc((void**)&ctx->arena, ctx->arenaBytes);
     if (e != cudaSuccess)
@@ -455,6 +461,7 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
     for (Texture& t : ctx->permanent) rebase(t);
     for (Texture& t : ctx->transient) rebase(t);
     for (Texture& t : ctx->user) rebase(t);
+    rebase(ctx->guide);
     *out = ctx;
     return Result::SUCCESS;
 }
@@ -623,6 +630,12 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         if (!t) return Fail(ctx, Result::INVALID_ARGUMENT, std::string("unbound resource ") + GetResourceTypeString(r.type) + " for " + d->name);
         p.tex[i] = ToSurf(ctx, *t);
     }
+    // decoded-guide cache: PrePass fills it, Blur / PostBlur of the same frame read it
+    const bool isReblurPrePass = !strncmp(shader, "REBLUR_", 7) && strstr(shader, "_PrePass.cs") != nullptr;
+    const bool readsGuide = !strncmp(shader, "REBLUR_", 7) && (strstr(shader, "_Blur.cs") != nullptr || strstr(shader, "_PostBlur") != nullptr);
+    if (!strcmp(shader, "REBLUR_ClassifyTiles.cs")) ctx->guideValid = false; // a new frame: the guides changed
+    p.guide = ToSurf(ctx, ctx->guide);
+    p.guideMode = isReblurPrePass ? 1 : (readsGuide && ctx->guideValid ? 2 : 0);
     // rows to produce: the context's strip (the full frame on one GPU)
     p.rowBegin = ctx->desc.stripY0;
     p.rowEnd = ctx->desc.stripY1;
@@ -642,12 +655,14 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     if (e == cudaErrorNotSupported) return Fail(ctx, Result::UNSUPPORTED, std::string("no CUDA kernel for pass ") + shader);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string(shader) + ": " + cudaGetErrorString(e));
     g_launchCount.fetch_add(1, std::memory_order_relaxed);
-    if (strncmp(shader, "Clear_", 6) != 0 && pushMask) // clears zero the ghost rows locally
+    if (isReblurPrePass) ctx->guideValid = true;
+    if (strncmp(shader, "Clear_", 6) != 0 && (pushMask || isReblurPrePass)) // clears zero the ghost rows locally
     {
-        const Texture* list[32];
+        const Texture* list[33];
         uint32_t n = 0;
         for (uint32_t i = 0; i < d->resourcesNum; i++)
             if ((pushMask >> i) & 1u) list[n++] = Resolve(ctx, d->resources[i].type, d->resources[i].indexInPool);
+        if (isReblurPrePass) list[n++] = &ctx->guide; // Blur / PostBlur of the neighbours read its boundary rows
         Result r = PushGhosts(ctx, list, n, p.stream);
         if (r != Result::SUCCESS) return r;
     }
