@@ -372,8 +372,8 @@ NRD_API void nrdCudaDestroyContext(NrdCudaContext* context);
 NRD_API nrd::Result nrdCudaSetUserTexture(NrdCudaContext* context, uint32_t resourceType, void* devicePtr, size_t pitchBytes, uint32_t format);
 // Looks a texture up exactly like a DispatchDesc resource would be resolved.
 NRD_API nrd::Result nrdCudaGetTexture(NrdCudaContext* context, uint32_t resourceType, uint32_t indexInPool, NrdCudaTextureInfo* info);
-// Launches the kernel for one DispatchDesc on `stream` (cudaStream_t).  Restricts the work to rows [rowBegin,rowEnd)
-// when rowEnd > rowBegin (used for halo recomputation); pass 0,0 for the context's whole strip+halo range.
+// Launches the kernel for one DispatchDesc on `stream` (cudaStream_t); the kernel produces the rows the context owns.  In strip
+// mode it is followed by the ghost-row refresh of the textures the pass wrote and by one inter-GPU barrier (same stream).
 NRD_API nrd::Result nrdCudaExecuteDispatch(NrdCudaContext* context, const nrd::DispatchDesc* dispatch, void* stream);
 // GetComputeDispatches + ExecuteDispatch for each, in order.  Returns the number of kernels launched in *launches.
 NRD_API nrd::Result nrdCudaDenoise(NrdCudaContext* context, const nrd::Identifier* identifiers, uint32_t identifiersNum, void* stream, uint32_t* launches);
