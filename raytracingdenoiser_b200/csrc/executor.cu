@@ -630,6 +630,13 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         if (!t) return Fail(ctx, Result::INVALID_ARGUMENT, std::string("unbound resource ") + GetResourceTypeString(r.type) + " for " + d->name);
         p.tex[i] = ToSurf(ctx, *t);
     }
+    // checkerboarded inputs bind the same passes (no separate shader name), so they have to be rejected here, loudly
+    if (!strncmp(shader, "REBLUR_", 7) && strcmp(shader, "REBLUR_ClassifyTiles.cs") != 0 && d->constantBufferData && d->constantBufferDataSize >= sizeof(ReblurConstants))
+    {
+        ReblurConstants rc;
+        memcpy(&rc, d->constantBufferData, sizeof(rc));
+        if (rc.gDiffCheckerboard != 2 || rc.gSpecCheckerboard != 2) return Fail(ctx, Result::UNSUPPORTED, "REBLUR checkerboard modes are not implemented by the CUDA executor");
+    }
     // decoded-guide cache: PrePass fills it, Blur / PostBlur of the same frame read it
     const bool isReblurPrePass = !strncmp(shader, "REBLUR_", 7) && strstr(shader, "_PrePass.cs") != nullptr;
     const bool readsGuide = !strncmp(shader, "REBLUR_", 7) && (strstr(shader, "_Blur.cs") != nullptr || strstr(shader, "_PostBlur") != nullptr);
