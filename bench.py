@@ -92,6 +92,8 @@ def run_cpu_reference(width, height, frames, steps, warmup):
     """Times the oracle chain (all host threads) on `frames`; returns (Mpx/s, ms per step, threads)."""
     import oracle_runner as orr
     from raytracingdenoiser_b200 import harness, nrd
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    orr.oracle_lib().oracle_set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cpu = orr.CpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, width, height)
     host = [{k: (v.cpu() if hasattr(v, "cpu") else v) for k, v in fr.items()} for fr in frames]
     times = []

@@ -18,6 +18,7 @@ struct OracleTexture
 // Returns 0 on success, -1 unknown pass, -2 bad constants.
 int oracle_dispatch(const char* shaderName, const void* constants, int constantsSize, const OracleTexture* textures, int texturesNum, int gridW, int gridH);
 int oracle_num_threads();
+void oracle_set_num_threads(int n);
 }
 
 int oracle_reblur_dispatch(const char* shaderName, const void* constants, int constantsSize, hlsl::Tex* tex, int texNum, int gridW, int gridH);

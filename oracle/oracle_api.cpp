@@ -37,3 +37,5 @@ extern "C" int oracle_dispatch(const char* shaderName, const void* constants, in
 }
 
 extern "C" int oracle_num_threads() { return omp_get_max_threads(); }
+// launchers such as torchrun export OMP_NUM_THREADS=1; the timed CPU baseline asks for all host cores explicitly
+extern "C" void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -32,6 +32,8 @@ def oracle_lib():
         _oracle.oracle_dispatch.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(OracleTexture), C.c_int, C.c_int, C.c_int]
         _oracle.oracle_dispatch.restype = C.c_int
         _oracle.oracle_num_threads.restype = C.c_int
+        _oracle.oracle_set_num_threads.argtypes = [C.c_int]
+        _oracle.oracle_set_num_threads.restype = None
     return _oracle
 
 
