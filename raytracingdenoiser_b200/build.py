@@ -103,7 +103,14 @@ def build_oracle(force=False):
 
 
 def build_all(force=False):
-    return build_product(force), build_oracle(force)
+    """Builds whatever is out of date.  Serialised across processes with a file lock: every rank of a torchrun job calls this."""
+    import fcntl
+    with open(os.path.join(PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build_product(force), build_oracle(force)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":
