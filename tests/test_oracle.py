@@ -95,3 +95,98 @@ def test_scene_encodings():
     n /= np.linalg.norm(n, axis=-1, keepdims=True)
     ground = (z < 5e5) & (np.abs(n[..., 1] - 1.0) < 0.01)
     assert ground.mean() > 0.1
+
+
+def _flat_frame(w, h, radiance_mode, value=(1.0, 0.5, 0.25)):
+    """Wall facing a static camera at z = 10, zero motion, constant radiance and hit distance (same as tests/test_gpu_properties.py)."""
+    import torch
+    z = torch.full((h, w), 10.0)
+    n = torch.zeros((h, w, 3))
+    n[..., 2] = -1.0
+    rough = torch.full((h, w), 0.5)
+    rad = torch.tensor(value).expand(h, w, 3)
+    hit = torch.full((h, w), 3.0)
+    sky = torch.zeros((h, w), dtype=torch.bool)
+    fr = {"IN_VIEWZ": z, "IN_NORMAL_ROUGHNESS": scene.pack_normal_roughness(n, rough, torch.zeros((h, w))), "IN_MV": torch.zeros((h, w, 4), dtype=torch.float16),
+          "IN_PENUMBRA": torch.full((h, w), 65504.0, dtype=torch.float16)}
+    if radiance_mode == "reblur":
+        fr["IN_DIFF_RADIANCE_HITDIST"] = scene.pack_reblur(rad, hit, z, torch.ones_like(rough), sky)
+        fr["IN_SPEC_RADIANCE_HITDIST"] = scene.pack_reblur(rad, hit, z, rough, sky)
+    else:
+        fr["IN_DIFF_RADIANCE_HITDIST"] = scene.pack_relax(rad, hit, sky)
+        fr["IN_SPEC_RADIANCE_HITDIST"] = scene.pack_relax(rad, hit, sky)
+    view = np.eye(4, dtype=np.float32)
+    fr.update({"viewToClip": scene.perspective_lh(60.0, w / float(h)), "worldToView": view, "worldToViewPrev": view})
+    return fr
+
+
+def _run_oracle(den, w, h, frames_fn, n):
+    cpu = orr.CpuDenoiser(den, w, h)
+    for f in range(n):
+        fr = frames_fn(f)
+        cpu.set_inputs(fr)
+        cpu.denoise(harness.make_common_settings(fr, w, h, f))
+        if f == 0:
+            cpu.set_inputs(fr)
+    return cpu, fr
+
+
+@pytest.mark.parametrize("denoiser", ["REBLUR_DIFFUSE_SPECULAR", "RELAX_DIFFUSE_SPECULAR"])
+def test_constant_signal_is_a_fixed_point_of_the_oracle(denoiser):
+    """Every weight of every pass is a convex combination: a constant signal on a flat surface must come out unchanged."""
+    den = getattr(nrd.Denoiser, denoiser)
+    w, h = 96, 64
+    fr0 = _flat_frame(w, h, harness.radiance_mode(den))
+    cpu, fr = _run_oracle(den, w, h, lambda f: fr0, 4)
+    for sig in ("DIFF", "SPEC"):
+        exp = fr["IN_%s_RADIANCE_HITDIST" % sig].float().numpy()
+        got = cpu.user["OUT_%s_RADIANCE_HITDIST" % sig].astype(np.float32)
+        assert np.isfinite(got).all()
+        assert np.abs(got[..., :3] - exp[..., :3]).max() <= 1e-3, (denoiser, sig)
+
+
+@pytest.mark.parametrize("penumbra,expected", [(65504.0, 255), (0.0, 0)])
+def test_sigma_oracle_passes_uniform_visibility_through(penumbra, expected):
+    import torch
+    w, h = 96, 64
+    fr0 = _flat_frame(w, h, "reblur")
+    fr0["IN_PENUMBRA"] = torch.full((h, w), penumbra, dtype=torch.float16)
+    cpu, _ = _run_oracle(nrd.Denoiser.SIGMA_SHADOW, w, h, lambda f: fr0, 3)
+    out = cpu.user["OUT_SHADOW_TRANSLUCENCY"]
+    assert int(out.min()) == expected and int(out.max()) == expected
+
+
+def test_oracle_result_does_not_depend_on_the_thread_count():
+    """The OpenMP loops write disjoint pixels: one thread and all threads must agree bit for bit (no races, no reductions)."""
+    lib = orr.oracle_lib()
+    threads = lib.oracle_num_threads()
+    w, h = 80, 48
+    outs = []
+    try:
+        for n in (1, max(threads, 2)):
+            lib.oracle_set_num_threads(n)
+            sc = scene.Scene(w, h)
+            cpu, _ = _run_oracle(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, w, h, lambda f: sc.frame(f, "relax"), 3)
+            outs.append({k: v.copy() for k, v in cpu.user.items() if k.startswith("OUT_")})
+    finally:
+        lib.oracle_set_num_threads(threads)
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k].view(np.uint16), outs[1][k].view(np.uint16)), k
+
+
+def test_relax_chain_properties():
+    W, H, N = 160, 90, 6
+    sc = scene.Scene(W, H)
+    cpu, fr = _run_oracle(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, W, H, lambda f: sc.frame(f, "relax"), N)
+    z = cpu.user["IN_VIEWZ"]
+    sky = z > 5e5
+    out = cpu.user["OUT_DIFF_RADIANCE_HITDIST"].astype(np.float32)
+    noisy = cpu.user["IN_DIFF_RADIANCE_HITDIST"].astype(np.float32)
+    assert not np.isnan(out).any()
+    lum = lambda a: 0.2126 * a[..., 0] + 0.7152 * a[..., 1] + 0.0722 * a[..., 2]
+    m_in, m_out = lum(noisy)[~sky].mean(), lum(out)[~sky].mean()
+    assert abs(m_in - m_out) / m_in < 0.08, (m_in, m_out)
+    hf = lambda a: np.abs(np.diff(lum(a), axis=1))[~sky[:, 1:] & ~sky[:, :-1]].mean()
+    assert hf(out) < 0.4 * hf(noisy)
+    # PREV_VIEWZ written by the first A-trous pass is the current viewZ everywhere (also on sky pixels)
+    assert np.array_equal(cpu.permanent[9], z)
