@@ -239,3 +239,61 @@ def test_right_handed_input_is_converted():
     a = inst_l.get_compute_dispatches([0])[-1].constants
     b = inst_r.get_compute_dispatches([0])[-1].constants
     np.testing.assert_allclose(np.frombuffer(a[:544], np.float32), np.frombuffer(b[:544], np.float32), atol=1e-6)
+
+
+def test_relax_constants_against_numpy_restatement():
+    """RELAX_SHARED_CONSTANTS (RELAX_Config.hlsli:21-99) as filled by Relax.cpp:60-180, restated independently."""
+    inst = nrd.Instance([(0, nrd.Denoiser.RELAX_DIFFUSE_SPECULAR)])
+    inst.set_common_settings(common(0)[0])
+    inst.get_compute_dispatches([0])
+    f = 5
+    cs, P, V, Vp = common(f, yaw=0.03, prev_yaw=0.01, eye=(0.2, 1.7, -3.8), prev_eye=(0.1, 1.7, -4.0))
+    inst.set_common_settings(cs)
+    ds = inst.get_compute_dispatches([0])
+    c = [d for d in ds if d.shaderFileName == "RELAX_DiffuseSpecular_TemporalAccumulation.cs"][0].constants
+    assert len(c) == 704
+    fl = lambda off, n: np.array(struct.unpack_from("%df" % n, c, off), dtype=np.float64)
+    mat = lambda off: fl(off, 16).reshape(4, 4).T
+
+    P64, V64, Vp64 = P.astype(np.float64), V.astype(np.float64), Vp.astype(np.float64)
+    v2w, v2w_prev = np.linalg.inv(V64), np.linalg.inv(Vp64)
+    delta = v2w_prev[:3, 3] - v2w[:3, 3]
+    v2w_rel = v2w.copy(); v2w_rel[:3, 3] = 0
+    v2w_prev_rel = v2w_prev.copy(); v2w_prev_rel[:3, 3] = delta
+    w2v_rel, w2v_prev_rel = np.linalg.inv(v2w_rel), np.linalg.inv(v2w_prev_rel)
+    np.testing.assert_allclose(mat(0), P64 @ w2v_rel, atol=2e-6)             # gWorldToClip
+    np.testing.assert_allclose(mat(64), P64 @ w2v_prev_rel, atol=4e-6)       # gWorldToClipPrev
+    np.testing.assert_allclose(mat(128), w2v_prev_rel, atol=2e-6)            # gWorldToViewPrev
+    np.testing.assert_allclose(mat(192), np.eye(4), atol=0)                  # gWorldPrevToWorld
+    np.testing.assert_allclose(fl(256, 4), _rotator(_weyl(0.5, f) * math.pi / 2), atol=2e-6)   # gRotatorPre
+    # world-space frustum axes: pixel ray = forward + right * (2u - 1) - up * (2v - 1), forward.z (view) = 1
+    t = math.tan(math.radians(30.0))
+    np.testing.assert_allclose(fl(272, 4), np.append(w2v_rel[0, :3] * t * W / H, 0.0), atol=2e-6)        # gFrustumRight
+    np.testing.assert_allclose(fl(288, 4), np.append(w2v_rel[1, :3] * t, 0.0), atol=2e-6)                # gFrustumUp
+    np.testing.assert_allclose(fl(304, 4), np.append(v2w_rel[:3, 2], 0.0), atol=2e-6)                    # gFrustumForward (symmetric projection)
+    np.testing.assert_allclose(fl(320, 4), np.append(w2v_prev_rel[0, :3] * t * W / H, 0.0), atol=2e-6)   # gPrevFrustumRight
+    np.testing.assert_allclose(fl(336, 4), np.append(w2v_prev_rel[1, :3] * t, 0.0), atol=2e-6)           # gPrevFrustumUp
+    np.testing.assert_allclose(fl(352, 4), np.append(v2w_prev_rel[:3, 2], 0.0), atol=2e-6)               # gPrevFrustumForward
+    np.testing.assert_allclose(fl(368, 4), np.append(delta, 0.0), atol=2e-6)                             # gCameraDelta
+    np.testing.assert_allclose(fl(384, 4), [1.0 / W, 1.0 / H, 1.0, 0.0], rtol=1e-6)                      # gMvScale
+    np.testing.assert_allclose(fl(400, 14), [0, 0, 1, 1, 0, 0, 1.0 / W, 1.0 / H, W, H, 1.0 / W, 1.0 / H, W, H], rtol=1e-6)   # jitter .. gRectSizePrev
+    np.testing.assert_allclose(fl(456, 2), [1.0 / W, 1.0 / H], rtol=1e-6)                                # gResourceSizeInvPrev
+    assert struct.unpack_from("4I2i", c, 464) == (9999, 9999, 0, 0, W, H)                                    # gPrintfAt, gRectOrigin, gRectSize
+    s = fl(488, 47)
+    np.testing.assert_allclose(s[0:4], [30.0, 6.0, 30.0, 6.0])                                           # accumulated frame limits
+    np.testing.assert_allclose(s[4:6], [0.01 + 1.0 / H, 0.05 + 1.0 / H], rtol=1e-6)                      # disocclusion thresholds (+ (1 + jitterDelta) / rectH)
+    np.testing.assert_allclose(s[6:9], [999.0, 999.0, 80e-6], rtol=1e-6)                                  # material ids, strand thickness
+    np.testing.assert_allclose(s[9:16], [0.15, 0.0, 0.0, 30.0, 50.0, 0.003, 0.5], rtol=1e-6)             # roughnessFraction .. gLobeAngleFraction
+    np.testing.assert_allclose(s[16], math.radians(0.15), rtol=1e-6)                                     # gSpecLobeAngleSlack is converted to radians
+    np.testing.assert_allclose(s[17:25], [8.0, 1.0, 0.3, 2.0, 0.3, 0.5, 4.5, 0.5], rtol=1e-6)            # edge stopping, colour box, anti-lag
+    np.testing.assert_allclose(s[25:28], [500000.0, 1.0, 2.0], rtol=1e-6)                                # denoising range, phi luminance
+    assert np.isinf(s[28]) and np.isinf(s[29])                                                           # -log(saturate(minLuminanceWeight = 0))
+    np.testing.assert_allclose(s[30], 1.0)                                # gLuminanceEdgeStoppingRelaxation takes roughnessEdgeStoppingRelaxation (Relax.cpp:154)
+    np.testing.assert_allclose(s[34:36], [0.0, 0.0])                                                     # gDebug, gOrthoMode
+    np.testing.assert_allclose(s[36], t / (0.5 * H), rtol=1e-6)                                          # gUnproject
+    np.testing.assert_allclose(s[37], 16.66 / 16.6667, rtol=1e-5)                                        # gFramerateScale
+    np.testing.assert_allclose(s[39:47], [0.0, 4.0, 14.0, 3.0, 1.0, 0.2, 4.0, 4.0], rtol=1e-6)           # jitterDelta .. min materials
+    assert struct.unpack_from("7I", c, 676) == (1, f, 2, 2, 0, 0, 0)
+    # the A-trous passes append gStepSize / gIsLastPass: 1, 2, 4, 8, 16 with the last one flagged
+    steps = [struct.unpack_from("2I", d.constants, 704) for d in ds if "Atrous" in d.shaderFileName]
+    assert steps == [(1, 0), (2, 0), (4, 0), (8, 0), (16, 1)]
