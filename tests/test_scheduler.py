@@ -297,3 +297,49 @@ def test_relax_constants_against_numpy_restatement():
     # the A-trous passes append gStepSize / gIsLastPass: 1, 2, 4, 8, 16 with the last one flagged
     steps = [struct.unpack_from("2I", d.constants, 704) for d in ds if "Atrous" in d.shaderFileName]
     assert steps == [(1, 0), (2, 0), (4, 0), (8, 0), (16, 1)]
+
+
+def test_sigma_constants_against_numpy_restatement():
+    """SIGMA_SHARED_CONSTANTS as filled by Sigma.cpp:92-144, restated independently."""
+    inst = nrd.Instance([(0, nrd.Denoiser.SIGMA_SHADOW)])
+    s = nrd.SigmaSettings()
+    light = np.array([0.3, 0.8, -0.5]) / np.linalg.norm([0.3, 0.8, -0.5])
+    for i in range(3):
+        s.lightDirection[i] = float(light[i])
+    inst.set_denoiser_settings(0, s)
+    inst.set_common_settings(common(0)[0])
+    inst.get_compute_dispatches([0])
+    f = 3
+    cs, P, V, Vp = common(f, yaw=0.04, prev_yaw=0.02, eye=(0.3, 1.7, -3.7), prev_eye=(0.2, 1.7, -3.9))
+    inst.set_common_settings(cs)
+    ds = inst.get_compute_dispatches([0])
+    c = [d for d in ds if d.shaderFileName == "SIGMA_Shadow_Blur.cs"][0].constants
+    assert len(c) in (516, 528)
+    fl = lambda off, n: np.array(struct.unpack_from("%df" % n, c, off), dtype=np.float64)
+    mat = lambda off: fl(off, 16).reshape(4, 4).T
+    P64, V64, Vp64 = P.astype(np.float64), V.astype(np.float64), Vp.astype(np.float64)
+    v2w, v2w_prev = np.linalg.inv(V64), np.linalg.inv(Vp64)
+    delta = v2w_prev[:3, 3] - v2w[:3, 3]
+    v2w_rel = v2w.copy(); v2w_rel[:3, 3] = 0
+    v2w_prev_rel = v2w_prev.copy(); v2w_prev_rel[:3, 3] = delta
+    w2v_rel, w2v_prev_rel = np.linalg.inv(v2w_rel), np.linalg.inv(v2w_prev_rel)
+    np.testing.assert_allclose(mat(0), w2v_rel, atol=2e-6)                    # gWorldToView (camera relative)
+    np.testing.assert_allclose(mat(64), P64, atol=1e-7)                       # gViewToClip
+    np.testing.assert_allclose(mat(128), P64 @ w2v_prev_rel, atol=4e-6)       # gWorldToClipPrev
+    np.testing.assert_allclose(mat(192), w2v_prev_rel, atol=2e-6)             # gWorldToViewPrev
+    bayer = lambda n: (n & 15) / 16.0
+    np.testing.assert_allclose(fl(256, 4), _combine(_rotator(_weyl(0.0, 2 * f) * math.pi / 2), _rotator(bayer(2 * f) * 2 * math.pi)), atol=2e-6)       # gRotator
+    np.testing.assert_allclose(fl(272, 4), _combine(_rotator(_weyl(0.0, 2 * f + 1) * math.pi / 2), _rotator(bayer(2 * f + 1) * 2 * math.pi)), atol=2e-6)  # gRotatorPost
+    np.testing.assert_allclose(fl(288, 3), -v2w_rel[:3, 2], atol=2e-6)         # gViewVectorWorld
+    np.testing.assert_allclose(fl(304, 4), np.append(w2v_rel[:3, :3] @ light, 0.0), atol=2e-6)   # gLightDirectionView
+    t = math.tan(math.radians(30.0))
+    np.testing.assert_allclose(fl(320, 4), [-t * W / H, t, 2 * t * W / H, -2 * t], rtol=1e-6)     # gFrustum
+    np.testing.assert_allclose(fl(336, 4), [-t * W / H, t, 2 * t * W / H, -2 * t], rtol=1e-6)     # gFrustumPrev
+    np.testing.assert_allclose(fl(352, 3), delta, atol=2e-6)                   # gCameraDelta
+    np.testing.assert_allclose(fl(368, 4), [1.0 / W, 1.0 / H, 1.0, 0.0], rtol=1e-6)               # gMvScale
+    np.testing.assert_allclose(fl(384, 14), [1.0 / W, 1.0 / H, 1.0 / W, 1.0 / H, W, H, 1.0 / W, 1.0 / H, W, H, 1, 1, 0, 0], rtol=1e-6)
+    assert struct.unpack_from("4I4i", c, 440) == (9999, 9999, 0, 0, W - 1, H - 1, (W + 15) // 16 - 1, (H + 15) // 16 - 1)
+    sc = fl(472, 9)
+    unproject = t / (0.5 * H)
+    np.testing.assert_allclose(sc, [0.0, unproject, 500000.0, 0.02, 5.0 / 6.0, 0.0, 0.0, 1.0, H * unproject], rtol=1e-6)
+    assert struct.unpack_from("2I", c, 508) == (f, 0)
