@@ -157,3 +157,56 @@ def compare(a, b, fmt, rel=1e-3, abs_tol=1e-4, layout=None):
     if ok.ndim == 3:
         ok = ok.all(axis=2)
     return float(ok.mean()), float(d.max())
+
+
+def _excess_map(a, b, fmt, rel, abs_tol, layout=None):
+    """Per-texel error in units of the tolerance (max over channels), and a mask of non-finite kernel values where the oracle is finite."""
+    fmt = nrd.Format(fmt)
+    if layout == "reblur_data2":
+        a64, b64 = a.astype(np.int64), b.astype(np.int64)
+        ex = np.where((a64 & 0xFF) == (b64 & 0xFF), 0.0, 1e9)
+        ex = np.maximum(ex, np.abs(((a64 >> 8) & 0xFF) - ((b64 >> 8) & 0xFF)).astype(np.float64))
+        ca = ((a64 >> 16) & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+        cb = ((b64 >> 16) & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+        bad = np.isfinite(ca) & ~np.isfinite(cb)
+        ca, cb = np.nan_to_num(ca, nan=1e30, posinf=1e30, neginf=-1e30), np.nan_to_num(cb, nan=1e30, posinf=1e30, neginf=-1e30)
+        ex = np.maximum(ex, np.abs(ca - cb) / (2e-3 * np.maximum(np.abs(ca), np.abs(cb)) + abs_tol))
+        return ex, bad
+    if fmt in (nrd.Format.RGBA16_SFLOAT, nrd.Format.R16_SFLOAT, nrd.Format.R32_SFLOAT):
+        x, y = a.astype(np.float64), b.astype(np.float64)
+        bad = np.isfinite(x) & ~np.isfinite(y)
+        x = np.nan_to_num(x, nan=1e30, posinf=1e30, neginf=-1e30)
+        y = np.nan_to_num(y, nan=1e30, posinf=1e30, neginf=-1e30)
+        ex = np.abs(x - y) / (rel * np.maximum(np.abs(x), np.abs(y)) + abs_tol)
+        if ex.ndim == 3:
+            ex, bad = ex.max(axis=2), bad.any(axis=2)
+        return ex, bad
+    ai, bi = a.astype(np.int64), b.astype(np.int64)
+    if fmt == nrd.Format.R10_G10_B10_A2_UNORM:
+        fields = ((0, 1023), (10, 1023), (20, 1023), (30, 3))
+    elif fmt == nrd.Format.R16_UINT:
+        fields = ((0, 63), (6, 63), (12, 15))
+    elif fmt == nrd.Format.R32_UINT:
+        return np.where(ai == bi, 0.0, 1e9), np.zeros(a.shape[:2], dtype=bool)
+    else:
+        d = np.abs(ai - bi).astype(np.float64)
+        return (d.max(axis=2) if d.ndim == 3 else d), np.zeros(a.shape[:2], dtype=bool)
+    d = np.zeros(a.shape, dtype=np.float64)
+    for shift, mask in fields:
+        d = np.maximum(d, np.abs(((ai >> shift) & mask) - ((bi >> shift) & mask)))
+    return d, np.zeros(a.shape[:2], dtype=bool)
+
+
+def outliers(a, b, fmt, rel=1e-3, abs_tol=1e-4, max_excess=10.0, layout=None, list_limit=16):
+    """Outlier gate of tests/parity.py: (number of texels further off than max_excess x tolerance, [[x, y, excess], ...] of the
+    worst `list_limit`, number of texels that are non-finite in `b` but finite in `a`).  LSB-compared formats count a texel
+    as an outlier when it is more than max_excess LSBs off."""
+    ex, bad = _excess_map(a, b, fmt, rel, abs_tol, layout)
+    mask = ex > max_excess
+    n = int(mask.sum())
+    where = []
+    if n:
+        ys, xs = np.nonzero(mask)
+        order = np.argsort(-ex[ys, xs])[:list_limit]
+        where = [[int(xs[i]), int(ys[i]), float(min(ex[ys[i], xs[i]], 1e9))] for i in order]
+    return n, where, int(bad.sum())

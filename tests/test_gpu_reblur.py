@@ -25,9 +25,7 @@ def test_reblur_per_pass_parity(denoiser_name, width, height, frames):
     sbs = parity.SideBySide(getattr(nrd.Denoiser, denoiser_name), width, height)
     report = sbs.run_per_pass(frames)
     _dump("parity_%s.json" % denoiser_name, report)
-    bad = sbs.failures()
-    assert not bad, "per-pass parity failures (fraction within 1e-3 rel + 1e-4 abs < %.4f):\n%s" % (
-        parity.MIN_FRACTION, "\n".join("f%d %s %s %s frac=%.5f worst=%.1f" % (r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["worst"]) for r in bad[:40]))
+    assert not sbs.failures(), sbs.describe_failures()
 
 
 def test_reblur_spatial_only_config():
@@ -40,7 +38,7 @@ def test_reblur_spatial_only_config():
     names = {r["shader"] for r in report}
     assert "REBLUR_Diffuse_PostBlur_NoTemporalStabilization.cs" in names and "REBLUR_Diffuse_PrePass.cs" not in names
     _dump("parity_spatial_only.json", report)
-    assert not sbs.failures(), sbs.failures()[:10]
+    assert not sbs.failures(), sbs.describe_failures()
 
 
 def test_reblur_sequence_parity():

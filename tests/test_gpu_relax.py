@@ -21,8 +21,7 @@ def test_relax_per_pass_parity(width, height, frames):
     sbs = parity.SideBySide(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, width, height)
     report = sbs.run_per_pass(frames)
     _dump("parity_RELAX_%dx%d.json" % (width, height), report)
-    bad = sbs.failures()
-    assert not bad, "\n".join("f%d %s %s %s frac=%.5f worst=%.1f" % (r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["worst"]) for r in bad[:40])
+    assert not sbs.failures(), sbs.describe_failures()
 
 
 def test_relax_settings_variants_per_pass():
@@ -38,8 +37,7 @@ def test_relax_settings_variants_per_pass():
     sbs = parity.SideBySide(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, 320, 180, settings=s)
     report = sbs.run_per_pass(4)
     _dump("parity_RELAX_variant.json", report)
-    bad = sbs.failures()
-    assert not bad, "\n".join("f%d %s %s %s frac=%.5f worst=%.1f" % (r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["worst"]) for r in bad[:40])
+    assert not sbs.failures(), sbs.describe_failures()
 
 
 def test_relax_sequence_parity():

@@ -21,8 +21,7 @@ def test_sigma_per_pass_parity(width, height, frames):
     sbs = parity.SideBySide(nrd.Denoiser.SIGMA_SHADOW, width, height)
     report = sbs.run_per_pass(frames)
     _dump("parity_SIGMA_%dx%d.json" % (width, height), report)
-    bad = sbs.failures()
-    assert not bad, "\n".join("f%d %s %s %s frac=%.5f worst=%.1f" % (r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["worst"]) for r in bad[:40])
+    assert not sbs.failures(), sbs.describe_failures()
 
 
 def test_sigma_sequence_parity():
