@@ -424,9 +424,9 @@ void TemporalStabilization(const Pass& P, Tex* t, int gridW, int gridH)
 
 int sigma_dispatch_impl(const char* shaderName, const void* constants, int constantsSize, Tex* tex, int gridW, int gridH)
 {
-    if (constantsSize < (int)sizeof(CB)) return -2;
-    CB cb;
-    memcpy(&cb, constants, sizeof(CB));
+    if (constantsSize < 516) return -2; // sizeof() of the reference's C++ struct; CB is padded to whole 16-byte registers
+    CB cb{};
+    memcpy(&cb, constants, constantsSize < (int)sizeof(CB) ? constantsSize : (int)sizeof(CB));
     Pass P(cb);
     if (!strcmp(shaderName, "SIGMA_Shadow_ClassifyTiles.cs")) ClassifyTiles(P, tex, gridW, gridH);
     else if (!strcmp(shaderName, "SIGMA_SmoothTiles.cs")) SmoothTiles(P, tex, gridW, gridH);

@@ -102,12 +102,28 @@ def build_oracle(force=False):
     return ORACLE_LIB
 
 
+def build_reference_host(force=False):
+    """oracle/_ref/libnrd_ref.so: the reference's own host code (pass scheduling) compiled from /root/reference by
+    oracle/Makefile.ref -- test infrastructure, only buildable where the reference tree is mounted (this container); the GPU box
+    uses the prebuilt file that travelled with the snapshot."""
+    if not os.path.isdir("/root/reference/Source"):
+        return None
+    if force:
+        import shutil
+        shutil.rmtree(os.path.join(ORACLE_DIR, "_ref"), ignore_errors=True)
+    r = subprocess.run(["make", "-s", "-f", "oracle/Makefile.ref"], cwd=ROOT, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference host build failed:\n%s%s" % (r.stdout, r.stderr))
+    return os.path.join(ORACLE_DIR, "_ref", "libnrd_ref.so")
+
+
 def build_all(force=False):
     """Builds whatever is out of date.  Serialised across processes with a file lock: every rank of a torchrun job calls this."""
     import fcntl
     with open(os.path.join(PKG, ".build.lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
+            build_reference_host(force)
             return build_product(force), build_oracle(force)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)

@@ -233,10 +233,11 @@ void Scheduler::AddReblur(DenoiserSlot& slot, bool hasDiff, bool hasSpec)
 
     BeginPass(denoiserName, "Validation");
     In(R(ResourceType::IN_NORMAL_ROUGHNESS)); In(R(ResourceType::IN_VIEWZ)); In(R(ResourceType::IN_MV)); In(T_DATA1); In(T_DATA2);
-    In(hasDiff ? IN_DIFF : kDummy);
-    In(hasSpec ? IN_SPEC : kDummy);
+    // a one-signal denoiser binds its only signal in both slots (Denoisers/Reblur_Diffuse.hpp, Reblur_Specular.hpp: REBLUR_ADD_VALIDATION_DISPATCH)
+    In(hasDiff ? IN_DIFF : IN_SPEC);
+    In(hasSpec ? IN_SPEC : IN_DIFF);
     Out(R(ResourceType::OUT_VALIDATION));
-    Emit("REBLUR_Validation.cs", 8, 16, cb + 16, kIgnoreRect);
+    Emit("REBLUR_Validation.cs", 8, 16, cb + 8, kIgnoreRect); // + gHasDiffuse, gHasSpecular (840 = sizeof of the reference struct)
 }
 
 void Scheduler::UpdateReblur(const DenoiserSlot& slot)

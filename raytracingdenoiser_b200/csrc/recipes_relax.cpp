@@ -42,7 +42,7 @@ void Scheduler::AddRelaxDiffuseSpecular(DenoiserSlot& slot)
     slot.settingsSize = sizeof(RelaxSettings);
     const char* dn = "RELAX_DiffuseSpecular";
     const uint32_t cb = kSharedSize;
-    const uint32_t cbAtrous = sizeof(RelaxConstants);
+    const uint32_t cbAtrous = offsetof(RelaxConstants, gIsLastPass) + sizeof(uint32_t); // 712: sizeof() of the reference struct, no register padding
 
     enum : uint16_t
     {

@@ -21,7 +21,8 @@ void Scheduler::AddSigmaShadow(DenoiserSlot& slot)
     new (&slot.settings.sigma) SigmaSettings();
     slot.settingsSize = sizeof(SigmaSettings);
     const char* dn = "SIGMA_Shadow";
-    const uint32_t cb = sizeof(SigmaConstants);
+    // the reference reports sizeof() of its C++ struct, which has no tail padding to a 16-byte register (516, not 528)
+    const uint32_t cb = offsetof(SigmaConstants, gIsRectChanged) + sizeof(uint32_t);
 
     const uint16_t P_HISTORY_LENGTH = kPermanentBase;
     AddPermanent(Format::R32_UINT);

@@ -495,12 +495,15 @@ void* Scheduler::Push(const DenoiserSlot& slot, uint32_t localPassIndex)
     d.resourcesNum = pt.resourcesNum;
     d.pipelineIndex = pt.pipelineIndex;
     d.constantBufferDataSize = pt.constantSize;
-    if (constantOffset_ + pt.constantSize <= kConstantArenaSize)
+    // blocks are placed on 16-byte boundaries and zero-padded to whole registers: the reported size is the reference's
+    // sizeof(), the kernels copy whole register-aligned structs (csrc/constants.h)
+    const uint32_t paddedSize = (pt.constantSize + 15u) & ~15u;
+    if (constantOffset_ + paddedSize <= kConstantArenaSize)
     {
         d.constantBufferData = constantArena_ + constantOffset_;
-        memset((void*)d.constantBufferData, 0, pt.constantSize);
+        memset((void*)d.constantBufferData, 0, paddedSize);
     }
-    constantOffset_ += pt.constantSize;
+    constantOffset_ += paddedSize;
 
     uint16_t w = common_.rectSize[0], h = common_.rectSize[1], ds = pt.downsample;
     if (ds == kUseMaxDims)

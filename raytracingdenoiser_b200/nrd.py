@@ -185,24 +185,31 @@ NrdCudaTextureInfo = _struct("NrdCudaTextureInfo", [("devicePtr", C.c_void_p), (
                                                     ("firstRow", u16), ("rowsNum", u16)])
 
 # ---- prototypes ---------------------------------------------------------------------------------------
-_lib.CreateInstance.argtypes = [C.POINTER(InstanceCreationDesc), C.POINTER(C.c_void_p)]
-_lib.CreateInstance.restype = u32
-_lib.DestroyInstance.argtypes = [C.c_void_p]
-_lib.DestroyInstance.restype = None
-_lib.GetLibraryDesc.argtypes = []
-_lib.GetLibraryDesc.restype = C.POINTER(LibraryDesc)
-_lib.GetInstanceDesc.argtypes = [C.c_void_p]
-_lib.GetInstanceDesc.restype = C.POINTER(InstanceDesc)
-_lib.SetCommonSettings.argtypes = [C.c_void_p, C.POINTER(CommonSettings)]
-_lib.SetCommonSettings.restype = u32
-_lib.SetDenoiserSettings.argtypes = [C.c_void_p, u32, C.c_void_p]
-_lib.SetDenoiserSettings.restype = u32
-_lib.GetComputeDispatches.argtypes = [C.c_void_p, C.POINTER(u32), u32, C.POINTER(C.POINTER(DispatchDesc)), C.POINTER(u32)]
-_lib.GetComputeDispatches.restype = u32
-_lib.GetResourceTypeString.argtypes = [u32]
-_lib.GetResourceTypeString.restype = C.c_char_p
-_lib.GetDenoiserString.argtypes = [u32]
-_lib.GetDenoiserString.restype = C.c_char_p
+def bind_nrd_api(lib):
+    """Declares the prototypes of the nine NRD entry points (Include/NRD.h:51-70) on `lib`.  Used for libnrd_b200.so and, in
+    tests/test_reference_scheduler.py, for the reference's own host library built by oracle/Makefile.ref."""
+    lib.CreateInstance.argtypes = [C.POINTER(InstanceCreationDesc), C.POINTER(C.c_void_p)]
+    lib.CreateInstance.restype = u32
+    lib.DestroyInstance.argtypes = [C.c_void_p]
+    lib.DestroyInstance.restype = None
+    lib.GetLibraryDesc.argtypes = []
+    lib.GetLibraryDesc.restype = C.POINTER(LibraryDesc)
+    lib.GetInstanceDesc.argtypes = [C.c_void_p]
+    lib.GetInstanceDesc.restype = C.POINTER(InstanceDesc)
+    lib.SetCommonSettings.argtypes = [C.c_void_p, C.POINTER(CommonSettings)]
+    lib.SetCommonSettings.restype = u32
+    lib.SetDenoiserSettings.argtypes = [C.c_void_p, u32, C.c_void_p]
+    lib.SetDenoiserSettings.restype = u32
+    lib.GetComputeDispatches.argtypes = [C.c_void_p, C.POINTER(u32), u32, C.POINTER(C.POINTER(DispatchDesc)), C.POINTER(u32)]
+    lib.GetComputeDispatches.restype = u32
+    lib.GetResourceTypeString.argtypes = [u32]
+    lib.GetResourceTypeString.restype = C.c_char_p
+    lib.GetDenoiserString.argtypes = [u32]
+    lib.GetDenoiserString.restype = C.c_char_p
+    return lib
+
+
+bind_nrd_api(_lib)
 _lib.nrdCudaCreateContext.argtypes = [C.c_void_p, C.POINTER(NrdCudaContextDesc), C.POINTER(C.c_void_p)]
 _lib.nrdCudaCreateContext.restype = u32
 _lib.nrdCudaDestroyContext.argtypes = [C.c_void_p]
@@ -293,7 +300,8 @@ class Dispatch(object):
 class Instance(object):
     """nrd::Instance (reference: CreateInstance / DestroyInstance, Source/Wrapper.cpp:246-289)."""
 
-    def __init__(self, denoisers):
+    def __init__(self, denoisers, lib=None):
+        self._lib = lib or _lib   # `lib`: another library exporting the NRD API (the reference build, tests only)
         arr = (DenoiserDesc * len(denoisers))()
         for i, (identifier, denoiser) in enumerate(denoisers):
             arr[i].identifier = identifier
@@ -302,7 +310,7 @@ class Instance(object):
         desc.denoisers = arr
         desc.denoisersNum = len(denoisers)
         self._handle = C.c_void_p()
-        r = _lib.CreateInstance(C.byref(desc), C.byref(self._handle))
+        r = self._lib.CreateInstance(C.byref(desc), C.byref(self._handle))
         if r != Result.SUCCESS:
             self._handle = None
             raise NrdError("CreateInstance", r)
@@ -310,7 +318,7 @@ class Instance(object):
 
     def destroy(self):
         if self._handle:
-            _lib.DestroyInstance(self._handle)
+            self._lib.DestroyInstance(self._handle)
             self._handle = None
 
     def __del__(self):
@@ -324,7 +332,7 @@ class Instance(object):
         return self._handle
 
     def get_instance_desc(self):
-        d = _lib.GetInstanceDesc(self._handle).contents
+        d = self._lib.GetInstanceDesc(self._handle).contents
         pipelines = []
         for i in range(d.pipelinesNum):
             p = d.pipelines[i]
@@ -337,13 +345,13 @@ class Instance(object):
                 "descriptorPoolDesc": {k: getattr(d.descriptorPoolDesc, k) for k, _ in DescriptorPoolDesc._fields_}}
 
     def set_common_settings(self, common_settings, check=True):
-        r = Result(_lib.SetCommonSettings(self._handle, C.byref(common_settings)))
+        r = Result(self._lib.SetCommonSettings(self._handle, C.byref(common_settings)))
         if check and r != Result.SUCCESS:
             raise NrdError("SetCommonSettings", r)
         return r
 
     def set_denoiser_settings(self, identifier, settings, check=True):
-        r = Result(_lib.SetDenoiserSettings(self._handle, identifier, C.byref(settings)))
+        r = Result(self._lib.SetDenoiserSettings(self._handle, identifier, C.byref(settings)))
         if check and r != Result.SUCCESS:
             raise NrdError("SetDenoiserSettings", r)
         return r
@@ -352,7 +360,7 @@ class Instance(object):
         ids = (u32 * max(len(identifiers), 1))(*identifiers)
         out = C.POINTER(DispatchDesc)()
         num = u32(0)
-        r = Result(_lib.GetComputeDispatches(self._handle, ids if identifiers else None, len(identifiers), C.byref(out), C.byref(num)))
+        r = Result(self._lib.GetComputeDispatches(self._handle, ids if identifiers else None, len(identifiers), C.byref(out), C.byref(num)))
         return r, out, num.value
 
     def get_compute_dispatches(self, identifiers, check=True):

@@ -94,7 +94,8 @@ class CpuDenoiser(object):
             texs[i].pitchBytes = arr.strides[0]
             texs[i].format = int(fmt)
             texs[i].firstRow = 0
-        buf = C.create_string_buffer(d.constants, len(d.constants)) if d.constants else None
+        # the reported size is the reference's sizeof() (not padded to a 16-byte register); the oracle copies whole registers
+        buf = C.create_string_buffer(d.constants, (len(d.constants) + 15) // 16 * 16) if d.constants else None
         r = lib.oracle_dispatch(d.shaderFileName.encode(), buf, len(d.constants), texs, len(d.resources), d.gridWidth, d.gridHeight)
         if r != 0:
             raise RuntimeError("oracle_dispatch(%s) failed with %d" % (d.shaderFileName, r))

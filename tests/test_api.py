@@ -131,3 +131,21 @@ def test_cuda_context_fails_loudly_without_gpu():
     inst = nrd.Instance([(0, nrd.Denoiser.REBLUR_DIFFUSE)])
     with pytest.raises(nrd.NrdError):
         nrd.CudaContext(inst, 64, 64)
+
+
+def test_public_struct_layout_matches_reference_headers():
+    """sizeof / alignof / default-initialised bytes of every public struct, enum extents and the version, probed by
+    tests/layout_probe.cpp: include/nrd_b200.h against the fixture generated from the reference's Include/NRD.h
+    (tests/golden/nrd_layout.json, generator tests/golden/make_layout_golden.py); regenerated live when the reference is here."""
+    import json
+    import sys
+    golden_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden_dir)
+    import make_layout_golden as m
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    golden = json.load(open(os.path.join(golden_dir, "nrd_layout.json")))
+    mine = json.loads(m.run_probe(os.path.join(root, "include"), "nrd_b200.h"))
+    assert mine == golden, [k for k in golden if golden[k] != mine.get(k)]
+    assert len(golden) == 23 and golden["CommonSettings"]["sizeof"] > 300
+    if os.path.isdir("/root/reference/Include"):
+        assert json.loads(m.run_probe("/root/reference/Include", "NRD.h")) == golden
