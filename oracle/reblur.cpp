@@ -182,16 +182,23 @@ struct Pass
         return origin - Iw * float3(D.w);
     }
     // :465-482
+    // Texel-selecting arithmetic is written with explicit fused multiply-adds (what an HLSL compiler emits for mad chains; the
+    // unfused form is an equally valid reading of the source).  The CUDA kernels use the same operations in the same order
+    // (device/reblur_spatial.cu), so both sides land on the same texel.
+    // Common.hlsli:472  RotateVector(rotator, v) = v.x * r.xz + v.y * r.yw
+    static float2 RotateVectorFma(float4 r, float2 v) { return float2(std::fma(v.x, r.x, v.y * r.y), std::fma(v.x, r.z, v.y * r.w)); }
+    // :465-482
     static float2 GetKernelSampleCoordinates(const float4x4& mToClip, float3 offset, float3 X, float3 T, float3 B, float4 rotator)
     {
-        float2 o = Geometry::RotateVector(rotator, offset.xy());
-        float3 p = X + T * float3(o.x) + B * float3(o.y);
-        float4 clip4 = Geometry::ProjectiveTransform(mToClip, p);
-        float3 clip = float3(clip4.x, clip4.y, clip4.w);
-        clip.x /= clip.z;
-        clip.y /= clip.z;
-        clip.y = -clip.y;
-        return float2(clip.x, clip.y) * float2(0.5f) + float2(0.5f);
+        float2 o = Geometry::RotateVector(rotator, offset.xy()); // per-frame uniform (host-evaluated by the kernels' launcher)
+        float3 p = float3(std::fma(B.x, o.y, std::fma(T.x, o.x, X.x)), std::fma(B.y, o.y, std::fma(T.y, o.x, X.y)), std::fma(B.z, o.y, std::fma(T.z, o.x, X.z)));
+        // ProjectiveTransform: clip = M * float4(p, 1), each row a mad chain that starts from the translation column
+        const float4x4& m = mToClip;
+        float cx = std::fma(m.c[2].x, p.z, std::fma(m.c[1].x, p.y, std::fma(m.c[0].x, p.x, m.c[3].x)));
+        float cy = std::fma(m.c[2].y, p.z, std::fma(m.c[1].y, p.y, std::fma(m.c[0].y, p.x, m.c[3].y)));
+        float cw = std::fma(m.c[2].w, p.z, std::fma(m.c[1].w, p.y, std::fma(m.c[0].w, p.x, m.c[3].w)));
+        float rw = 1.0f / cw; // clip.xy / clip.w as one reciprocal and two products
+        return float2(std::fma(cx * rw, 0.5f, 0.5f), std::fma(cy * rw, -0.5f, 0.5f));
     }
     // :486-540
     static float GetNormalWeightParam(float nonLinearAccumSpeed, float lobeAngleFraction, float roughness = 1.0f)
@@ -480,7 +487,7 @@ void DiffuseSpatialFilter(const Pass& P, const SpatialCtx& s, float sum, float4 
         for (uint n = 0; n < 8; n++)
         {
             float3 offset = g_Special8[n];
-            float2 uv = s.pixelUv + Geometry::RotateVector(scaledRotator, offset.xy());
+            float2 uv = s.pixelUv + Pass::RotateVectorFma(scaledRotator, offset.xy());
             uv = floor(uv * c.gRectSize) + float2(0.5f);
             if (pre) uv = Pass::ApplyCheckerboardShift(uv, c.gDiffCheckerboard, n, c.gFrameIndex);
             uv *= c.gRectSizeInv;
@@ -610,7 +617,7 @@ void SpecularSpatialFilter(const Pass& P, const SpatialCtx& s, float sum, float4
         {
             float3 offset = g_Special8[n];
             float2 uv;
-            if (pre) uv = s.pixelUv + Geometry::RotateVector(scaledRotator, offset.xy());
+            if (pre) uv = s.pixelUv + Pass::RotateVectorFma(scaledRotator, offset.xy());
             else uv = Pass::GetKernelSampleCoordinates(c.gViewToClip, offset, s.Xv, Tv, Bv, s.rotator);
             uv = floor(uv * c.gRectSize) + float2(0.5f);
             if (pre) uv = Pass::ApplyCheckerboardShift(uv, c.gSpecCheckerboard, n, c.gFrameIndex);

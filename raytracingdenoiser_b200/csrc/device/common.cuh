@@ -64,11 +64,13 @@ static __device__ __forceinline__ const uint8_t* PeerRow(const Surf& s, int y)
 
 template <class T> __device__ __forceinline__ const T* TexelPtr(const Surf& s, int x, int y)
 {
+#if defined(NRD_B200_NO_STRIPS)
+    return reinterpret_cast<const T*>(s.base + (size_t)y * s.pitch) + x; // the whole texture is local: ly0 == 0 (executor.cu ToSurf)
+#else
     const int ly = y - s.ly0;
-#if !defined(NRD_B200_NO_STRIPS)
     if (s.stripRows != 0 && (unsigned)ly >= s.lrows) return reinterpret_cast<const T*>(PeerRow(s, y)) + x;
-#endif
     return reinterpret_cast<const T*>(s.base + (size_t)ly * s.pitch) + x;
+#endif
 }
 // The owner lookup above costs a divergent branch and ~10 instructions of code around EVERY load.  Kernels avoid it where the
 // row is known to be local: Near(s) is a view of the surface whose loads skip the lookup (stripRows = 0 is a compile-time
@@ -95,7 +97,11 @@ __device__ __forceinline__ bool RowsLocal(const Surf& s, int ya, int yb)
 }
 template <class T> __device__ __forceinline__ T* TexelPtrRW(const Surf& s, int x, int y)
 {
+#if defined(NRD_B200_NO_STRIPS)
+    return reinterpret_cast<T*>(s.base + (size_t)y * s.pitch) + x;
+#else
     return reinterpret_cast<T*>(s.base + (size_t)(y - s.ly0) * s.pitch) + x;
+#endif
 }
 __device__ __forceinline__ bool Inside(const Surf& s, int x, int y) { return (unsigned)x < (unsigned)s.w && (unsigned)y < (unsigned)s.h; }
 
@@ -136,6 +142,29 @@ __device__ __forceinline__ f3 normalize(f3 a) { return a * rsqrtf(dot(a, a)); }
 __device__ __forceinline__ f3 cross(f3 a, f3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 __device__ __forceinline__ f3 reflect(f3 i, f3 n) { return i - n * (2.0f * dot(i, n)); }
 __device__ __forceinline__ float saturate(float x) { return __saturatef(x); } // NaN -> 0, like HLSL
+// Saturating arithmetic as ONE instruction.  nvcc does not fold __saturatef() (cvt.sat) or fabsf() into the producing FADD / FFMA
+// when -ftz is on: saturate(1 - |x|) compiles to three instructions (FADD |x|, FADD 1 - x, FADD.SAT) -- and these kernels are
+// issue-bound.  Spelled as PTX the .sat and the |.| / - operand modifiers land on the arithmetic instruction itself.
+__device__ __forceinline__ float SatFma(float a, float b, float c)
+{
+    float r;
+    asm("fma.rn.sat.ftz.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float SatAdd(float a, float b)
+{
+    float r;
+    asm("add.sat.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float SatMul(float a, float b)
+{
+    float r;
+    asm("mul.sat.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float OneMinusSat(float x) { return SatFma(x, -1.0f, 1.0f); }       // saturate(1 - x)
+__device__ __forceinline__ float OneMinusAbsSat(float x) { return SatFma(fabsf(x), -1.0f, 1.0f); } // saturate(1 - |x|)
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return a + (b - a) * t; }
 __device__ __forceinline__ f2 lerp2(f2 a, f2 b, float t) { return {lerpf(a.x, b.x, t), lerpf(a.y, b.y, t)}; }
 __device__ __forceinline__ f3 lerp3(f3 a, f3 b, float t) { return {lerpf(a.x, b.x, t), lerpf(a.y, b.y, t), lerpf(a.z, b.z, t)}; }

@@ -43,17 +43,21 @@ __device__ __forceinline__ Guide DecodeGuide(unsigned packed)
 
 // ---- scalar helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ float SmoothStep01(float x) { float t = saturate(x); return t * t * (3.0f - 2.0f * t); }
-__device__ __forceinline__ float LinearStep(float a, float b, float x) { return saturate((x - a) / (b - a)); }
+__device__ __forceinline__ float LinearStep(float a, float b, float x) { return SatMul(x - a, __fdividef(1.0f, b - a)); }
 __device__ __forceinline__ float SmoothStep(float a, float b, float x) { return SmoothStep01(LinearStep(a, b, x)); }
 __device__ __forceinline__ float Sqrt01(float x) { return sqrtf(saturate(x)); }
 __device__ __forceinline__ float Pow01(float x, float y) { return powf(saturate(x), y); }
 __device__ __forceinline__ float PositiveRcp(float x) { return 1.0f / fmaxf(x, 1e-15f); }
-__device__ __forceinline__ float AcosApprox(float x) { return 1.41421356f * sqrtf(saturate(1.0f - x)); }
-__device__ __forceinline__ float Pow5(float x) { float t = saturate(1.0f - x); float t2 = t * t; return t2 * t2 * t; } // pow(saturate(1-x),5)
+__device__ __forceinline__ float AcosApprox(float x) { return 1.41421356f * sqrtf(OneMinusSat(x)); }
+__device__ __forceinline__ float Pow5(float x) { float t = OneMinusSat(x); float t2 = t * t; return t2 * t2 * t; } // pow(saturate(1-x),5)
 __device__ __forceinline__ float GetStdDev(float m1, float m2) { return sqrtf(fabsf(m2 - m1 * m1)); }
 
 // weights: Common.hlsli:547-574 (SmoothStep(1,0,x) == smoothstep01(1 - x))
-__device__ __forceinline__ float NonExpWeight(float x, float px, float py) { return SmoothStep01(1.0f - fabsf(x * px + py)); }
+__device__ __forceinline__ float NonExpWeight(float x, float px, float py)
+{
+    const float u = OneMinusAbsSat(fmaf(x, px, py));
+    return u * u * fmaf(-2.0f, u, 3.0f);
+}
 __device__ __forceinline__ float NonExpWeightWithSigma(float x, float px, float py, float sigma) { return SmoothStep01(1.0f - (fabsf(x * px + py) - sigma * px)); }
 __device__ __forceinline__ float ExpWeight(float x, float px, float py)
 {

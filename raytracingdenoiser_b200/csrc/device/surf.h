@@ -47,10 +47,14 @@ struct PassLaunch
     int rowBegin, rowEnd;  // rows this launch must produce, in the pass's own pixel units
     cudaStream_t stream;
     bool preloadOnly;      // do not launch: only make the driver load the kernel this pass maps to (see NRD_B200_LAUNCH)
-    // Decoded-guide cache (executor-owned RGBA32F surface, not part of the DispatchDesc): {N.x, N.y, N.z, raw viewZ} of the
-    // current frame's IN_NORMAL_ROUGHNESS / IN_VIEWZ.  guideMode 1 = this pass writes it (REBLUR PrePass), 2 = it is valid and
-    // may be read instead of decoding the packed normal at every tap (REBLUR Blur / PostBlur), 0 = not available.
-    Surf guide;
+    // Decoded-guide surface (executor-owned RGBA32F, not part of the DispatchDesc): {N.x, N.y, N.z, raw viewZ} of the current
+    // frame's IN_NORMAL_ROUGHNESS / IN_VIEWZ.  guideMode 1 = this pass writes it (REBLUR ClassifyTiles, the first pass of every
+    // frame; guideNr = IN_NORMAL_ROUGHNESS, which that dispatch does not bind itself), 2 = it is complete and the filter passes
+    // read it at every tap (REBLUR PrePass / Blur / PostBlur), 0 = not used by this pass.
+    Surf guide, guideNr;
     int guideMode;
+    // 1024 x float4 {SpecMagicCurve(r), lerp(1, hitDistParams.z, saturate(exp2(hitDistParams.w r^2))), 0.298475 log(39.4115 - 39.0029 r), r}
+    // for r = i / 1023: every function of the 10-bit roughness alone, evaluated by the executor with the host libm
+    const void* roughnessLut;
 };
 } // namespace nrdb200_abi

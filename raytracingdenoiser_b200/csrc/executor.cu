@@ -55,6 +55,7 @@ std::mutex g_slotMutex;
 bool g_slotUsed[kMaxPeerSlots] = {};
 
 constexpr size_t kArenaHeader = 256;           // barrier flags: kMaxPeers x u32 (slot s = last epoch signalled by rank s), then the error word
+constexpr unsigned kPushCounterWord = 16;      // u32 index in the header: ticket counter of the fused ghost push + barrier kernel
 constexpr long long kBarrierTimeoutCycles = 4000000000ll; // ~2 s: a missing peer turns into an error instead of a hung GPU
 
 uint32_t BytesPerTexel(Format f)
@@ -106,10 +107,14 @@ struct NrdCudaContext
     size_t arenaBytes = 0;
     std::vector<Texture> permanent, transient;
     Texture user[(size_t)ResourceType::MAX_NUM];
-    // decoded-guide cache of the REBLUR spatial passes (surf.h PassLaunch::guide): written by PrePass, valid until the next
-    // frame starts (REBLUR ClassifyTiles is the first pass of every frame)
+    // decoded-guide surface of the REBLUR spatial passes (surf.h PassLaunch::guide): written by ClassifyTiles, the first pass
+    // of every REBLUR frame, read by PrePass / Blur / PostBlur of the same frame
     Texture guide;
     bool guideValid = false;
+    // roughness table of the REBLUR spatial passes (surf.h PassLaunch::roughnessLut), rebuilt when hitDistanceParameters change
+    float* roughnessLut = nullptr;
+    float lutKey[2] = {0.0f, 0.0f};
+    bool lutValid = false;
     // strip mode
     uint32_t rank = 0, world = 1;
     int peerSlot = -1;
@@ -188,6 +193,47 @@ Surf ToSurf(const NrdCudaContext* ctx, const Texture& t)
     else if (StripMode(ctx))
         s.base += (size_t)t.haloRows * t.pitch, s.lrows = t.rows; // a strip-mode context that holds the whole frame
     return s;
+}
+
+// Roughness table: every function of the 10-bit roughness code alone that the REBLUR spatial filters need, evaluated with the
+// host libm in the reference's operation order (Common.hlsli:311-317 GetSpecMagicCurve, NRD.hlsli:520-523
+// _REBLUR_GetHitDistanceNormalization, NRD.hlsli:386-392 _NRD_GetSpecularDominantFactor).  `volatile` keeps every intermediate a
+// rounded float (no contraction, no excess precision), so the entries are what a plain IEEE evaluation of the HLSL gives.
+Result UpdateRoughnessLut(NrdCudaContext* ctx, const float* hitDistParams, cudaStream_t stream)
+{
+    if (ctx->lutValid && ctx->lutKey[0] == hitDistParams[2] && ctx->lutKey[1] == hitDistParams[3]) return Result::SUCCESS;
+    if (!ctx->roughnessLut && cudaMalloc((void**)&ctx->roughnessLut, 1024 * 4 * sizeof(float)) != cudaSuccess) return Fail(ctx, Result::FAILURE, "cudaMalloc(roughness table)");
+    static thread_local float table[1024 * 4];
+    for (int i = 0; i < 1024; i++)
+    {
+        volatile float r = (float)i / 1023.0f;
+        volatile float rr = r * r;
+        volatile float e0 = exp2f(-200.0f * rr);
+        volatile float f = 1.0f - e0;
+        volatile float pw = powf(r, 0.25f); // Pow01: r is already in [0, 1]
+        volatile float smc = f * pw;
+        // p.w * roughness * roughness: left to right
+        volatile float t0 = hitDistParams[3] * r;
+        volatile float t1 = t0 * r;
+        volatile float e1 = exp2f(t1);
+        float sat = e1 > 0.0f ? (e1 < 1.0f ? e1 : 1.0f) : 0.0f;
+        volatile float d = (hitDistParams[2] - 1.0f) * sat;
+        volatile float hitK = 1.0f + d;
+        volatile float la = 39.0029f * r;
+        volatile float lb = 39.4115f - la;
+        volatile float aLog = 0.298475f * logf(lb);
+        table[i * 4 + 0] = smc;
+        table[i * 4 + 1] = hitK;
+        table[i * 4 + 2] = aLog;
+        table[i * 4 + 3] = r;
+    }
+    // pageable source: the runtime stages it before returning, so the static buffer can be rewritten by the next call
+    cudaError_t e = cudaMemcpyAsync(ctx->roughnessLut, table, sizeof(table), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("roughness table upload: ") + cudaGetErrorString(e));
+    ctx->lutKey[0] = hitDistParams[2];
+    ctx->lutKey[1] = hitDistParams[3];
+    ctx->lutValid = true;
+    return Result::SUCCESS;
 }
 
 // "REBLUR_DiffuseSpecular_Blur.cs" -> family REBLUR, signal 2, pass "Blur"
@@ -292,12 +338,8 @@ cudaError_t LaunchClear(const PassLaunch& p)
     return cudaGetLastError();
 }
 
-// All-to-all flag barrier over NVLink: lane t tells rank t "I finished epoch e" (a store into t's arena header) and then
-// waits until rank t has told us the same.  Everything the previous kernel wrote is visible device-wide when this kernel
-// starts (stream order); the system-scope fences order it against the flag for the remote readers.
-__global__ void StripBarrierKernel(const __grid_constant__ BarrierArgs a)
+__device__ __forceinline__ void StripBarrierBody(const BarrierArgs& a, unsigned t)
 {
-    const unsigned t = threadIdx.x;
     if (t >= a.world) return;
     __threadfence_system();
     volatile unsigned* remote = (volatile unsigned*)((uint8_t*)a.flags + a.delta[t]) + a.rank;
@@ -316,23 +358,42 @@ __global__ void StripBarrierKernel(const __grid_constant__ BarrierArgs a)
     __threadfence_system();
 }
 
+// All-to-all flag barrier over NVLink: lane t tells rank t "I finished epoch e" (a store into t's arena header) and then
+// waits until rank t has told us the same.  Everything the previous kernel wrote is visible device-wide when this kernel
+// starts (stream order); the system-scope fences order it against the flag for the remote readers.
+__global__ void StripBarrierKernel(const __grid_constant__ BarrierArgs a) { StripBarrierBody(a, threadIdx.x); }
+
 // Ghost refresh: after a pass wrote its strip of a texture, the first / last `halo` rows of the strip are stored into the
 // ghost rows of the neighbour above / below (contiguous blocks of whole pitched rows, 16-byte NVLink stores).
-__global__ void __launch_bounds__(256) GhostPushKernel(const __grid_constant__ PushArgs a)
+// With `fused` the block that finishes last also runs the inter-GPU barrier of this pass (one launch instead of two): every
+// block fences its stores system-wide before it takes a ticket, the holder of the last ticket fences again and signals.
+__global__ void __launch_bounds__(256) GhostPushKernel(const __grid_constant__ PushArgs a, const __grid_constant__ BarrierArgs b, int fused)
 {
     const PushItem& it = a.items[blockIdx.y];
     const uint4* src = (const uint4*)it.src;
     uint4* dst = (uint4*)it.dst;
     const size_t n = it.bytes / 16;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    if (!fused) return;
+    __shared__ unsigned last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned* counter = b.flags + kPushCounterWord;
+        const unsigned ticket = atomicAdd(counter, 1u);
+        last = ticket == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+        if (last) *counter = 0u; // ready for the next launch (stream order)
+    }
+    __syncthreads();
+    if (last) StripBarrierBody(b, threadIdx.x);
 }
 } // namespace nrdb200
 
 namespace
 {
-Result Barrier(NrdCudaContext* ctx, cudaStream_t stream)
+BarrierArgs NextBarrier(NrdCudaContext* ctx)
 {
-    if (!StripMode(ctx) || ctx->world <= 1) return Result::SUCCESS;
     BarrierArgs a{};
     a.flags = (unsigned*)ctx->arena;
     for (uint32_t i = 0; i < ctx->world; i++) a.delta[i] = ctx->peerDelta[i];
@@ -340,24 +401,36 @@ Result Barrier(NrdCudaContext* ctx, cudaStream_t stream)
     a.world = ctx->world;
     a.epoch = ++ctx->epoch;
     a.timeout = kBarrierTimeoutCycles;
+    return a;
+}
+
+Result Barrier(NrdCudaContext* ctx, cudaStream_t stream)
+{
+    if (!StripMode(ctx) || ctx->world <= 1) return Result::SUCCESS;
+    const BarrierArgs a = NextBarrier(ctx);
     StripBarrierKernel<<<1, 32, 0, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, std::string("strip barrier: ") + cudaGetErrorString(e));
 }
 
-// Sends the boundary rows of `textures` (arena-owned, just written by this rank) to the ghost rows of the two neighbours.
-Result PushGhosts(NrdCudaContext* ctx, const Texture* const* textures, uint32_t n, cudaStream_t stream)
+// Sends the boundary rows of `textures` (arena-owned, just written by this rank) to the ghost rows of the two neighbours and
+// then meets all ranks (the barrier rides on the last push launch; without anything to push it is a launch of its own).
+Result PushGhostsAndBarrier(NrdCudaContext* ctx, const Texture* const* textures, uint32_t n, cudaStream_t stream)
 {
-    if (!StripMode(ctx) || ctx->world <= 1 || ctx->halo == 0 || n == 0) return Result::SUCCESS;
+    if (!StripMode(ctx) || ctx->world <= 1) return Result::SUCCESS;
+    if (ctx->halo == 0 || n == 0) return Barrier(ctx, stream);
     PushArgs a{};
     uint32_t items = 0;
     unsigned long long maxBytes = 0;
-    auto flush = [&]() -> Result {
+    bool barrierDone = false;
+    auto flush = [&](bool fuse) -> Result {
         if (!items) return Result::SUCCESS;
         unsigned blocksX = (unsigned)((maxBytes / 16 + 256 * 8 - 1) / (256 * 8)); // ~8 x 16 B per thread
         if (blocksX < 1) blocksX = 1;
         if (blocksX > 148 * 4) blocksX = 148 * 4;
-        GhostPushKernel<<<dim3(blocksX, items), 256, 0, stream>>>(a);
+        BarrierArgs b{};
+        if (fuse) b = NextBarrier(ctx), barrierDone = true;
+        GhostPushKernel<<<dim3(blocksX, items), 256, 0, stream>>>(a, b, fuse ? 1 : 0);
         cudaError_t e = cudaGetLastError();
         items = 0;
         maxBytes = 0;
@@ -384,11 +457,13 @@ Result PushGhosts(NrdCudaContext* ctx, const Texture* const* textures, uint32_t 
         }
         if (items + 2 > (uint32_t)kMaxPushItems)
         {
-            Result r = flush();
+            Result r = flush(false);
             if (r != Result::SUCCESS) return r;
         }
     }
-    return flush();
+    Result r = flush(true);
+    if (r != Result::SUCCESS) return r;
+    return barrierDone ? Result::SUCCESS : Barrier(ctx, stream);
 }
 } // namespace
 
@@ -455,6 +530,9 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
         return Result::FAILURE;
     }
     cudaMemset(ctx->arena, 0, ctx->arenaBytes);
+    // the memset runs on the legacy default stream, the context is used on the caller's (non-blocking) streams and by peers:
+    // nothing may touch the arena (barrier flags included) before it is zero
+    cudaDeviceSynchronize();
     auto rebase = [&](Texture& t) {
         if (t.owned) t.ptr = ctx->arena + (size_t)t.ptr;
     };
@@ -479,6 +557,7 @@ NRD_API void nrdCudaDestroyContext(NrdCudaContext* ctx)
         g_slotUsed[ctx->peerSlot] = false;
     }
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->roughnessLut) cudaFree(ctx->roughnessLut);
     delete ctx;
 }
 
@@ -637,12 +716,27 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         memcpy(&rc, d->constantBufferData, sizeof(rc));
         if (rc.gDiffCheckerboard != 2 || rc.gSpecCheckerboard != 2) return Fail(ctx, Result::UNSUPPORTED, "REBLUR checkerboard modes are not implemented by the CUDA executor");
     }
-    // decoded-guide cache: PrePass fills it, Blur / PostBlur of the same frame read it
-    const bool isReblurPrePass = !strncmp(shader, "REBLUR_", 7) && strstr(shader, "_PrePass.cs") != nullptr;
-    const bool readsGuide = !strncmp(shader, "REBLUR_", 7) && (strstr(shader, "_Blur.cs") != nullptr || strstr(shader, "_PostBlur") != nullptr);
-    if (!strcmp(shader, "REBLUR_ClassifyTiles.cs")) ctx->guideValid = false; // a new frame: the guides changed
+    // decoded-guide surface: ClassifyTiles (first pass of every REBLUR frame) fills it, PrePass / Blur / PostBlur read it
+    const bool buildsGuide = !strcmp(shader, "REBLUR_ClassifyTiles.cs");
+    const bool readsGuide = !strncmp(shader, "REBLUR_", 7) && (strstr(shader, "_PrePass.cs") != nullptr || strstr(shader, "_Blur.cs") != nullptr || strstr(shader, "_PostBlur") != nullptr);
     p.guide = ToSurf(ctx, ctx->guide);
-    p.guideMode = isReblurPrePass ? 1 : (readsGuide && ctx->guideValid ? 2 : 0);
+    if (buildsGuide)
+    {
+        const Texture* nr = Resolve(ctx, ResourceType::IN_NORMAL_ROUGHNESS, 0);
+        if (!nr) return Fail(ctx, Result::INVALID_ARGUMENT, "unbound resource IN_NORMAL_ROUGHNESS for REBLUR_ClassifyTiles (it also builds the guide surface)");
+        p.guideNr = ToSurf(ctx, *nr);
+        p.guideMode = 1;
+    }
+    else if (readsGuide)
+    {
+        if (!ctx->guideValid) return Fail(ctx, Result::FAILURE, std::string(shader) + " dispatched before REBLUR_ClassifyTiles of the same frame");
+        ReblurConstants rc;
+        memcpy(&rc, d->constantBufferData, sizeof(rc));
+        Result lr = UpdateRoughnessLut(ctx, rc.gHitDistParams, (cudaStream_t)stream);
+        if (lr != Result::SUCCESS) return lr;
+        p.roughnessLut = ctx->roughnessLut;
+        p.guideMode = 2;
+    }
     // rows to produce: the context's strip (the full frame on one GPU)
     p.rowBegin = ctx->desc.stripY0;
     p.rowEnd = ctx->desc.stripY1;
@@ -657,23 +751,32 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     // separately and differ in the last bits (FMA contraction); N-GPU results are bit-identical to THIS configuration.
     const bool stripBuild = (StripMode(ctx) && ctx->world > 1) || getenv("NRD_B200_FORCE_STRIP_KERNELS") != nullptr;
     const Launchers& L = stripBuild ? kStripLaunchers : kSingleLaunchers;
-    cudaError_t e = LaunchByName(L, p, shader);
+    cudaError_t e;
+    const Texture* clearTarget = !strncmp(shader, "Clear_", 6) && d->resourcesNum ? Resolve(ctx, d->resources[0].type, d->resources[0].indexInPool) : nullptr;
+    if (clearTarget && !clearTarget->owned)
+    {
+        // an application texture (IN_MV / OUT_* are storage outputs of some passes): its pitch may exceed the row and the bytes
+        // between rows are not ours -- clear exactly width x height texels
+        e = clearTarget->rows ? cudaMemset2DAsync(clearTarget->ptr, clearTarget->pitch, 0, (size_t)clearTarget->width * BytesPerTexel(clearTarget->format), clearTarget->rows,
+                                                  (cudaStream_t)stream)
+                              : cudaSuccess;
+    }
+    else
+        e = LaunchByName(L, p, shader);
 
     if (e == cudaErrorNotSupported) return Fail(ctx, Result::UNSUPPORTED, std::string("no CUDA kernel for pass ") + shader);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string(shader) + ": " + cudaGetErrorString(e));
     g_launchCount.fetch_add(1, std::memory_order_relaxed);
-    if (isReblurPrePass) ctx->guideValid = true;
-    if (strncmp(shader, "Clear_", 6) != 0 && (pushMask || isReblurPrePass)) // clears zero the ghost rows locally
+    if (buildsGuide) ctx->guideValid = true;
+    const Texture* list[33];
+    uint32_t n = 0;
+    if (strncmp(shader, "Clear_", 6) != 0 && (pushMask || buildsGuide)) // clears zero the ghost rows locally
     {
-        const Texture* list[33];
-        uint32_t n = 0;
         for (uint32_t i = 0; i < d->resourcesNum; i++)
             if ((pushMask >> i) & 1u) list[n++] = Resolve(ctx, d->resources[i].type, d->resources[i].indexInPool);
-        if (isReblurPrePass) list[n++] = &ctx->guide; // Blur / PostBlur of the neighbours read its boundary rows
-        Result r = PushGhosts(ctx, list, n, p.stream);
-        if (r != Result::SUCCESS) return r;
+        if (buildsGuide) list[n++] = &ctx->guide; // the filter passes of the neighbours read its boundary rows
     }
-    return Barrier(ctx, p.stream);
+    return PushGhostsAndBarrier(ctx, list, n, p.stream);
 }
 
 uint32_t StorageMask(const DispatchDesc* d)
@@ -696,8 +799,7 @@ Result FrameStart(NrdCudaContext* ctx, void* stream)
             const char* name = GetResourceTypeString((ResourceType)t);
             if (ctx->user[t].ptr && name && !strncmp(name, "IN_", 3)) list[n++] = &ctx->user[t];
         }
-        Result r = PushGhosts(ctx, list, n, (cudaStream_t)stream);
-        if (r != Result::SUCCESS) return r;
+        return PushGhostsAndBarrier(ctx, list, n, (cudaStream_t)stream);
     }
     return Barrier(ctx, (cudaStream_t)stream);
 }

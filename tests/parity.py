@@ -84,6 +84,11 @@ class SideBySide(object):
             r, raw, n = self.instance.get_compute_dispatches_raw([self.identifier])
             assert r == nrd.Result.SUCCESS
             pipelines = self.instance.get_instance_desc()["pipelines"]
+            # the frame's inputs are on the device before its first pass, like in an application: REBLUR ClassifyTiles decodes
+            # IN_NORMAL_ROUGHNESS into the executor's guide surface although its DispatchDesc only binds IN_VIEWZ
+            for name, arr in self.cpu.user.items():
+                if name.startswith("IN_"):
+                    self.ctx.upload(getattr(nrd.ResourceType, name), 0, np.ascontiguousarray(arr))
             for i in range(n):
                 d = nrd.Dispatch(raw[i], pipelines)
                 self._sync_to_gpu(d)
