@@ -213,6 +213,7 @@ def main():
         base["config"]["strips"] = [list(p) for p in partition[1]]
         gpu.connect()
         y0, y1 = gpu.y0, gpu.y1
+        full_frames = frames if rank == 0 else None   # rank 0 re-denoises the sequence on one GPU afterwards: the N-GPU output is checked, not assumed
         frames = [{k: (v[y0:y1].contiguous() if k in in_names else v) for k, v in fr.items() if k in in_names or not k.startswith("IN_")} for fr in frames]
         torch.cuda.empty_cache()
 
@@ -254,6 +255,38 @@ def main():
     if world > 1:
         gpu.synchronize()  # raises if an inter-GPU barrier timed out
     value = W * H * K / (ms_total * 1e-3) / 1e6
+
+    # ---- N > 1: the strips of the last timed frame against the one-GPU result of the same sequence.  Rank 0 runs the whole
+    # sequence through a one-GPU context on the strip build of the kernels (the build the strips run), so the comparison is bitwise.
+    check = None
+    if world > 1:
+        def digest(t):
+            v = t.contiguous().view(torch.int16).to(torch.int64).reshape(-1)
+            w = (torch.arange(v.numel(), device=v.device, dtype=torch.int64) % 8191) + 1
+            return torch.stack([v.sum(), (v * w).sum()])
+        mine = torch.stack([digest(t) for _, t in sorted(gpu.read_outputs(stream=stream).items())])
+        torch.cuda.synchronize(dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        if rank == 0:
+            os.environ["NRD_B200_FORCE_STRIP_KERNELS"] = "1"
+            try:
+                ref = harness.GpuDenoiser(den, W, H, device=local_rank)
+                for i in range(Wm + K):
+                    ref.set_inputs(full_frames[i])
+                    ref.denoise(harness.make_common_settings(full_frames[i], W, H, i))
+                torch.cuda.synchronize(dev)
+                outs = sorted(ref.outputs().items())
+                rows = base["config"]["strips"]
+                same = [bool(torch.equal(torch.stack([digest(t[a:b]) for _, t in outs]), every[r].to(dev))) for r, (a, b) in enumerate(rows)]
+                check = {"against": "one-GPU run of the same %d frames (strip build of the kernels), position-weighted checksums per strip and output" % (Wm + K),
+                         "strips_bit_identical": same, "ok": all(same)}
+                ref.destroy()
+                del ref, full_frames
+                torch.cuda.empty_cache()
+            finally:
+                del os.environ["NRD_B200_FORCE_STRIP_KERNELS"]
+        dist.barrier()
 
     # ---- per-pass breakdown with CUDA events around every dispatch (separate run, not part of `value`)
     per_pass = {}
@@ -371,6 +404,8 @@ def main():
 
     out = dict(base)
     out.update({"value": value, "ms_per_step": ms_total / K, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e})
+    if check is not None:
+        out["output_check"] = check
 
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         sample_frames = 3
