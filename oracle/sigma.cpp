@@ -1,5 +1,6 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h).  PARITY UNPINNED (no reference golden vectors exist).
-// CPU restatement of the reference's SIGMA_SHADOW passes at the default compile-time switches (SIGMA_Config.hlsli:13-43):
+// CPU restatement of the reference's SIGMA_SHADOW / SIGMA_SHADOW_TRANSLUCENCY passes at the default compile-time switches
+// (SIGMA_Config.hlsli:13-43; SIGMA_TYPE is float / float4: the signal is carried as float4 here, the scalar variant uses .x only):
 //   ClassifyTiles            Shaders/Include/SIGMA_ClassifyTiles.hlsli:10-81
 //   SmoothTiles              Shaders/Include/SIGMA_SmoothTiles.hlsli:10-48
 //   Copy                     Shaders/Include/SIGMA_Copy.hlsli:10-24
@@ -33,9 +34,11 @@ const float SIGMA_MAX_PIXEL_RADIUS = 32.0f;
 const float SIGMA_TS_SIGMA_SCALE = 3.0f;
 const float SIGMA_MAX_ACCUM_FRAME_NUM = 7.0f;
 
-float PackShadow(float s) { return Math::Sqrt01(s); }                  // SIGMA_Common.hlsli:13
+float4 PackShadow(float4 s) { return sqrt(saturate(s)); }              // SIGMA_Common.hlsli:13 (Math::Sqrt01 per component)
 bool IsLit(float p) { return p >= NRD_FP16_MAX; }                      // :14
-float UnpackShadow(float s) { return s * s; }                          // NRD.hlsli:931
+float4 UnpackShadow(float4 s) { return s * s; }                        // NRD.hlsli:931
+float4 GetStdDev4(float4 m1, float4 m2) { return sqrt(abs(m2 - m1 * m1)); }
+float4 clamp4(float4 v, float4 a, float4 b) { return float4(clamp(v.x, a.x, b.x), clamp(v.y, a.y, b.y), clamp(v.z, a.z, b.z), clamp(v.w, a.w, b.w)); }
 
 float GetKernelRadiusInPixels(float hitDist, float unprojectZ, float scale = 1.0f)   // SIGMA_Common.hlsli:21-34
 {
@@ -94,11 +97,12 @@ struct Pass
     float3 GetViewVector(float3 X, bool isViewSpace) const { return c.gOrthoMode == 0.0f ? normalize(-X) : (isViewSpace ? float3(0, 0, -1) : c.gViewVectorWorld.xyz()); }
 };
 
-void ClassifyTiles(const Pass& P, Tex* t, int gridW, int gridH)
+void ClassifyTiles(const Pass& P, bool translucent, Tex* t, int gridW, int gridH)
 {
     const CB& c = P.c;
     const Tex &gIn_ViewZ = t[0], &gIn_Penumbra = t[1];
-    Tex& gOut_Tiles = t[2];
+    const Tex* gIn_Shadow_Translucency = translucent ? &t[2] : nullptr;
+    Tex& gOut_Tiles = t[translucent ? 3 : 2];
 #pragma omp parallel for schedule(static)
     for (int ty = 0; ty < gridH; ty++)
         for (int tx = 0; tx < gridW; tx++)
@@ -114,8 +118,14 @@ void ClassifyTiles(const Pass& P, Tex* t, int gridW, int gridH)
                     bool isInf = viewZ > c.gDenoisingRange;
                     bool isShadow = h == 0.0f;
                     bool isLit = IsLit(h);
+                    bool isOpaque = true;
+                    if (translucent) // SIGMA_ClassifyTiles.hlsli:45-48
+                    {
+                        float4 tr = gIn_Shadow_Translucency->load(x, y);
+                        isOpaque = Color::Luminance(float3(tr.y, tr.z, tr.w)) < 0.003f;
+                    }
                     mask += ((isLit || isInf || isShadow) ? 1u : 0u) << 0;
-                    mask += ((!isLit || isInf || isShadow) ? 1u : 0u) << 9;
+                    mask += (((!isLit && isOpaque) || isInf || isShadow) ? 1u : 0u) << 9;
                     mask += (isInf ? 1u : 0u) << 18;
                     float hitDist = (isLit || isInf) ? 0.0f : h;
                     float pixelSize = PixelRadiusToWorld(c.gUnproject, c.gOrthoMode, 1.0f, viewZ);
@@ -175,13 +185,15 @@ void Copy(const Pass& P, Tex* t, int gridW, int gridH)
         }
 }
 
-void Blur(const Pass& P, bool firstPass, Tex* t, int gridW, int gridH)
+void Blur(const Pass& P, bool firstPass, bool translucent, Tex* t, int gridW, int gridH)
 {
     const CB& c = P.c;
     const Tex &gIn_ViewZ = t[0], &gIn_Normal_Roughness = t[1], &gIn_Penumbra = t[2], &gIn_Tiles = t[3];
-    const Tex* gIn_Shadow = firstPass ? nullptr : &t[4];
-    Tex& gOut_Penumbra = t[firstPass ? 4 : 5];
-    Tex& gOut_Shadow = t[firstPass ? 5 : 6];
+    // gIn_Shadow_Translucency is bound unless this is the first pass of the opaque variant (SIGMA_Blur.resources.hlsli:25-27)
+    const bool hasShadowInput = !firstPass || translucent;
+    const Tex* gIn_Shadow = hasShadowInput ? &t[4] : nullptr;
+    Tex& gOut_Penumbra = t[hasShadowInput ? 5 : 4];
+    Tex& gOut_Shadow = t[hasShadowInput ? 6 : 5];
     const int2 rectMax(c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1]);
     const int BORDER = 2;
 
@@ -199,7 +211,7 @@ void Blur(const Pass& P, bool firstPass, Tex* t, int gridW, int gridH)
             };
             auto sShadow = [&](int i, int j) {
                 int2 p = clamp(int2(x + i - BORDER, y + j - BORDER), int2(0), rectMax);
-                float s = firstPass ? float(IsLit(gIn_Penumbra.load(p).x)) : gIn_Shadow->load(p).x;
+                float4 s = hasShadowInput ? gIn_Shadow->load(p) : float4(float(IsLit(gIn_Penumbra.load(p).x)));
                 if (!firstPass) s = UnpackShadow(s);
                 return s;
             };
@@ -226,13 +238,14 @@ void Blur(const Pass& P, bool firstPass, Tex* t, int gridW, int gridH)
             float2 geometryWeightParams = GetGeometryWeightParams(c.gPlaneDistSensitivity, frustumSize, Xv, Nv);
 
             float2 sum(0.0f);
-            float penumbra = 0.0f, result = 0.0f, centerTap = 0.0f;
+            float penumbra = 0.0f;
+            float4 result(0.0f), centerTap(0.0f);
             for (int j = 0; j <= BORDER * 2; j++)
                 for (int i = 0; i <= BORDER * 2; i++)
                 {
                     float2 data = sPenumbraViewZ(i, j);
                     float penum = data.x, zs = data.y;
-                    float s = sShadow(i, j);
+                    float4 s = sShadow(i, j);
                     float w = 1.0f;
                     if (i == BORDER && j == BORDER) centerTap = s;
                     else
@@ -243,14 +256,14 @@ void Blur(const Pass& P, bool firstPass, Tex* t, int gridW, int gridH)
                         w *= AreBothLitOrUnlit(centerPenumbra, penum);
                         w *= GetGaussianWeight(length(float2(float(i - BORDER), float(j - BORDER)) / float2(float(BORDER))));
                     }
-                    result += w == 0.0f ? 0.0f : s * w;
+                    result += w == 0.0f ? float4(0.0f) : s * float4(w);
                     sum.x += w;
                     w *= pixelSize / (pixelSize + penum);
                     w *= float(!IsLit(penum));
                     penumbra += w == 0.0f ? 0.0f : penum * w;
                     sum.y += w;
                 }
-            result /= sum.x;
+            result /= float4(sum.x);
             sum.x = 1.0f;
             penumbra /= max(sum.y, NRD_EPS);
             sum.y = float(sum.y != 0.0f);
@@ -260,7 +273,7 @@ void Blur(const Pass& P, bool firstPass, Tex* t, int gridW, int gridH)
             result = lerp(centerTap, result, f);
 
             f = lerp(4.0f, 1.0f, f);
-            result *= f;
+            result *= float4(f);
             penumbra *= f;
             sum *= float2(f);
 
@@ -280,7 +293,7 @@ void Blur(const Pass& P, bool firstPass, Tex* t, int gridW, int gridH)
                 float2 uvScaled = P.ClampUvToViewport(uv);
                 float penum = gIn_Penumbra.sampleNearest(uvScaled).x;
                 float zs = P.UnpackViewZ(gIn_ViewZ.sampleNearest(uvScaled).x);
-                float s = firstPass ? float(IsLit(penum)) : gIn_Shadow->sampleNearest(uvScaled).x;
+                float4 s = hasShadowInput ? gIn_Shadow->sampleNearest(uvScaled) : float4(float(IsLit(penum)));
                 if (!firstPass) s = UnpackShadow(s);
                 float3 Xvs = Geometry::ReconstructViewPosition(uv, c.gFrustum, zs, c.gOrthoMode);
                 float w = IsInScreenNearest(uv);
@@ -288,14 +301,14 @@ void Blur(const Pass& P, bool firstPass, Tex* t, int gridW, int gridH)
                 w *= AreBothLitOrUnlit(centerPenumbra, penum);
                 w *= GetGaussianWeight(offset.z);
                 w *= saturate(penum * invEstimatedPenumbra);
-                result += w == 0.0f ? 0.0f : s * w;
+                result += w == 0.0f ? float4(0.0f) : s * float4(w);
                 sum.x += w;
                 w *= pixelSize / (pixelSize + penum);
                 w *= float(!IsLit(penum));
                 penumbra += w == 0.0f ? 0.0f : penum * w;
                 sum.y += w;
             }
-            result /= sum.x;
+            result /= float4(sum.x);
             penumbra = sum.y == 0.0f ? centerPenumbra : penumbra / sum.y;
 
             if (firstPass || c.gStabilizationStrength != 0.0f) gOut_Penumbra.store(pixelPos, penumbra);
@@ -324,7 +337,7 @@ void TemporalStabilization(const Pass& P, Tex* t, int gridW, int gridH)
         {
             const int2 pixelPos(x, y);
             float isSky = gIn_Tiles.load(x >> 4, y >> 4).x;
-            auto sShadow = [&](int i, int j) { return UnpackShadow(gIn_Shadow.load(clamp(int2(x + i - BORDER, y + j - BORDER), int2(0), rectMax)).x); };
+            auto sShadow = [&](int i, int j) { return UnpackShadow(gIn_Shadow.load(clamp(int2(x + i - BORDER, y + j - BORDER), int2(0), rectMax))); };
             auto sPenumbra = [&](int i, int j) { return gIn_Penumbra.load(clamp(int2(x + i - BORDER, y + j - BORDER), int2(0), rectMax)).x; };
             float viewZ = P.UnpackViewZ(gIn_ViewZ.load(pixelPos).x);
             if (isSky != 0.0f || x > rectMax.x || y > rectMax.y || viewZ > c.gDenoisingRange) continue;
@@ -340,11 +353,12 @@ void TemporalStabilization(const Pass& P, Tex* t, int gridW, int gridH)
                 continue;
             }
 
-            float sum = 0.0f, m1 = 0.0f, m2 = 0.0f, input = 0.0f;
+            float sum = 0.0f;
+            float4 m1(0.0f), m2(0.0f), input(0.0f);
             for (int j = 0; j <= BORDER * 2; j++)
                 for (int i = 0; i <= BORDER * 2; i++)
                 {
-                    float s = sShadow(i, j);
+                    float4 s = sShadow(i, j);
                     float w = 1.0f;
                     if (i == BORDER && j == BORDER) input = s;
                     else
@@ -353,13 +367,13 @@ void TemporalStabilization(const Pass& P, Tex* t, int gridW, int gridH)
                         w = AreBothLitOrUnlit(centerPenumbra, penum);
                         w *= GetGaussianWeight(length(float2(float(i - BORDER), float(j - BORDER)) / float2(float(BORDER))));
                     }
-                    m1 += s * w;
-                    m2 += s * s * w;
+                    m1 += s * float4(w);
+                    m2 += s * s * float4(w);
                     sum += w;
                 }
-            m1 /= sum;
-            m2 /= sum;
-            float sigma = GetStdDev(m1, m2);
+            m1 /= float4(sum);
+            m2 /= float4(sum);
+            float4 sigma = GetStdDev4(m1, m2);
 
             float3 Xv = Geometry::ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
             float3 X = Geometry::RotateVectorInverse(c.gWorldToView, Xv);
@@ -398,22 +412,22 @@ void TemporalStabilization(const Pass& P, Tex* t, int gridW, int gridH)
             float historyLength = Filtering::ApplyBilinearCustomWeights(prevHistoryLength.x, prevHistoryLength.y, prevHistoryLength.z, prevHistoryLength.w, smbOcclusionWeights);
 
             bool isCatRomAllowed = dot(smbOcclusionWeights, float4(1.0f)) > 3.5f;
-            float history = BicubicCustom(saturate(smbPixelUv) * c.gRectSizePrev, c.gResourceSizeInvPrev, smbOcclusionWeights, isCatRomAllowed, gIn_History).x;
+            float4 history = BicubicCustom(saturate(smbPixelUv) * c.gRectSizePrev, c.gResourceSizeInvPrev, smbOcclusionWeights, isCatRomAllowed, gIn_History);
             history = saturate(history);
             history = UnpackShadow(history);
 
-            sigma *= lerp(SIGMA_TS_SIGMA_SCALE, 1.0f, 1.0f / (1.0f + historyLength));
-            float inputMin = m1 - sigma, inputMax = m1 + sigma;
-            float historyClamped = clamp(history, inputMin, inputMax);
+            sigma *= float4(lerp(SIGMA_TS_SIGMA_SCALE, 1.0f, 1.0f / (1.0f + historyLength)));
+            float4 inputMin = m1 - sigma, inputMax = m1 + sigma;
+            float4 historyClamped = clamp4(history, inputMin, inputMax);
 
-            float antilag = abs(historyClamped - history);
+            float antilag = abs(historyClamped.x - history.x); // ".x" only, also for the translucent variant (:174)
             antilag = Math::Sqrt01(antilag);
             antilag = saturate(1.0f - antilag);
             historyLength *= antilag;
             float historyWeight = historyLength / (1.0f + historyLength);
             float streetMagic = 0.6f * historyWeight * antilag;
             historyClamped = lerp(historyClamped, history, streetMagic);
-            float result = lerp(input, historyClamped, min(c.gStabilizationStrength, historyWeight));
+            float4 result = lerp(input, historyClamped, min(c.gStabilizationStrength, historyWeight));
             historyLength = min(historyLength + 1.0f, SIGMA_MAX_ACCUM_FRAME_NUM);
 
             gOut_Shadow.store(pixelPos, PackShadow(result));
@@ -428,13 +442,20 @@ int sigma_dispatch_impl(const char* shaderName, const void* constants, int const
     CB cb{};
     memcpy(&cb, constants, constantsSize < (int)sizeof(CB) ? constantsSize : (int)sizeof(CB));
     Pass P(cb);
-    if (!strcmp(shaderName, "SIGMA_Shadow_ClassifyTiles.cs")) ClassifyTiles(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "SIGMA_SmoothTiles.cs")) SmoothTiles(P, tex, gridW, gridH);
+    if (!strcmp(shaderName, "SIGMA_SmoothTiles.cs")) SmoothTiles(P, tex, gridW, gridH);
     else if (!strcmp(shaderName, "SIGMA_Copy.cs")) Copy(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "SIGMA_Shadow_Blur.cs")) Blur(P, true, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "SIGMA_Shadow_PostBlur.cs")) Blur(P, false, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "SIGMA_Shadow_TemporalStabilization.cs")) TemporalStabilization(P, tex, gridW, gridH);
-    else return -1;
+    else
+    {
+        // "SIGMA_Shadow_<pass>.cs" (SIGMA_TYPE float) / "SIGMA_ShadowTranslucency_<pass>.cs" (SIGMA_TRANSLUCENT, SIGMA_TYPE float4)
+        const bool translucent = !strncmp(shaderName, "SIGMA_ShadowTranslucency_", 25);
+        if (!translucent && strncmp(shaderName, "SIGMA_Shadow_", 13) != 0) return -1;
+        const char* pass = shaderName + (translucent ? 25 : 13);
+        if (!strcmp(pass, "ClassifyTiles.cs")) ClassifyTiles(P, translucent, tex, gridW, gridH);
+        else if (!strcmp(pass, "Blur.cs")) Blur(P, true, translucent, tex, gridW, gridH);
+        else if (!strcmp(pass, "PostBlur.cs")) Blur(P, false, translucent, tex, gridW, gridH);
+        else if (!strcmp(pass, "TemporalStabilization.cs")) TemporalStabilization(P, tex, gridW, gridH);
+        else return -1;
+    }
     return 0;
 }
 } // namespace hlsl

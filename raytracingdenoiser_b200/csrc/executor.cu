@@ -112,7 +112,9 @@ struct NrdCudaContext
     Texture guide;
     bool guideValid = false;
     // roughness table of the REBLUR spatial passes (surf.h PassLaunch::roughnessLut), rebuilt when hitDistanceParameters change
-    float* roughnessLut = nullptr;
+    float* roughnessLut = nullptr;     // device, 1024 x float4 (allocated with the context: no cudaMalloc -- an implicit device
+    float* roughnessLutStaging = nullptr; // synchronisation -- may happen while a strip barrier spins); pinned staging copy
+    cudaEvent_t lutUploaded = nullptr;
     float lutKey[2] = {0.0f, 0.0f};
     bool lutValid = false;
     // strip mode
@@ -202,8 +204,9 @@ Surf ToSurf(const NrdCudaContext* ctx, const Texture& t)
 Result UpdateRoughnessLut(NrdCudaContext* ctx, const float* hitDistParams, cudaStream_t stream)
 {
     if (ctx->lutValid && ctx->lutKey[0] == hitDistParams[2] && ctx->lutKey[1] == hitDistParams[3]) return Result::SUCCESS;
-    if (!ctx->roughnessLut && cudaMalloc((void**)&ctx->roughnessLut, 1024 * 4 * sizeof(float)) != cudaSuccess) return Fail(ctx, Result::FAILURE, "cudaMalloc(roughness table)");
-    static thread_local float table[1024 * 4];
+    if (!ctx->roughnessLut || !ctx->roughnessLutStaging) return Fail(ctx, Result::FAILURE, "roughness table was not allocated");
+    if (ctx->lutValid) cudaEventSynchronize(ctx->lutUploaded); // the previous upload has left the staging buffer
+    float* table = ctx->roughnessLutStaging;
     for (int i = 0; i < 1024; i++)
     {
         volatile float r = (float)i / 1023.0f;
@@ -227,8 +230,8 @@ Result UpdateRoughnessLut(NrdCudaContext* ctx, const float* hitDistParams, cudaS
         table[i * 4 + 2] = aLog;
         table[i * 4 + 3] = r;
     }
-    // pageable source: the runtime stages it before returning, so the static buffer can be rewritten by the next call
-    cudaError_t e = cudaMemcpyAsync(ctx->roughnessLut, table, sizeof(table), cudaMemcpyHostToDevice, stream);
+    cudaError_t e = cudaMemcpyAsync(ctx->roughnessLut, table, 1024 * 4 * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->lutUploaded, stream);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("roughness table upload: ") + cudaGetErrorString(e));
     ctx->lutKey[0] = hitDistParams[2];
     ctx->lutKey[1] = hitDistParams[3];
@@ -529,6 +532,12 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
         delete ctx;
         return Result::FAILURE;
     }
+    if (cudaMalloc((void**)&ctx->roughnessLut, 1024 * 4 * sizeof(float)) != cudaSuccess || cudaMallocHost((void**)&ctx->roughnessLutStaging, 1024 * 4 * sizeof(float)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->lutUploaded, cudaEventDisableTiming) != cudaSuccess)
+    {
+        nrdCudaDestroyContext(ctx);
+        return Result::FAILURE;
+    }
     cudaMemset(ctx->arena, 0, ctx->arenaBytes);
     // the memset runs on the legacy default stream, the context is used on the caller's (non-blocking) streams and by peers:
     // nothing may touch the arena (barrier flags included) before it is zero
@@ -558,6 +567,8 @@ NRD_API void nrdCudaDestroyContext(NrdCudaContext* ctx)
     }
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->roughnessLut) cudaFree(ctx->roughnessLut);
+    if (ctx->roughnessLutStaging) cudaFreeHost(ctx->roughnessLutStaging);
+    if (ctx->lutUploaded) cudaEventDestroy(ctx->lutUploaded);
     delete ctx;
 }
 

@@ -1,5 +1,5 @@
-// SIGMA_SHADOW pass graph and per-frame schedule.
-// Restates the reference's Source/Denoisers/Sigma_Shadow.hpp:11-170 (pools, bindings) and
+// SIGMA_SHADOW / SIGMA_SHADOW_TRANSLUCENCY pass graphs and per-frame schedule.
+// Restates the reference's Source/Denoisers/Sigma_Shadow.hpp:11-170, Sigma_ShadowTranslucency.hpp:11-173 (pools, bindings) and
 // Source/Sigma.cpp:25-90 (Update_SigmaShadow), :92-145 (AddSharedConstants_Sigma).
 #include "scheduler.h"
 
@@ -16,11 +16,25 @@ constexpr uint16_t R(ResourceType t) { return (uint16_t)t; }
 enum SigmaPass : uint32_t { SG_CLASSIFY_TILES, SG_SMOOTH_TILES, SG_COPY, SG_BLUR, SG_POST_BLUR /* 2 */, SG_TEMPORAL_STABILIZATION = SG_POST_BLUR + 2, SG_SPLIT_SCREEN };
 } // namespace
 
-void Scheduler::AddSigmaShadow(DenoiserSlot& slot)
+// translucent = SIGMA_SHADOW_TRANSLUCENCY: the shadow signal is a float4 (SIGMA_TYPE, SIGMA_Config.hlsli:38-43) in RGBA8 textures,
+// IN_TRANSLUCENCY feeds ClassifyTiles / Blur / SplitScreen, and Blur runs at the rect size instead of USE_MAX_DIMS
+void Scheduler::AddSigmaShadow(DenoiserSlot& slot, bool translucent)
 {
     new (&slot.settings.sigma) SigmaSettings();
     slot.settingsSize = sizeof(SigmaSettings);
-    const char* dn = "SIGMA_Shadow";
+    const char* dn = translucent ? "SIGMA_ShadowTranslucency" : "SIGMA_Shadow";
+    const Format shadowFormat = translucent ? Format::RGBA8_UNORM : Format::R8_UNORM;
+    // "SIGMA_Shadow_<pass>.cs" / "SIGMA_ShadowTranslucency_<pass>.cs" (string literals: they outlive every instance)
+    static const char* const kNames[2][5] = {
+        {"SIGMA_Shadow_ClassifyTiles.cs", "SIGMA_Shadow_Blur.cs", "SIGMA_Shadow_PostBlur.cs", "SIGMA_Shadow_TemporalStabilization.cs", "SIGMA_Shadow_SplitScreen.cs"},
+        {"SIGMA_ShadowTranslucency_ClassifyTiles.cs", "SIGMA_ShadowTranslucency_Blur.cs", "SIGMA_ShadowTranslucency_PostBlur.cs",
+         "SIGMA_ShadowTranslucency_TemporalStabilization.cs", "SIGMA_ShadowTranslucency_SplitScreen.cs"}};
+    auto shader = [&](const char* pass) {
+        static const char* const passes[5] = {"ClassifyTiles", "Blur", "PostBlur", "TemporalStabilization", "SplitScreen"};
+        for (int i = 0; i < 5; i++)
+            if (!strcmp(pass, passes[i])) return kNames[translucent ? 1 : 0][i];
+        return (const char*)nullptr;
+    };
     // the reference reports sizeof() of its C++ struct, which has no tail padding to a 16-byte register (516, not 528)
     const uint32_t cb = offsetof(SigmaConstants, gIsRectChanged) + sizeof(uint32_t);
 
@@ -31,17 +45,18 @@ void Scheduler::AddSigmaShadow(DenoiserSlot& slot)
                    T_HISTORY = kTransientBase + 4, T_HISTORY_LENGTH = kTransientBase + 5, T_TILES = kTransientBase + 6, T_SMOOTHED_TILES = kTransientBase + 7;
     AddTransient(Format::R16_SFLOAT);
     AddTransient(Format::R16_SFLOAT);
-    AddTransient(Format::R8_UNORM);
-    AddTransient(Format::R8_UNORM);
-    AddTransient(Format::R8_UNORM);
+    AddTransient(shadowFormat);
+    AddTransient(shadowFormat);
+    AddTransient(shadowFormat);
     AddTransient(Format::R32_UINT);
     AddTransient(Format::RGBA8_UNORM, 16);
     AddTransient(Format::RG8_UNORM, 16);
 
     BeginPass(dn, "Classify tiles");
     In(R(ResourceType::IN_VIEWZ)); In(R(ResourceType::IN_PENUMBRA));
+    if (translucent) In(R(ResourceType::IN_TRANSLUCENCY));
     Out(T_TILES);
-    Emit("SIGMA_Shadow_ClassifyTiles.cs", 16, 16, cb);
+    Emit(shader("ClassifyTiles"), 16, 16, cb);
 
     BeginPass(dn, "Smooth tiles");
     In(T_TILES);
@@ -55,8 +70,9 @@ void Scheduler::AddSigmaShadow(DenoiserSlot& slot)
 
     BeginPass(dn, "Blur");
     In(R(ResourceType::IN_VIEWZ)); In(R(ResourceType::IN_NORMAL_ROUGHNESS)); In(R(ResourceType::IN_PENUMBRA)); In(T_SMOOTHED_TILES);
+    if (translucent) In(R(ResourceType::IN_TRANSLUCENCY));
     Out(T_DATA_1); Out(T_TEMP_1);
-    Emit("SIGMA_Shadow_Blur.cs", 8, 16, cb, kUseMaxDims);
+    Emit(shader("Blur"), 8, 16, cb, translucent ? (uint16_t)1 : kUseMaxDims);
 
     for (int i = 0; i < 2; i++)
     {
@@ -65,18 +81,19 @@ void Scheduler::AddSigmaShadow(DenoiserSlot& slot)
         In(R(ResourceType::IN_VIEWZ)); In(R(ResourceType::IN_NORMAL_ROUGHNESS)); In(T_DATA_1); In(T_SMOOTHED_TILES); In(T_TEMP_1);
         Out(T_DATA_2);
         Out(stabilized ? T_TEMP_2 : R(ResourceType::OUT_SHADOW_TRANSLUCENCY));
-        Emit("SIGMA_Shadow_PostBlur.cs", 8, 16, cb);
+        Emit(shader("PostBlur"), 8, 16, cb);
     }
 
     BeginPass(dn, "Temporal stabilization");
     In(R(ResourceType::IN_VIEWZ)); In(R(ResourceType::IN_MV)); In(T_DATA_2); In(T_TEMP_2); In(T_HISTORY); In(T_HISTORY_LENGTH); In(T_SMOOTHED_TILES);
     Out(R(ResourceType::OUT_SHADOW_TRANSLUCENCY)); Out(P_HISTORY_LENGTH);
-    Emit("SIGMA_Shadow_TemporalStabilization.cs", 8, 16, cb);
+    Emit(shader("TemporalStabilization"), 8, 16, cb);
 
     BeginPass(dn, "Split screen");
     In(R(ResourceType::IN_VIEWZ)); In(R(ResourceType::IN_PENUMBRA));
+    if (translucent) In(R(ResourceType::IN_TRANSLUCENCY));
     Out(R(ResourceType::OUT_SHADOW_TRANSLUCENCY));
-    Emit("SIGMA_Shadow_SplitScreen.cs", 8, 16, cb);
+    Emit(shader("SplitScreen"), 8, 16, cb);
 }
 
 void Scheduler::UpdateSigma(const DenoiserSlot& slot)

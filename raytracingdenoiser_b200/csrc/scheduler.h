@@ -134,7 +134,7 @@ private:
     void AddRelaxDiffuseSpecular(DenoiserSlot& slot);
     void UpdateRelax(const DenoiserSlot& slot);
     void FillRelaxConstants(const nrd::RelaxSettings& s, void* data);
-    void AddSigmaShadow(DenoiserSlot& slot);
+    void AddSigmaShadow(DenoiserSlot& slot, bool translucent);
     void UpdateSigma(const DenoiserSlot& slot);
     void FillSigmaConstants(const nrd::SigmaSettings& s, void* data);
 

@@ -32,45 +32,47 @@ def _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call, weigh
         partition = strips.partition_rows_weighted(h, world, cost, min_rows=max(halo, 16))
         assert len(set(y1 - y0 for y0, y1 in partition[1])) > 1, partition
     parts = [strips.StripDenoiser(den, w, h, r, world, halo_rows=halo, partition=partition) for r in range(world)]
-    for p in parts:
-        p.connect_local(parts)
-    streams = [torch.cuda.Stream() for _ in parts]
-    sc = scene.Scene(w, h)
-    for f in range(frames):
-        fr = sc.frame(f, mode)
-        cs = harness.make_common_settings(fr, w, h, f)
-        full.set_inputs(fr)
-        full.denoise(cs)
+    try:  # a failing case must not leak its strip-mode contexts (there are only kMaxPeerSlots per process)
+        for p in parts:
+            p.connect_local(parts)
+        streams = [torch.cuda.Stream() for _ in parts]
+        sc = scene.Scene(w, h)
+        for f in range(frames):
+            fr = sc.frame(f, mode)
+            cs = harness.make_common_settings(fr, w, h, f)
+            full.set_inputs(fr)
+            full.denoise(cs)
+            torch.cuda.synchronize()
+            if whole_frame_call:
+                # nrdCudaDenoise per rank (with the ghost look-ahead): all launches are asynchronous, the ranks meet on the device
+                for p, st in zip(parts, streams):
+                    p.set_inputs(fr, st)
+                    p.denoise(cs, st)
+            else:
+                lists = []
+                for p, st in zip(parts, streams):
+                    p.set_inputs(fr, st)
+                    lists.append(p.dispatches(cs))
+                    p.ctx.barrier(st.cuda_stream)
+                n = lists[0][1]
+                assert all(m == n for _, m in lists)
+                # application-driven dispatch loop, ranks interleaved pass by pass
+                for i in range(n):
+                    for p, st, (raw, _) in zip(parts, streams, lists):
+                        p.ctx.execute_raw(C.byref(raw[i]), st.cuda_stream)
+            for p, st in zip(parts, streams):
+                p.synchronize(st)
+        ref = full.outputs()
+        outs = [p.read_outputs(stream=st) for p, st in zip(parts, streams)]
         torch.cuda.synchronize()
-        if whole_frame_call:
-            # nrdCudaDenoise per rank (with the ghost look-ahead): all launches are asynchronous, the ranks meet on the device
-            for p, st in zip(parts, streams):
-                p.set_inputs(fr, st)
-                p.denoise(cs, st)
-        else:
-            lists = []
-            for p, st in zip(parts, streams):
-                p.set_inputs(fr, st)
-                lists.append(p.dispatches(cs))
-                p.ctx.barrier(st.cuda_stream)
-            n = lists[0][1]
-            assert all(m == n for _, m in lists)
-            # application-driven dispatch loop, ranks interleaved pass by pass
-            for i in range(n):
-                for p, st, (raw, _) in zip(parts, streams, lists):
-                    p.ctx.execute_raw(C.byref(raw[i]), st.cuda_stream)
-        for p, st in zip(parts, streams):
-            p.synchronize(st)
-    ref = full.outputs()
-    outs = [p.read_outputs(stream=st) for p, st in zip(parts, streams)]
-    torch.cuda.synchronize()
-    for name, t in ref.items():
-        got = torch.cat([o[name] for o in outs], dim=0)
-        same = (got.view(torch.uint8) == t.view(torch.uint8))
-        assert bool(same.all()), (name, float(same.float().mean()))
-    for p in parts:
-        p.destroy()
-    full.destroy()
+        for name, t in ref.items():
+            got = torch.cat([o[name] for o in outs], dim=0)
+            same = (got.view(torch.uint8) == t.view(torch.uint8))
+            assert bool(same.all()), (name, float(same.float().mean()))
+    finally:
+        for p in parts:
+            p.destroy()
+        full.destroy()
 
 
 @pytest.mark.parametrize("denoiser,w,h,world,frames,halo,whole_frame_call", [
