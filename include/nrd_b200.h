@@ -368,7 +368,7 @@ NRD_API nrd::Result nrdCudaCreateContext(nrd::Instance* instance, const NrdCudaC
 NRD_API void nrdCudaDestroyContext(NrdCudaContext* context);
 // Binds an application texture (IN_* / OUT_*).  Required formats: IN_MV RGBA16_SFLOAT, IN_NORMAL_ROUGHNESS
 // R10_G10_B10_A2_UNORM, IN_VIEWZ R32_SFLOAT, IN/OUT_*_RADIANCE_HITDIST RGBA16_SFLOAT, IN_PENUMBRA R16_SFLOAT,
-// OUT_SHADOW_TRANSLUCENCY R8_UNORM.  `devicePtr` addresses texel (0, firstRow of the context).
+// IN_TRANSLUCENCY RGBA8_UNORM, OUT_SHADOW_TRANSLUCENCY R8_UNORM (SIGMA_SHADOW) / RGBA8_UNORM (SIGMA_SHADOW_TRANSLUCENCY).  `devicePtr` addresses texel (0, firstRow of the context).
 NRD_API nrd::Result nrdCudaSetUserTexture(NrdCudaContext* context, uint32_t resourceType, void* devicePtr, size_t pitchBytes, uint32_t format);
 // Looks a texture up exactly like a DispatchDesc resource would be resolved.
 NRD_API nrd::Result nrdCudaGetTexture(NrdCudaContext* context, uint32_t resourceType, uint32_t indexInPool, NrdCudaTextureInfo* info);

@@ -1,4 +1,6 @@
-// SIGMA_SHADOW passes on sm_100a: ClassifyTiles, SmoothTiles, Copy, Blur / PostBlur, TemporalStabilization.
+// SIGMA_SHADOW / SIGMA_SHADOW_TRANSLUCENCY passes on sm_100a: ClassifyTiles, SmoothTiles, Copy, Blur / PostBlur, TemporalStabilization.
+// The shadow signal is SIGMA_TYPE (SIGMA_Config.hlsli:38-43): a float in R8 textures, or -- translucent variant, template flag TR --
+// a float4 {shadow, translucency.rgb} in RGBA8 textures fed by IN_TRANSLUCENCY.  The kernels are written once over sgt:: overloads.
 // Semantics: reference Shaders/Include/SIGMA_ClassifyTiles.hlsli:10-81, SIGMA_SmoothTiles.hlsli:10-48, SIGMA_Copy.hlsli:10-24,
 // SIGMA_Blur.hlsli:11-268, SIGMA_TemporalStabilization.hlsli:10-226, SIGMA_Common.hlsli:13-130 (default switches:
 // 5x5 dense estimate, sparse 8-tap blur in screen space, NRD_FRAME rotators, CatRom history).
@@ -64,15 +66,46 @@ __device__ __forceinline__ f2 TextureCubic(const Surf& s, float u, float v)
 }
 } // namespace sg
 
+// the shadow signal: float (opaque) or f4 (translucent); one set of overloads so that every kernel is written once
+namespace sgt
+{
+template <bool TR> struct Sig { typedef float T; };
+template <> struct Sig<true> { typedef f4 T; };
+__device__ __forceinline__ float Splat(float v, float) { return v; }
+__device__ __forceinline__ f4 Splat(float v, f4) { return mk4(v); }
+__device__ __forceinline__ float X(float v) { return v; }
+__device__ __forceinline__ float X(f4 v) { return v.x; }
+__device__ __forceinline__ float Scale(float v, float w) { return v * w; }
+__device__ __forceinline__ f4 Scale(f4 v, float w) { return v * w; }
+__device__ __forceinline__ float Sq(float v) { return v * v; }
+__device__ __forceinline__ f4 Sq(f4 v) { return v * v; }
+__device__ __forceinline__ float Lerp(float a, float b, float t) { return lerpf(a, b, t); }
+__device__ __forceinline__ f4 Lerp(f4 a, f4 b, float t) { return lerp4(a, b, t); }
+__device__ __forceinline__ float Clamp(float v, float a, float b) { return clampf(v, a, b); }
+__device__ __forceinline__ f4 Clamp(f4 v, f4 a, f4 b) { return mk4(clampf(v.x, a.x, b.x), clampf(v.y, a.y, b.y), clampf(v.z, a.z, b.z), clampf(v.w, a.w, b.w)); }
+__device__ __forceinline__ float Sat(float v) { return saturate(v); }
+__device__ __forceinline__ f4 Sat(f4 v) { return mk4(saturate(v.x), saturate(v.y), saturate(v.z), saturate(v.w)); }
+__device__ __forceinline__ float Pack(float v) { return Sqrt01(v); } // PackShadow (SIGMA_Common.hlsli:13)
+__device__ __forceinline__ f4 Pack(f4 v) { return mk4(Sqrt01(v.x), Sqrt01(v.y), Sqrt01(v.z), Sqrt01(v.w)); }
+__device__ __forceinline__ float StdDev(float m1, float m2) { return GetStdDev(m1, m2); }
+__device__ __forceinline__ f4 StdDev(f4 m1, f4 m2) { return mk4(GetStdDev(m1.x, m2.x), GetStdDev(m1.y, m2.y), GetStdDev(m1.z, m2.z), GetStdDev(m1.w, m2.w)); }
+// texel access in the signal's storage format (R8_UNORM / RGBA8_UNORM)
+__device__ __forceinline__ void Load(const Surf& s, int x, int y, float& v) { v = LoadR8Unorm(s, x, y); }
+__device__ __forceinline__ void Load(const Surf& s, int x, int y, f4& v) { v = UnpackRGBA8(LoadU32(s, x, y)); }
+__device__ __forceinline__ void Store(const Surf& s, int x, int y, float v) { StoreR8Unorm(s, x, y, v); }
+__device__ __forceinline__ void Store(const Surf& s, int x, int y, f4 v) { StoreU32(s, x, y, PackRGBA8(v)); }
+} // namespace sgt
+
 // ---------------------------------------------------------------------------------------------
 struct SigmaTilesArgs
 {
-    Surf z, penumbra, tiles;
+    Surf z, penumbra, translucency, tiles;
     float viewZScale, denoisingRange, unproject, orthoMode;
     int tilesW, tilesH;
 };
 
 // one warp per 16x16 tile: 3 counters + max radius reduced with shuffles (no shared-memory atomics)
+template <bool TR>
 __global__ void __launch_bounds__(256) SigmaClassifyTilesKernel(const __grid_constant__ SigmaTilesArgs a)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -87,15 +120,21 @@ __global__ void __launch_bounds__(256) SigmaClassifyTilesKernel(const __grid_con
         int idx = i * 32 + lane;
         int x = tx * 16 + (idx & 15), y = ty * 16 + (idx >> 4);
         float h = 0.0f, z = 0.0f;
+        bool isOpaque = true;
         if (Inside(a.z, x, y))
         {
             h = LoadR16F(a.penumbra, x, y);
             z = LoadR32F(a.z, x, y);
+            if (TR) // SIGMA_ClassifyTiles.hlsli:45-48: luminance of the translucency colour (out-of-bounds loads read 0: opaque)
+            {
+                const f4 t = UnpackRGBA8(LoadU32(a.translucency, x, y));
+                isOpaque = (t.y * 0.2126f + t.z * 0.7152f + t.w * 0.0722f) < 0.003f;
+            }
         }
         float viewZ = fabsf(z * a.viewZScale);
         bool isInf = viewZ > a.denoisingRange, isShadow = h == 0.0f, isLit = sg::IsLit(h);
         nLit += (isLit || isInf || isShadow) ? 1 : 0;
-        nUmbra += (!isLit || isInf || isShadow) ? 1 : 0;
+        nUmbra += ((!isLit && isOpaque) || isInf || isShadow) ? 1 : 0;
         nInf += isInf ? 1 : 0;
         float hitDist = (isLit || isInf) ? 0.0f : h;
         float pixelSize = a.unproject * lerpf(viewZ, 1.0f, fabsf(a.orthoMode));
@@ -150,12 +189,14 @@ struct SigmaCopyArgs
     int w, h, isRectChanged, rowBegin, rowEnd;
 };
 
+template <bool TR>
 __global__ void __launch_bounds__(256) SigmaCopyKernel(const __grid_constant__ SigmaCopyArgs a)
 {
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
     if (x >= a.w || y >= a.h || y >= a.rowEnd) return;
     if (LoadRG8Unorm(a.tiles, x >> 4, y >> 4).x != 0.0f && !a.isRectChanged) return;
-    StoreU8(a.outHistory, x, y, LoadU8(a.inHistory, x, y));
+    if (TR) StoreU32(a.outHistory, x, y, LoadU32(a.inHistory, x, y));
+    else StoreU8(a.outHistory, x, y, LoadU8(a.inHistory, x, y));
     StoreU32(a.outLength, x, y, LoadU32(a.inLength, x, y));
 }
 
@@ -167,9 +208,10 @@ struct SigmaBlurArgs
     int rowBegin, rowEnd;
 };
 
-template <bool FIRST>
+template <bool FIRST, bool TR>
 __global__ void __launch_bounds__(256) SigmaBlurKernel(const __grid_constant__ SigmaBlurArgs a)
 {
+    typedef typename sgt::Sig<TR>::T S;
     const SigmaConstants& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
@@ -180,10 +222,13 @@ __global__ void __launch_bounds__(256) SigmaBlurKernel(const __grid_constant__ S
     const float viewZ = fabsf(LoadR32F(a.z, x, y) * c.gViewZScale);
     if (viewZ > c.gDenoisingRange) return;
 
-    auto shadowAt = [&](int px, int py, float penum) {
-        if (FIRST) return sg::IsLit(penum) ? 1.0f : 0.0f;
-        float s = LoadR8Unorm(a.shadow, px, py);
-        return s * s;
+    // SIGMA_Blur.hlsli:24-34: the signal comes from a texture unless this is the first pass of the opaque variant; only the
+    // second pass reads a packed (sqrt) value
+    auto shadowAt = [&](int px, int py, float penum) -> S {
+        if (FIRST && !TR) return sgt::Splat(sg::IsLit(penum) ? 1.0f : 0.0f, S());
+        S s;
+        sgt::Load(a.shadow, px, py, s);
+        return FIRST ? s : sgt::Sq(s);
     };
 
     const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
@@ -191,7 +236,7 @@ __global__ void __launch_bounds__(256) SigmaBlurKernel(const __grid_constant__ S
     if (tileValue == 0.0f || centerPenumbra == 0.0f)
     {
         StoreR16F(a.outPenumbra, x, y, centerPenumbra);
-        StoreR8Unorm(a.outShadow, x, y, Sqrt01(shadowAt(x, y, centerPenumbra)));
+        sgt::Store(a.outShadow, x, y, sgt::Pack(shadowAt(x, y, centerPenumbra)));
         return;
     }
 
@@ -205,7 +250,8 @@ __global__ void __launch_bounds__(256) SigmaBlurKernel(const __grid_constant__ S
     const float geoA = 1.0f / (c.gPlaneDistSensitivity * frustumSize), geoB = -dot(Nv, Xv) * geoA;
 
     // dense 5x5: shadow filter + penumbra size estimate
-    float sumX = 0.0f, sumY = 0.0f, penumbra = 0.0f, result = 0.0f, centerTap = 0.0f;
+    float sumX = 0.0f, sumY = 0.0f, penumbra = 0.0f;
+    S result = sgt::Splat(0.0f, S()), centerTap = sgt::Splat(0.0f, S());
 #pragma unroll
     for (int j = -2; j <= 2; j++)
 #pragma unroll
@@ -213,7 +259,7 @@ __global__ void __launch_bounds__(256) SigmaBlurKernel(const __grid_constant__ S
         {
             int px = clampi(x + i, 0, maxX), py = clampi(y + j, 0, maxY);
             float penum = LoadR16F(a.penumbra, px, py);
-            float s = shadowAt(px, py, penum);
+            S s = shadowAt(px, py, penum);
             float w = 1.0f;
             if (i == 0 && j == 0) centerTap = s;
             else
@@ -226,22 +272,22 @@ __global__ void __launch_bounds__(256) SigmaBlurKernel(const __grid_constant__ S
                 float r2 = (float)(i * i + j * j) * 0.25f; // (length(offset / BORDER))^2
                 w *= __expf(-0.66f * r2);
             }
-            result += w == 0.0f ? 0.0f : s * w;
+            if (w != 0.0f) result = result + sgt::Scale(s, w);
             sumX += w;
             w *= pixelSize / (pixelSize + penum);
             w *= sg::IsLit(penum) ? 0.0f : 1.0f;
             penumbra += w == 0.0f ? 0.0f : penum * w;
             sumY += w;
         }
-    result /= sumX;
+    result = sgt::Scale(result, 1.0f / sumX);
     sumX = 1.0f;
     penumbra /= fmaxf(sumY, kEps);
     sumY = sumY != 0.0f ? 1.0f : 0.0f;
 
     float f = SmoothStep(0.0f, 2.0f, penumbra / pixelSize);
-    result = lerpf(centerTap, result, f);
+    result = sgt::Lerp(centerTap, result, f);
     f = lerpf(4.0f, 1.0f, f);
-    result *= f;
+    result = sgt::Scale(result, f);
     penumbra *= f;
     sumX *= f;
     sumY *= f;
@@ -268,7 +314,7 @@ __global__ void __launch_bounds__(256) SigmaBlurKernel(const __grid_constant__ S
         int tx = clampi(ix, 0, W - 1), ty = clampi(iy, 0, H - 1);
         float penum = LoadR16F(a.penumbra, tx, ty);
         float zs = fabsf(LoadR32F(a.z, tx, ty) * c.gViewZScale);
-        float s = shadowAt(tx, ty, penum);
+        S s = shadowAt(tx, ty, penum);
         f2 uvs = mk2(__fmul_rn(__fadd_rn(fx, 0.5f), c.gRectSizeInv[0]), __fmul_rn(__fadd_rn(fy, 0.5f), c.gRectSizeInv[1]));
         f3 Xvs = ReconstructViewPosition(uvs, c.gFrustum, zs, c.gOrthoMode);
         float w = inScreen ? 1.0f : 0.0f;
@@ -276,18 +322,18 @@ __global__ void __launch_bounds__(256) SigmaBlurKernel(const __grid_constant__ S
         w *= sg::BothLitOrUnlit(centerPenumbra, penum);
         w *= n < 4 ? 0.516851340f : 0.847893725f; // exp(-0.66 * r^2), r = 1 / 0.5
         w *= saturate(penum * invEstimatedPenumbra);
-        result += w == 0.0f ? 0.0f : s * w;
+        if (w != 0.0f) result = result + sgt::Scale(s, w);
         sumX += w;
         w *= pixelSize / (pixelSize + penum);
         w *= sg::IsLit(penum) ? 0.0f : 1.0f;
         penumbra += w == 0.0f ? 0.0f : penum * w;
         sumY += w;
     }
-    result /= sumX;
+    result = sgt::Scale(result, 1.0f / sumX);
     penumbra = sumY == 0.0f ? centerPenumbra : penumbra / sumY;
 
     if (FIRST || c.gStabilizationStrength != 0.0f) StoreR16F(a.outPenumbra, x, y, penumbra);
-    StoreR8Unorm(a.outShadow, x, y, Sqrt01(result));
+    sgt::Store(a.outShadow, x, y, sgt::Pack(result));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -303,17 +349,24 @@ __device__ __forceinline__ unsigned PackViewZAndHistoryLength(float viewZ, float
     return (__float_as_uint(viewZ) & ~7u) | min((unsigned)(historyLength + 0.5f), 7u);
 }
 
-__device__ __forceinline__ float R8Clamped(const Surf& s, int x, int y) { return LoadR8Unorm(s, clampi(x, 0, s.w - 1), clampi(y, 0, s.h - 1)); }
-__device__ __forceinline__ float SampleLinearR8(const Surf& s, float u, float v)
+template <class S> __device__ __forceinline__ S SigClamped(const Surf& s, int x, int y)
+{
+    S v;
+    sgt::Load(s, clampi(x, 0, s.w - 1), clampi(y, 0, s.h - 1), v);
+    return v;
+}
+template <class S> __device__ __forceinline__ S SampleLinearSig(const Surf& s, float u, float v)
 {
     float px = u * (float)s.w - 0.5f, py = v * (float)s.h - 0.5f;
     float fx = floorf(px), fy = floorf(py), wx = px - fx, wy = py - fy;
     int x0 = (int)fx, y0 = (int)fy;
-    return lerpf(lerpf(R8Clamped(s, x0, y0), R8Clamped(s, x0 + 1, y0), wx), lerpf(R8Clamped(s, x0, y0 + 1), R8Clamped(s, x0 + 1, y0 + 1), wx), wy);
+    return sgt::Lerp(sgt::Lerp(SigClamped<S>(s, x0, y0), SigClamped<S>(s, x0 + 1, y0), wx), sgt::Lerp(SigClamped<S>(s, x0, y0 + 1), SigClamped<S>(s, x0 + 1, y0 + 1), wx), wy);
 }
 
+template <bool TR>
 __global__ void __launch_bounds__(256) SigmaTemporalStabilizationKernel(const __grid_constant__ SigmaTsArgs a)
 {
+    typedef typename sgt::Sig<TR>::T S;
     const SigmaConstants& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
@@ -327,21 +380,24 @@ __global__ void __launch_bounds__(256) SigmaTemporalStabilizationKernel(const __
     const float tileValue = sg::TextureCubic(a.tiles, pixelUv.x * c.gResolutionScale[0], pixelUv.y * c.gResolutionScale[1]).y;
     if (tileValue == 0.0f || centerPenumbra == 0.0f)
     {
-        float s = LoadR8Unorm(a.shadow, x, y);
-        StoreR8Unorm(a.outShadow, x, y, Sqrt01(s * s));
+        S s;
+        sgt::Load(a.shadow, x, y, s);
+        sgt::Store(a.outShadow, x, y, sgt::Pack(sgt::Sq(s)));
         StoreU32(a.outLength, x, y, PackViewZAndHistoryLength(viewZ, 7.0f));
         return;
     }
 
-    float sum = 0.0f, m1 = 0.0f, m2 = 0.0f, input = 0.0f;
+    float sum = 0.0f;
+    S m1 = sgt::Splat(0.0f, S()), m2 = sgt::Splat(0.0f, S()), input = sgt::Splat(0.0f, S());
 #pragma unroll
     for (int j = -2; j <= 2; j++)
 #pragma unroll
         for (int i = -2; i <= 2; i++)
         {
             int px = clampi(x + i, 0, maxX), py = clampi(y + j, 0, maxY);
-            float s = LoadR8Unorm(a.shadow, px, py);
-            s *= s;
+            S s;
+            sgt::Load(a.shadow, px, py, s);
+            s = sgt::Sq(s);
             float w = 1.0f;
             if (i == 0 && j == 0) input = s;
             else
@@ -349,13 +405,13 @@ __global__ void __launch_bounds__(256) SigmaTemporalStabilizationKernel(const __
                 w = sg::BothLitOrUnlit(centerPenumbra, LoadR16F(a.penumbra, px, py));
                 w *= __expf(-0.66f * (float)(i * i + j * j) * 0.25f);
             }
-            m1 += s * w;
-            m2 += s * s * w;
+            m1 = m1 + sgt::Scale(s, w);
+            m2 = m2 + sgt::Scale(sgt::Sq(s), w);
             sum += w;
         }
-    m1 /= sum;
-    m2 /= sum;
-    float sigma = GetStdDev(m1, m2);
+    m1 = sgt::Scale(m1, 1.0f / sum);
+    m2 = sgt::Scale(m2, 1.0f / sum);
+    S sigma = sgt::StdDev(m1, m2);
 
     const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
     const f3 X = PinnedRotateInverse(c.gWorldToView, Xv);
@@ -399,52 +455,51 @@ __global__ void __launch_bounds__(256) SigmaTemporalStabilizationKernel(const __
 
     // history: CatRom-12 when the whole footprint is valid, else custom-weight bilinear (through the bilinear sampler taps)
     const bool useBicubic = wsum > 3.5f;
-    float history;
+    S history;
     {
         float spx = saturate(smbPixelUv.x) * c.gRectSizePrev[0], spy = saturate(smbPixelUv.y) * c.gRectSizePrev[1];
         float cx = floorf(spx - 0.5f) + 0.5f, cy = floorf(spy - 0.5f) + 0.5f;
         float fx = saturate(spx - cx), fy = saturate(spy - cy);
-        const float S = 0.5f;
-        float w0x = fx * (fx * (-S * fx + 2.0f * S) - S), w0y = fy * (fy * (-S * fy + 2.0f * S) - S);
-        float w1x = fx * (fx * ((2.0f - S) * fx - (3.0f - S))) + 1.0f, w1y = fy * (fy * ((2.0f - S) * fy - (3.0f - S))) + 1.0f;
-        float w2x = fx * (fx * (-(2.0f - S) * fx + (3.0f - 2.0f * S)) + S), w2y = fy * (fy * (-(2.0f - S) * fy + (3.0f - 2.0f * S)) + S);
-        float w3x = fx * (fx * (S * fx - S)), w3y = fy * (fy * (S * fy - S));
+        const float kS = 0.5f; // CatRom sharpness
+        float w0x = fx * (fx * (-kS * fx + 2.0f * kS) - kS), w0y = fy * (fy * (-kS * fy + 2.0f * kS) - kS);
+        float w1x = fx * (fx * ((2.0f - kS) * fx - (3.0f - kS))) + 1.0f, w1y = fy * (fy * ((2.0f - kS) * fy - (3.0f - kS))) + 1.0f;
+        float w2x = fx * (fx * (-(2.0f - kS) * fx + (3.0f - 2.0f * kS)) + kS), w2y = fy * (fy * (-(2.0f - kS) * fy + (3.0f - 2.0f * kS)) + kS);
+        float w3x = fx * (fx * (kS * fx - kS)), w3y = fy * (fy * (kS * fy - kS));
         float w12x = w1x + w2x, w12y = w1y + w2y, tcx = w2x / w12x, tcy = w2y / w12y;
         f4 w = useBicubic ? mk4(w12x * w0y, w0x * w12y, w12x * w12y, w3x * w12y) : w4;
         float wl = useBicubic ? w12x * w3y : 0.0f;
         float total = w.x + w.y + w.z + w.w + wl;
         const float ix = c.gResourceSizeInvPrev[0], iy = c.gResourceSizeInvPrev[1];
-        float col;
+        S col;
         if (useBicubic)
         {
-            col = SampleLinearR8(a.history, (cx + tcx) * ix, (cy - 1.0f) * iy) * w.x;
-            col += SampleLinearR8(a.history, (cx - 1.0f) * ix, (cy + tcy) * iy) * w.y;
-            col += SampleLinearR8(a.history, (cx + tcx) * ix, (cy + tcy) * iy) * w.z;
-            col += SampleLinearR8(a.history, (cx + 2.0f) * ix, (cy + tcy) * iy) * w.w;
-            col += SampleLinearR8(a.history, (cx + tcx) * ix, (cy + 2.0f) * iy) * wl;
+            col = sgt::Scale(SampleLinearSig<S>(a.history, (cx + tcx) * ix, (cy - 1.0f) * iy), w.x);
+            col = col + sgt::Scale(SampleLinearSig<S>(a.history, (cx - 1.0f) * ix, (cy + tcy) * iy), w.y);
+            col = col + sgt::Scale(SampleLinearSig<S>(a.history, (cx + tcx) * ix, (cy + tcy) * iy), w.z);
+            col = col + sgt::Scale(SampleLinearSig<S>(a.history, (cx + 2.0f) * ix, (cy + tcy) * iy), w.w);
+            col = col + sgt::Scale(SampleLinearSig<S>(a.history, (cx + tcx) * ix, (cy + 2.0f) * iy), wl);
         }
         else
         {
-            col = SampleLinearR8(a.history, cx * ix, cy * iy) * w.x;
-            col += SampleLinearR8(a.history, (cx + 1.0f) * ix, cy * iy) * w.y;
-            col += SampleLinearR8(a.history, cx * ix, (cy + 1.0f) * iy) * w.z;
-            col += SampleLinearR8(a.history, (cx + 1.0f) * ix, (cy + 1.0f) * iy) * w.w;
+            col = sgt::Scale(SampleLinearSig<S>(a.history, cx * ix, cy * iy), w.x);
+            col = col + sgt::Scale(SampleLinearSig<S>(a.history, (cx + 1.0f) * ix, cy * iy), w.y);
+            col = col + sgt::Scale(SampleLinearSig<S>(a.history, cx * ix, (cy + 1.0f) * iy), w.z);
+            col = col + sgt::Scale(SampleLinearSig<S>(a.history, (cx + 1.0f) * ix, (cy + 1.0f) * iy), w.w);
         }
-        history = total < 0.0001f ? 0.0f : col / total;
+        history = total < 0.0001f ? sgt::Splat(0.0f, S()) : sgt::Scale(col, 1.0f / total);
     }
-    history = saturate(history);
-    history *= history;
+    history = sgt::Sq(sgt::Sat(history));
 
-    sigma *= lerpf(3.0f, 1.0f, 1.0f / (1.0f + historyLength));
-    float historyClamped = clampf(history, m1 - sigma, m1 + sigma);
-    float antilag = saturate(1.0f - Sqrt01(fabsf(historyClamped - history)));
+    sigma = sgt::Scale(sigma, lerpf(3.0f, 1.0f, 1.0f / (1.0f + historyLength)));
+    S historyClamped = sgt::Clamp(history, m1 - sigma, m1 + sigma);
+    float antilag = saturate(1.0f - Sqrt01(fabsf(sgt::X(historyClamped) - sgt::X(history)))); // ".x" only (SIGMA_TemporalStabilization.hlsli:174)
     historyLength *= antilag;
     float historyWeight = historyLength / (1.0f + historyLength);
-    historyClamped = lerpf(historyClamped, history, 0.6f * historyWeight * antilag);
-    float result = lerpf(input, historyClamped, fminf(c.gStabilizationStrength, historyWeight));
+    historyClamped = sgt::Lerp(historyClamped, history, 0.6f * historyWeight * antilag);
+    S result = sgt::Lerp(input, historyClamped, fminf(c.gStabilizationStrength, historyWeight));
     historyLength = fminf(historyLength + 1.0f, 7.0f);
 
-    StoreR8Unorm(a.outShadow, x, y, Sqrt01(result));
+    sgt::Store(a.outShadow, x, y, sgt::Pack(result));
     StoreU32(a.outLength, x, y, PackViewZAndHistoryLength(viewZ, historyLength));
 }
 
@@ -453,14 +508,21 @@ cudaError_t LaunchSigma(const PassLaunch& p, const char* shader)
 {
     const SigmaConstants& c = *(const SigmaConstants*)p.constants;
     const int W = (int)c.gRectSize[0];
-    if (!strcmp(shader, "SIGMA_Shadow_ClassifyTiles.cs"))
+    // "SIGMA_Shadow_<pass>.cs" (SIGMA_TYPE float) / "SIGMA_ShadowTranslucency_<pass>.cs" (float4); SmoothTiles and Copy are shared, Copy
+    // sees which one it serves from the format of the history texture (p.texBytes)
+    const bool translucent = !strncmp(shader, "SIGMA_ShadowTranslucency_", 25);
+    const char* pass = translucent ? shader + 25 : (!strncmp(shader, "SIGMA_Shadow_", 13) ? shader + 13 : shader);
+    if (!strcmp(pass, "ClassifyTiles.cs"))
     {
         SigmaTilesArgs a;
-        a.z = p.tex[0]; a.penumbra = p.tex[1]; a.tiles = p.tex[2];
+        a.z = p.tex[0]; a.penumbra = p.tex[1];
+        if (translucent) a.translucency = p.tex[2];
+        a.tiles = p.tex[translucent ? 3 : 2];
         a.viewZScale = c.gViewZScale; a.denoisingRange = c.gDenoisingRange; a.unproject = c.gUnproject; a.orthoMode = c.gOrthoMode;
         a.tilesW = p.gridW; a.tilesH = p.gridH;
         int warps = a.tilesW * a.tilesH;
-        NRD_B200_LAUNCH(p, (warps * 32 + 255) / 256, 256, a, SigmaClassifyTilesKernel);
+        if (translucent) NRD_B200_LAUNCH(p, (warps * 32 + 255) / 256, 256, a, SigmaClassifyTilesKernel<true>);
+        else NRD_B200_LAUNCH(p, (warps * 32 + 255) / 256, 256, a, SigmaClassifyTilesKernel<false>);
     }
     else if (!strcmp(shader, "SIGMA_SmoothTiles.cs"))
     {
@@ -474,30 +536,37 @@ cudaError_t LaunchSigma(const PassLaunch& p, const char* shader)
         SigmaCopyArgs a;
         a.tiles = p.tex[0]; a.inHistory = p.tex[1]; a.inLength = p.tex[2]; a.outHistory = p.tex[3]; a.outLength = p.tex[4];
         a.w = a.inHistory.w; a.h = a.inHistory.h; a.isRectChanged = c.gIsRectChanged; a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, dim3((a.w + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), dim3(32, 8), a, SigmaCopyKernel);
+        const dim3 grid((a.w + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
+        if (p.preloadOnly || p.texBytes[3] == 4) NRD_B200_LAUNCH(p, grid, block, a, SigmaCopyKernel<true>);
+        if (p.preloadOnly || p.texBytes[3] != 4) NRD_B200_LAUNCH(p, grid, block, a, SigmaCopyKernel<false>);
     }
-    else if (!strcmp(shader, "SIGMA_Shadow_Blur.cs") || !strcmp(shader, "SIGMA_Shadow_PostBlur.cs"))
+    else if (!strcmp(pass, "Blur.cs") || !strcmp(pass, "PostBlur.cs"))
     {
-        const bool first = !strcmp(shader, "SIGMA_Shadow_Blur.cs");
+        const bool first = !strcmp(pass, "Blur.cs");
+        const bool hasShadowInput = !first || translucent; // SIGMA_Blur.resources.hlsli:25-27
         SigmaBlurArgs a;
         a.c = c;
         a.z = p.tex[0]; a.nr = p.tex[1]; a.penumbra = p.tex[2]; a.tiles = p.tex[3];
-        if (!first) a.shadow = p.tex[4];
-        a.outPenumbra = p.tex[first ? 4 : 5];
-        a.outShadow = p.tex[first ? 5 : 6];
+        if (hasShadowInput) a.shadow = p.tex[4];
+        a.outPenumbra = p.tex[hasShadowInput ? 5 : 4];
+        a.outShadow = p.tex[hasShadowInput ? 6 : 5];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
         dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
-        if (first) NRD_B200_LAUNCH(p, grid, block, a, SigmaBlurKernel<true>);
-        else NRD_B200_LAUNCH(p, grid, block, a, SigmaBlurKernel<false>);
+        if (first && translucent) NRD_B200_LAUNCH(p, grid, block, a, SigmaBlurKernel<true, true>);
+        else if (first) NRD_B200_LAUNCH(p, grid, block, a, SigmaBlurKernel<true, false>);
+        else if (translucent) NRD_B200_LAUNCH(p, grid, block, a, SigmaBlurKernel<false, true>);
+        else NRD_B200_LAUNCH(p, grid, block, a, SigmaBlurKernel<false, false>);
     }
-    else if (!strcmp(shader, "SIGMA_Shadow_TemporalStabilization.cs"))
+    else if (!strcmp(pass, "TemporalStabilization.cs"))
     {
         SigmaTsArgs a;
         a.c = c;
         a.z = p.tex[0]; a.mv = p.tex[1]; a.penumbra = p.tex[2]; a.shadow = p.tex[3]; a.history = p.tex[4]; a.historyLength = p.tex[5]; a.tiles = p.tex[6];
         a.outShadow = p.tex[7]; a.outLength = p.tex[8];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, dim3((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), dim3(32, 8), a, SigmaTemporalStabilizationKernel);
+        const dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
+        if (translucent) NRD_B200_LAUNCH(p, grid, block, a, SigmaTemporalStabilizationKernel<true>);
+        else NRD_B200_LAUNCH(p, grid, block, a, SigmaTemporalStabilizationKernel<false>);
     }
     else
         return cudaErrorNotSupported;

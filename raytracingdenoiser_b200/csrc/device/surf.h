@@ -42,6 +42,7 @@ struct PassLaunch
     const void* constants; // host pointer to the dispatch's constant block
     uint32_t constantsSize;
     Surf tex[32];          // bindings in DispatchDesc order
+    uint8_t texBytes[32];  // bytes per texel of every binding (passes shared by denoisers with different storage formats look at it)
     uint32_t texNum;
     int gridW, gridH;      // DispatchDesc grid (reference thread-group counts)
     int rowBegin, rowEnd;  // rows this launch must produce, in the pass's own pixel units

@@ -81,10 +81,12 @@ struct Texture
 };
 
 // user textures the supported denoisers consume, with the one format the kernels are written for
-bool ExpectedUserFormat(ResourceType type, Format& expected)
+// (OUT_SHADOW_TRANSLUCENCY: R8 for SIGMA_SHADOW, RGBA8 for SIGMA_SHADOW_TRANSLUCENCY -- `translucent` picks)
+bool ExpectedUserFormat(ResourceType type, Format& expected, bool translucent = false)
 {
     switch (type)
     {
+        case ResourceType::IN_TRANSLUCENCY: expected = Format::RGBA8_UNORM; return true;
         case ResourceType::IN_MV: expected = Format::RGBA16_SFLOAT; return true;
         case ResourceType::IN_NORMAL_ROUGHNESS: expected = Format::R10_G10_B10_A2_UNORM; return true;
         case ResourceType::IN_VIEWZ: expected = Format::R32_SFLOAT; return true;
@@ -93,7 +95,7 @@ bool ExpectedUserFormat(ResourceType type, Format& expected)
         case ResourceType::OUT_DIFF_RADIANCE_HITDIST:
         case ResourceType::OUT_SPEC_RADIANCE_HITDIST: expected = Format::RGBA16_SFLOAT; return true;
         case ResourceType::IN_PENUMBRA: expected = Format::R16_SFLOAT; return true;
-        case ResourceType::OUT_SHADOW_TRANSLUCENCY: expected = Format::R8_UNORM; return true;
+        case ResourceType::OUT_SHADOW_TRANSLUCENCY: expected = translucent ? Format::RGBA8_UNORM : Format::R8_UNORM; return true;
         default: return false;
     }
 }
@@ -510,7 +512,7 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
         for (uint32_t t = 0; t < (uint32_t)ResourceType::MAX_NUM; t++)
         {
             Format f;
-            if (ExpectedUserFormat((ResourceType)t, f)) DescribeTexture(ctx, f, 1, ctx->user[t]);
+            if (ExpectedUserFormat((ResourceType)t, f, ((Scheduler*)instance)->HasDenoiser(Denoiser::SIGMA_SHADOW_TRANSLUCENCY))) DescribeTexture(ctx, f, 1, ctx->user[t]);
         }
     }
     // one arena, identical layout on every rank
@@ -577,7 +579,8 @@ NRD_API Result nrdCudaSetUserTexture(NrdCudaContext* ctx, uint32_t resourceType,
     if (!ctx || resourceType >= (uint32_t)ResourceType::TRANSIENT_POOL || format >= (uint32_t)Format::MAX_NUM) return Result::INVALID_ARGUMENT;
     if (StripMode(ctx)) return Fail(ctx, Result::UNSUPPORTED, "strip mode: user textures live in the context's arena, fill them through nrdCudaGetTexture / nrdCudaCopyTexture");
     Format expected;
-    if (!ExpectedUserFormat((ResourceType)resourceType, expected)) return Fail(ctx, Result::UNSUPPORTED, "resource type not consumed by the supported denoisers");
+    if (!ExpectedUserFormat((ResourceType)resourceType, expected, ((Scheduler*)ctx->instance)->HasDenoiser(Denoiser::SIGMA_SHADOW_TRANSLUCENCY)))
+        return Fail(ctx, Result::UNSUPPORTED, "resource type not consumed by the supported denoisers");
     if ((Format)format != expected) return Fail(ctx, Result::UNSUPPORTED, "unsupported format for this resource type (see nrd_b200.h)");
     Texture& t = ctx->user[resourceType];
     t.ptr = devicePtr;
@@ -719,6 +722,7 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         const Texture* t = Resolve(ctx, r.type, r.indexInPool);
         if (!t) return Fail(ctx, Result::INVALID_ARGUMENT, std::string("unbound resource ") + GetResourceTypeString(r.type) + " for " + d->name);
         p.tex[i] = ToSurf(ctx, *t);
+        p.texBytes[i] = (uint8_t)BytesPerTexel(t->format);
     }
     // checkerboarded inputs bind the same passes (no separate shader name), so they have to be rejected here, loudly
     if (!strncmp(shader, "REBLUR_", 7) && strcmp(shader, "REBLUR_ClassifyTiles.cs") != 0 && d->constantBufferData && d->constantBufferDataSize >= sizeof(ReblurConstants))

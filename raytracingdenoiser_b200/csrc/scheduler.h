@@ -100,6 +100,12 @@ public:
     const nrd::InstanceDesc& GetDesc() const { return desc_; }
     const MemoryHooks& Hooks() const { return hooks_; }
     const nrd::CommonSettings& Common() const { return common_; }
+    bool HasDenoiser(nrd::Denoiser d) const
+    {
+        for (size_t i = 0; i < slots_.size(); i++)
+            if (slots_[i].desc.denoiser == d) return true;
+        return false;
+    }
 
     // ---- recipe building blocks (used by recipes_*.cpp) ----
     void AddPermanent(nrd::Format f, uint16_t downsample = 1) { permanentPool_.push_back({f, downsample}); }

@@ -19,7 +19,17 @@ USER_FORMATS = {
     "OUT_SPEC_RADIANCE_HITDIST": (nrd.Format.RGBA16_SFLOAT, torch.float16, 4),
     "IN_PENUMBRA": (nrd.Format.R16_SFLOAT, torch.float16, 1),
     "OUT_SHADOW_TRANSLUCENCY": (nrd.Format.R8_UNORM, torch.uint8, 1),
+    "IN_TRANSLUCENCY": (nrd.Format.RGBA8_UNORM, torch.uint8, 4),
+    "OUT_SHADOW_TRANSLUCENCY#RGBA8": (nrd.Format.RGBA8_UNORM, torch.uint8, 4),   # SIGMA_SHADOW_TRANSLUCENCY writes float4
 }
+
+
+def user_format(denoiser, name):
+    """(format, torch dtype, channels) of a user texture; OUT_SHADOW_TRANSLUCENCY is RGBA8 for the translucent SIGMA variant."""
+    if name == "OUT_SHADOW_TRANSLUCENCY" and denoiser == nrd.Denoiser.SIGMA_SHADOW_TRANSLUCENCY:
+        return USER_FORMATS["OUT_SHADOW_TRANSLUCENCY#RGBA8"]
+    return USER_FORMATS[name]
+
 
 DENOISER_RESOURCES = {
     nrd.Denoiser.REBLUR_DIFFUSE: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_DIFF_RADIANCE_HITDIST", "OUT_DIFF_RADIANCE_HITDIST"],
@@ -29,6 +39,7 @@ DENOISER_RESOURCES = {
     nrd.Denoiser.RELAX_DIFFUSE_SPECULAR: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_DIFF_RADIANCE_HITDIST", "IN_SPEC_RADIANCE_HITDIST",
                                           "OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"],
     nrd.Denoiser.SIGMA_SHADOW: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_PENUMBRA", "OUT_SHADOW_TRANSLUCENCY"],
+    nrd.Denoiser.SIGMA_SHADOW_TRANSLUCENCY: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_PENUMBRA", "IN_TRANSLUCENCY", "OUT_SHADOW_TRANSLUCENCY"],
 }
 
 
@@ -62,7 +73,7 @@ class GpuDenoiser(object):
         self.ctx = nrd.CudaContext(self.instance, width, height, device=device)
         self.tex = {}
         for name in DENOISER_RESOURCES[denoiser]:
-            fmt, dtype, ch = USER_FORMATS[name]
+            fmt, dtype, ch = user_format(denoiser, name)
             shape = (height, width, ch) if ch > 1 else (height, width)
             t = torch.zeros(shape, dtype=dtype, device=self.device)
             self.tex[name] = t

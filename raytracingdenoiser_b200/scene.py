@@ -236,7 +236,18 @@ class Scene(object):
         penumbra = torch.where(ndl <= 0.0, torch.zeros_like(penumbra), penumbra)
         penumbra = torch.where(sky, torch.full_like(penumbra, 65504.0), penumbra)
 
+        # IN_TRANSLUCENCY for SIGMA_SHADOW_TRANSLUCENCY (SIGMA_FrontEnd_PackTranslucency, NRD.hlsli:848-857): every second sphere is a
+        # coloured translucent occluder, the rest are opaque; a miss transmits everything
+        occ = idl.clamp(min=0).to(torch.float32)
+        tcol = torch.stack([0.5 + 0.5 * torch.cos(occ * 1.3), 0.5 + 0.5 * torch.cos(occ * 2.1 + 1.0), 0.5 + 0.5 * torch.cos(occ * 2.9 + 2.0)], -1) * 0.8
+        tcol = torch.where(((idl % 2) == 0)[..., None] & (idl >= 0)[..., None], tcol, torch.zeros_like(tcol))
+        tcol = torch.where((dist_occ >= 65504.0)[..., None], torch.ones_like(tcol), tcol)
+        tcol = torch.where((ndl <= 0.0)[..., None] & ~sky[..., None], torch.zeros_like(tcol), tcol)
+        transl = torch.cat([((dist_occ >= 65504.0) | sky).to(torch.float32)[..., None], torch.clamp(tcol, 0.0, 1.0)], -1)
+        transl = torch.floor(transl * 255.0 + 0.5).to(torch.uint8).contiguous()
+
         out = {
+            "IN_TRANSLUCENCY": transl,
             "IN_VIEWZ": viewz.to(torch.float32).contiguous(),
             "IN_NORMAL_ROUGHNESS": pack_normal_roughness(n, rough, mat),
             "IN_MV": mv.to(torch.float16).contiguous(),

@@ -139,7 +139,7 @@ class StripDenoiser(object):
         res = {}
         for name in self.names:
             if name.startswith("OUT_"):
-                fmt, dtype, ch = harness.USER_FORMATS[name]
+                fmt, dtype, ch = harness.user_format(self.denoiser, name)
                 rows = self.y1 - self.y0
                 t = out[name] if out is not None else torch.empty((rows, self.width, ch) if ch > 1 else (rows, self.width), dtype=dtype, device=self.device)
                 self.ctx.copy(getattr(nrd.ResourceType, name), 0, t.data_ptr(), t.stride(0) * t.element_size(), False, s)

@@ -63,7 +63,7 @@ class CpuDenoiser(object):
         self.user = {}
         self.user_fmt = {}
         for name in harness.DENOISER_RESOURCES[denoiser]:
-            fmt = harness.USER_FORMATS[name][0]
+            fmt = harness.user_format(denoiser, name)[0]
             self.user[name] = alloc(fmt, width, height)
             self.user_fmt[name] = fmt
 

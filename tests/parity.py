@@ -39,7 +39,7 @@ class SideBySide(object):
         self.torch = torch
         self.dev_user = {}
         for name in harness.DENOISER_RESOURCES[denoiser]:
-            fmt, dtype, ch = harness.USER_FORMATS[name]
+            fmt, dtype, ch = harness.user_format(denoiser, name)
             t = torch.zeros((height, width, ch) if ch > 1 else (height, width), dtype=dtype, device="cuda:%d" % device)
             self.dev_user[name] = t
             self.ctx.set_user_texture(getattr(nrd.ResourceType, name), t.data_ptr(), t.stride(0) * t.element_size(), fmt)

@@ -24,6 +24,28 @@ def test_sigma_per_pass_parity(width, height, frames):
     assert not sbs.failures(), sbs.describe_failures()
 
 
+@pytest.mark.parametrize("width,height,frames", [(640, 360, 3), (250, 141, 5)])
+def test_sigma_translucency_per_pass_parity(width, height, frames):
+    """SIGMA_SHADOW_TRANSLUCENCY: float4 signal in RGBA8 textures, IN_TRANSLUCENCY feeds ClassifyTiles and the first blur."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    sbs = parity.SideBySide(nrd.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, width, height)
+    report = sbs.run_per_pass(frames)
+    assert {"SIGMA_ShadowTranslucency_ClassifyTiles.cs", "SIGMA_ShadowTranslucency_Blur.cs", "SIGMA_ShadowTranslucency_PostBlur.cs",
+            "SIGMA_ShadowTranslucency_TemporalStabilization.cs", "SIGMA_Copy.cs"} <= {r["shader"] for r in report}
+    _dump("parity_SIGMA_TRANSLUCENCY_%dx%d.json" % (width, height), report)
+    assert not sbs.failures(), sbs.describe_failures()
+
+
+def test_sigma_translucency_sequence_parity():
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    res = parity.run_sequence(nrd.Denoiser.SIGMA_SHADOW_TRANSLUCENCY, 320, 180, 10)
+    _dump("sequence_sigma_translucency.json", res)
+    for name, (frac, psnr) in res.items():
+        assert frac >= 0.99 and psnr >= 45.0, (name, frac, psnr)   # RGBA8 output: 1 LSB = 1/255
+
+
 def test_sigma_sequence_parity():
     import parity
     from raytracingdenoiser_b200 import nrd
