@@ -19,22 +19,25 @@ class OracleTexture(C.Structure):
     _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pitchBytes", C.c_int32), ("format", C.c_int32), ("firstRow", C.c_int32)]
 
 
-_oracle = None
+_oracle = {}
 
 
-def oracle_lib():
-    global _oracle
-    if _oracle is None:
-        if not os.path.exists(_ORACLE_PATH):
+def oracle_lib(variant=""):
+    """variant "": the oracle (no FMA contraction); "fma": the same sources compiled with contraction allowed -- a second
+    IEEE-legal evaluation, used only to measure the rounding-noise floor of the temporal chains (tests/parity.py)."""
+    if variant not in _oracle:
+        path = _ORACLE_PATH if not variant else _ORACLE_PATH.replace("liboracle.so", "liboracle_%s.so" % variant)
+        if not os.path.exists(path):
             from raytracingdenoiser_b200 import build
-            build.build_oracle()
-        _oracle = C.CDLL(_ORACLE_PATH)
-        _oracle.oracle_dispatch.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(OracleTexture), C.c_int, C.c_int, C.c_int]
-        _oracle.oracle_dispatch.restype = C.c_int
-        _oracle.oracle_num_threads.restype = C.c_int
-        _oracle.oracle_set_num_threads.argtypes = [C.c_int]
-        _oracle.oracle_set_num_threads.restype = None
-    return _oracle
+            build.build_oracle(force=True)
+        lib = C.CDLL(path)
+        lib.oracle_dispatch.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(OracleTexture), C.c_int, C.c_int, C.c_int]
+        lib.oracle_dispatch.restype = C.c_int
+        lib.oracle_num_threads.restype = C.c_int
+        lib.oracle_set_num_threads.argtypes = [C.c_int]
+        lib.oracle_set_num_threads.restype = None
+        _oracle[variant] = lib
+    return _oracle[variant]
 
 
 _NP = {nrd.Format.R8_UNORM: (np.uint8, 1), nrd.Format.R8_UINT: (np.uint8, 1), nrd.Format.RG8_UNORM: (np.uint8, 2), nrd.Format.RGBA8_UNORM: (np.uint8, 4),
@@ -50,9 +53,10 @@ def alloc(fmt, w, h):
 class CpuDenoiser(object):
     """Mirror of harness.GpuDenoiser on the CPU: same scheduler (the product's), oracle passes, numpy textures."""
 
-    def __init__(self, denoiser, width, height, identifier=0, settings=None, user_formats=None, instance=None):
+    def __init__(self, denoiser, width, height, identifier=0, settings=None, user_formats=None, instance=None, variant=""):
         from raytracingdenoiser_b200 import harness
         self.width, self.height, self.identifier = width, height, identifier
+        self.lib = oracle_lib(variant)
         self.instance = instance or nrd.Instance([(identifier, denoiser)])
         if settings is not None and instance is None:
             self.instance.set_denoiser_settings(identifier, settings)
@@ -83,7 +87,7 @@ class CpuDenoiser(object):
                 arr[...] = src.view(arr.dtype).reshape(arr.shape)
 
     def run_dispatch(self, d):
-        lib = oracle_lib()
+        lib = self.lib
         texs = (OracleTexture * len(d.resources))()
         keep = []
         for i, (_, rtype, index) in enumerate(d.resources):

@@ -112,21 +112,27 @@ def outlier_budget(texels):
     return max(OUTLIER_FLOOR, int(OUTLIER_BUDGET * texels))
 
 
-def run_sequence(denoiser, width, height, frames, settings=None, device=0):
-    """Statistical gate: independent end-to-end runs; returns {output name: (fraction within tolerance, PSNR dB)}."""
+def run_sequence(denoiser, width, height, frames, settings=None, device=0, noise_floor=False):
+    """Statistical gate: independent end-to-end runs; returns {output name: (fraction within tolerance, PSNR dB)}.
+    noise_floor=True additionally runs the FMA-contracted build of the oracle on the same frames and returns
+    {name: (fraction, PSNR, floor fraction)}: `floor` is how far two IEEE-legal CPU evaluations of the same math drift apart --
+    the chains are chaotic (step functions on noisy data feed back through the history), so this, not 100 %, is the yardstick."""
     import torch
     sc = scene.Scene(width, height, device=_scene_device(width, height, device))
     cpu = orr.CpuDenoiser(denoiser, width, height, settings=settings)
+    cpu_fma = orr.CpuDenoiser(denoiser, width, height, settings=settings, variant="fma") if noise_floor else None
     gpu = harness.GpuDenoiser(denoiser, width, height, device=device, settings=settings)
     for f in range(frames):
         fr = sc.frame(f, harness.radiance_mode(denoiser))
         cs = harness.make_common_settings(fr, width, height, f)
-        cpu.set_inputs(fr)
-        cpu.denoise(cs)
+        for c in (cpu, cpu_fma):
+            if c is not None:
+                c.set_inputs(fr)
+                c.denoise(cs)
+                if f == 0:
+                    c.set_inputs(fr)
         gpu.set_inputs(fr)
         gpu.denoise(cs)
-        if f == 0:
-            cpu.set_inputs(fr)
     torch.cuda.synchronize()
     out = {}
     for name, t in gpu.outputs().items():
@@ -139,5 +145,7 @@ def run_sequence(denoiser, width, height, frames, settings=None, device=0):
         peak = float(max(np.abs(a).max(), 1e-6))
         psnr = 10.0 * np.log10(peak * peak / mse) if mse > 0 else 200.0
         out[name] = (frac, psnr)
+        if cpu_fma is not None:
+            out[name] = (frac, psnr, orr.compare(ref, cpu_fma.user[name], cpu.user_fmt[name], REL, ABS)[0])
     gpu.destroy()
     return out

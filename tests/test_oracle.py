@@ -190,3 +190,28 @@ def test_relax_chain_properties():
     assert hf(out) < 0.4 * hf(noisy)
     # PREV_VIEWZ written by the first A-trous pass is the current viewZ everywhere (also on sky pixels)
     assert np.array_equal(cpu.permanent[9], z)
+
+
+def test_rounding_noise_floor_of_the_reblur_chain():
+    """Two IEEE-legal CPU evaluations of the same oracle sources (with / without FMA contraction) drift apart frame by frame:
+    REBLUR's temporal feedback is chaotic at the 1e-3 level.  This is the yardstick the long-sequence GPU gate is read against
+    (tests/test_gpu_baseline_configs.py::test_config3...)."""
+    import numpy as np
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    den, w, h = nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, 256, 144
+    a, b = orr.CpuDenoiser(den, w, h), orr.CpuDenoiser(den, w, h, variant="fma")
+    sc = scene.Scene(w, h)
+    fractions = []
+    for f in range(24):
+        fr = sc.frame(f)
+        cs = harness.make_common_settings(fr, w, h, f)
+        for c in (a, b):
+            c.set_inputs(fr)
+            c.denoise(cs)
+            if f == 0:
+                c.set_inputs(fr)
+        fractions.append(min(orr.compare(a.user[n], b.user[n], a.user_fmt[n])[0] for n in ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST")))
+    assert fractions[0] > 0.999                       # one frame: the two evaluations agree almost everywhere
+    assert fractions[-1] < fractions[0] and fractions[-1] < 0.999   # ... and drift apart through the history feedback
+    assert fractions[-1] > 0.9 and np.isfinite(a.user["OUT_DIFF_RADIANCE_HITDIST"].astype(np.float32)).all()
