@@ -30,11 +30,17 @@ def _scene_device(width, height, device):
 
 
 class SideBySide(object):
-    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0):
+    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False):
+        """noise_floor=True: every dispatch is also run by the FMA-contracted build of the oracle on the same re-synchronised
+        inputs; its disagreement with the oracle is the rounding-noise floor of the pass (two IEEE-legal evaluations of the same
+        math).  A pass whose floor is below the plain gate (RELAX temporal accumulation: acos of nearly parallel vectors, sigma of
+        cancelling moments) is held to its floor instead -- the kernel must agree with the oracle at least as well as the oracle
+        agrees with itself."""
         import torch
         self.denoiser, self.w, self.h, self.identifier = denoiser, width, height, identifier
         self.cpu = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, settings=settings)
         self.instance = self.cpu.instance
+        self.cpu_fma = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, instance=self.instance, variant="fma") if noise_floor else None
         self.ctx = nrd.CudaContext(self.instance, width, height, device=device)
         self.torch = torch
         self.dev_user = {}
@@ -61,10 +67,19 @@ class SideBySide(object):
             layout = "reblur_data2" if ("REBLUR" in d.shaderFileName and "TemporalAccumulation" in d.shaderFileName and fmt == nrd.Format.R32_UINT) else None
             frac, worst = orr.compare(ref, got, fmt, REL, ABS, layout=layout)
             n_out, where, nonfinite = orr.outliers(ref, got, fmt, REL, ABS, MAX_EXCESS, layout=layout)
-            self.report.append({"frame": frame, "pass": d.name, "shader": d.shaderFileName, "resource": "%s[%d]" % (nrd.ResourceType(rtype).name, index),
-                                "format": nrd.Format(fmt).name, "fraction": frac, "worst": worst, "texels": int(ref.shape[0] * ref.shape[1]),
-                                "outliers": n_out, "outlier_budget": outlier_budget(ref.shape[0] * ref.shape[1]), "outliers_at": where, "nonfinite": nonfinite,
-                                "outlier_cause": "decision flip (tap texel / step threshold within rounding distance)" if n_out else None})
+            rec = {"frame": frame, "pass": d.name, "shader": d.shaderFileName, "resource": "%s[%d]" % (nrd.ResourceType(rtype).name, index),
+                   "format": nrd.Format(fmt).name, "fraction": frac, "worst": worst, "texels": int(ref.shape[0] * ref.shape[1]),
+                   "outliers": n_out, "outlier_budget": outlier_budget(ref.shape[0] * ref.shape[1]), "outliers_at": where, "nonfinite": nonfinite,
+                   "outlier_cause": "decision flip (tap texel / step threshold within rounding distance)" if n_out else None,
+                   "min_fraction": MIN_FRACTION}
+            if self.cpu_fma is not None:
+                alt, _ = self.cpu_fma.resolve(rtype, index)
+                rec["floor_fraction"] = orr.compare(ref, alt, fmt, REL, ABS, layout=layout)[0]
+                rec["floor_outliers"] = orr.outliers(ref, alt, fmt, REL, ABS, MAX_EXCESS, layout=layout)[0]
+                # held to the floor where the floor is below the plain gate
+                rec["min_fraction"] = min(MIN_FRACTION, rec["floor_fraction"])
+                rec["outlier_budget"] = max(rec["outlier_budget"], rec["floor_outliers"])
+            self.report.append(rec)
 
     def run_per_pass(self, frames, first_frame=0, warmup=0):
         """Hard gate.  Returns the list of per-(frame, pass, output) comparison records.  `warmup` frames are run by the oracle
@@ -92,20 +107,26 @@ class SideBySide(object):
             for i in range(n):
                 d = nrd.Dispatch(raw[i], pipelines)
                 self._sync_to_gpu(d)
+                if self.cpu_fma is not None:
+                    for _, rtype, index in d.resources:
+                        self.cpu_fma.resolve(rtype, index)[0][...] = self.cpu.resolve(rtype, index)[0]
                 self.ctx.execute_raw(C.byref(raw[i]))
                 self.torch.cuda.synchronize()
                 self.cpu.run_dispatch(d)
+                if self.cpu_fma is not None:
+                    self.cpu_fma.run_dispatch(d)
                 self._compare_outputs(f, d)
             if f == 0:
                 self.cpu.set_inputs(fr)  # the frame-0 clears also zero IN_MV (reference quirk), restore it
         return self.report
 
     def failures(self):
-        return [r for r in self.report if r["fraction"] < MIN_FRACTION or r["outliers"] > r["outlier_budget"] or r["nonfinite"]]
+        return [r for r in self.report if r["fraction"] < r["min_fraction"] or r["outliers"] > r["outlier_budget"] or r["nonfinite"]]
 
     def describe_failures(self, limit=40):
-        return "\n".join("f%d %s %s %s frac=%.5f worst=%.1f outliers=%d/%d nonfinite=%d" % (
-            r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["worst"], r["outliers"], r["outlier_budget"], r["nonfinite"]) for r in self.failures()[:limit])
+        return "\n".join("f%d %s %s %s frac=%.5f (gate %.5f) worst=%.1f outliers=%d/%d nonfinite=%d" % (
+            r["frame"], r["shader"], r["resource"], r["format"], r["fraction"], r["min_fraction"], r["worst"], r["outliers"], r["outlier_budget"], r["nonfinite"])
+                         for r in self.failures()[:limit])
 
 
 def outlier_budget(texels):

