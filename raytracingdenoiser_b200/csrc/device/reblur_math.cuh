@@ -24,6 +24,7 @@ struct Guide
     f3 N;
     float roughness;
     float materialID;
+    float smc, hitK, aLog; // roughness-table entry (LoadGuideLut): SpecMagicCurve, hit-distance normalisation factor, dominant-direction log term
 };
 __device__ __forceinline__ Guide DecodeGuide(unsigned packed)
 {
@@ -38,6 +39,37 @@ __device__ __forceinline__ Guide DecodeGuide(unsigned packed)
     g.N = mk3(nx * inv, ny * inv, nz * inv);
     g.roughness = (float)((packed >> 20) & 1023u) / 1023.0f;
     g.materialID = ((float)(packed >> 30) / 3.0f) * 3.0f;
+    return g;
+}
+
+// Guides through the decoded-guide surface (surf.h PassLaunch::guide: {N.xyz bit-exact, raw viewZ}, written by ClassifyTiles at
+// the start of every frame): one 16-byte load instead of the octahedral decode; roughness / material straight from the packed
+// bits (loads whose result is unused are removed by the compiler).
+__device__ __forceinline__ Guide LoadGuide(const Surf& guide, const Surf& nr, int x, int y)
+{
+    const f4 q = LoadRGBA32F(guide, x, y);
+    const unsigned p = LoadU32(nr, x, y);
+    Guide g;
+    g.N = mk3(q.x, q.y, q.z);
+    g.roughness = (float)((p >> 20) & 1023u) * (1.0f / 1023.0f);
+    g.materialID = (float)(p >> 30);
+    return g;
+}
+
+// ... plus everything that depends on the 10-bit roughness alone, from the host-built table (surf.h PassLaunch::roughnessLut):
+// no powf / exp2f / logf in the kernel, and the values are the oracle's bit for bit
+__device__ __forceinline__ Guide LoadGuideLut(const Surf& guide, const Surf& nr, const float4* lut, int x, int y)
+{
+    const f4 q = LoadRGBA32F(guide, x, y);
+    const unsigned p = LoadU32(nr, x, y);
+    const float4 t = __ldg(&lut[(p >> 20) & 1023u]);
+    Guide g;
+    g.N = mk3(q.x, q.y, q.z);
+    g.roughness = t.w; // exactly i / 1023
+    g.materialID = (float)(p >> 30);
+    g.smc = t.x;
+    g.hitK = t.y;
+    g.aLog = t.z;
     return g;
 }
 
@@ -69,11 +101,13 @@ __device__ __forceinline__ float HitDistNormalization(float viewZ, const float* 
 {
     return (p[0] + fabsf(viewZ) * p[1]) * lerpf(1.0f, p[2], saturate(exp2f(p[3] * roughness * roughness)));
 }
-__device__ __forceinline__ float SpecMagicCurve(float roughness, float power = 0.25f) // Common.hlsli:311-317
+__device__ __forceinline__ float SpecMagicCurve(float roughness) // Common.hlsli:311-317, power = 0.25: the fourth root as two square roots
 {
     float f = 1.0f - exp2f(-200.0f * roughness * roughness);
-    return f * Pow01(roughness, power);
+    return f * sqrtf(sqrtf(saturate(roughness)));
 }
+// pow(saturate(x), y) for a smooth, non-selecting use: exp2(y * log2(x)) on the special-function unit (relative error ~y * 2^-22)
+__device__ __forceinline__ float Pow01Fast(float x, float y) { return exp2f(y * __log2f(saturate(x))); }
 __device__ __forceinline__ float LobeTanHalfAngle(float roughness, float percentOfVolume) // MathLib ImportanceSampling (restated, see oracle/mathlib.h)
 {
     float m = saturate(roughness);
@@ -105,6 +139,13 @@ __device__ __forceinline__ float SpecularDominantFactor(float NoV, float roughne
 {
     float a = 0.298475f * logf(39.4115f - 39.0029f * roughness);
     return saturate(powf(saturate(1.0f - NoV), 10.8649f) * (1.0f - a) + a);
+}
+// the same with the roughness-only log term a = 0.298475 log(39.4115 - 39.0029 r) taken from the roughness table
+__device__ __forceinline__ float SpecularDominantFactorLut(float NoV, float aLog) { return SatFma(powf(OneMinusSat(NoV), 10.8649f), 1.0f - aLog, aLog); }
+__device__ __forceinline__ f4 SpecularDominantDirectionLut(f3 N, f3 V, float aLog)
+{
+    const float f = SpecularDominantFactorLut(fabsf(dot(N, V)), aLog);
+    return mk4(normalize(lerp3(N, reflect(-V, N), f)), f);
 }
 __device__ __forceinline__ f4 SpecularDominantDirection(f3 N, f3 V, float roughness) // NRD.hlsli:394-400
 {
@@ -163,7 +204,8 @@ __device__ __forceinline__ unsigned PackInternalData(float diffAccum, float spec
 }
 __device__ __forceinline__ f3 UnpackInternalData(unsigned p)
 {
-    return mk3((float)(p & 63u) / 63.0f * kMaxAccum, (float)((p >> 6) & 63u) / 63.0f * kMaxAccum, (float)((p >> 12) & 15u) / 15.0f * kMaxMaterial);
+    // (n / 63) * 63 and (n / 15) * 15 of the reference are n up to one rounding: no divisions
+    return mk3((float)(p & 63u), (float)((p >> 6) & 63u), (float)((p >> 12) & 15u));
 }
 __device__ __forceinline__ unsigned PackData2(float fbits, float curvature, float virtualHistoryAmount)
 {

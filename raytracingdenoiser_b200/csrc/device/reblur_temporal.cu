@@ -187,9 +187,9 @@ __device__ __forceinline__ float ResolveBilinearCustom1(const CatRomSetup& s, co
 }
 
 // thin-lens virtual position (Common.hlsli:404-461, NRD_USE_SPECULAR_MOTION_V2 = 1)
-__device__ __forceinline__ f3 GetXvirtual(float hitDist, float curvature, f3 X, f3 Xprev, f3 N, f3 V, float roughness)
+__device__ __forceinline__ f3 GetXvirtual(float hitDist, float curvature, f3 X, f3 Xprev, f3 N, f3 V, float aLog)
 {
-    f4 D = SpecularDominantDirection(N, V, roughness);
+    f4 D = SpecularDominantDirectionLut(N, V, aLog); // aLog: roughness-table entry of the pixel's roughness
     f3 ray = xyz(D) * hitDist;
     f3 T, B;
     GetBasis(N, T, B);
@@ -225,6 +225,8 @@ struct TaArgs
     Surf tiles, nr, z, mv, prevZ, prevNr, prevInternal;
     Surf inDiff, inSpec, histDiff, histSpec, histDiffFast, histSpecFast, prevHitDist, inHitDist;
     Surf outDiff, outSpec, outDiffFast, outSpecFast, outHitDist, outData1, outData2;
+    Surf guide;          // decoded guides of the current frame (surf.h PassLaunch::guide)
+    const float4* lut;   // roughness table (surf.h PassLaunch::roughnessLut)
     int rowBegin, rowEnd;
 };
 
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         for (int i = 0; i <= 2; i++)
         {
             int px = clampi(x + i - 1, 0, maxX), py = clampi(y + j - 1, 0, maxY);
-            Guide g = DecodeGuide(LoadU32(Near(a.nr), px, py));
+            const Guide g = LoadGuide(Near(a.guide), Near(a.nr), px, py);
             if (i < 2 && j < 2) Navg = Navg + g.N;
             if (i == 2 && j == 1) n10 = g.N;
             if (i == 1 && j == 2) n01 = g.N;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         }
     Navg = Navg * 0.25f;
 
-    const Guide g0 = DecodeGuide(LoadU32(Near(a.nr), x, y));
+    const Guide g0 = LoadGuideLut(Near(a.guide), Near(a.nr), a.lut, x, y);
     const f3 N = g0.N;
     const float roughness = g0.roughness, materialID = g0.materialID;
 
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         roughnessSigma = GetStdDev(roughnessM1, roughnessM2);
         rng.Initialize(x, y, c.gFrameIndex);
         hitDistForTracking = hitDistForTracking == kInf ? 0.0f : hitDistForTracking;
-        hitDistNormalization = HitDistNormalization(viewZ, c.gHitDistParams, roughness);
+        hitDistNormalization = (c.gHitDistParams[0] + viewZ * c.gHitDistParams[1]) * g0.hitK;
         hitDistForTracking *= c.gSpecPrepassBlurRadius == 0.0f ? hitDistNormalization : 1.0f;
         StoreR16F(a.outHitDist, x, y, hitDistForTracking);
     }
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         }
 
         // virtual motion
-        const f3 Xvirtual = GetXvirtual(hitDistForTracking, curvature, X, Xprev, N, V, roughness);
+        const f3 Xvirtual = GetXvirtual(hitDistForTracking, curvature, X, Xprev, N, V, g0.aLog);
         const float XvirtualLength = length(Xvirtual);
         f2 vmbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xvirtual);
         if (materialID == c.gCameraAttachedReflectionMaterialID) vmbPixelUv = smbPixelUv;
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         };
         const Guide vmbGuide = stochasticNr(vmbPixelUv);
         const f3 vmbN = Rotate(c.gWorldPrevToWorld, vmbGuide.N);
-        const float Dfactor = SpecularDominantFactor(NoV, roughness);
+        const float Dfactor = SpecularDominantFactorLut(NoV, g0.aLog);
         float virtualHistoryNormalBasedConfidence = 1.0f / (1.0f + 0.5f * Dfactor * saturate(length(N - vmbN) - kNormalEncodingError) * vmbPixelsTraveled);
 
         if (smbFootprintQuality == 0.0f) smbNavg = vmbN;
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         float virtualHistoryParallaxBasedConfidence;
         {
             float hitDistForTrackingPrev = SampleLinear1(a.prevHitDist, vmbPixelUv.x * c.gResolutionScalePrev[0], vmbPixelUv.y * c.gResolutionScalePrev[1]);
-            f3 XvirtualPrev = GetXvirtual(hitDistForTrackingPrev, curvature, X, Xprev, N, V, roughness);
+            f3 XvirtualPrev = GetXvirtual(hitDistForTrackingPrev, curvature, X, Xprev, N, V, g0.aLog);
             f2 vmbPixelUvPrev = GetScreenUv(c.gWorldToClipPrev, XvirtualPrev);
             if (materialID == c.gCameraAttachedReflectionMaterialID) vmbPixelUvPrev = smbPixelUv;
             float pixelSizeAtXvirtual = c.gUnproject * lerpf(XvirtualLength, 1.0f, fabsf(c.gOrthoMode));
@@ -620,6 +622,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         f4 smbSpecHistory = ResolveCatRom4(smbSetup, a.histSpec);
         const float smbSpecFastHistory = ResolveBilinearCustom1(smbSetup, a.histSpecFast, smbOcclusionWeights);
 
+        const float smcModified = SpecMagicCurve(roughnessModified); // used twice below
         float surfaceHistoryConfidence;
         {
             float ang = atanf(smbParallaxInPixelsMax * pixelSize / length(X));
@@ -631,17 +634,17 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
             tana0 /= saturate(h / frustumSize) + kEps;
             float a0 = fmaxf(atanf(tana0), kNormalEncodingError);
             float f = LinearStep(a0, 0.0f, ang);
-            surfaceHistoryConfidence = Pow01(f, 4.0f);
+            surfaceHistoryConfidence = (f * f) * (f * f); // Pow01(f, 4): f is already saturated
         }
 
         f2 maxResponsiveFrameNum;
         {
             float responsiveFactor = SmoothStep01((roughness + kEps) / (c.gResponsiveAccumulationRoughnessThreshold + kEps));
-            float smc = SpecMagicCurve(roughnessModified);
+            float smc = smcModified;
             float fx = dot(N, normalize(smbNavg)), fy = dot(N, vmbN);
             float e = lerpf(32.0f, 1.0f, smc) * (1.0f - responsiveFactor), k = lerpf(smc, 1.0f, responsiveFactor);
-            fx = k * Pow01(fx, e);
-            fy = k * Pow01(fy, e);
+            fx = k * Pow01Fast(fx, e);
+            fy = k * Pow01Fast(fy, e);
             maxResponsiveFrameNum = mk2(fmaxf(c.gMaxAccumulatedFrameNum * fx, c.gHistoryFixFrameNum), fmaxf(c.gMaxAccumulatedFrameNum * fy, c.gHistoryFixFrameNum));
         }
 
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         vmbSpecHistory = ClampNegativeToZero(vmbSpecHistory);
 
         const float smbNl = 1.0f / (1.0f + smbSpecAccumSpeed), vmbNl = 1.0f / (1.0f + vmbSpecAccumSpeed);
-        const float minHitNl = 1.0f / (1.0f + 0.5f * SpecMagicCurve(roughnessModified) * c.gMaxAccumulatedFrameNum);
+        const float minHitNl = 1.0f / (1.0f + 0.5f * smcModified * c.gMaxAccumulatedFrameNum);
         f4 smbSpec = lerp4(smbSpecHistory, spec, smbNl);
         smbSpec.w = lerpf(smbSpecHistory.w, spec.w, fmaxf(smbNl, minHitNl));
         f4 vmbSpec = lerp4(vmbSpecHistory, spec, vmbNl);
@@ -709,7 +712,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         const float smbDiffFastHistory = ResolveBilinearCustom1(smbSetup, a.histDiffFast, smbOcclusionWeights);
 
         const float nl = 1.0f / (1.0f + diffAccumSpeed);
-        const float minHitNl = 1.0f / (1.0f + 0.5f * SpecMagicCurve(1.0f) * c.gMaxAccumulatedFrameNum);
+        const float minHitNl = 1.0f / (1.0f + 0.5f * __ldg(&a.lut[1023]).x * c.gMaxAccumulatedFrameNum); // SpecMagicCurve(1)
         f4 diffResult = lerp4(smbDiffHistory, diff, nl);
         diffResult.w = lerpf(smbDiffHistory.w, diff.w, fmaxf(nl, minHitNl));
 
@@ -742,6 +745,8 @@ struct HfArgs
 {
     ReblurConstants c;
     Surf tiles, nr, data1, z, inDiff, inSpec, inDiffFast, inSpecFast, outDiff, outSpec, outDiffFast, outSpecFast;
+    Surf guide;
+    const float4* lut;
     int rowBegin, rowEnd;
 };
 
@@ -765,7 +770,7 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
     const float roughness = g0.roughness;
     const float minMaterial = IS_SPEC ? c.gSpecMinMaterial : c.gDiffMinMaterial;
     f4 sig = LoadRGBA16F(Near(inSig), x, y);
-    const float smc = SpecMagicCurve(roughness);
+    const float smc = g0.smc;
     float stride = strideBase * (fn < c.gHistoryFixFrameNum ? 1.0f : 0.0f);
     if (IS_SPEC) stride *= lerpf(0.5f, 1.0f, smc);
     stride = floorf(stride);
@@ -778,14 +783,14 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
         const float normalParam = NormalWeightParam(nl, c.gLobeAngleFraction, r);
         const float geoA = 1.0f / (c.gPlaneDistSensitivity * frustumSize), geoB = -dot(Nv, Xv) * geoA;
         const f2 rrp = RelaxedRoughnessWeightParams(roughness * roughness, sqrtf(c.gRoughnessFraction));
-        const float hitDistScale = HitDistNormalization(viewZ, c.gHitDistParams, r);
+        const float hitDistScale = (c.gHitDistParams[0] + viewZ * c.gHitDistParams[1]) * (IS_SPEC ? g0.hitK : __ldg(&a.lut[1023]).y);
         const float hitDist = sig.w * hitDistScale;
         const float hitDistFactor = saturate(hitDist / frustumSize);
-        const f2 hp = HitDistanceWeightParams(hitDistFactor, nl, IS_SPEC ? smc : SpecMagicCurve(1.0f));
+        const f2 hp = HitDistanceWeightParams(hitDistFactor, nl, IS_SPEC ? smc : __ldg(&a.lut[1023]).x);
         float sum = 1.0f + fn;
         sig = sig * sum;
         // the 20 taps reach +-2 strides: one owner test for all of them
-        auto taps = [&](const Surf& zS, const Surf& nrS, const Surf& data1S, const Surf& sigS) {
+        auto taps = [&](const Surf& zS, const Surf& nrS, const Surf& guideS, const Surf& data1S, const Surf& sigS) {
             for (int j = -2; j <= 2; j++)
                 for (int i = -2; i <= 2; i++)
                 {
@@ -794,8 +799,8 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
                     float u = __fadd_rn(pixelUv.x, __fmul_rn(__fmul_rn((float)i, stride), c.gRectSizeInv[0]));
                     float v = __fadd_rn(pixelUv.y, __fmul_rn(__fmul_rn((float)j, stride), c.gRectSizeInv[1]));
                     int px = clampi(x + i * stridei, 0, maxX), py = clampi(y + j * stridei, 0, maxY);
+                    const Guide gs = LoadGuide(guideS, nrS, px, py);
                     float zs = fabsf(LoadR32F(zS, px, py) * c.gViewZScale);
-                    Guide gs = DecodeGuide(LoadU32(nrS, px, py));
                     f3 Xvs = ReconstructViewPosition(mk2(u, v), c.gFrustum, zs, c.gOrthoMode);
                     float w = (u > 0.0f && v > 0.0f && u < 1.0f && v < 1.0f) ? 1.0f : 0.0f;
                     w *= NonExpWeight(dot(Nv, Xvs), geoA, geoB);
@@ -820,8 +825,8 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
                     }
                 }
         };
-        if (FootprintLocal(a.z, y - 2 * stridei, y + 2 * stridei)) taps(Near(a.z), Near(a.nr), Near(a.data1), Near(inSig));
-        else taps(a.z, a.nr, a.data1, inSig);
+        if (FootprintLocal(a.z, y - 2 * stridei, y + 2 * stridei)) taps(Near(a.z), Near(a.nr), Near(a.guide), Near(a.data1), Near(inSig));
+        else taps(a.z, a.nr, a.guide, a.data1, inSig);
         sig = sig * PositiveRcp(sum);
     }
 
@@ -880,7 +885,7 @@ __global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS) ReblurHistoryFixK
     const float viewZ = fabsf(LoadR32F(Near(a.z), x, y) * c.gViewZScale);
     if (viewZ > c.gDenoisingRange) return;
 
-    const Guide g0 = DecodeGuide(LoadU32(Near(a.nr), x, y));
+    const Guide g0 = LoadGuideLut(Near(a.guide), Near(a.nr), a.lut, x, y);
     const float frustumSize = c.gMinRectDimMulUnproject * lerpf(viewZ, 1.0f, fabsf(c.gOrthoMode));
     const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
     const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
@@ -900,6 +905,8 @@ struct TsArgs
     ReblurConstants c;
     Surf tiles, nr, z, data1, data2, inDiff, inSpec, histDiffStab, histSpecStab, hitDist, mv;
     Surf outInternal, outDiff, outSpec, outDiffStab, outSpecStab;
+    Surf guide;
+    const float4* lut;
     int rowBegin, rowEnd;
 };
 
@@ -974,7 +981,7 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
         smbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xprev);
     }
 
-    const Guide g0 = DecodeGuide(LoadU32(Near(a.nr), x, y));
+    const Guide g0 = LoadGuideLut(Near(a.guide), Near(a.nr), a.lut, x, y);
     f2 data1 = LoadFrames<DIFF && SPEC>(Near(a.data1), x, y);
     const unsigned d2 = SPEC ? LoadU32(Near(a.data2), x, y) : LoadU8(Near(a.data2), x, y);
     const unsigned bits = d2 & 0xFFu;
@@ -1018,11 +1025,11 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
         if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
 
         f4 spec = LoadRGBA16F(Near(a.inSpec), x, y);
-        float hitDistForTracking = spec.w * HitDistNormalization(viewZ, c.gHitDistParams, g0.roughness);
+        float hitDistForTracking = spec.w * ((c.gHitDistParams[0] + viewZ * c.gHitDistParams[1]) * g0.hitK);
         if (c.gSpecPrepassBlurRadius != 0.0f) hitDistForTracking = fminf(hitDistForTracking, LoadR16F(Near(a.hitDist), x, y));
 
         const f3 V = c.gOrthoMode == 0.0f ? normalize(-X) : mk3(c.gViewVectorWorld[0], c.gViewVectorWorld[1], c.gViewVectorWorld[2]);
-        const f3 Xvirtual = GetXvirtual(hitDistForTracking, curvature, X, Xprev, g0.N, V, g0.roughness);
+        const f3 Xvirtual = GetXvirtual(hitDistForTracking, curvature, X, Xprev, g0.N, V, g0.aLog);
         f2 vmbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xvirtual);
         if (g0.materialID == c.gCameraAttachedReflectionMaterialID) vmbPixelUv = pixelUv;
 
@@ -1050,7 +1057,7 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
         historyWeight *= virtualHistoryAmount != 0.0f ? (vmbPixelUv.x >= c.gSplitScreenPrev ? 1.0f : 0.0f) : 1.0f;
 
         const float responsiveFactor = SmoothStep01((g0.roughness + kEps) / (c.gResponsiveAccumulationRoughnessThreshold + kEps));
-        const float smc = SpecMagicCurve(g0.roughness);
+        const float smc = g0.smc;
         const float acceleration = lerpf(smc, 1.0f, 0.5f + responsiveFactor * 0.5f);
         historyWeight *= g0.materialID == c.gStrandMaterialID ? 0.5f : acceleration;
 
@@ -1073,6 +1080,9 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchTa(const PassLaunch& p)
 {
     TaArgs a;
     a.c = *(const ReblurConstants*)p.constants;
+    a.guide = p.guide;
+    a.lut = (const float4*)p.roughnessLut;
+    if (!p.preloadOnly && (p.guideMode != 2 || !p.roughnessLut)) return cudaErrorInvalidValue; // the executor always provides both
     int k = 0;
     a.tiles = p.tex[k++]; a.nr = p.tex[k++]; a.z = p.tex[k++]; a.mv = p.tex[k++];
     a.prevZ = p.tex[k++]; a.prevNr = p.tex[k++]; a.prevInternal = p.tex[k++];
@@ -1109,6 +1119,9 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchHf(const PassLaunch& p)
 {
     HfArgs a;
     a.c = *(const ReblurConstants*)p.constants;
+    a.guide = p.guide;
+    a.lut = (const float4*)p.roughnessLut;
+    if (!p.preloadOnly && (p.guideMode != 2 || !p.roughnessLut)) return cudaErrorInvalidValue; // the executor always provides both
     int k = 0;
     a.tiles = p.tex[k++]; a.nr = p.tex[k++]; a.data1 = p.tex[k++]; a.z = p.tex[k++];
     if (DIFF) a.inDiff = p.tex[k++];
@@ -1137,6 +1150,9 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchTs(const PassLaunch& p)
 {
     TsArgs a;
     a.c = *(const ReblurConstants*)p.constants;
+    a.guide = p.guide;
+    a.lut = (const float4*)p.roughnessLut;
+    if (!p.preloadOnly && (p.guideMode != 2 || !p.roughnessLut)) return cudaErrorInvalidValue; // the executor always provides both
     int k = 0;
     a.tiles = p.tex[k++]; a.nr = p.tex[k++];
     if (SPEC) k++; // gIn_BaseColor_Metalness (dummy)

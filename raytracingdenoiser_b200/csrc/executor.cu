@@ -731,9 +731,9 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         memcpy(&rc, d->constantBufferData, sizeof(rc));
         if (rc.gDiffCheckerboard != 2 || rc.gSpecCheckerboard != 2) return Fail(ctx, Result::UNSUPPORTED, "REBLUR checkerboard modes are not implemented by the CUDA executor");
     }
-    // decoded-guide surface: ClassifyTiles (first pass of every REBLUR frame) fills it, PrePass / Blur / PostBlur read it
+    // decoded-guide surface: ClassifyTiles (first pass of every REBLUR frame) fills it, all later passes of the frame read it
     const bool buildsGuide = !strcmp(shader, "REBLUR_ClassifyTiles.cs");
-    const bool readsGuide = !strncmp(shader, "REBLUR_", 7) && (strstr(shader, "_PrePass.cs") != nullptr || strstr(shader, "_Blur.cs") != nullptr || strstr(shader, "_PostBlur") != nullptr);
+    const bool readsGuide = !strncmp(shader, "REBLUR_", 7) && !buildsGuide; // every other REBLUR pass reads it (and the roughness table)
     p.guide = ToSurf(ctx, ctx->guide);
     if (buildsGuide)
     {
