@@ -723,6 +723,91 @@ bool SpatialPrologue(const Pass& P, SpatialCtx& s, const Tex& gIn_Tiles, const T
     return true;
 }
 
+// REBLUR_HitDistReconstruction.hlsli:10-155 (REBLUR_USE_DECOMPRESSED_HIT_DIST_IN_RECONSTRUCTION = 0, not performance mode):
+// a pixel whose ray missed (hit distance 0) borrows the hit distance of its 3x3 / 5x5 neighbourhood
+void HitDistReconstruction(const Pass& P, Signals sg, int border, Tex* t, int W, int H)
+{
+    const CB& c = P.c;
+    int k = 0;
+    const Tex& gIn_Tiles = t[k++];
+    const Tex& gIn_Normal_Roughness = t[k++];
+    const Tex& gIn_ViewZ = t[k++];
+    const Tex* gIn_Diff = sg.diff ? &t[k++] : nullptr;
+    const Tex* gIn_Spec = sg.spec ? &t[k++] : nullptr;
+    Tex* gOut_Diff = sg.diff ? &t[k++] : nullptr;
+    Tex* gOut_Spec = sg.spec ? &t[k++] : nullptr;
+    const int2 rectMax(c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1]);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++)
+        {
+            const int2 pixelPos(x, y);
+            float isSky = gIn_Tiles.load(x >> 4, y >> 4).x;
+            if (isSky != 0.0f || x > rectMax.x || y > rectMax.y) continue;
+            // "shared memory" of the reference: clamped loads (Preload :13-41)
+            auto sData = [&](int i, int j, float4& normalAndRoughness) {
+                int2 p = clamp(int2(x + i - border, y + j - border), int2(0), rectMax);
+                normalAndRoughness = NRD_FrontEnd_UnpackNormalAndRoughness(gIn_Normal_Roughness.load(p));
+                float3 d;
+                d.x = gIn_Diff ? gIn_Diff->load(p).w : 0.0f;
+                d.y = gIn_Spec ? gIn_Spec->load(p).w : 0.0f;
+                d.z = P.UnpackViewZ(gIn_ViewZ.load(p).x);
+                return d;
+            };
+            float4 normalAndRoughness;
+            float3 center = sData(border, border, normalAndRoughness);
+            if (center.z > c.gDenoisingRange) continue;
+            float3 N = normalAndRoughness.xyz();
+            float roughness = normalAndRoughness.w;
+            float2 pixelUv = (tofloat(pixelPos) + float2(0.5f)) * c.gRectSizeInv;
+            float3 Xv = Geometry::ReconstructViewPosition(pixelUv, c.gFrustum, center.z, c.gOrthoMode);
+            float3 Nv = Geometry::RotateVectorInverse(c.gViewToWorld, N);
+            float frustumSize = P.GetFrustumSize(c.gMinRectDimMulUnproject, c.gOrthoMode, center.z);
+            float2 geometryWeightParams = Pass::GetGeometryWeightParams(c.gPlaneDistSensitivity, frustumSize, Xv, Nv);
+            float2 relaxedRoughnessWeightParams = Pass::GetRelaxedRoughnessWeightParams(roughness * roughness);
+            float diffNormalWeightParam = Pass::GetNormalWeightParam(1.0f, 1.0f);
+            float specNormalWeightParam = Pass::GetNormalWeightParam(1.0f, 1.0f, roughness);
+
+            float2 sum = float2(1000.0f) * float2(float(center.x != 0.0f), float(center.y != 0.0f));
+            float2 acc = float2(center.x, center.y) * sum;
+            for (int j = 0; j <= border * 2; j++)
+                for (int i = 0; i <= border * 2; i++)
+                {
+                    float2 o = float2(float(i), float(j)) - float2(float(border));
+                    if (o.x == 0.0f && o.y == 0.0f) continue;
+                    float4 nr;
+                    float3 data = sData(i, j, nr);
+                    float2 uv = pixelUv + o * c.gRectSizeInv;
+                    float w = Pass::IsInScreenNearest(uv);
+                    w *= Pass::GetGaussianWeight(length(o) * 0.5f);
+                    float3 Xvs = Geometry::ReconstructViewPosition(uv, c.gFrustum, data.z, c.gOrthoMode);
+                    w *= Pass::ComputeWeight(dot(Nv, Xvs), geometryWeightParams.x, geometryWeightParams.y);
+                    float2 ww(w);
+                    float cosa = dot(N, nr.xyz());
+                    float angle = Math::AcosApprox(cosa);
+                    ww.x *= Pass::ComputeExponentialWeight(angle, diffNormalWeightParam, 0.0f);
+                    ww.y *= Pass::ComputeExponentialWeight(angle, specNormalWeightParam, 0.0f);
+                    ww.y *= Pass::ComputeExponentialWeight(nr.w * nr.w, relaxedRoughnessWeightParams.x, relaxedRoughnessWeightParams.y);
+                    data.x = ww.x == 0.0f ? 0.0f : data.x; // Denanify
+                    data.y = ww.y == 0.0f ? 0.0f : data.y;
+                    ww *= float2(float(data.x != 0.0f), float(data.y != 0.0f));
+                    acc += float2(data.x, data.y) * ww;
+                    sum += ww;
+                }
+            acc /= max(sum, float2(NRD_EPS));
+            if (gOut_Diff)
+            {
+                float4 d = gIn_Diff->load(pixelPos);
+                gOut_Diff->store(pixelPos, float4(d.x, d.y, d.z, acc.x));
+            }
+            if (gOut_Spec)
+            {
+                float4 sp = gIn_Spec->load(pixelPos);
+                gOut_Spec->store(pixelPos, float4(sp.x, sp.y, sp.z, acc.y));
+            }
+        }
+}
+
 void PrePass(const Pass& P, Signals sg, Tex* t, int W, int H)
 {
     const CB& c = P.c;
@@ -1806,7 +1891,9 @@ int hlsl::reblur_dispatch_impl(const char* shaderName, const void* constants, in
     else return -1;
 
     const int W = gridW * 8, H = gridH * 16; // all these passes run 8x16 groups; overhanging threads early-out / drop stores
-    if (!strcmp(p, "PrePass.cs")) PrePass(P, sg, tex, W, H);
+    if (!strcmp(p, "HitDistReconstruction.cs")) HitDistReconstruction(P, sg, 1, tex, W, H);
+    else if (!strcmp(p, "HitDistReconstruction_5x5.cs")) HitDistReconstruction(P, sg, 2, tex, W, H);
+    else if (!strcmp(p, "PrePass.cs")) PrePass(P, sg, tex, W, H);
     else if (!strcmp(p, "TemporalAccumulation.cs")) TemporalAccumulation(P, sg, tex, W, H);
     else if (!strcmp(p, "HistoryFix.cs")) HistoryFix(P, sg, tex, W, H);
     else if (!strcmp(p, "Blur.cs")) Blur(P, sg, tex, W, H);

@@ -8,6 +8,7 @@
     namespace NS                                                                                                \
     {                                                                                                           \
     cudaError_t LaunchReblurClassifyTiles(const nrdb200_abi::PassLaunch& p);                                    \
+    cudaError_t LaunchReblurHitDistReconstruction(const nrdb200_abi::PassLaunch& p, int signal, bool is5x5);   \
     cudaError_t LaunchReblurPrePass(const nrdb200_abi::PassLaunch& p, int signal);                              \
     cudaError_t LaunchReblurTemporalAccumulation(const nrdb200_abi::PassLaunch& p, int signal);                 \
     cudaError_t LaunchReblurHistoryFix(const nrdb200_abi::PassLaunch& p, int signal);                           \
@@ -25,6 +26,7 @@ namespace nrdb200
 {
 // peer address table of one context slot, replicated into the constant memory of every kernel translation unit
 cudaError_t SetPeerTableReblurSpatial(int slot, const nrdb200_abi::PeerTable* table);
+cudaError_t SetPeerTableReblurHitDist(int slot, const nrdb200_abi::PeerTable* table);
 cudaError_t SetPeerTableReblurTemporal(int slot, const nrdb200_abi::PeerTable* table);
 cudaError_t SetPeerTableSigma(int slot, const nrdb200_abi::PeerTable* table);
 cudaError_t SetPeerTableRelax(int slot, const nrdb200_abi::PeerTable* table);

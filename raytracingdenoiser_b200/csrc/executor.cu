@@ -34,6 +34,7 @@ namespace
 struct Launchers
 {
     cudaError_t (*classifyTiles)(const PassLaunch&);
+    cudaError_t (*hitDistReconstruction)(const PassLaunch&, int, bool);
     cudaError_t (*prePass)(const PassLaunch&, int);
     cudaError_t (*temporalAccumulation)(const PassLaunch&, int);
     cudaError_t (*historyFix)(const PassLaunch&, int);
@@ -43,10 +44,10 @@ struct Launchers
     cudaError_t (*sigma)(const PassLaunch&, const char*);
     cudaError_t (*relax)(const PassLaunch&, const char*);
 };
-const Launchers kStripLaunchers = {nrdb200::LaunchReblurClassifyTiles, nrdb200::LaunchReblurPrePass, nrdb200::LaunchReblurTemporalAccumulation,
+const Launchers kStripLaunchers = {nrdb200::LaunchReblurClassifyTiles, nrdb200::LaunchReblurHitDistReconstruction, nrdb200::LaunchReblurPrePass, nrdb200::LaunchReblurTemporalAccumulation,
                                    nrdb200::LaunchReblurHistoryFix, nrdb200::LaunchReblurBlur, nrdb200::LaunchReblurPostBlur,
                                    nrdb200::LaunchReblurTemporalStabilization, nrdb200::LaunchSigma, nrdb200::LaunchRelax};
-const Launchers kSingleLaunchers = {nrdb200_single::LaunchReblurClassifyTiles, nrdb200_single::LaunchReblurPrePass, nrdb200_single::LaunchReblurTemporalAccumulation,
+const Launchers kSingleLaunchers = {nrdb200_single::LaunchReblurClassifyTiles, nrdb200_single::LaunchReblurHitDistReconstruction, nrdb200_single::LaunchReblurPrePass, nrdb200_single::LaunchReblurTemporalAccumulation,
                                     nrdb200_single::LaunchReblurHistoryFix, nrdb200_single::LaunchReblurBlur, nrdb200_single::LaunchReblurPostBlur,
                                     nrdb200_single::LaunchReblurTemporalStabilization, nrdb200_single::LaunchSigma, nrdb200_single::LaunchRelax};
 
@@ -264,6 +265,8 @@ cudaError_t LaunchByName(const Launchers& L, const PassLaunch& p, const char* sh
     if (!strcmp(shader, "REBLUR_ClassifyTiles.cs")) return L.classifyTiles(p);
     if (ParseReblur(shader, signal, pass))
     {
+        if (!strcmp(pass, "HitDistReconstruction.cs")) return L.hitDistReconstruction(p, signal, false);
+        if (!strcmp(pass, "HitDistReconstruction_5x5.cs")) return L.hitDistReconstruction(p, signal, true);
         if (!strcmp(pass, "PrePass.cs")) return L.prePass(p, signal);
         if (!strcmp(pass, "TemporalAccumulation.cs")) return L.temporalAccumulation(p, signal);
         if (!strcmp(pass, "HistoryFix.cs")) return L.historyFix(p, signal);
@@ -677,6 +680,7 @@ NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t 
     for (uint32_t i = 0; i <= (uint32_t)kMaxPeers; i++) table.start[i] = i <= worldSize ? (int)ctx->stripStart[i] : 0x7fffffff;
     if (worldSize < (uint32_t)kMaxPeers) table.start[worldSize] = 0x7fffffff; // rows >= start[world] do not exist: never counted as an owner change
     cudaError_t e = SetPeerTableReblurSpatial(ctx->peerSlot, &table);
+    if (e == cudaSuccess) e = SetPeerTableReblurHitDist(ctx->peerSlot, &table);
     if (e == cudaSuccess) e = SetPeerTableReblurTemporal(ctx->peerSlot, &table);
     if (e == cudaSuccess) e = SetPeerTableSigma(ctx->peerSlot, &table);
     if (e == cudaSuccess) e = SetPeerTableRelax(ctx->peerSlot, &table);

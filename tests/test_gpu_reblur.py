@@ -49,3 +49,21 @@ def test_reblur_sequence_parity():
     _dump("sequence_reblur.json", res)
     for name, (frac, psnr) in res.items():
         assert frac >= 0.99 and psnr >= 60.0, (name, frac, psnr)
+
+
+@pytest.mark.parametrize("denoiser_name,mode,width,height", [
+    ("REBLUR_DIFFUSE_SPECULAR", "AREA_3X3", 250, 141),
+    ("REBLUR_DIFFUSE_SPECULAR", "AREA_5X5", 640, 360),
+    ("REBLUR_DIFFUSE", "AREA_5X5", 256, 144),
+    ("REBLUR_SPECULAR", "AREA_3X3", 256, 144),
+])
+def test_reblur_hit_distance_reconstruction_per_pass(denoiser_name, mode, width, height):
+    """ReblurSettings::hitDistanceReconstructionMode: the extra 3x3 / 5x5 pass (shared-memory tile staged by TMA) and the chain behind it."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    s = nrd.ReblurSettings(hitDistanceReconstructionMode=int(getattr(nrd.HitDistanceReconstructionMode, mode)))
+    sbs = parity.SideBySide(getattr(nrd.Denoiser, denoiser_name), width, height, settings=s)
+    report = sbs.run_per_pass(3)
+    assert any("HitDistReconstruction" in r["shader"] for r in report)
+    _dump("parity_hitdist_%s_%s.json" % (denoiser_name, mode), report)
+    assert not sbs.failures(), sbs.describe_failures()
