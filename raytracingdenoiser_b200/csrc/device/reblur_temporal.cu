@@ -5,6 +5,7 @@
 // disocclusion-mix / base-colour inputs.  Reprojection footprints are selected with pinned arithmetic (common.cuh).
 #include "reblur_math.cuh"
 #include "launch.h"
+#include "tma.cuh"
 
 namespace nrdb200
 {
@@ -761,9 +762,12 @@ template <bool BOTH> __device__ __forceinline__ f2 LoadFrames(const Surf& s, int
     return mk2(d, d);
 }
 
+// fast-history tile of the CTA: 32 x 8 texels + 2 of halo, rows padded to whole 16-byte units for the TMA box (surf.h / tma.cuh)
+constexpr int kHfBorder = 2, kHfBoxW = 40, kHfBoxH = 8 + 2 * kHfBorder;
+
 template <bool IS_SPEC, bool BOTH>
-__device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, const Surf& inSig, const Surf& inFast, const Surf& outSig, const Surf& outFast,
-                                                 float viewZ, const Guide& g0, f3 Nv, f3 Xv, f2 pixelUv, float frustumSize, float fn, float strideBase)
+__device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, const Surf& inSig, const Surf& inFast, const __half (*sFast)[kHfBoxW], const Surf& outSig,
+                                                 const Surf& outFast, float viewZ, const Guide& g0, f3 Nv, f3 Xv, f2 pixelUv, float frustumSize, float fn, float strideBase)
 {
     const ReblurConstants& c = a.c;
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
@@ -830,15 +834,16 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
         sig = sig * PositiveRcp(sum);
     }
 
-    // 5x5 moments of the fast history (clamped reads)
-    float center = LoadR16F(Near(inFast), x, y);
+    // 5x5 moments of the fast history from the staged tile (clamp-to-edge was patched into its halo): LDS with constant offsets
+    const int cx = threadIdx.x + kHfBorder, cy = threadIdx.y + kHfBorder;
+    float center = __half2float(sFast[cy][cx]);
     float m1 = 0.0f, m2 = 0.0f;
 #pragma unroll
     for (int j = -2; j <= 2; j++)
 #pragma unroll
         for (int i = -2; i <= 2; i++)
         {
-            float d = LoadR16F(Near(inFast), clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)); // +-2 rows: inside the ghost rows
+            float d = __half2float(sFast[cy + j][cx + i]);
             m1 += d;
             m2 += d * d;
         }
@@ -875,9 +880,31 @@ template <bool DIFF, bool SPEC>
 #ifndef NRD_B200_HF_MIN_BLOCKS
 #define NRD_B200_HF_MIN_BLOCKS 4 // <= 64 registers
 #endif
-__global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS) ReblurHistoryFixKernel(const __grid_constant__ HfArgs a)
+__global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS)
+    ReblurHistoryFixKernel(const __grid_constant__ HfArgs a, const __grid_constant__ CUtensorMap diffFastMap, const __grid_constant__ CUtensorMap specFastMap)
 {
+    // The CTA stages the fast-history window of both signals (tile + 2 texels of halo) with TMA bulk tensor copies on one
+    // mbarrier: the 5x5 moments of every pixel are then 25 shared-memory loads at constant offsets instead of 25 clamped global ones.
+    __shared__ __align__(128) __half sFastDiff[DIFF ? kHfBoxH : 1][kHfBoxW];
+    __shared__ __align__(128) __half sFastSpec[SPEC ? kHfBoxH : 1][kHfBoxW];
+    __shared__ __align__(8) uint64_t bar;
     const ReblurConstants& c = a.c;
+    {
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        const int boxX0 = blockIdx.x * 32 - kHfBorder, boxY0 = a.rowBegin + blockIdx.y * 8 - kHfBorder;
+        if (tid == 0) nrdb200_tma::BarrierInit(&bar);
+        __syncthreads();
+        if (tid == 0)
+        {
+            nrdb200_tma::BarrierExpect(&bar, (uint32_t)((DIFF ? sizeof(sFastDiff) : 0) + (SPEC ? sizeof(sFastSpec) : 0)));
+            if (DIFF) nrdb200_tma::IssueTile2D(sFastDiff, &diffFastMap, boxX0, boxY0 - a.inDiffFast.ly0, &bar);
+            if (SPEC) nrdb200_tma::IssueTile2D(sFastSpec, &specFastMap, boxX0, boxY0 - a.inSpecFast.ly0, &bar);
+        }
+        nrdb200_tma::BarrierWait(&bar, 0);
+        if (DIFF) nrdb200_tma::PatchClampToEdge<__half, kHfBoxW, kHfBoxH>(sFastDiff, boxX0, boxY0, c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1], tid, 256);
+        if (SPEC) nrdb200_tma::PatchClampToEdge<__half, kHfBoxW, kHfBoxH>(sFastSpec, boxX0, boxY0, c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1], tid, 256);
+        __syncthreads();
+    }
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
     if (x > c.gRectSizeMinusOne[0] || y > c.gRectSizeMinusOne[1] || y >= a.rowEnd) return;
@@ -893,8 +920,8 @@ __global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS) ReblurHistoryFixK
     const f2 frameNum = LoadFrames<DIFF && SPEC>(Near(a.data1), x, y);
     const f2 stride = mk2(__fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.x)), __fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.y)));
 
-    if (DIFF) HistoryFixSignal<false, DIFF && SPEC>(a, x, y, a.inDiff, a.inDiffFast, a.outDiff, a.outDiffFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.x, stride.x);
-    if (SPEC) HistoryFixSignal<true, DIFF && SPEC>(a, x, y, a.inSpec, a.inSpecFast, a.outSpec, a.outSpecFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.y, stride.y);
+    if (DIFF) HistoryFixSignal<false, DIFF && SPEC>(a, x, y, a.inDiff, a.inDiffFast, sFastDiff, a.outDiff, a.outDiffFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.x, stride.x);
+    if (SPEC) HistoryFixSignal<true, DIFF && SPEC>(a, x, y, a.inSpec, a.inSpecFast, sFastSpec, a.outSpec, a.outSpecFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.y, stride.y);
 }
 
 // =============================================================================================
@@ -1136,7 +1163,18 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchHf(const PassLaunch& p)
     a.rowEnd = p.rowEnd;
     const int W = (int)a.c.gRectSize[0];
     dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
-    NRD_B200_LAUNCH(p, grid, block, a, ReblurHistoryFixKernel<DIFF, SPEC>);
+    if (p.preloadOnly)
+    {
+        cudaFuncAttributes fa;
+        return cudaFuncGetAttributes(&fa, ReblurHistoryFixKernel<DIFF, SPEC>);
+    }
+    // TMA descriptors of the two fast-history textures (pool textures: 256-byte aligned rows, device/tma.cuh)
+    CUtensorMap diffMap, specMap;
+    memset(&diffMap, 0, sizeof(diffMap));
+    memset(&specMap, 0, sizeof(specMap));
+    if (DIFF && !nrdb200_tma::MakeSurfaceMap16(a.inDiffFast, kHfBoxW, kHfBoxH, &diffMap)) return cudaErrorInvalidValue;
+    if (SPEC && !nrdb200_tma::MakeSurfaceMap16(a.inSpecFast, kHfBoxW, kHfBoxH, &specMap)) return cudaErrorInvalidValue;
+    ReblurHistoryFixKernel<DIFF, SPEC><<<grid, block, 0, p.stream>>>(a, diffMap, specMap);
     return cudaGetLastError();
 }
 cudaError_t LaunchReblurHistoryFix(const PassLaunch& p, int signal)

@@ -29,6 +29,18 @@ inline CUresult EncodeTiled(CUtensorMap* map, CUtensorMapDataType type, cuuint32
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
+// Tensor map over the rows a context holds of a surface of 2-byte texels (R16F).  Coordinates of a copy: x in texels, y in local rows.
+// The box width must make whole 16-byte rows in shared memory (a multiple of 8 texels).
+inline bool MakeSurfaceMap16(const nrdb200_abi::Surf& s, int boxTexelsX, int boxRows, CUtensorMap* map)
+{
+    if (((uintptr_t)s.base & 15) != 0 || (s.pitch & 15) != 0 || (boxTexelsX & 7) != 0 || boxTexelsX > 256 || boxRows > 256) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)s.w, (cuuint64_t)s.lrows};
+    const cuuint64_t strides[1] = {(cuuint64_t)s.pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)boxTexelsX, (cuuint32_t)boxRows};
+    const cuuint32_t es[2] = {1, 1};
+    return EncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, s.base, dims, strides, box, es) == CUDA_SUCCESS;
+}
+
 // Tensor map over the rows a context holds of a surface whose texels are `floatsPerTexel` 32-bit words (RGBA32F: 4).  Coordinates
 // of a copy: x in 32-bit words (texel x * floatsPerTexel), y in local rows (row - surf.ly0).  Needs a 16-byte aligned base and pitch.
 inline bool MakeSurfaceMap(const nrdb200_abi::Surf& s, int floatsPerTexel, int boxTexelsX, int boxRows, CUtensorMap* map)
@@ -49,13 +61,35 @@ __device__ __forceinline__ void BarrierInit(uint64_t* bar)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(SmemAddr(bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// one thread: announce `bytes` and start the bulk tensor copy of the box whose first element is (x32, yLocal) into `dst`
-__device__ __forceinline__ void LoadTile2D(void* dst, const CUtensorMap* map, int x32, int yLocal, uint64_t* bar, uint32_t bytes)
+// one thread: the single arrival of the barrier, announcing the bytes of ALL copies that will complete on it
+__device__ __forceinline__ void BarrierExpect(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(SmemAddr(dst)), "l"(map), "r"(x32), "r"(yLocal),
+}
+// one thread: start the bulk tensor copy of the box whose first element is (x, yLocal) (in elements of the map) into `dst`
+__device__ __forceinline__ void IssueTile2D(void* dst, const CUtensorMap* map, int x, int yLocal, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(SmemAddr(dst)), "l"(map), "r"(x), "r"(yLocal),
                  "r"(SmemAddr(bar))
                  : "memory");
+}
+__device__ __forceinline__ void LoadTile2D(void* dst, const CUtensorMap* map, int x, int yLocal, uint64_t* bar, uint32_t bytes)
+{
+    BarrierExpect(bar, bytes);
+    IssueTile2D(dst, map, x, yLocal, bar);
+}
+// Clamp-to-edge for a staged box whose cell (lx, ly) holds texel (boxX0 + lx, boxY0 + ly): cells outside [0, maxX] x [0, maxY]
+// (zero-filled by TMA) take the value of the clamped texel, which is always inside the box.  Only CTAs on the frame edge do
+// anything; callers __syncthreads() afterwards.  Readers and writers are disjoint cells, so one pass is enough.
+template <class T, int BW, int BH> __device__ __forceinline__ void PatchClampToEdge(T (*tile)[BW], int boxX0, int boxY0, int maxX, int maxY, int tid, int threads)
+{
+    if (boxX0 >= 0 && boxY0 >= 0 && boxX0 + BW - 1 <= maxX && boxY0 + BH - 1 <= maxY) return;
+    for (int i = tid; i < BW * BH; i += threads)
+    {
+        const int lx = i % BW, ly = i / BW, gx = boxX0 + lx, gy = boxY0 + ly;
+        const int cx = min(max(gx, 0), maxX), cy = min(max(gy, 0), maxY);
+        if ((cx != gx || cy != gy) && cx - boxX0 < BW && cy - boxY0 < BH) tile[ly][lx] = tile[cy - boxY0][cx - boxX0];
+    }
 }
 // every thread that reads the tile
 __device__ __forceinline__ void BarrierWait(uint64_t* bar, uint32_t phase)
