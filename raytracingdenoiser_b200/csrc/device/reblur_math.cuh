@@ -42,6 +42,21 @@ __device__ __forceinline__ Guide DecodeGuide(unsigned packed)
     return g;
 }
 
+// NRD_FrontEnd_UnpackNormalAndRoughness (NRD.hlsli:600-628, R10G10B10A2) in the oracle's operation order with IEEE division and
+// square root: the stored normal is bit-identical to the oracle's.  Once per pixel and frame, so the ~20 extra instructions are free.
+__device__ __forceinline__ f3 DecodeNormalExact(unsigned packed)
+{
+    const float px = __fdiv_rn((float)(packed & 1023u), 1023.0f), py = __fdiv_rn((float)((packed >> 10) & 1023u), 1023.0f);
+    float nx = __fadd_rn(__fmul_rn(px, 2.0f), -1.0f), ny = __fadd_rn(__fmul_rn(py, 2.0f), -1.0f);
+    const float nz = __fadd_rn(__fadd_rn(1.0f, -fabsf(nx)), -fabsf(ny));
+    const float t = saturate(-nz);
+    nx = __fadd_rn(nx, nx >= 0.0f ? -t : t);
+    ny = __fadd_rn(ny, ny >= 0.0f ? -t : t);
+    const float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)), 1e-9f);
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(d));
+    return mk3(__fmul_rn(nx, inv), __fmul_rn(ny, inv), __fmul_rn(nz, inv));
+}
+
 // Guides through the decoded-guide surface (surf.h PassLaunch::guide: {N.xyz bit-exact, raw viewZ}, written by ClassifyTiles at
 // the start of every frame): one 16-byte load instead of the octahedral decode; roughness / material straight from the packed
 // bits (loads whose result is unused are removed by the compiler).

@@ -43,7 +43,9 @@ __device__ __forceinline__ bool SameMaterial(float m0, float m, float minm) { re
 // exact UNORM8 decode times 255 (history length, material id): decisions depend on it, so keep IEEE division
 __device__ __forceinline__ float LoadR8Times255(const Surf& s, int x, int y) { return __fmul_rn(__fdiv_rn((float)LoadU8(s, x, y), 255.0f), 255.0f); }
 __device__ __forceinline__ float LoadR8UnormExactClamped(const Surf& s, int x, int y) { return __fdiv_rn((float)LoadU8(s, clampi(x, 0, s.w - 1), clampi(y, 0, s.h - 1)), 255.0f); }
-__device__ __forceinline__ Guide LoadGuide(const Surf& s, int x, int y) { return DecodeGuide(LoadU32(s, x, y)); }
+// current-frame guides: the normal comes decoded from the guide surface RELAX_ClassifyTiles filled (one 16-byte load instead of the
+// octahedral decode at every tap of every A-trous iteration), roughness / material from the packed bits
+#define RX_GUIDE(a, x, y) rb::LoadGuide((a).guide, (a).nr, x, y)
 __device__ __forceinline__ bool IsSkyTile(const Surf& tiles, int x, int y) { return LoadU8(tiles, x >> 4, y >> 4) != 0; }
 
 // RELAX_Common.hlsli:66-96
@@ -207,9 +209,10 @@ __device__ __forceinline__ f3 YCoCgToRgb(f3 c)
 // =============================================================================================
 struct RxTilesArgs
 {
-    Surf z, tiles;
+    Surf z, tiles, nr, guide;
     float denoisingRange;
     int tilesW, tilesH;
+    int buildGuide; // also decode IN_NORMAL_ROUGHNESS of the tile into the guide surface (surf.h PassLaunch::guide)
 };
 __global__ void __launch_bounds__(256) RelaxClassifyTilesKernel(const __grid_constant__ RxTilesArgs a)
 {
@@ -223,7 +226,12 @@ __global__ void __launch_bounds__(256) RelaxClassifyTilesKernel(const __grid_con
     {
         int i = k * 32 + lane;
         int x = tx * 16 + (i & 15), y = ty * 16 + (i >> 4);
-        float z = Inside(a.z, x, y) ? LoadR32F(a.z, x, y) : 0.0f;
+        float z = 0.0f;
+        if (Inside(a.z, x, y))
+        {
+            z = LoadR32F(a.z, x, y);
+            if (a.buildGuide) StoreRGBA32F(a.guide, x, y, mk4(rb::DecodeNormalExact(LoadU32(a.nr, x, y)), z));
+        }
         allSky = allSky && (fabsf(z) > a.denoisingRange);
     }
     allSky = __all_sync(0xffffffffu, allSky);
@@ -237,6 +245,7 @@ struct RxPrePassArgs
 {
     RC c;
     Surf tiles, spec, diff, nr, z, outSpec, outDiff;
+    Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
 __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant__ RxPrePassArgs a)
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant_
     const float centerViewZ = UnpackViewZ(c, LoadR32F(a.z, x, y));
     if (centerViewZ > c.gDenoisingRange) return;
 
-    const Guide g = LoadGuide(a.nr, x, y);
+    const Guide g = RX_GUIDE(a, x, y);
     const f3 centerNormal = g.N;
     const float centerRoughness = g.roughness;
     const f3 centerWorldPos = CurWorldPos(c, x, y, centerViewZ);
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant_
                 int tx, ty;
                 float csx, csy;
                 bool inScreen = tapPos(i, blurRadius, tx, ty, csx, csy);
-                Guide sg = LoadGuide(a.nr, tx, ty);
+                Guide sg = RX_GUIDE(a, tx, ty);
                 float sz = UnpackViewZ(c, LoadR32F(a.z, tx, ty));
                 f3 sw = CurWorldPosFromClip(c, csx, csy, sz);
                 float w = inScreen ? 1.0f : 0.0f;
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant_
                 int tx, ty;
                 float csx, csy;
                 bool inScreen = tapPos(i, blurRadius, tx, ty, csx, csy);
-                Guide sg = LoadGuide(a.nr, tx, ty);
+                Guide sg = RX_GUIDE(a, tx, ty);
                 float sz = UnpackViewZ(c, LoadR32F(a.z, tx, ty));
                 float w = inScreen ? 1.0f : 0.0f;
                 w *= sz < c.gDenoisingRange ? 1.0f : 0.0f;
@@ -378,6 +387,7 @@ struct RxTaArgs
     RC c;
     Surf tiles, spec, diff, mv, nr, z, histSpecFast, histDiffFast, histSpec, histDiff, prevNr, prevZ, prevHitDist, prevLength, prevMaterial;
     Surf outSpec, outDiff, outSpecFast, outDiffFast, outHitDist, outLength, outConfidence;
+    Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
 __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const __grid_constant__ RxTaArgs a)
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
     if (currentLinearZ > c.gDenoisingRange) return;
     const float fW = (float)W, fH = (float)H;
 
-    const Guide g = LoadGuide(a.nr, x, y);
+    const Guide g = RX_GUIDE(a, x, y);
     const f3 currentNormal = g.N;
     const float currentRoughness = g.roughness;
     const float currentMaterialID = g.materialID;
@@ -436,7 +446,7 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
         {
             if (i == 0 && j == 0) continue;
             int px = clampi(x + i, 0, W - 1), py = clampi(y + j, 0, H - 1);
-            f3 n = LoadGuide(a.nr, px, py).N;
+            f3 n = RX_GUIDE(a, px, py).N;
             float h = LoadRGBA16F(a.spec, px, py).w;
             minHitDist3x3 = fminf(minHitDist3x3, h == 0.0f ? kInf : h);
             currentNormalAveraged = currentNormalAveraged + n;
@@ -616,7 +626,7 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
             int ix = (int)fx, iy = (int)fy;
             float zHigh = UnpackViewZ(c, LoadR32F(a.z, ix, iy));
             f3 xHigh = CurWorldPosFromClip(c, (fx + 0.5f) * c.gRectSizeInv[0] * 2.0f - 1.0f, (fy + 0.5f) * c.gRectSizeInv[1] * 2.0f - 1.0f, zHigh);
-            f3 nHigh = LoadGuide(a.nr, ix, iy).N;
+            f3 nHigh = RX_GUIDE(a, ix, iy).N;
             float zError = fabsf(zHigh - currentLinearZ) / fmaxf(zHigh, currentLinearZ);
             bool cmp = zError < kCurvatureZThreshold;
             n = cmp ? nHigh : n;
@@ -782,6 +792,7 @@ struct RxHfArgs
 {
     RC c;
     Surf tiles, spec, diff, length, nr, z, outSpec, outDiff;
+    Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
 __global__ void __launch_bounds__(256) RelaxHistoryFixKernel(const __grid_constant__ RxHfArgs a)
@@ -957,6 +968,7 @@ struct RxAtrousArgs
 {
     RC c;
     Surf tiles, spec, diff, length, confidence, nr, z, outSpec, outDiff, outNr, outMaterial, outZ;
+    Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
 __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_constant__ RxAtrousArgs a)
@@ -974,7 +986,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
     g.N = mk3(0.0f);
     g.roughness = 0.0f;
     g.materialID = 0.0f;
-    if (!isSky) g = LoadGuide(a.nr, x, y);
+    if (!isSky) g = RX_GUIDE(a, x, y);
     const float centerViewZ = UnpackViewZ(c, viewZpacked);
     f4 nr = mk4(g.N, g.roughness);
     if (centerViewZ > c.gDenoisingRange) nr = mk4(1.0f / 255.0f);
@@ -1027,7 +1039,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
                 const bool isInside = x + cx >= 0 && y + cy >= 0 && x + cx < W && y + cy < H;
                 const int px = clampi(x + cx, 0, W - 1), py = clampi(y + cy, 0, H - 1);
                 const float kernelW = isInside ? (cx == 0 ? 0.44198f : 0.27901f) * (cy == 0 ? 0.44198f : 0.27901f) : 0.0f;
-                const Guide sg = LoadGuide(a.nr, px, py);
+                const Guide sg = RX_GUIDE(a, px, py);
                 const f3 sw = CurWorldPos(c, px, py, UnpackViewZ(c, LoadR32F(a.z, px, py)));
                 float geometryW = PlaneDistWeightAtrous(centerWorldPos, centerNormal, sw, depthThreshold) * kernelW;
                 const float angles = AcosApprox(dot(centerNormal, sg.N));
@@ -1074,7 +1086,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
             for (int cy = -2; cy <= 2; cy++)
             {
                 const int px = clampi(x + cx, 0, W - 1), py = clampi(y + cy, 0, H - 1);
-                const Guide sg = LoadGuide(a.nr, px, py);
+                const Guide sg = RX_GUIDE(a, px, py);
                 const float normalW = NonExpWeight(AcosApprox(dot(centerNormal, sg.N)), normalWeightParam, 0.0f);
                 const f4 ss = LoadRGBA16F(a.spec, px, py);
                 const float specularW = normalW * (SameMaterial(sg.materialID, centerMaterialID, c.gSpecMinMaterial) ? 1.0f : 0.0f);
@@ -1113,7 +1125,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
     if (IsSkyTile(a.tiles, x, y)) return;
     const float centerViewZ = UnpackViewZ(c, LoadR32F(a.z, x, y));
     if (centerViewZ > c.gDenoisingRange) return;
-    const Guide g = LoadGuide(a.nr, x, y);
+    const Guide g = RX_GUIDE(a, x, y);
     const f3 centerNormal = g.N;
     const float historyLength = LoadR8Times255(a.length, x, y);
     const int step = (int)c.gStepSize;
@@ -1161,7 +1173,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
             const int px = x + offx + xx * step, py = y + offy + yy * step;
             if (px < 0 || py < 0 || px >= W || py >= H) continue; // geometry weight is zero outside
             const float kernelW = (xx == 0 ? 0.44198f : 0.27901f) * (yy == 0 ? 0.44198f : 0.27901f);
-            const Guide sg = LoadGuide(a.nr, px, py);
+            const Guide sg = RX_GUIDE(a, px, py);
             const float sz = UnpackViewZ(c, LoadR32F(a.z, px, py));
             const f3 sw = CurWorldPos(c, px, py, sz);
             float geometryW = PlaneDistWeightAtrous(centerWorldPos, centerNormal, sw, depthThreshold) * kernelW;
@@ -1214,6 +1226,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
     if (!strcmp(shader, "RELAX_ClassifyTiles.cs"))
     {
         RxTilesArgs a;
+        a.nr = p.guideNr; a.guide = p.guide; a.buildGuide = p.guideMode == 1 ? 1 : 0;
         a.z = p.tex[0]; a.tiles = p.tex[1];
         a.denoisingRange = c.gDenoisingRange; a.tilesW = p.gridW; a.tilesH = p.gridH;
         int warps = a.tilesW * a.tilesH;
@@ -1223,6 +1236,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
     {
         RxPrePassArgs a;
         a.c = c;
+        a.guide = p.guide;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.nr = p.tex[3]; a.z = p.tex[4]; a.outSpec = p.tex[5]; a.outDiff = p.tex[6];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
         NRD_B200_LAUNCH(p, grid, block, a, RelaxPrePassKernel);
@@ -1231,6 +1245,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
     {
         RxTaArgs a;
         a.c = c;
+        a.guide = p.guide;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.mv = p.tex[3]; a.nr = p.tex[4]; a.z = p.tex[5];
         a.histSpecFast = p.tex[6]; a.histDiffFast = p.tex[7]; a.histSpec = p.tex[8]; a.histDiff = p.tex[9];
         a.prevNr = p.tex[10]; a.prevZ = p.tex[11]; a.prevHitDist = p.tex[12]; a.prevLength = p.tex[13]; a.prevMaterial = p.tex[14];
@@ -1243,6 +1258,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
     {
         RxHfArgs a;
         a.c = c;
+        a.guide = p.guide;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.length = p.tex[3]; a.nr = p.tex[4]; a.z = p.tex[5]; a.outSpec = p.tex[6]; a.outDiff = p.tex[7];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
         NRD_B200_LAUNCH(p, grid, block, a, RelaxHistoryFixKernel);
@@ -1262,6 +1278,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         const bool smem = !strcmp(shader, "RELAX_DiffuseSpecular_AtrousSmem.cs");
         RxAtrousArgs a;
         a.c = c;
+        a.guide = p.guide;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.length = p.tex[3]; a.confidence = p.tex[4]; a.nr = p.tex[5]; a.z = p.tex[6];
         a.outSpec = p.tex[9]; a.outDiff = p.tex[10];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;

@@ -736,24 +736,28 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         if (rc.gDiffCheckerboard != 2 || rc.gSpecCheckerboard != 2) return Fail(ctx, Result::UNSUPPORTED, "REBLUR checkerboard modes are not implemented by the CUDA executor");
     }
     // decoded-guide surface: ClassifyTiles (first pass of every REBLUR frame) fills it, all later passes of the frame read it
-    const bool buildsGuide = !strcmp(shader, "REBLUR_ClassifyTiles.cs");
-    const bool readsGuide = !strncmp(shader, "REBLUR_", 7) && !buildsGuide; // every other REBLUR pass reads it (and the roughness table)
+    const bool isReblur = !strncmp(shader, "REBLUR_", 7), isRelax = !strncmp(shader, "RELAX_", 6);
+    const bool buildsGuide = !strcmp(shader, "REBLUR_ClassifyTiles.cs") || !strcmp(shader, "RELAX_ClassifyTiles.cs");
+    const bool readsGuide = (isReblur || isRelax) && !buildsGuide; // every other REBLUR / RELAX pass reads it (REBLUR: and the roughness table)
     p.guide = ToSurf(ctx, ctx->guide);
     if (buildsGuide)
     {
         const Texture* nr = Resolve(ctx, ResourceType::IN_NORMAL_ROUGHNESS, 0);
-        if (!nr) return Fail(ctx, Result::INVALID_ARGUMENT, "unbound resource IN_NORMAL_ROUGHNESS for REBLUR_ClassifyTiles (it also builds the guide surface)");
+        if (!nr) return Fail(ctx, Result::INVALID_ARGUMENT, "unbound resource IN_NORMAL_ROUGHNESS for ClassifyTiles (it also builds the guide surface)");
         p.guideNr = ToSurf(ctx, *nr);
         p.guideMode = 1;
     }
     else if (readsGuide)
     {
-        if (!ctx->guideValid) return Fail(ctx, Result::FAILURE, std::string(shader) + " dispatched before REBLUR_ClassifyTiles of the same frame");
-        ReblurConstants rc;
-        memcpy(&rc, d->constantBufferData, sizeof(rc));
-        Result lr = UpdateRoughnessLut(ctx, rc.gHitDistParams, (cudaStream_t)stream);
-        if (lr != Result::SUCCESS) return lr;
-        p.roughnessLut = ctx->roughnessLut;
+        if (!ctx->guideValid) return Fail(ctx, Result::FAILURE, std::string(shader) + " dispatched before ClassifyTiles of the same frame");
+        if (isReblur)
+        {
+            ReblurConstants rc;
+            memcpy(&rc, d->constantBufferData, sizeof(rc));
+            Result lr = UpdateRoughnessLut(ctx, rc.gHitDistParams, (cudaStream_t)stream);
+            if (lr != Result::SUCCESS) return lr;
+            p.roughnessLut = ctx->roughnessLut;
+        }
         p.guideMode = 2;
     }
     // rows to produce: the context's strip (the full frame on one GPU)
