@@ -1,0 +1,11 @@
+#!/bin/bash
+# GPU job on N GPUs of one box: cross-process bit-identity of the strips (tests/multi_gpu_check.py) and the bench line at N (and N/2)
+cd "$(dirname "$0")/.."
+O=gpurun_out
+N=${1:-2}
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py > $O/r2_multi_check_n$N.log 2>&1; tail -6 $O/r2_multi_check_n$N.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > $O/r2_bench_n$N.json 2> $O/r2_bench_n$N.err; tail -c 900 $O/r2_bench_n$N.json; tail -3 $O/r2_bench_n$N.err
+if [ "$N" -ge 4 ]; then
+  H=$((N/2))
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $H --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $H --steps 20 --warmup 5 > $O/r2_bench_n$H.json 2> $O/r2_bench_n$H.err; tail -c 600 $O/r2_bench_n$H.json
+fi
