@@ -3,7 +3,12 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out
 N=${1:-2}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py > $O/r2_multi_check_n$N.log 2>&1; tail -6 $O/r2_multi_check_n$N.log
+: > $O/r2_multi_check_n$N.log
+for cfg in "REBLUR_DIFFUSE_SPECULAR 3840 2160 5" "RELAX_DIFFUSE_SPECULAR 1920 1080 4" "SIGMA_SHADOW 1920 1080 4"; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py $cfg >> $O/r2_multi_check_n$N.log 2>&1
+  echo "rc=$? $cfg" >> $O/r2_multi_check_n$N.log
+done
+grep -E "^rc=|strips_vs_full_frame" $O/r2_multi_check_n$N.log | cut -c1-300
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > $O/r2_bench_n$N.json 2> $O/r2_bench_n$N.err; tail -c 900 $O/r2_bench_n$N.json; tail -3 $O/r2_bench_n$N.err
 if [ "$N" -ge 4 ]; then
   H=$((N/2))
