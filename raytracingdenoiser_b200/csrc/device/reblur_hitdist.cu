@@ -22,6 +22,7 @@ struct HitDistArgs
     Surf tiles, nr, inDiff, inSpec, outDiff, outSpec, guide;
     const float4* lut;
     int rowBegin, rowEnd;
+    int useTma; // the guide window is staged by TMA (else by clamped loads)
 };
 
 constexpr int kHdTileW = 32, kHdTileH = 8;
@@ -40,10 +41,13 @@ __global__ void __launch_bounds__(kHdTileW* kHdTileH) ReblurHitDistReconstructio
     const int tileX0 = blockIdx.x * kHdTileW, tileY0 = a.rowBegin + blockIdx.y * kHdTileH;
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
 
-    if (tid == 0) nrdb200_tma::BarrierInit(&bar);
-    __syncthreads();
-    // x in 32-bit words, y in rows held locally; negative / beyond-the-edge parts of the box arrive as zeros
-    if (tid == 0) nrdb200_tma::LoadTile2D(sGuide, &guideMap, (tileX0 - BORDER) * 4, tileY0 - BORDER - a.guide.ly0, &bar, (uint32_t)sizeof(sGuide));
+    if (a.useTma)
+    {
+        if (tid == 0) nrdb200_tma::BarrierInit(&bar);
+        __syncthreads();
+        // x in 32-bit words, y in rows held locally; negative / beyond-the-edge parts of the box arrive as zeros
+        if (tid == 0) nrdb200_tma::LoadTile2D(sGuide, &guideMap, (tileX0 - BORDER) * 4, tileY0 - BORDER - a.guide.ly0, &bar, (uint32_t)sizeof(sGuide));
+    }
 
     // meanwhile: hit distances and roughness of the window, clamped to the rect like the reference's Preload (:13-41)
     for (int i = tid; i < BW * BH; i += kHdTileW * kHdTileH)
@@ -55,8 +59,9 @@ __global__ void __launch_bounds__(kHdTileW* kHdTileH) ReblurHitDistReconstructio
         if (SPEC) h.y = LoadRGBA16F(Near(a.inSpec), gx, gy).w;
         sHit[ly][lx] = h;
         if (SPEC) sRough[ly][lx] = (float)((LoadU32(Near(a.nr), gx, gy) >> 20) & 1023u) * (1.0f / 1023.0f);
+        if (!a.useTma) sGuide[ly][lx] = __ldg(TexelPtr<float4>(Near(a.guide), gx, gy));
     }
-    nrdb200_tma::BarrierWait(&bar, 0);
+    if (a.useTma) nrdb200_tma::BarrierWait(&bar, 0);
     __syncthreads();
 
     const int x = tileX0 + threadIdx.x, y = tileY0 + threadIdx.y;
@@ -149,7 +154,7 @@ template <bool DIFF, bool SPEC, int BORDER> static cudaError_t LaunchHitDist(con
     a.rowEnd = p.rowEnd;
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    if (!p.preloadOnly && !nrdb200_tma::MakeSurfaceMap(a.guide, 4, kHdTileW + 2 * BORDER, kHdTileH + 2 * BORDER, &map)) return cudaErrorInvalidValue;
+    a.useTma = !p.preloadOnly && nrdb200_tma::Enabled() && nrdb200_tma::MakeSurfaceMap(a.guide, 4, kHdTileW + 2 * BORDER, kHdTileH + 2 * BORDER, &map);
     const int W = (int)a.c.gRectSize[0];
     dim3 grid((W + kHdTileW - 1) / kHdTileW, (p.rowEnd - p.rowBegin + kHdTileH - 1) / kHdTileH), block(kHdTileW, kHdTileH);
     if (p.preloadOnly)

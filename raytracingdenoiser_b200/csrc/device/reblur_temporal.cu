@@ -749,6 +749,7 @@ struct HfArgs
     Surf guide;
     const float4* lut;
     int rowBegin, rowEnd;
+    int useTma; // the fast-history window is staged by TMA (else by clamped loads)
 };
 
 template <bool BOTH> __device__ __forceinline__ f2 LoadFrames(const Surf& s, int x, int y)
@@ -892,17 +893,31 @@ __global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS)
     {
         const int tid = threadIdx.y * 32 + threadIdx.x;
         const int boxX0 = blockIdx.x * 32 - kHfBorder, boxY0 = a.rowBegin + blockIdx.y * 8 - kHfBorder;
-        if (tid == 0) nrdb200_tma::BarrierInit(&bar);
-        __syncthreads();
-        if (tid == 0)
+        if (a.useTma)
         {
-            nrdb200_tma::BarrierExpect(&bar, (uint32_t)((DIFF ? sizeof(sFastDiff) : 0) + (SPEC ? sizeof(sFastSpec) : 0)));
-            if (DIFF) nrdb200_tma::IssueTile2D(sFastDiff, &diffFastMap, boxX0, boxY0 - a.inDiffFast.ly0, &bar);
-            if (SPEC) nrdb200_tma::IssueTile2D(sFastSpec, &specFastMap, boxX0, boxY0 - a.inSpecFast.ly0, &bar);
+            if (tid == 0) nrdb200_tma::BarrierInit(&bar);
+            __syncthreads();
+            if (tid == 0)
+            {
+                nrdb200_tma::BarrierExpect(&bar, (uint32_t)((DIFF ? sizeof(sFastDiff) : 0) + (SPEC ? sizeof(sFastSpec) : 0)));
+                if (DIFF) nrdb200_tma::IssueTile2D(sFastDiff, &diffFastMap, boxX0, boxY0 - a.inDiffFast.ly0, &bar);
+                if (SPEC) nrdb200_tma::IssueTile2D(sFastSpec, &specFastMap, boxX0, boxY0 - a.inSpecFast.ly0, &bar);
+            }
+            nrdb200_tma::BarrierWait(&bar, 0);
+            if (DIFF) nrdb200_tma::PatchClampToEdge<__half, kHfBoxW, kHfBoxH>(sFastDiff, boxX0, boxY0, c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1], tid, 256);
+            if (SPEC) nrdb200_tma::PatchClampToEdge<__half, kHfBoxW, kHfBoxH>(sFastSpec, boxX0, boxY0, c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1], tid, 256);
         }
-        nrdb200_tma::BarrierWait(&bar, 0);
-        if (DIFF) nrdb200_tma::PatchClampToEdge<__half, kHfBoxW, kHfBoxH>(sFastDiff, boxX0, boxY0, c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1], tid, 256);
-        if (SPEC) nrdb200_tma::PatchClampToEdge<__half, kHfBoxW, kHfBoxH>(sFastSpec, boxX0, boxY0, c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1], tid, 256);
+        else
+        {
+            // same window staged with clamped loads (a surface TMA cannot address: base or pitch not 16-byte aligned; NRD_B200_NO_TMA=1)
+            for (int i = tid; i < kHfBoxW * kHfBoxH; i += 256)
+            {
+                const int lx = i % kHfBoxW, ly = i / kHfBoxW;
+                const int gx = clampi(boxX0 + lx, 0, c.gRectSizeMinusOne[0]), gy = clampi(boxY0 + ly, 0, c.gRectSizeMinusOne[1]);
+                if (DIFF) sFastDiff[ly][lx] = __ushort_as_half((unsigned short)LoadU16(Near(a.inDiffFast), gx, gy));
+                if (SPEC) sFastSpec[ly][lx] = __ushort_as_half((unsigned short)LoadU16(Near(a.inSpecFast), gx, gy));
+            }
+        }
         __syncthreads();
     }
     const int x = blockIdx.x * 32 + threadIdx.x;
@@ -1172,8 +1187,8 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchHf(const PassLaunch& p)
     CUtensorMap diffMap, specMap;
     memset(&diffMap, 0, sizeof(diffMap));
     memset(&specMap, 0, sizeof(specMap));
-    if (DIFF && !nrdb200_tma::MakeSurfaceMap16(a.inDiffFast, kHfBoxW, kHfBoxH, &diffMap)) return cudaErrorInvalidValue;
-    if (SPEC && !nrdb200_tma::MakeSurfaceMap16(a.inSpecFast, kHfBoxW, kHfBoxH, &specMap)) return cudaErrorInvalidValue;
+    a.useTma = nrdb200_tma::Enabled() && (!DIFF || nrdb200_tma::MakeSurfaceMap16(a.inDiffFast, kHfBoxW, kHfBoxH, &diffMap)) &&
+               (!SPEC || nrdb200_tma::MakeSurfaceMap16(a.inSpecFast, kHfBoxW, kHfBoxH, &specMap));
     ReblurHistoryFixKernel<DIFF, SPEC><<<grid, block, 0, p.stream>>>(a, diffMap, specMap);
     return cudaGetLastError();
 }

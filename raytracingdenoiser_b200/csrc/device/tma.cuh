@@ -6,11 +6,18 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "surf.h"
 
 namespace nrdb200_tma
 {
+// NRD_B200_NO_TMA=1 in the environment makes every kernel stage its tiles with plain clamped loads (A/B and triage)
+inline bool Enabled()
+{
+    static const bool on = getenv("NRD_B200_NO_TMA") == nullptr;
+    return on;
+}
 // cuTensorMapEncodeTiled through the runtime's driver entry point query: libnrd_b200.so does not link libcuda
 inline CUresult EncodeTiled(CUtensorMap* map, CUtensorMapDataType type, cuuint32_t rank, void* base, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
                             const cuuint32_t* elementStrides)
