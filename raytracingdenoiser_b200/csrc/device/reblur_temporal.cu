@@ -763,8 +763,10 @@ template <bool BOTH> __device__ __forceinline__ f2 LoadFrames(const Surf& s, int
     return mk2(d, d);
 }
 
-// fast-history tile of the CTA: 32 x 8 texels + 2 of halo, rows padded to whole 16-byte units for the TMA box (surf.h / tma.cuh)
-constexpr int kHfBorder = 2, kHfBoxW = 40, kHfBoxH = 8 + 2 * kHfBorder;
+// fast-history tile of the CTA: 32 x 8 texels + 2 of halo.  A TMA box must START on a 16-byte boundary of the row (8 texels of
+// R16F; a start at tile - 2 faults with "illegal instruction", tools/tma_probe.cu) and hold whole 16-byte units: the box begins
+// kHfPad = 8 texels left of the tile and is 48 texels wide, the kernel reads its columns 6..41.
+constexpr int kHfBorder = 2, kHfPad = 8, kHfBoxW = 32 + 2 * kHfPad, kHfBoxH = 8 + 2 * kHfBorder;
 
 template <bool IS_SPEC, bool BOTH>
 __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, const Surf& inSig, const Surf& inFast, const __half (*sFast)[kHfBoxW], const Surf& outSig,
@@ -836,7 +838,7 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
     }
 
     // 5x5 moments of the fast history from the staged tile (clamp-to-edge was patched into its halo): LDS with constant offsets
-    const int cx = threadIdx.x + kHfBorder, cy = threadIdx.y + kHfBorder;
+    const int cx = threadIdx.x + kHfPad, cy = threadIdx.y + kHfBorder;
     float center = __half2float(sFast[cy][cx]);
     float m1 = 0.0f, m2 = 0.0f;
 #pragma unroll
@@ -892,7 +894,7 @@ __global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS)
     const ReblurConstants& c = a.c;
     {
         const int tid = threadIdx.y * 32 + threadIdx.x;
-        const int boxX0 = blockIdx.x * 32 - kHfBorder, boxY0 = a.rowBegin + blockIdx.y * 8 - kHfBorder;
+        const int boxX0 = blockIdx.x * 32 - kHfPad, boxY0 = a.rowBegin + blockIdx.y * 8 - kHfBorder;
         if (a.useTma)
         {
             if (tid == 0) nrdb200_tma::BarrierInit(&bar);

@@ -37,7 +37,9 @@ inline CUresult EncodeTiled(CUtensorMap* map, CUtensorMapDataType type, cuuint32
 }
 
 // Tensor map over the rows a context holds of a surface of 2-byte texels (R16F).  Coordinates of a copy: x in texels, y in local rows.
-// The box width must make whole 16-byte rows in shared memory (a multiple of 8 texels).
+// The box width must make whole 16-byte rows in shared memory (a multiple of 8 texels), and the x of every copy must be a multiple
+// of 8 texels too: the first byte of a box row has to be 16-byte aligned in global memory (measured: anything else raises
+// "illegal instruction" at the UTMALDG, profiles/r2_tma_probe.txt).
 inline bool MakeSurfaceMap16(const nrdb200_abi::Surf& s, int boxTexelsX, int boxRows, CUtensorMap* map)
 {
     if (((uintptr_t)s.base & 15) != 0 || (s.pitch & 15) != 0 || (boxTexelsX & 7) != 0 || boxTexelsX > 256 || boxRows > 256) return false;
