@@ -269,6 +269,12 @@ struct Tex
     float4 sampleNearest(float2 uv) const { return texel((int)std::floor(uv.x * w), (int)std::floor(uv.y * h)); }
     float4 sampleLinear(float2 uv) const
     {
+#ifdef ORACLE_NUDGE_UV
+        // noise-floor variant (liboracle_uv.so): the uv of every bilinear fetch moved by one float ulp -- the sub-texel position a
+        // shader hands to the sampler is only known to ulp(uv) * size (2.4e-4 texel at 4K), tests/parity.py
+        uv.x = std::nextafter(uv.x, 2.0f);
+        uv.y = std::nextafter(uv.y, 2.0f);
+#endif
         float px = uv.x * w - 0.5f, py = uv.y * h - 0.5f;
         float fx = std::floor(px), fy = std::floor(py);
         float wx = px - fx, wy = py - fy;

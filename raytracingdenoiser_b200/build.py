@@ -20,7 +20,8 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 # the same oracle sources with FMA contraction allowed: a second, equally IEEE-legal evaluation of the same math.  Tests use the
 # pair to measure the rounding-noise floor of the (chaotic) temporal chains: how far two legal CPU evaluations drift apart.
-ORACLE_FMA_LIB = os.path.join(ORACLE_DIR, "liboracle_fma.so")
+ORACLE_FMA_LIB = os.path.join(ORACLE_DIR, "liboracle_fma.so")  # noise-floor variant: FMA contraction allowed
+ORACLE_UV_LIB = os.path.join(ORACLE_DIR, "liboracle_uv.so")    # noise-floor variant: bilinear fetches one float ulp further (oracle/hlsl.h)
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
@@ -96,9 +97,11 @@ def build_product(force=False):
 def build_oracle(force=False):
     srcs = [os.path.join(ORACLE_DIR, f) for f in sorted(os.listdir(ORACLE_DIR)) if f.endswith(".cpp")]
     deps = srcs + [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".h")]
-    if not force and os.path.exists(ORACLE_LIB) and os.path.exists(ORACLE_FMA_LIB) and all(min(os.path.getmtime(ORACLE_LIB), os.path.getmtime(ORACLE_FMA_LIB)) >= os.path.getmtime(d) for d in deps):
+    libs = ((ORACLE_LIB, ORACLE_FLAGS), (ORACLE_FMA_LIB, [f if f != "-ffp-contract=off" else "-ffp-contract=fast" for f in ORACLE_FLAGS]),
+            (ORACLE_UV_LIB, ORACLE_FLAGS + ["-DORACLE_NUDGE_UV"]))
+    if not force and all(os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps) for lib, _ in libs):
         return ORACLE_LIB
-    for lib, flags in ((ORACLE_LIB, ORACLE_FLAGS), (ORACLE_FMA_LIB, [f if f != "-ffp-contract=off" else "-ffp-contract=fast" for f in ORACLE_FLAGS])):
+    for lib, flags in libs:
         r = subprocess.run(["g++"] + flags + ["-o", lib] + srcs, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("oracle build failed:\n%s%s" % (r.stdout, r.stderr))

@@ -121,8 +121,6 @@ __device__ __forceinline__ float SpecMagicCurve(float roughness) // Common.hlsli
     float f = 1.0f - exp2f(-200.0f * roughness * roughness);
     return f * sqrtf(sqrtf(saturate(roughness)));
 }
-// pow(saturate(x), y) for a smooth, non-selecting use: exp2(y * log2(x)) on the special-function unit (relative error ~y * 2^-22)
-__device__ __forceinline__ float Pow01Fast(float x, float y) { return exp2f(y * __log2f(saturate(x))); }
 __device__ __forceinline__ float LobeTanHalfAngle(float roughness, float percentOfVolume) // MathLib ImportanceSampling (restated, see oracle/mathlib.h)
 {
     float m = saturate(roughness);

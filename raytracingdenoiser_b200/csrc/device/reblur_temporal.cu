@@ -644,8 +644,8 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
             float smc = smcModified;
             float fx = dot(N, normalize(smbNavg)), fy = dot(N, vmbN);
             float e = lerpf(32.0f, 1.0f, smc) * (1.0f - responsiveFactor), k = lerpf(smc, 1.0f, responsiveFactor);
-            fx = k * Pow01Fast(fx, e);
-            fy = k * Pow01Fast(fy, e);
+            fx = k * Pow01(fx, e); // not the fast exp2(e log2 x): fx and fy are nearly equal and the ORDER of the two results selects a branch below
+            fy = k * Pow01(fy, e);
             maxResponsiveFrameNum = mk2(fmaxf(c.gMaxAccumulatedFrameNum * fx, c.gHistoryFixFrameNum), fmaxf(c.gMaxAccumulatedFrameNum * fy, c.gHistoryFixFrameNum));
         }
 
@@ -952,6 +952,7 @@ struct TsArgs
     Surf guide;
     const float4* lut;
     int rowBegin, rowEnd;
+    int useTma; // the signal tiles are staged by TMA (else by clamped loads)
 };
 
 __device__ __forceinline__ float Antilag(const ReblurConstants& c, float history, float avg, float sigma, float accumSpeed) // REBLUR_Common.hlsli:244-274, mode 2
@@ -963,13 +964,18 @@ __device__ __forceinline__ float Antilag(const ReblurConstants& c, float history
     return 1.0f / (1.0f + d * accumSpeed / magic);
 }
 
-// 3x3 luma statistics of a YCoCg signal (clamped reads)
-// 3x3 luma moments.  sigma = sqrt(|m2 - m1^2|) cancels catastrophically on flat regions (the result is rounding noise of
-// relative size ~3e-4 that then scales the clamping box), so the moments are accumulated in the oracle's order with
-// individually rounded operations: centre first, then row-major, true division by 9.
-__device__ __forceinline__ void LumaStats3x3(const Surf& s, int x, int y, int maxX, int maxY, float& luma, float& m1, float& m2, float& mn, float& mx)
+// signal tile of the CTA: 32 x 8 texels of RGBA16F + 1 of halo.  The TMA box starts 2 texels (16 bytes) left of the tile (tma.cuh:
+// the first byte of a box row must be 16-byte aligned) and is 36 texels wide; the kernel reads its columns 1..34.
+constexpr int kTsPad = 2, kTsBoxW = 32 + 2 * kTsPad, kTsBoxH = 8 + 2;
+__device__ __forceinline__ float TileLuma(uint2 t) { return __half2float(__ushort_as_half((unsigned short)(t.x & 0xFFFFu))); }
+
+// 3x3 luma moments of a YCoCg signal from the staged tile (clamp-to-edge already in its halo).  sigma = sqrt(|m2 - m1^2|) cancels
+// catastrophically on flat regions (the result is rounding noise of relative size ~3e-4 that then scales the clamping box), so the
+// moments are accumulated in the oracle's order with individually rounded operations: centre first, then row-major, true division by 9.
+__device__ __forceinline__ void LumaStats3x3(const uint2 (*tile)[kTsBoxW], float& luma, float& m1, float& m2, float& mn, float& mx)
 {
-    luma = LoadRGBA16F(Near(s), x, y).x;
+    const int cx = threadIdx.x + kTsPad, cy = threadIdx.y + 1;
+    luma = TileLuma(tile[cy][cx]);
     m1 = luma;
     m2 = __fmul_rn(luma, luma);
     mn = kInf;
@@ -980,7 +986,7 @@ __device__ __forceinline__ void LumaStats3x3(const Surf& s, int x, int y, int ma
         for (int i = -1; i <= 1; i++)
         {
             if (i == 0 && j == 0) continue;
-            float d = LoadRGBA16F(Near(s), clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)).x;
+            float d = TileLuma(tile[cy + j][cx + i]);
             m1 = __fadd_rn(m1, d);
             m2 = __fadd_rn(m2, __fmul_rn(d, d));
             mn = fminf(mn, d);
@@ -992,12 +998,48 @@ __device__ __forceinline__ void LumaStats3x3(const Surf& s, int x, int y, int ma
 __device__ __forceinline__ float PinnedStdDev(float m1, float m2) { return __fsqrt_rn(fabsf(__fadd_rn(m2, -__fmul_rn(m1, m1)))); }
 
 template <bool DIFF, bool SPEC>
-__global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const __grid_constant__ TsArgs a)
+__global__ void __launch_bounds__(256)
+    ReblurTemporalStabilizationKernel(const __grid_constant__ TsArgs a, const __grid_constant__ CUtensorMap diffMap, const __grid_constant__ CUtensorMap specMap)
 {
+    // The CTA stages the signal window of both signals (tile + 1 texel of halo, whole RGBA16F texels) with TMA bulk tensor copies on
+    // one mbarrier: the 3x3 luma moments and the centre texel of every pixel are shared-memory loads at constant offsets.
+    __shared__ __align__(128) uint2 sDiff[DIFF ? kTsBoxH : 1][kTsBoxW];
+    __shared__ __align__(128) uint2 sSpec[SPEC ? kTsBoxH : 1][kTsBoxW];
+    __shared__ __align__(8) uint64_t bar;
     const ReblurConstants& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
+    {
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        const int boxX0 = blockIdx.x * 32 - kTsPad, boxY0 = a.rowBegin + blockIdx.y * 8 - 1;
+        if (a.useTma)
+        {
+            if (tid == 0) nrdb200_tma::BarrierInit(&bar);
+            __syncthreads();
+            if (tid == 0)
+            {
+                // x of the copy in 32-bit words (2 per texel), y in rows held locally
+                nrdb200_tma::BarrierExpect(&bar, (uint32_t)((DIFF ? sizeof(sDiff) : 0) + (SPEC ? sizeof(sSpec) : 0)));
+                if (DIFF) nrdb200_tma::IssueTile2D(sDiff, &diffMap, boxX0 * 2, boxY0 - a.inDiff.ly0, &bar);
+                if (SPEC) nrdb200_tma::IssueTile2D(sSpec, &specMap, boxX0 * 2, boxY0 - a.inSpec.ly0, &bar);
+            }
+            nrdb200_tma::BarrierWait(&bar, 0);
+            if (DIFF) nrdb200_tma::PatchClampToEdge<uint2, kTsBoxW, kTsBoxH>(sDiff, boxX0, boxY0, maxX, maxY, tid, 256);
+            if (SPEC) nrdb200_tma::PatchClampToEdge<uint2, kTsBoxW, kTsBoxH>(sSpec, boxX0, boxY0, maxX, maxY, tid, 256);
+        }
+        else
+        {
+            for (int i = tid; i < kTsBoxW * kTsBoxH; i += 256)
+            {
+                const int lx = i % kTsBoxW, ly = i / kTsBoxW;
+                const int gx = clampi(boxX0 + lx, 0, maxX), gy = clampi(boxY0 + ly, 0, maxY);
+                if (DIFF) sDiff[ly][lx] = __ldg(TexelPtr<uint2>(Near(a.inDiff), gx, gy));
+                if (SPEC) sSpec[ly][lx] = __ldg(TexelPtr<uint2>(Near(a.inSpec), gx, gy));
+            }
+        }
+        __syncthreads();
+    }
     if (x > maxX || y > maxY || y >= a.rowEnd) return;
     if (LoadU8(Near(a.tiles), x >> 4, y >> 4) != 0) return;
     const float viewZ = fabsf(LoadR32F(Near(a.z), x, y) * c.gViewZScale);
@@ -1043,7 +1085,7 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
     if (DIFF)
     {
         float luma, m1, m2, mn, mx;
-        LumaStats3x3(a.inDiff, x, y, maxX, maxY, luma, m1, m2, mn, mx);
+        LumaStats3x3(sDiff, luma, m1, m2, mn, mx);
         const float sigma = PinnedStdDev(m1, m2);
         if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
         float history = fmaxf(ResolveCatRom1(smbSetup, a.histDiffStab), 0.0f);
@@ -1055,7 +1097,7 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
         const float k = sigma * (1.0f + 3.0f * c.gFramerateScale * tw);
         history = clampf(history, m1 - k, m1 + k);
         const float stabilized = lerpf(luma, history, fminf(historyWeight, c.gStabilizationStrength));
-        StoreRGBA16F(a.outDiff, x, y, ChangeLuma(LoadRGBA16F(Near(a.inDiff), x, y), stabilized));
+        StoreRGBA16F(a.outDiff, x, y, ChangeLuma(UnpackHalf4(sDiff[threadIdx.y + 1][threadIdx.x + kTsPad]), stabilized));
         StoreR16F(a.outDiffStab, x, y, stabilized);
         data1.x += 1.0f;
         data1.x = lerpf(fminf(data1.x, c.gHistoryFixFrameNum), data1.x, antilag);
@@ -1064,11 +1106,11 @@ __global__ void __launch_bounds__(256) ReblurTemporalStabilizationKernel(const _
     if (SPEC)
     {
         float luma, m1, m2, mn, mx;
-        LumaStats3x3(a.inSpec, x, y, maxX, maxY, luma, m1, m2, mn, mx);
+        LumaStats3x3(sSpec, luma, m1, m2, mn, mx);
         const float sigma = PinnedStdDev(m1, m2);
         if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
 
-        f4 spec = LoadRGBA16F(Near(a.inSpec), x, y);
+        f4 spec = UnpackHalf4(sSpec[threadIdx.y + 1][threadIdx.x + kTsPad]);
         float hitDistForTracking = spec.w * ((c.gHitDistParams[0] + viewZ * c.gHitDistParams[1]) * g0.hitK);
         if (c.gSpecPrepassBlurRadius != 0.0f) hitDistForTracking = fminf(hitDistForTracking, LoadR16F(Near(a.hitDist), x, y));
 
@@ -1226,7 +1268,19 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchTs(const PassLaunch& p)
     a.rowEnd = p.rowEnd;
     const int W = (int)a.c.gRectSize[0];
     dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
-    NRD_B200_LAUNCH(p, grid, block, a, ReblurTemporalStabilizationKernel<DIFF, SPEC>);
+    if (p.preloadOnly)
+    {
+        cudaFuncAttributes fa;
+        return cudaFuncGetAttributes(&fa, ReblurTemporalStabilizationKernel<DIFF, SPEC>);
+    }
+    // TMA descriptors of the two signals (RGBA16F = 2 words per texel); user textures whose base or pitch is not 16-byte aligned
+    // are staged with clamped loads instead
+    CUtensorMap diffMap, specMap;
+    memset(&diffMap, 0, sizeof(diffMap));
+    memset(&specMap, 0, sizeof(specMap));
+    a.useTma = nrdb200_tma::Enabled() && (!DIFF || nrdb200_tma::MakeSurfaceMap(a.inDiff, 2, kTsBoxW, kTsBoxH, &diffMap)) &&
+               (!SPEC || nrdb200_tma::MakeSurfaceMap(a.inSpec, 2, kTsBoxW, kTsBoxH, &specMap));
+    ReblurTemporalStabilizationKernel<DIFF, SPEC><<<grid, block, 0, p.stream>>>(a, diffMap, specMap);
     return cudaGetLastError();
 }
 cudaError_t LaunchReblurTemporalStabilization(const PassLaunch& p, int signal)

@@ -400,6 +400,17 @@ __global__ void __launch_bounds__(256) GhostPushKernel(const __grid_constant__ P
 
 namespace
 {
+// The executor's own kernels are preloaded like the pass kernels (NRD_B200_LAUNCH): the stand-alone barrier is first needed by a
+// pass that pushes nothing, i.e. possibly while this rank's previous (fused) barrier still spins for a peer whose launches the host
+// has not issued yet -- a lazy load at that point would wait for the spinning kernel.
+void PreloadExecutorKernels()
+{
+    cudaFuncAttributes fa;
+    (void)cudaFuncGetAttributes(&fa, nrdb200::ClearKernel);
+    (void)cudaFuncGetAttributes(&fa, nrdb200::StripBarrierKernel);
+    (void)cudaFuncGetAttributes(&fa, nrdb200::GhostPushKernel);
+}
+
 BarrierArgs NextBarrier(NrdCudaContext* ctx)
 {
     BarrierArgs a{};
@@ -689,6 +700,7 @@ NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t 
     ctx->world = worldSize;
     ctx->connected = true;
     PreloadKernels(ctx, worldSize > 1 ? kStripLaunchers : kSingleLaunchers);
+    PreloadExecutorKernels();
     return Result::SUCCESS;
 }
 

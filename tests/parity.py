@@ -30,17 +30,21 @@ def _scene_device(width, height, device):
 
 
 class SideBySide(object):
-    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False):
-        """noise_floor=True: every dispatch is also run by the FMA-contracted build of the oracle on the same re-synchronised
-        inputs; its disagreement with the oracle is the rounding-noise floor of the pass (two IEEE-legal evaluations of the same
-        math).  A pass whose floor is below the plain gate (RELAX temporal accumulation: acos of nearly parallel vectors, sigma of
-        cancelling moments) is held to its floor instead -- the kernel must agree with the oracle at least as well as the oracle
-        agrees with itself."""
+    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",)):
+        """noise_floor=True: the dispatches whose shader name contains one of `floor_passes` are also run, on the same re-synchronised
+        inputs, by two perturbed builds of the oracle -- "fma" (FMA contraction allowed: a second IEEE-legal evaluation of the same
+        expressions) and "uv" (the uv of every bilinear fetch moved by one float ulp: the sub-texel position a shader hands to the
+        sampler is only known to ulp(uv) * size = 2.4e-4 texel at 4K; the kernels merge the bilinear taps of the CatRom filter with
+        exact weights).  Their disagreement with the oracle is the rounding-noise floor of the pass.  A pass whose floor is below
+        the plain gate (RELAX temporal accumulation: acos of nearly parallel vectors, sigma of cancelling moments, CatRom history
+        of the second moment across a contrast edge) is held to its floor instead -- the kernel must agree with the oracle at
+        least as well as the oracle agrees with itself."""
         import torch
         self.denoiser, self.w, self.h, self.identifier = denoiser, width, height, identifier
         self.cpu = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, settings=settings)
         self.instance = self.cpu.instance
-        self.cpu_fma = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, instance=self.instance, variant="fma") if noise_floor else None
+        self.floor_passes = tuple(floor_passes)
+        self.cpu_alt = [orr.CpuDenoiser(denoiser, width, height, identifier=identifier, instance=self.instance, variant=v) for v in ("fma", "uv")] if noise_floor else []
         self.ctx = nrd.CudaContext(self.instance, width, height, device=device)
         self.torch = torch
         self.dev_user = {}
@@ -51,6 +55,9 @@ class SideBySide(object):
             self.ctx.set_user_texture(getattr(nrd.ResourceType, name), t.data_ptr(), t.stride(0) * t.element_size(), fmt)
         self.scene = scene.Scene(width, height, device=_scene_device(width, height, device))
         self.report = []
+
+    def _has_floor(self, d):
+        return any(k in d.shaderFileName for k in self.floor_passes)
 
     def _sync_to_gpu(self, d):
         for _, rtype, index in d.resources:
@@ -72,10 +79,11 @@ class SideBySide(object):
                    "outliers": n_out, "outlier_budget": outlier_budget(ref.shape[0] * ref.shape[1]), "outliers_at": where, "nonfinite": nonfinite,
                    "outlier_cause": "decision flip (tap texel / step threshold within rounding distance)" if n_out else None,
                    "min_fraction": MIN_FRACTION}
-            if self.cpu_fma is not None:
-                alt, _ = self.cpu_fma.resolve(rtype, index)
-                rec["floor_fraction"] = orr.compare(ref, alt, fmt, REL, ABS, layout=layout)[0]
-                rec["floor_outliers"] = orr.outliers(ref, alt, fmt, REL, ABS, MAX_EXCESS, layout=layout)[0]
+            if self.cpu_alt and self._has_floor(d):
+                for alt_den in self.cpu_alt:
+                    alt, _ = alt_den.resolve(rtype, index)
+                    rec["floor_fraction"] = min(rec.get("floor_fraction", 1.0), orr.compare(ref, alt, fmt, REL, ABS, layout=layout)[0])
+                    rec["floor_outliers"] = max(rec.get("floor_outliers", 0), orr.outliers(ref, alt, fmt, REL, ABS, MAX_EXCESS, layout=layout)[0])
                 # held to the floor where the floor is below the plain gate
                 rec["min_fraction"] = min(MIN_FRACTION, rec["floor_fraction"])
                 rec["outlier_budget"] = max(rec["outlier_budget"], rec["floor_outliers"])
@@ -107,14 +115,17 @@ class SideBySide(object):
             for i in range(n):
                 d = nrd.Dispatch(raw[i], pipelines)
                 self._sync_to_gpu(d)
-                if self.cpu_fma is not None:
-                    for _, rtype, index in d.resources:
-                        self.cpu_fma.resolve(rtype, index)[0][...] = self.cpu.resolve(rtype, index)[0]
+                floor = self.cpu_alt and self._has_floor(d)
+                if floor:
+                    for alt_den in self.cpu_alt:
+                        for _, rtype, index in d.resources:
+                            alt_den.resolve(rtype, index)[0][...] = self.cpu.resolve(rtype, index)[0]
                 self.ctx.execute_raw(C.byref(raw[i]))
                 self.torch.cuda.synchronize()
                 self.cpu.run_dispatch(d)
-                if self.cpu_fma is not None:
-                    self.cpu_fma.run_dispatch(d)
+                if floor:
+                    for alt_den in self.cpu_alt:
+                        alt_den.run_dispatch(d)
                 self._compare_outputs(f, d)
             if f == 0:
                 self.cpu.set_inputs(fr)  # the frame-0 clears also zero IN_MV (reference quirk), restore it
