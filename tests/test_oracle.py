@@ -215,3 +215,45 @@ def test_rounding_noise_floor_of_the_reblur_chain():
     assert fractions[0] > 0.999                       # one frame: the two evaluations agree almost everywhere
     assert fractions[-1] < fractions[0] and fractions[-1] < 0.999   # ... and drift apart through the history feedback
     assert fractions[-1] > 0.9 and np.isfinite(a.user["OUT_DIFF_RADIANCE_HITDIST"].astype(np.float32)).all()
+
+
+def test_subtexel_noise_floor_of_relax_temporal_accumulation():
+    """The third build of the oracle moves the uv of every bilinear fetch by one float ulp (oracle/hlsl.h, ORACLE_NUDGE_UV): the
+    CatRom history of RELAX's temporal accumulation reacts to it -- per pass, on identical inputs -- because the sub-texel position
+    a shader hands to the sampler is only known to ulp(uv) * size texels and the second moment has contrast edges.  The kernels
+    merge the CatRom's bilinear taps with exact weights, so this floor (not the plain 99.9 % gate) is what their temporal
+    accumulation is read against at 4K (tests/test_gpu_baseline_configs.py::test_config4...)."""
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    den, w, h = nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, 512, 288
+    a = orr.CpuDenoiser(den, w, h)
+    b = orr.CpuDenoiser(den, w, h, instance=a.instance, variant="uv")
+    sc = scene.Scene(w, h)
+    worst = {}
+    for f in range(5):
+        fr = sc.frame(f)
+        a.set_inputs(fr)
+        cs = harness.make_common_settings(fr, w, h, f)
+        a.instance.set_common_settings(cs)
+        r, raw, n = a.instance.get_compute_dispatches_raw([0])
+        assert r == nrd.Result.SUCCESS
+        pipelines = a.instance.get_instance_desc()["pipelines"]
+        for i in range(n):
+            d = nrd.Dispatch(raw[i], pipelines)
+            for _, rtype, index in d.resources:  # same inputs for both builds, pass by pass
+                b.resolve(rtype, index)[0][...] = a.resolve(rtype, index)[0]
+            a.run_dispatch(d)
+            b.run_dispatch(d)
+            for dtype_, rtype, index in d.resources:
+                if dtype_ != nrd.DescriptorType.STORAGE_TEXTURE:
+                    continue
+                ref, fmt = a.resolve(rtype, index)
+                frac = orr.compare(ref, b.resolve(rtype, index)[0], fmt)[0]
+                worst[d.shaderFileName] = min(worst.get(d.shaderFileName, 1.0), frac)
+        if f == 0:
+            a.set_inputs(fr)
+    ta = worst["RELAX_DiffuseSpecular_TemporalAccumulation.cs"]
+    assert ta < 1.0, worst               # the pass does react to a one-ulp move of its fetches ...
+    assert ta > 0.99, worst              # ... mildly (the effect grows with the frame size: ulp(uv) * size)
+    # passes that only point-sample are untouched
+    assert worst["RELAX_DiffuseSpecular_HistoryClamping.cs"] == 1.0, worst
