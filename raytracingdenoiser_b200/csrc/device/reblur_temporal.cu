@@ -768,72 +768,163 @@ template <bool BOTH> __device__ __forceinline__ f2 LoadFrames(const Surf& s, int
 // kHfPad = 8 texels left of the tile and is 48 texels wide, the kernel reads its columns 6..41.
 constexpr int kHfBorder = 2, kHfPad = 8, kHfBoxW = 32 + 2 * kHfPad, kHfBoxH = 8 + 2 * kHfBorder;
 
+// ---- sparse reconstruction of young history (REBLUR_HistoryFix.hlsli:63-167 / :268-371) -------------------------------------------
+// Only pixels whose history is younger than gHistoryFixFrameNum frames run the 20-tap reconstruction: in steady state that is ~6 % of
+// the specular and ~1 % of the diffuse pixels (disocclusions), but they are spread over ~20 % of the warps -- evaluated per pixel,
+// every such warp walks the 20 taps with one or two live lanes.  The CTA therefore collects its (pixel, signal) items in shared
+// memory and spreads item x tap tasks over all 256 threads; the pixel that owns an item then sums its 20 taps in the reference's tap
+// order, so the result does not depend on which thread evaluated a tap.  CTAs with more than kHfMaxItems items (the first frames,
+// where every pixel is young and no lane idles) keep the per-pixel loop.
+struct HfItem
+{
+    int x, y, stridei, isSpec;
+    float stride, u, v;                  // pixelUv
+    float Nvx, Nvy, Nvz, geoA, geoB;     // plane-distance weight
+    float Nx, Ny, Nz, material;          // material = max(materialID, minMaterial)
+    float minMaterial, normalParam, rrpx, rrpy, roughness;
+    float hitDistScale, hitDist, hpx, hpy, frustumSize;
+};
+struct HfTap
+{
+    float w;
+    unsigned lo, hi; // the tap's RGBA16F texel as loaded (12-byte records in shared memory)
+};
+constexpr int kHfTaps = 20, kHfMaxItems = 64;
+// taps (i, j), j-major, centre and the four corners skipped: the reference's loop order
+__constant__ signed char kHfTapI[kHfTaps] = {-1, 0, 1, -2, -1, 0, 1, 2, -2, -1, 1, 2, -2, -1, 0, 1, 2, -1, 0, 1};
+__constant__ signed char kHfTapJ[kHfTaps] = {-2, -2, -2, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2};
+
+// stride of the reconstruction of one signal; 0 = history old enough, nothing to do
+template <bool IS_SPEC> __device__ __forceinline__ float HfStride(const ReblurConstants& c, float strideBase, float fn, float smc)
+{
+    float stride = strideBase * (fn < c.gHistoryFixFrameNum ? 1.0f : 0.0f);
+    if (IS_SPEC) stride *= lerpf(0.5f, 1.0f, smc);
+    return floorf(stride);
+}
+
+template <bool IS_SPEC>
+__device__ __forceinline__ HfItem HfMakeItem(const HfArgs& a, int x, int y, float stride, float sigW, float viewZ, const Guide& g0, f3 Nv, f3 Xv, f2 pixelUv, float frustumSize, float fn)
+{
+    const ReblurConstants& c = a.c;
+    HfItem it;
+    it.x = x;
+    it.y = y;
+    it.stridei = (int)(stride + 0.5f);
+    it.isSpec = IS_SPEC ? 1 : 0;
+    it.stride = stride;
+    it.u = pixelUv.x;
+    it.v = pixelUv.y;
+    const float nl = 1.0f / (1.0f + fn);
+    const float roughness = g0.roughness, smc = g0.smc;
+    it.minMaterial = IS_SPEC ? c.gSpecMinMaterial : c.gDiffMinMaterial;
+    it.normalParam = NormalWeightParam(nl, c.gLobeAngleFraction, IS_SPEC ? roughness : 1.0f);
+    it.geoA = 1.0f / (c.gPlaneDistSensitivity * frustumSize);
+    it.geoB = -dot(Nv, Xv) * it.geoA;
+    it.Nvx = Nv.x; it.Nvy = Nv.y; it.Nvz = Nv.z;
+    it.Nx = g0.N.x; it.Ny = g0.N.y; it.Nz = g0.N.z;
+    it.material = fmaxf(g0.materialID, it.minMaterial);
+    const f2 rrp = RelaxedRoughnessWeightParams(roughness * roughness, sqrtf(c.gRoughnessFraction));
+    it.rrpx = rrp.x; it.rrpy = rrp.y;
+    it.roughness = roughness;
+    it.hitDistScale = (c.gHitDistParams[0] + viewZ * c.gHitDistParams[1]) * (IS_SPEC ? g0.hitK : __ldg(&a.lut[1023]).y);
+    it.hitDist = sigW * it.hitDistScale;
+    const float hitDistFactor = saturate(it.hitDist / frustumSize);
+    const f2 hp = HitDistanceWeightParams(hitDistFactor, nl, IS_SPEC ? smc : __ldg(&a.lut[1023]).x);
+    it.hpx = hp.x; it.hpy = hp.y;
+    it.frustumSize = frustumSize;
+    return it;
+}
+
+// one tap of one item: weight and texel (isSpec is a compile-time constant on the per-pixel path)
+template <bool BOTH>
+__device__ __forceinline__ HfTap HfEvalTap(const ReblurConstants& c, const HfItem& it, bool isSpec, int i, int j, const Surf& zS, const Surf& nrS, const Surf& guideS,
+                                           const Surf& data1S, const Surf& sigS)
+{
+    const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
+    // uv for the in-screen test / view position is NOT clamped, the texel is
+    const float u = __fadd_rn(it.u, __fmul_rn(__fmul_rn((float)i, it.stride), c.gRectSizeInv[0]));
+    const float v = __fadd_rn(it.v, __fmul_rn(__fmul_rn((float)j, it.stride), c.gRectSizeInv[1]));
+    const int px = clampi(it.x + i * it.stridei, 0, maxX), py = clampi(it.y + j * it.stridei, 0, maxY);
+    const Guide gs = LoadGuide(guideS, nrS, px, py);
+    const float zs = fabsf(LoadR32F(zS, px, py) * c.gViewZScale);
+    const f3 Xvs = ReconstructViewPosition(mk2(u, v), c.gFrustum, zs, c.gOrthoMode);
+    float w = (u > 0.0f && v > 0.0f && u < 1.0f && v < 1.0f) ? 1.0f : 0.0f;
+    w *= NonExpWeight(it.Nvx * Xvs.x + it.Nvy * Xvs.y + it.Nvz * Xvs.z, it.geoA, it.geoB);
+    w *= it.material == fmaxf(gs.materialID, it.minMaterial) ? 1.0f : 0.0f;
+    w *= ExpWeight(AcosApprox(gs.N.x * it.Nx + gs.N.y * it.Ny + gs.N.z * it.Nz), it.normalParam, 0.0f);
+    if (isSpec) w *= ExpWeight(gs.roughness * gs.roughness, it.rrpx, it.rrpy);
+    const f2 fr = LoadFrames<BOTH>(data1S, px, py);
+    w *= 1.0f + (isSpec ? fr.y : fr.x);
+    HfTap t;
+    t.lo = t.hi = 0u;
+    if (w != 0.0f)
+    {
+        const uint2 sv = __ldg(TexelPtr<uint2>(sigS, px, py));
+        t.lo = sv.x;
+        t.hi = sv.y;
+        const float hs = __half2float(__ushort_as_half((unsigned short)(sv.y >> 16))) * it.hitDistScale;
+        w *= ExpWeight(saturate(hs / it.frustumSize), it.hpx, it.hpy);
+        if (isSpec)
+        {
+            const float d = fabsf(it.hitDist - hs) / (fmaxf(it.hitDist, hs) + 0.001f);
+            const float b = LinearStep(0.03f, 0.05f, it.roughness);
+            w *= SmoothStep(0.2f + b, 0.05f + b, d);
+        }
+    }
+    t.w = w;
+    return t;
+}
+template <bool BOTH> __device__ __forceinline__ HfTap HfEvalTapAnywhere(const HfArgs& a, const HfItem& it, bool isSpec, int k)
+{
+    const int i = kHfTapI[k], j = kHfTapJ[k];
+    const Surf& sig = isSpec ? a.inSpec : a.inDiff;
+    // the 20 taps reach +-2 strides: one owner test for all of them
+    if (FootprintLocal(a.z, it.y - 2 * it.stridei, it.y + 2 * it.stridei)) return HfEvalTap<BOTH>(a.c, it, isSpec, i, j, Near(a.z), Near(a.nr), Near(a.guide), Near(a.data1), Near(sig));
+    return HfEvalTap<BOTH>(a.c, it, isSpec, i, j, a.z, a.nr, a.guide, a.data1, sig);
+}
+
+// the rest of the pass for one signal of one pixel: sum the taps (from shared memory, or evaluated here), fast-history clamp, stores
 template <bool IS_SPEC, bool BOTH>
 __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, const Surf& inSig, const Surf& inFast, const __half (*sFast)[kHfBoxW], const Surf& outSig,
-                                                 const Surf& outFast, float viewZ, const Guide& g0, f3 Nv, f3 Xv, f2 pixelUv, float frustumSize, float fn, float strideBase)
+                                                 const Surf& outFast, float viewZ, const Guide& g0, f3 Nv, f3 Xv, f2 pixelUv, float frustumSize, float fn, float stride,
+                                                 const HfTap* taps)
 {
     const ReblurConstants& c = a.c;
     const int maxX = c.gRectSizeMinusOne[0], maxY = c.gRectSizeMinusOne[1];
-    const float roughness = g0.roughness;
-    const float minMaterial = IS_SPEC ? c.gSpecMinMaterial : c.gDiffMinMaterial;
     f4 sig = LoadRGBA16F(Near(inSig), x, y);
     const float smc = g0.smc;
-    float stride = strideBase * (fn < c.gHistoryFixFrameNum ? 1.0f : 0.0f);
-    if (IS_SPEC) stride *= lerpf(0.5f, 1.0f, smc);
-    stride = floorf(stride);
 
     if (stride != 0.0f)
     {
-        const int stridei = (int)(stride + 0.5f);
-        const float nl = 1.0f / (1.0f + fn);
-        const float r = IS_SPEC ? roughness : 1.0f;
-        const float normalParam = NormalWeightParam(nl, c.gLobeAngleFraction, r);
-        const float geoA = 1.0f / (c.gPlaneDistSensitivity * frustumSize), geoB = -dot(Nv, Xv) * geoA;
-        const f2 rrp = RelaxedRoughnessWeightParams(roughness * roughness, sqrtf(c.gRoughnessFraction));
-        const float hitDistScale = (c.gHitDistParams[0] + viewZ * c.gHitDistParams[1]) * (IS_SPEC ? g0.hitK : __ldg(&a.lut[1023]).y);
-        const float hitDist = sig.w * hitDistScale;
-        const float hitDistFactor = saturate(hitDist / frustumSize);
-        const f2 hp = HitDistanceWeightParams(hitDistFactor, nl, IS_SPEC ? smc : __ldg(&a.lut[1023]).x);
         float sum = 1.0f + fn;
+        const float sigW = sig.w;
         sig = sig * sum;
-        // the 20 taps reach +-2 strides: one owner test for all of them
-        auto taps = [&](const Surf& zS, const Surf& nrS, const Surf& guideS, const Surf& data1S, const Surf& sigS) {
-            for (int j = -2; j <= 2; j++)
-                for (int i = -2; i <= 2; i++)
+        if (taps)
+        {
+#pragma unroll 4
+            for (int k = 0; k < kHfTaps; k++)
+            {
+                const HfTap t = taps[k];
+                if (t.w != 0.0f)
                 {
-                    if ((i == 0 && j == 0) || (abs(i) + abs(j) == 4)) continue;
-                    // uv for the in-screen test / view position is NOT clamped, the texel is
-                    float u = __fadd_rn(pixelUv.x, __fmul_rn(__fmul_rn((float)i, stride), c.gRectSizeInv[0]));
-                    float v = __fadd_rn(pixelUv.y, __fmul_rn(__fmul_rn((float)j, stride), c.gRectSizeInv[1]));
-                    int px = clampi(x + i * stridei, 0, maxX), py = clampi(y + j * stridei, 0, maxY);
-                    const Guide gs = LoadGuide(guideS, nrS, px, py);
-                    float zs = fabsf(LoadR32F(zS, px, py) * c.gViewZScale);
-                    f3 Xvs = ReconstructViewPosition(mk2(u, v), c.gFrustum, zs, c.gOrthoMode);
-                    float w = (u > 0.0f && v > 0.0f && u < 1.0f && v < 1.0f) ? 1.0f : 0.0f;
-                    w *= NonExpWeight(dot(Nv, Xvs), geoA, geoB);
-                    w *= fmaxf(g0.materialID, minMaterial) == fmaxf(gs.materialID, minMaterial) ? 1.0f : 0.0f;
-                    w *= ExpWeight(AcosApprox(dot(gs.N, g0.N)), normalParam, 0.0f);
-                    if (IS_SPEC) w *= ExpWeight(gs.roughness * gs.roughness, rrp.x, rrp.y);
-                    f2 fr = LoadFrames<BOTH>(data1S, px, py);
-                    w *= 1.0f + (IS_SPEC ? fr.y : fr.x);
-                    if (w != 0.0f)
-                    {
-                        f4 sv = LoadRGBA16F(sigS, px, py);
-                        float hs = sv.w * hitDistScale;
-                        w *= ExpWeight(saturate(hs / frustumSize), hp.x, hp.y);
-                        if (IS_SPEC)
-                        {
-                            float d = fabsf(hitDist - hs) / (fmaxf(hitDist, hs) + 0.001f);
-                            float b = LinearStep(0.03f, 0.05f, roughness);
-                            w *= SmoothStep(0.2f + b, 0.05f + b, d);
-                        }
-                        sum += w;
-                        sig = sig + sv * w;
-                    }
+                    sum += t.w;
+                    sig = sig + UnpackHalf4(make_uint2(t.lo, t.hi)) * t.w;
                 }
-        };
-        if (FootprintLocal(a.z, y - 2 * stridei, y + 2 * stridei)) taps(Near(a.z), Near(a.nr), Near(a.guide), Near(a.data1), Near(inSig));
-        else taps(a.z, a.nr, a.guide, a.data1, inSig);
+            }
+        }
+        else
+        {
+            const HfItem it = HfMakeItem<IS_SPEC>(a, x, y, stride, sigW, viewZ, g0, Nv, Xv, pixelUv, frustumSize, fn);
+            for (int k = 0; k < kHfTaps; k++)
+            {
+                const HfTap t = HfEvalTapAnywhere<BOTH>(a, it, IS_SPEC, k);
+                if (t.w != 0.0f)
+                {
+                    sum += t.w;
+                    sig = sig + UnpackHalf4(make_uint2(t.lo, t.hi)) * t.w;
+                }
+            }
+        }
         sig = sig * PositiveRcp(sum);
     }
 
@@ -891,10 +982,14 @@ __global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS)
     __shared__ __align__(128) __half sFastDiff[DIFF ? kHfBoxH : 1][kHfBoxW];
     __shared__ __align__(128) __half sFastSpec[SPEC ? kHfBoxH : 1][kHfBoxW];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ HfItem sItems[kHfMaxItems];
+    __shared__ HfTap sTaps[kHfMaxItems * kHfTaps];
+    __shared__ int sCount;
     const ReblurConstants& c = a.c;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
     {
-        const int tid = threadIdx.y * 32 + threadIdx.x;
         const int boxX0 = blockIdx.x * 32 - kHfPad, boxY0 = a.rowBegin + blockIdx.y * 8 - kHfBorder;
+        if (tid == 0) sCount = 0;
         if (a.useTma)
         {
             if (tid == 0) nrdb200_tma::BarrierInit(&bar);
@@ -905,6 +1000,60 @@ __global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS)
                 if (DIFF) nrdb200_tma::IssueTile2D(sFastDiff, &diffFastMap, boxX0, boxY0 - a.inDiffFast.ly0, &bar);
                 if (SPEC) nrdb200_tma::IssueTile2D(sFastSpec, &specFastMap, boxX0, boxY0 - a.inSpecFast.ly0, &bar);
             }
+        }
+    }
+
+    // per pixel: what the reconstruction needs, and whether it runs at all (while the tiles are in flight)
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
+    bool active = x <= c.gRectSizeMinusOne[0] && y <= c.gRectSizeMinusOne[1] && y < a.rowEnd;
+    if (active) active = LoadU8(Near(a.tiles), x >> 4, y >> 4) == 0;
+    float viewZ = 0.0f;
+    if (active)
+    {
+        viewZ = fabsf(LoadR32F(Near(a.z), x, y) * c.gViewZScale);
+        active = viewZ <= c.gDenoisingRange;
+    }
+    Guide g0 = {};
+    float frustumSize = 0.0f;
+    f2 pixelUv = mk2(0.0f, 0.0f), frameNum = mk2(0.0f, 0.0f), stride = mk2(0.0f, 0.0f);
+    f3 Xv = mk3(0.0f), Nv = mk3(0.0f);
+    if (active)
+    {
+        g0 = LoadGuideLut(Near(a.guide), Near(a.nr), a.lut, x, y);
+        frustumSize = c.gMinRectDimMulUnproject * lerpf(viewZ, 1.0f, fabsf(c.gOrthoMode));
+        pixelUv = PixelUv(x, y, c.gRectSizeInv);
+        Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
+        Nv = RotateInverse(c.gViewToWorld, g0.N);
+        frameNum = LoadFrames<DIFF && SPEC>(Near(a.data1), x, y);
+        if (DIFF) stride.x = HfStride<false>(c, __fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.x)), frameNum.x, g0.smc);
+        if (SPEC) stride.y = HfStride<true>(c, __fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.y)), frameNum.y, g0.smc);
+    }
+    __syncthreads(); // sCount = 0 is visible
+    int slotD = -1, slotS = -1;
+    if (DIFF && stride.x != 0.0f) slotD = atomicAdd(&sCount, 1);
+    if (SPEC && stride.y != 0.0f) slotS = atomicAdd(&sCount, 1);
+    __syncthreads();
+    const int items = sCount;
+    const bool compact = items > 0 && items <= kHfMaxItems; // the same decision in every thread of the CTA
+    if (compact)
+    {
+        if (slotD >= 0) sItems[slotD] = HfMakeItem<false>(a, x, y, stride.x, LoadRGBA16F(Near(a.inDiff), x, y).w, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.x);
+        if (slotS >= 0) sItems[slotS] = HfMakeItem<true>(a, x, y, stride.y, LoadRGBA16F(Near(a.inSpec), x, y).w, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.y);
+        __syncthreads();
+        for (int t = tid; t < items * kHfTaps; t += 256)
+        {
+            const int item = t / kHfTaps, k = t - item * kHfTaps;
+            const HfItem it = sItems[item];
+            sTaps[t] = HfEvalTapAnywhere<DIFF && SPEC>(a, it, it.isSpec != 0, k);
+        }
+    }
+
+    // fast-history tiles
+    {
+        const int boxX0 = blockIdx.x * 32 - kHfPad, boxY0 = a.rowBegin + blockIdx.y * 8 - kHfBorder;
+        if (a.useTma)
+        {
             nrdb200_tma::BarrierWait(&bar, 0);
             if (DIFF) nrdb200_tma::PatchClampToEdge<__half, kHfBoxW, kHfBoxH>(sFastDiff, boxX0, boxY0, c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1], tid, 256);
             if (SPEC) nrdb200_tma::PatchClampToEdge<__half, kHfBoxW, kHfBoxH>(sFastSpec, boxX0, boxY0, c.gRectSizeMinusOne[0], c.gRectSizeMinusOne[1], tid, 256);
@@ -920,25 +1069,16 @@ __global__ void __launch_bounds__(256, NRD_B200_HF_MIN_BLOCKS)
                 if (SPEC) sFastSpec[ly][lx] = __ushort_as_half((unsigned short)LoadU16(Near(a.inSpecFast), gx, gy));
             }
         }
-        __syncthreads();
+        __syncthreads(); // tiles patched, taps of the compact path written
     }
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
-    if (x > c.gRectSizeMinusOne[0] || y > c.gRectSizeMinusOne[1] || y >= a.rowEnd) return;
-    if (LoadU8(Near(a.tiles), x >> 4, y >> 4) != 0) return;
-    const float viewZ = fabsf(LoadR32F(Near(a.z), x, y) * c.gViewZScale);
-    if (viewZ > c.gDenoisingRange) return;
+    if (!active) return;
 
-    const Guide g0 = LoadGuideLut(Near(a.guide), Near(a.nr), a.lut, x, y);
-    const float frustumSize = c.gMinRectDimMulUnproject * lerpf(viewZ, 1.0f, fabsf(c.gOrthoMode));
-    const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
-    const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
-    const f3 Nv = RotateInverse(c.gViewToWorld, g0.N);
-    const f2 frameNum = LoadFrames<DIFF && SPEC>(Near(a.data1), x, y);
-    const f2 stride = mk2(__fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.x)), __fdiv_rn(c.gHistoryFixBasePixelStride, __fadd_rn(2.0f, frameNum.y)));
-
-    if (DIFF) HistoryFixSignal<false, DIFF && SPEC>(a, x, y, a.inDiff, a.inDiffFast, sFastDiff, a.outDiff, a.outDiffFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.x, stride.x);
-    if (SPEC) HistoryFixSignal<true, DIFF && SPEC>(a, x, y, a.inSpec, a.inSpecFast, sFastSpec, a.outSpec, a.outSpecFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.y, stride.y);
+    if (DIFF)
+        HistoryFixSignal<false, DIFF && SPEC>(a, x, y, a.inDiff, a.inDiffFast, sFastDiff, a.outDiff, a.outDiffFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.x, stride.x,
+                                              compact && slotD >= 0 ? &sTaps[slotD * kHfTaps] : nullptr);
+    if (SPEC)
+        HistoryFixSignal<true, DIFF && SPEC>(a, x, y, a.inSpec, a.inSpecFast, sFastSpec, a.outSpec, a.outSpecFast, viewZ, g0, Nv, Xv, pixelUv, frustumSize, frameNum.y, stride.y,
+                                             compact && slotS >= 0 ? &sTaps[slotS * kHfTaps] : nullptr);
 }
 
 // =============================================================================================
