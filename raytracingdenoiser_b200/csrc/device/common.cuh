@@ -95,6 +95,33 @@ __device__ __forceinline__ bool RowsLocal(const Surf& s, int ya, int yb)
     return (unsigned)(ya - s.ly0) < s.lrows && (unsigned)(yb - s.ly0) < s.lrows;
 #endif
 }
+// One owner lookup for several surfaces of the same geometry (full-resolution pool / user / guide surfaces share strip rows, halo and
+// the peers' arena deltas): RefRow() resolves row y once, TexelAt() addresses any of those surfaces with it.
+struct RowRef
+{
+    long long delta; // 0 = held locally (own rows or ghost rows), else the owner's arena delta
+    int row;         // row index inside the holder's copy of the surface
+};
+__device__ __forceinline__ RowRef RefRow(const Surf& s, int y)
+{
+#if defined(NRD_B200_NO_STRIPS)
+    (void)s;
+    return {0, y};
+#else
+    const int ly = y - s.ly0;
+    if (s.stripRows == 0 || (unsigned)ly < s.lrows) return {0, ly};
+    const PeerTable& t = g_peerTable[s.peerSlot];
+    const int yFull = y << s.rowShift;
+    int owner = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxPeers; k++) owner += yFull >= t.start[k] ? 1 : 0;
+    return {t.delta[owner], y - (t.start[owner] >> s.rowShift) + s.halo};
+#endif
+}
+template <class T> __device__ __forceinline__ const T* TexelAt(const Surf& s, RowRef r, int x)
+{
+    return reinterpret_cast<const T*>(s.base + r.delta + (size_t)r.row * s.pitch) + x;
+}
 template <class T> __device__ __forceinline__ T* TexelPtrRW(const Surf& s, int x, int y)
 {
 #if defined(NRD_B200_NO_STRIPS)
