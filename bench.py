@@ -208,9 +208,41 @@ def main():
         from raytracingdenoiser_b200 import strips
         # cost-balanced partition from the sky mask of the first frame (every rank computes the same one): tiles beyond the
         # denoising range are skipped by every pass, so uniform strips would leave the rank that owns the sky idle
-        partition = strips.partition_rows_weighted(H, world, strips.tile_row_cost_from_viewz(frames[0]["IN_VIEWZ"]), min_rows=strips.DEFAULT_HALO_ROWS)
+        cost = strips.tile_row_cost_from_viewz(frames[0]["IN_VIEWZ"])
+        partition = strips.partition_rows_weighted(H, world, cost, min_rows=strips.DEFAULT_HALO_ROWS)
+        # measured re-balancing (set-up, untimed): the first frames are denoised on the trial partition with per-dispatch timing on
+        # (nrdCudaSetTiming: kernel time without barrier waits), the per-strip kernel times correct the cost of the tile rows and the
+        # strips are cut again; the contexts are then rebuilt, so the benchmark itself starts from an empty history on the final strips
+        balance = []
+        for trial in range(int(os.environ.get("NRD_B200_BALANCE_TRIALS", "2"))):
+            gpu = strips.StripDenoiser(den, W, H, rank, world, device=local_rank, partition=partition)
+            gpu.connect()
+            gpu.ctx.set_timing(True)
+            mine = 0.0
+            ncal = min(6, len(frames))
+            for i in range(ncal):
+                gpu.set_input_strips({n: frames[i][n][gpu.y0:gpu.y1].contiguous() for n in in_names}, stream)
+                gpu.denoise(harness.make_common_settings(frames[i], W, H, i))
+                gpu.synchronize()
+                kernel_ms, _ = gpu.ctx.get_timing()
+                if i >= ncal - 3:
+                    mine += sum(kernel_ms)
+            t = torch.tensor([mine], device=dev)
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            ms = [float(e.item()) for e in every]
+            balance.append({"strips": [list(p) for p in partition[1]], "kernel_ms_per_rank": [round(m / 3.0, 4) for m in ms]})
+            gpu.destroy()
+            del gpu
+            torch.cuda.empty_cache()
+            dist.barrier()
+            if max(ms) <= 1.03 * min(ms):
+                break
+            cost = strips.rebalance_tile_row_cost(cost, partition[1], ms)
+            partition = strips.partition_rows_weighted(H, world, cost, min_rows=strips.DEFAULT_HALO_ROWS)
         gpu = strips.StripDenoiser(den, W, H, rank, world, device=local_rank, partition=partition)
         base["config"]["strips"] = [list(p) for p in partition[1]]
+        base["config"]["strip_balance"] = {"method": "sky-tile cost model, then strips re-cut from measured per-rank kernel time (set-up, untimed)", "trials": balance}
         gpu.connect()
         y0, y1 = gpu.y0, gpu.y1
         full_frames = frames if rank == 0 else None   # rank 0 re-denoises the sequence on one GPU afterwards: the N-GPU output is checked, not assumed

@@ -406,6 +406,12 @@ NRD_API nrd::Result nrdCudaBarrier(NrdCudaContext* context, void* stream);
 NRD_API nrd::Result nrdCudaSynchronize(NrdCudaContext* context, void* stream);
 
 // Last CUDA error string seen by the executor ("" if none).
+// Profiling aid (multi-GPU balance): with timing on, every dispatch of nrdCudaDenoise / nrdCudaExecuteDispatch is bracketed by CUDA
+// events on its stream -- kernelMs[i] = the pass kernel alone, exchangeMs[i] = its ghost-row push + inter-GPU barrier (i.e. the
+// NVLink copy plus the wait for the slowest neighbour).  nrdCudaGetTiming synchronises the events recorded since the last call
+// (at most 64 dispatches are kept) and returns how many there were.
+NRD_API nrd::Result nrdCudaSetTiming(NrdCudaContext* context, int32_t enable);
+NRD_API nrd::Result nrdCudaGetTiming(NrdCudaContext* context, float* kernelMs, float* exchangeMs, uint32_t capacity, uint32_t* count);
 NRD_API const char* nrdCudaGetLastError(NrdCudaContext* context);
 // Total kernels launched by this library in the process (for bench.py's gpu_launches).
 NRD_API uint64_t nrdCudaGetLaunchCount();

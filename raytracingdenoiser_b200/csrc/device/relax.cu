@@ -219,7 +219,9 @@ __global__ void __launch_bounds__(256) RelaxClassifyTilesKernel(const __grid_con
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.tilesW * a.tilesH) return;
     int tx = warp % a.tilesW, ty = warp / a.tilesW;
-    if (ty < a.tiles.y0 || ty >= a.tiles.y1) return; // tile rows of another strip
+    const bool ownTile = ty >= a.tiles.y0 && ty < a.tiles.y1;
+    // tiles of another strip: only their rows that this rank holds as ghost rows matter (guide build, see below)
+    if (!ownTile && (!a.buildGuide || ty * 16 + 15 < a.guide.ly0 || ty * 16 >= a.guide.ly0 + (int)a.guide.lrows)) return;
     bool allSky = true;
 #pragma unroll
     for (int k = 0; k < 8; k++)
@@ -229,13 +231,16 @@ __global__ void __launch_bounds__(256) RelaxClassifyTilesKernel(const __grid_con
         float z = 0.0f;
         if (Inside(a.z, x, y))
         {
-            z = LoadR32F(a.z, x, y);
-            if (a.buildGuide) StoreRGBA32F(a.guide, x, y, mk4(rb::DecodeNormalExact(LoadU32(a.nr, x, y)), z));
+            // the guide is built for every row held locally: the ghost rows of IN_VIEWZ / IN_NORMAL_ROUGHNESS arrived with the
+            // frame-start push, so the guide's ghost rows are decoded here instead of being sent by the neighbour
+            const bool held = a.buildGuide && (unsigned)(y - a.guide.ly0) < a.guide.lrows;
+            if (ownTile || held) z = LoadR32F(Near(a.z), x, y);
+            if (held) StoreRGBA32F(a.guide, x, y, mk4(rb::DecodeNormalExact(LoadU32(Near(a.nr), x, y)), z));
         }
         allSky = allSky && (fabsf(z) > a.denoisingRange);
     }
     allSky = __all_sync(0xffffffffu, allSky);
-    if (lane == 0) StoreU8(a.tiles, tx, ty, allSky ? 255u : 0u);
+    if (lane == 0 && ownTile) StoreU8(a.tiles, tx, ty, allSky ? 255u : 0u);
 }
 
 // =============================================================================================

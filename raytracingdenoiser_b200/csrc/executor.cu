@@ -118,6 +118,9 @@ struct NrdCudaContext
     float* roughnessLut = nullptr;     // device, 1024 x float4 (allocated with the context: no cudaMalloc -- an implicit device
     float* roughnessLutStaging = nullptr; // synchronisation -- may happen while a strip barrier spins); pinned staging copy
     cudaEvent_t lutUploaded = nullptr;
+    bool timing = false;                  // nrdCudaSetTiming: three events per dispatch (before the kernel, after it, after push + barrier)
+    cudaEvent_t timingEvents[3 * 64] = {};
+    uint32_t timingCount = 0;
     float lutKey[2] = {0.0f, 0.0f};
     bool lutValid = false;
     // strip mode
@@ -585,6 +588,8 @@ NRD_API void nrdCudaDestroyContext(NrdCudaContext* ctx)
     if (ctx->roughnessLut) cudaFree(ctx->roughnessLut);
     if (ctx->roughnessLutStaging) cudaFreeHost(ctx->roughnessLutStaging);
     if (ctx->lutUploaded) cudaEventDestroy(ctx->lutUploaded);
+    for (cudaEvent_t ev : ctx->timingEvents)
+        if (ev) cudaEventDestroy(ev);
     delete ctx;
 }
 
@@ -787,6 +792,8 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     const bool stripBuild = (StripMode(ctx) && ctx->world > 1) || getenv("NRD_B200_FORCE_STRIP_KERNELS") != nullptr;
     const Launchers& L = stripBuild ? kStripLaunchers : kSingleLaunchers;
     cudaError_t e;
+    const bool timed = ctx->timing && ctx->timingCount < 64 && strncmp(shader, "Clear_", 6) != 0;
+    const uint32_t slot = ctx->timingCount;
     const Texture* clearTarget = !strncmp(shader, "Clear_", 6) && d->resourcesNum ? Resolve(ctx, d->resources[0].type, d->resources[0].indexInPool) : nullptr;
     if (clearTarget && !clearTarget->owned)
     {
@@ -797,7 +804,11 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
                               : cudaSuccess;
     }
     else
+    {
+        if (timed) cudaEventRecord(ctx->timingEvents[3 * slot + 0], p.stream);
         e = LaunchByName(L, p, shader);
+        if (timed) cudaEventRecord(ctx->timingEvents[3 * slot + 1], p.stream);
+    }
 
     if (e == cudaErrorNotSupported) return Fail(ctx, Result::UNSUPPORTED, std::string("no CUDA kernel for pass ") + shader);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string(shader) + ": " + cudaGetErrorString(e));
@@ -805,13 +816,20 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     if (buildsGuide) ctx->guideValid = true;
     const Texture* list[33];
     uint32_t n = 0;
-    if (strncmp(shader, "Clear_", 6) != 0 && (pushMask || buildsGuide)) // clears zero the ghost rows locally
+    if (strncmp(shader, "Clear_", 6) != 0 && pushMask) // clears zero the ghost rows locally
     {
         for (uint32_t i = 0; i < d->resourcesNum; i++)
             if ((pushMask >> i) & 1u) list[n++] = Resolve(ctx, d->resources[i].type, d->resources[i].indexInPool);
-        if (buildsGuide) list[n++] = &ctx->guide; // the filter passes of the neighbours read its boundary rows
     }
-    return PushGhostsAndBarrier(ctx, list, n, p.stream);
+    // (the guide surface needs no push: ClassifyTiles decodes its ghost rows from the ghost rows of the inputs, which arrived with the
+    // frame-start push; the barrier below still separates it from the neighbours' far taps, which load the guide from its owner)
+    const Result pr = PushGhostsAndBarrier(ctx, list, n, p.stream);
+    if (timed)
+    {
+        cudaEventRecord(ctx->timingEvents[3 * slot + 2], p.stream);
+        ctx->timingCount = slot + 1;
+    }
+    return pr;
 }
 
 uint32_t StorageMask(const DispatchDesc* d)
@@ -941,6 +959,35 @@ NRD_API Result nrdCudaSynchronize(NrdCudaContext* ctx, void* stream)
         if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, cudaGetErrorString(e));
         if (err) return Fail(ctx, Result::FAILURE, "strip barrier timed out waiting for a peer (epoch " + std::to_string(err) + ")");
     }
+    return Result::SUCCESS;
+}
+
+NRD_API Result nrdCudaSetTiming(NrdCudaContext* ctx, int32_t enable)
+{
+    if (!ctx) return Result::INVALID_ARGUMENT;
+    if (enable && !ctx->timingEvents[0])
+        for (cudaEvent_t& ev : ctx->timingEvents)
+            if (cudaEventCreate(&ev) != cudaSuccess) return Fail(ctx, Result::FAILURE, "cudaEventCreate failed");
+    ctx->timing = enable != 0;
+    ctx->timingCount = 0;
+    return Result::SUCCESS;
+}
+
+NRD_API Result nrdCudaGetTiming(NrdCudaContext* ctx, float* kernelMs, float* exchangeMs, uint32_t capacity, uint32_t* count)
+{
+    if (!ctx || !count) return Result::INVALID_ARGUMENT;
+    const uint32_t n = ctx->timingCount < capacity ? ctx->timingCount : capacity;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        float k = 0.0f, x = 0.0f;
+        if (cudaEventSynchronize(ctx->timingEvents[3 * i + 2]) != cudaSuccess || cudaEventElapsedTime(&k, ctx->timingEvents[3 * i], ctx->timingEvents[3 * i + 1]) != cudaSuccess ||
+            cudaEventElapsedTime(&x, ctx->timingEvents[3 * i + 1], ctx->timingEvents[3 * i + 2]) != cudaSuccess)
+            return Fail(ctx, Result::FAILURE, "timing events are not complete");
+        if (kernelMs) kernelMs[i] = k;
+        if (exchangeMs) exchangeMs[i] = x;
+    }
+    *count = n;
+    ctx->timingCount = 0;
     return Result::SUCCESS;
 }
 

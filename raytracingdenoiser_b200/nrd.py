@@ -242,12 +242,16 @@ _lib.nrdCudaBarrier.argtypes = [C.c_void_p, C.c_void_p]
 _lib.nrdCudaBarrier.restype = u32
 _lib.nrdCudaSynchronize.argtypes = [C.c_void_p, C.c_void_p]
 _lib.nrdCudaSynchronize.restype = u32
+_lib.nrdCudaSetTiming.argtypes = [C.c_void_p, C.c_int32]
+_lib.nrdCudaSetTiming.restype = u32
+_lib.nrdCudaGetTiming.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint32)]
+_lib.nrdCudaGetTiming.restype = u32
 IPC_HANDLE_SIZE = 64
 
 EXPORTED_SYMBOLS = ["CreateInstance", "DestroyInstance", "GetLibraryDesc", "GetInstanceDesc", "SetCommonSettings", "SetDenoiserSettings",
                     "GetComputeDispatches", "GetResourceTypeString", "GetDenoiserString", "nrdCudaCreateContext", "nrdCudaDestroyContext",
                     "nrdCudaSetUserTexture", "nrdCudaGetTexture", "nrdCudaExecuteDispatch", "nrdCudaDenoise", "nrdCudaUploadTexture", "nrdCudaDownloadTexture", "nrdCudaGetLastError", "nrdCudaGetLaunchCount",
-                    "nrdCudaCopyTexture", "nrdCudaGetArena", "nrdCudaGetIpcHandle", "nrdCudaConnectPeers", "nrdCudaBarrier", "nrdCudaSynchronize"]
+                    "nrdCudaCopyTexture", "nrdCudaGetArena", "nrdCudaGetIpcHandle", "nrdCudaConnectPeers", "nrdCudaBarrier", "nrdCudaSynchronize", "nrdCudaSetTiming", "nrdCudaGetTiming"]
 
 
 class NrdError(RuntimeError):
@@ -457,6 +461,15 @@ class CudaContext(object):
 
     def synchronize(self, stream=0):
         self._check("nrdCudaSynchronize", _lib.nrdCudaSynchronize(self._ctx, C.c_void_p(stream)))
+
+    def set_timing(self, enable):
+        self._check("nrdCudaSetTiming", _lib.nrdCudaSetTiming(self._ctx, 1 if enable else 0))
+
+    def get_timing(self):
+        """(kernel_ms, exchange_ms) lists of the dispatches executed since the last call (timing must be on)."""
+        k, x, n = (C.c_float * 64)(), (C.c_float * 64)(), C.c_uint32(0)
+        self._check("nrdCudaGetTiming", _lib.nrdCudaGetTiming(self._ctx, k, x, 64, C.byref(n)))
+        return list(k[:n.value]), list(x[:n.value])
 
     def execute_raw(self, raw_dispatch_ptr, stream=0):
         self._check("nrdCudaExecuteDispatch", _lib.nrdCudaExecuteDispatch(self._ctx, raw_dispatch_ptr, C.c_void_p(stream)))

@@ -66,6 +66,25 @@ def tile_row_cost_from_viewz(viewz, denoising_range=500000.0):
     return (live.float().sum(dim=1) + 0.02 * tw).tolist()   # a skipped tile still costs its early-out
 
 
+def rebalance_tile_row_cost(tile_row_cost, strips, measured_ms):
+    """Measured re-balancing: strips = [(y0, y1)] that were just run, measured_ms[r] = kernel time of rank r over them
+    (nrdCudaGetTiming: kernels only, no barrier waits).  Returns the per-tile-row costs scaled strip by strip so that each
+    strip's total is proportional to what it actually took; feeding them to partition_rows_weighted moves the boundaries
+    towards equal time.  (The cost model only knows sky tiles; blur radii, young history, specular work per pixel are content.)"""
+    cost = [float(c) for c in tile_row_cost]
+    total_ms = float(sum(measured_ms)) or 1.0
+    total_cost = sum(cost) or 1.0
+    for (y0, y1), ms in zip(strips, measured_ms):
+        t0, t1 = y0 // TILE, (y1 + TILE - 1) // TILE
+        predicted = sum(cost[t0:t1])
+        if predicted <= 0.0 or t1 <= t0:
+            continue
+        k = (ms / total_ms) / (predicted / total_cost)
+        for t in range(t0, t1):
+            cost[t] *= k
+    return cost
+
+
 def exchange_ipc_handles(local_handle, group=None):
     """all_gather of the per-rank 64-byte CUDA IPC handles (works on the gloo and the nccl backend)."""
     import torch.distributed as dist

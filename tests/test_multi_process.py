@@ -87,3 +87,26 @@ def test_cross_process_strips_bit_identical(denoiser):
            os.path.join(HERE, "multi_gpu_check.py"), denoiser, "640", "368", "4"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_measured_rebalancing_moves_rows_away_from_the_slow_rank():
+    """strips.rebalance_tile_row_cost: per-rank kernel times of a trial partition correct the per-tile-row costs; cutting again moves
+    the boundaries towards equal time (bench.py does this during set-up at N > 1)."""
+    from raytracingdenoiser_b200 import strips
+    h, world = 2160, 4
+    cost = [1.0] * ((h + 15) // 16)
+    cap, part = strips.partition_rows_weighted(h, world, cost, min_rows=96)
+    # rows of rank 0 cost twice as much per row as the model thinks
+    ms = [2.0 * (y1 - y0) if r == 0 else 1.0 * (y1 - y0) for r, (y0, y1) in enumerate(part)]
+    cost2 = strips.rebalance_tile_row_cost(cost, part, ms)
+    cap2, part2 = strips.partition_rows_weighted(h, world, cost2, min_rows=96)
+    assert part2[0][1] - part2[0][0] < part[0][1] - part[0][0]
+    assert part2[0][0] == 0 and part2[-1][1] == h and all(a[1] == b[0] for a, b in zip(part2, part2[1:]))
+    assert all(y0 % 16 == 0 for y0, _ in part2) and cap2 >= max(y1 - y0 for y0, y1 in part2)
+
+    def time_of(p):  # what the strips would take under the true cost density
+        return [sum((2.0 if y < part[0][1] else 1.0) for y in range(y0, y1)) for y0, y1 in p]
+    assert max(time_of(part2)) < 0.8 * max(time_of(part))
+    # balanced measurements leave the costs proportional to what they were
+    same = strips.rebalance_tile_row_cost(cost, part, [float(y1 - y0) for y0, y1 in part])
+    assert max(abs(a - b) for a, b in zip(same, cost)) < 1e-6
