@@ -182,23 +182,49 @@ struct Pass
         return origin - Iw * float3(D.w);
     }
     // :465-482
-    // Texel-selecting arithmetic is written with explicit fused multiply-adds (what an HLSL compiler emits for mad chains; the
-    // unfused form is an equally valid reading of the source).  The CUDA kernels use the same operations in the same order
-    // (device/reblur_spatial.cu), so both sides land on the same texel.
-    // Common.hlsli:472  RotateVector(rotator, v) = v.x * r.xz + v.y * r.yw
-    static float2 RotateVectorFma(float4 r, float2 v) { return float2(std::fma(v.x, r.x, v.y * r.y), std::fma(v.x, r.z, v.y * r.w)); }
-    // :465-482
-    static float2 GetKernelSampleCoordinates(const float4x4& mToClip, float3 offset, float3 X, float3 T, float3 B, float4 rotator)
+    // Texel selection of the Poisson taps.  The reference hands a uv to a nearest-neighbour sampler (fixed-point texel selection in
+    // hardware, Common.hlsli:465-482 / REBLUR_Common_*SpatialFilter.hlsli); which texel a tap within rounding distance of a texel
+    // border lands on is not defined by the HLSL source.  The oracle fixes ONE evaluation: the tap position is computed directly in
+    // texel units, as fused multiply-add chains that start from the exact pixel centre.  The CUDA kernels use the same operations in
+    // the same order (device/reblur_spatial.cu), so both sides land on the same texel.
+    //   screen-space taps (Common.hlsli:472 RotateVector(rotator, v) = v.x * r.xz + v.y * r.yw, rotator scaled to pixels):
+    //     t = pixelPos + 0.5 + RotateVector(rotator * skewInPixels.xxyy, offset)
+    static float2 TapTexelScreen(int2 pixelPos, float4 R, float2 o)
+    {
+        float px = float(pixelPos.x) + 0.5f, py = float(pixelPos.y) + 0.5f;
+        return float2(std::fma(o.x, R.x, std::fma(o.y, R.y, px)), std::fma(o.x, R.z, std::fma(o.y, R.w, py)));
+    }
+    //   world-space taps (Common.hlsli:465-482 GetKernelSampleCoordinates): p = X + T * o.x + B * o.y is affine in the (per-frame
+    //   uniform) rotated offset o, so is clip = M * (p, 1): the clip-space images of X, T and B are evaluated once per pixel, with
+    //   the x / y rows pre-scaled to texels (uv * rectSize = clip.xy / clip.w * (0.5, -0.5) * rectSize + 0.5 * rectSize)
+    struct KernelProjection
+    {
+        float X0, XT, XB, Y0, YT, YB, W0, WT, WB, hW, hH;
+    };
+    static KernelProjection ProjectKernel(const float4x4& m, float2 rectSize, float3 X, float3 T, float3 B)
+    {
+        KernelProjection k;
+        k.hW = 0.5f * rectSize.x;
+        k.hH = 0.5f * rectSize.y;
+        k.X0 = std::fma(m.c[2].x, X.z, std::fma(m.c[1].x, X.y, std::fma(m.c[0].x, X.x, m.c[3].x))) * k.hW;
+        k.Y0 = std::fma(m.c[2].y, X.z, std::fma(m.c[1].y, X.y, std::fma(m.c[0].y, X.x, m.c[3].y))) * -k.hH;
+        k.W0 = std::fma(m.c[2].w, X.z, std::fma(m.c[1].w, X.y, std::fma(m.c[0].w, X.x, m.c[3].w)));
+        k.XT = std::fma(m.c[2].x, T.z, std::fma(m.c[1].x, T.y, m.c[0].x * T.x)) * k.hW;
+        k.YT = std::fma(m.c[2].y, T.z, std::fma(m.c[1].y, T.y, m.c[0].y * T.x)) * -k.hH;
+        k.WT = std::fma(m.c[2].w, T.z, std::fma(m.c[1].w, T.y, m.c[0].w * T.x));
+        k.XB = std::fma(m.c[2].x, B.z, std::fma(m.c[1].x, B.y, m.c[0].x * B.x)) * k.hW;
+        k.YB = std::fma(m.c[2].y, B.z, std::fma(m.c[1].y, B.y, m.c[0].y * B.x)) * -k.hH;
+        k.WB = std::fma(m.c[2].w, B.z, std::fma(m.c[1].w, B.y, m.c[0].w * B.x));
+        return k;
+    }
+    static float2 TapTexelWorld(const KernelProjection& k, float3 offset, float4 rotator)
     {
         float2 o = Geometry::RotateVector(rotator, offset.xy()); // per-frame uniform (host-evaluated by the kernels' launcher)
-        float3 p = float3(std::fma(B.x, o.y, std::fma(T.x, o.x, X.x)), std::fma(B.y, o.y, std::fma(T.y, o.x, X.y)), std::fma(B.z, o.y, std::fma(T.z, o.x, X.z)));
-        // ProjectiveTransform: clip = M * float4(p, 1), each row a mad chain that starts from the translation column
-        const float4x4& m = mToClip;
-        float cx = std::fma(m.c[2].x, p.z, std::fma(m.c[1].x, p.y, std::fma(m.c[0].x, p.x, m.c[3].x)));
-        float cy = std::fma(m.c[2].y, p.z, std::fma(m.c[1].y, p.y, std::fma(m.c[0].y, p.x, m.c[3].y)));
-        float cw = std::fma(m.c[2].w, p.z, std::fma(m.c[1].w, p.y, std::fma(m.c[0].w, p.x, m.c[3].w)));
-        float rw = 1.0f / cw; // clip.xy / clip.w as one reciprocal and two products
-        return float2(std::fma(cx * rw, 0.5f, 0.5f), std::fma(cy * rw, -0.5f, 0.5f));
+        float cx = std::fma(o.y, k.XB, std::fma(o.x, k.XT, k.X0));
+        float cy = std::fma(o.y, k.YB, std::fma(o.x, k.YT, k.Y0));
+        float cw = std::fma(o.y, k.WB, std::fma(o.x, k.WT, k.W0));
+        float rw = 1.0f / cw; // clip.xy / clip.w as one reciprocal and two fused products
+        return float2(std::fma(cx, rw, k.hW), std::fma(cy, rw, k.hH));
     }
     // :486-540
     static float GetNormalWeightParam(float nonLinearAccumSpeed, float lobeAngleFraction, float roughness = 1.0f)
@@ -481,14 +507,13 @@ void DiffuseSpatialFilter(const Pass& P, const SpatialCtx& s, float sum, float4 
             skew = lerp(float2(1.0f) - abs(s.Nv.xy()), float2(1.0f), s.NoV);
             skew /= float2(max(skew.x, skew.y));
         }
-        skew *= c.gRectSizeInv * float2(blurRadius);
+        skew *= float2(blurRadius); // in pixels: uv * rectSize is evaluated directly (Pass::TapTexelScreen)
         float4 scaledRotator = Geometry::ScaleRotator(s.rotator, skew);
 
         for (uint n = 0; n < 8; n++)
         {
             float3 offset = g_Special8[n];
-            float2 uv = s.pixelUv + Pass::RotateVectorFma(scaledRotator, offset.xy());
-            uv = floor(uv * c.gRectSize) + float2(0.5f);
+            float2 uv = floor(Pass::TapTexelScreen(s.pixelPos, scaledRotator, offset.xy())) + float2(0.5f);
             if (pre) uv = Pass::ApplyCheckerboardShift(uv, c.gDiffCheckerboard, n, c.gFrameIndex);
             uv *= c.gRectSizeInv;
 
@@ -596,7 +621,7 @@ void SpecularSpatialFilter(const Pass& P, const SpatialCtx& s, float sum, float4
         if (pre)
         {
             float2 skew(1.0f);
-            skew *= c.gRectSizeInv * float2(blurRadius);
+            skew *= float2(blurRadius); // in pixels (Pass::TapTexelScreen)
             scaledRotator = Geometry::ScaleRotator(s.rotator, skew);
         }
         else
@@ -612,14 +637,15 @@ void SpecularSpatialFilter(const Pass& P, const SpatialCtx& s, float sum, float4
             Tv *= float3(worldRadius * skewFactor);
             Bv *= float3(worldRadius / skewFactor);
         }
+        const Pass::KernelProjection kernelProjection = Pass::ProjectKernel(c.gViewToClip, c.gRectSize, s.Xv, Tv, Bv);
 
         for (uint n = 0; n < 8; n++)
         {
             float3 offset = g_Special8[n];
             float2 uv;
-            if (pre) uv = s.pixelUv + Pass::RotateVectorFma(scaledRotator, offset.xy());
-            else uv = Pass::GetKernelSampleCoordinates(c.gViewToClip, offset, s.Xv, Tv, Bv, s.rotator);
-            uv = floor(uv * c.gRectSize) + float2(0.5f);
+            if (pre) uv = Pass::TapTexelScreen(s.pixelPos, scaledRotator, offset.xy());
+            else uv = Pass::TapTexelWorld(kernelProjection, offset, s.rotator);
+            uv = floor(uv) + float2(0.5f);
             if (pre) uv = Pass::ApplyCheckerboardShift(uv, c.gSpecCheckerboard, n, c.gFrameIndex);
             uv *= c.gRectSizeInv;
 

@@ -3,7 +3,7 @@
 // (REBLUR_USE_DECOMPRESSED_HIT_DIST_IN_RECONSTRUCTION = 0, not performance mode): a pixel whose ray missed (hit distance 0) takes the
 // weighted hit distance of its neighbourhood -- plane-distance weight (strict), gaussian, normal and roughness weights (exponential).
 //
-// How: a dense stencil, so the CTA stages what all its threads share.  The decoded guides {N.xyz, raw viewZ} of tile + halo come from
+// How: a dense stencil, so the CTA stages what all its threads share.  The decoded guides {N.xyz, unpacked viewZ} of tile + halo come from
 // the guide surface with ONE TMA bulk tensor copy (cp.async.bulk.tensor.2d -> UTMALDG, completion on an mbarrier) issued by one
 // thread while all threads stage the two hit distances and the roughness of the same window with clamped loads; the taps are then
 // LDS only.  TMA zero-fills outside the surface where the reference clamps to the rect edge: taps index the tile with clamped
@@ -31,7 +31,7 @@ template <bool DIFF, bool SPEC, int BORDER>
 __global__ void __launch_bounds__(kHdTileW* kHdTileH) ReblurHitDistReconstructionKernel(const __grid_constant__ HitDistArgs a, const __grid_constant__ CUtensorMap guideMap)
 {
     constexpr int BW = kHdTileW + 2 * BORDER, BH = kHdTileH + 2 * BORDER;
-    __shared__ __align__(128) float4 sGuide[BH][BW]; // {N.xyz, raw viewZ}
+    __shared__ __align__(128) float4 sGuide[BH][BW]; // {N.xyz, unpacked viewZ}
     __shared__ float2 sHit[BH][BW];                  // {diffuse, specular} normalised hit distance
     __shared__ float sRough[BH][BW];
     __shared__ __align__(8) uint64_t bar;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kHdTileW* kHdTileH) ReblurHitDistReconstructio
 
     const int cx = threadIdx.x + BORDER, cy = threadIdx.y + BORDER;
     const float4 g0 = sGuide[cy][cx];
-    const float viewZ = fabsf(g0.w * c.gViewZScale);
+    const float viewZ = g0.w; // the guide holds |viewZ * gViewZScale|
     if (viewZ > c.gDenoisingRange) return;
 
     const f3 N = mk3(g0.x, g0.y, g0.z);
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kHdTileW* kHdTileH) ReblurHitDistReconstructio
             if ((unsigned)(x + i) > (unsigned)maxX || (unsigned)(y + j) > (unsigned)maxY) continue;
             const int sx = cx + i, sy = cy + j; // in-rect neighbours are never clamped
             const float4 g = sGuide[sy][sx];
-            const float zs = fabsf(g.w * c.gViewZScale);
+            const float zs = g.w;
             const f2 uv = mk2(pixelUv.x + (float)i * c.gRectSizeInv[0], pixelUv.y + (float)j * c.gRectSizeInv[1]);
             const f3 Xvs = ReconstructViewPosition(uv, c.gFrustum, zs, c.gOrthoMode);
             float w = __expf(-0.66f * 0.25f * (float)(i * i + j * j)); // GetGaussianWeight(length(o) * 0.5)

@@ -57,7 +57,7 @@ __device__ __forceinline__ f3 DecodeNormalExact(unsigned packed)
     return mk3(__fmul_rn(nx, inv), __fmul_rn(ny, inv), __fmul_rn(nz, inv));
 }
 
-// Guides through the decoded-guide surface (surf.h PassLaunch::guide: {N.xyz bit-exact, raw viewZ}, written by ClassifyTiles at
+// Guides through the decoded-guide surface (surf.h PassLaunch::guide: {N.xyz bit-exact, |viewZ * gViewZScale| for REBLUR, raw viewZ for RELAX}, written by ClassifyTiles at
 // the start of every frame): one 16-byte load instead of the octahedral decode; roughness / material straight from the packed
 // bits (loads whose result is unused are removed by the compiler).
 __device__ __forceinline__ Guide LoadGuide(const Surf& guide, const Surf& nr, int x, int y)

@@ -224,6 +224,7 @@ struct TaArgs
 {
     ReblurConstants c;
     Surf tiles, nr, z, mv, prevZ, prevNr, prevInternal;
+    Surf mix, diffConfidence, specConfidence; // optional R8_UNORM inputs (REBLUR_TemporalAccumulation.hlsli:220-221, :327-328, :830-831), read only when the constants say so
     Surf inDiff, inSpec, histDiff, histSpec, histDiffFast, histSpecFast, prevHitDist, inHitDist;
     Surf outDiff, outSpec, outDiffFast, outSpecFast, outHitDist, outData1, outData2;
     Surf guide;          // decoded guides of the current frame (surf.h PassLaunch::guide)
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
     const float frustumSize = c.gMinRectDimMulUnproject * lerpf(viewZ, 1.0f, fabsf(c.gOrthoMode));
     float disocclusionThresholdMix = 0.0f;
     if (materialID == c.gStrandMaterialID) disocclusionThresholdMix = pixelSize / (pixelSize + c.gStrandThickness);
+    if (c.gHasDisocclusionThresholdMix) disocclusionThresholdMix = LoadR8Unorm(Near(a.mix), x, y);
     float disocclusionThreshold = lerpf(c.gDisocclusionThreshold, c.gDisocclusionThresholdAlternate, disocclusionThresholdMix);
     const float smallParallax = LinearStep(0.25f, 0.0f, smbParallaxInPixelsMax);
     disocclusionThreshold += 0.05f * smallParallax;
@@ -425,7 +427,9 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
     float specAccumSpeed = 0.0f, curvature = 0.0f, virtualHistoryAmount = 0.0f;
     if (SPEC)
     {
-        smbSpecAccumSpeed *= lerpf(smbFootprintQuality, 1.0f, 1.0f / (1.0f + smbSpecAccumSpeed));
+        float specHistoryConfidence = smbFootprintQuality;
+        if (c.gHasHistoryConfidence) specHistoryConfidence *= LoadR8Unorm(Near(a.specConfidence), x, y);
+        smbSpecAccumSpeed *= lerpf(specHistoryConfidence, 1.0f, 1.0f / (1.0f + smbSpecAccumSpeed));
         smbSpecAccumSpeed = fminf(smbSpecAccumSpeed, c.gMaxAccumulatedFrameNum);
         const f4 spec = LoadRGBA16F(Near(a.inSpec), x, y);
 
@@ -704,7 +708,9 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
 
     if (DIFF)
     {
-        diffAccumSpeed *= lerpf(smbFootprintQuality, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
+        float diffHistoryConfidence = smbFootprintQuality;
+        if (c.gHasHistoryConfidence) diffHistoryConfidence *= LoadR8Unorm(Near(a.diffConfidence), x, y);
+        diffAccumSpeed *= lerpf(diffHistoryConfidence, 1.0f, 1.0f / (1.0f + diffAccumSpeed));
         diffAccumSpeed = fminf(diffAccumSpeed, c.gMaxAccumulatedFrameNum);
         const f4 diff = LoadRGBA16F(Near(a.inDiff), x, y);
 
@@ -1312,9 +1318,9 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchTa(const PassLaunch& p)
     int k = 0;
     a.tiles = p.tex[k++]; a.nr = p.tex[k++]; a.z = p.tex[k++]; a.mv = p.tex[k++];
     a.prevZ = p.tex[k++]; a.prevNr = p.tex[k++]; a.prevInternal = p.tex[k++];
-    k++;               // gIn_DisocclusionThresholdMix (dummy: the executor rejects isDisocclusionThresholdMixAvailable)
-    if (DIFF) k++;     // gIn_DiffConfidence (dummy)
-    if (SPEC) k++;     // gIn_SpecConfidence (dummy)
+    a.mix = p.tex[k++];                      // gIn_DisocclusionThresholdMix (bound to IN_VIEWZ when absent, never read then)
+    if (DIFF) a.diffConfidence = p.tex[k++]; // gIn_DiffConfidence
+    if (SPEC) a.specConfidence = p.tex[k++]; // gIn_SpecConfidence
     if (DIFF) a.inDiff = p.tex[k++];
     if (SPEC) a.inSpec = p.tex[k++];
     if (DIFF && SPEC) { a.histDiff = p.tex[k++]; a.histSpec = p.tex[k++]; a.histDiffFast = p.tex[k++]; a.histSpecFast = p.tex[k++]; }

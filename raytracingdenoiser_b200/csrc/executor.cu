@@ -96,6 +96,10 @@ bool ExpectedUserFormat(ResourceType type, Format& expected, bool translucent = 
         case ResourceType::OUT_DIFF_RADIANCE_HITDIST:
         case ResourceType::OUT_SPEC_RADIANCE_HITDIST: expected = Format::RGBA16_SFLOAT; return true;
         case ResourceType::IN_PENUMBRA: expected = Format::R16_SFLOAT; return true;
+        // optional inputs (CommonSettings::isHistoryConfidenceAvailable / isDisocclusionThresholdMixAvailable)
+        case ResourceType::IN_DIFF_CONFIDENCE:
+        case ResourceType::IN_SPEC_CONFIDENCE:
+        case ResourceType::IN_DISOCCLUSION_THRESHOLD_MIX: expected = Format::R8_UNORM; return true;
         case ResourceType::OUT_SHADOW_TRANSLUCENCY: expected = translucent ? Format::RGBA8_UNORM : Format::R8_UNORM; return true;
         default: return false;
     }
@@ -724,8 +728,8 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     if (cs.rectSize[0] != cs.resourceSize[0] || cs.rectSize[1] != cs.resourceSize[1] || cs.rectOrigin[0] || cs.rectOrigin[1] ||
         cs.resourceSize[0] != ctx->desc.resourceWidth || cs.resourceSize[1] != ctx->desc.resourceHeight)
         return Fail(ctx, Result::UNSUPPORTED, "dynamic resolution (rectSize != resourceSize) is not implemented by the CUDA executor");
-    if (cs.isHistoryConfidenceAvailable || cs.isDisocclusionThresholdMixAvailable || cs.isBaseColorMetalnessAvailable)
-        return Fail(ctx, Result::UNSUPPORTED, "confidence / disocclusion-mix / base-colour inputs are not implemented by the CUDA executor");
+    if (cs.isBaseColorMetalnessAvailable)
+        return Fail(ctx, Result::UNSUPPORTED, "the base-colour / metalness input (specular motion-vector patch) is not implemented by the CUDA executor");
     if (StripMode(ctx) && !ctx->connected && (ctx->desc.stripY0 != 0 || ctx->desc.stripY1 != ctx->desc.resourceHeight))
         return Fail(ctx, Result::FAILURE, "strip-mode context used before nrdCudaConnectPeers");
 

@@ -27,6 +27,12 @@ WANT = [
     ("L1 hit %", "l1tex__t_sector_hit_rate.pct"),
     ("L2 hit %", "lts__t_sector_hit_rate.pct"),
     ("dram throughput % of peak", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+    ("L1/TEX throughput %", "l1tex__throughput.avg.pct_of_peak_sustained_active"),
+    ("L2 throughput %", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+    ("L1 global load sectors", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"),
+    ("L1 global load requests", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"),
+    ("L2 sectors", "lts__t_sectors.sum"),
+    ("SM throughput %", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("smem loads (wavefronts)", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum"),
 ]
 STALLS = "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio"
