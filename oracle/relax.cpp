@@ -992,10 +992,78 @@ void HistoryClamping(const Pass& P, Tex* t, int gridW, int gridH)
         }
 }
 
+// RELAX_Copy.hlsli:11-24
+void Copy(const Pass&, Tex* t, int gridW, int gridH)
+{
+    const Tex &gIn_Spec = t[0], &gIn_Diff = t[1];
+    Tex &gOut_Spec = t[2], &gOut_Diff = t[3];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < gridH * 8; y++)
+        for (int x = 0; x < gridW * 8; x++)
+        {
+            gOut_Spec.store(int2(x, y), gIn_Spec.load(x, y));
+            gOut_Diff.store(int2(x, y), gIn_Diff.load(x, y));
+        }
+}
+
+// RELAX_AntiFirefly.hlsli:11-222: cross-bilateral rank-conditioned rank-selection over the 3x3 neighbourhood
+void AntiFirefly(const Pass& P, Tex* t, int gridW, int gridH)
+{
+    const CB& c = P.c;
+    const Tex &gIn_Tiles = t[0], &gIn_Spec = t[1], &gIn_Diff = t[2], &gIn_Normal_Roughness = t[3], &gIn_ViewZ = t[4];
+    Tex &gOut_Spec = t[5], &gOut_Diff = t[6];
+    const int2 rectMax(c.gRectSize[0] - 1, c.gRectSize[1] - 1);
+
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < gridH * 8; y++)
+        for (int x = 0; x < gridW * 8; x++)
+        {
+            const int2 pixelPos(x, y);
+            float isSky = gIn_Tiles.load(x >> 4, y >> 4).x;
+            if (isSky != 0.0f || x >= c.gRectSize[0] || y >= c.gRectSize[1]) continue;
+            float centerViewZ = P.UnpackViewZ(gIn_ViewZ.load(pixelPos).x);
+            if (centerViewZ > c.gDenoisingRange) continue;
+
+            // the shared-memory tile of the reference holds clamped texels (Preload, :22-38)
+            auto material = [&](int2 p) {
+                float m;
+                NRD_FrontEnd_UnpackNormalAndRoughness(gIn_Normal_Roughness.load(clamp(p, int2(0), rectMax)), m);
+                return m;
+            };
+            float centerMaterialID = material(pixelPos);
+            auto rcrs = [&](const Tex& in, float minMaterial) {
+                float4 center = in.load(pixelPos);
+                float centerLuminance = Color::Luminance(center.xyz());
+                float maxLuminance = -1.0f, minLuminance = 1.0e6f;
+                int2 maxCoords = pixelPos, minCoords = pixelPos;
+                for (int yy = -1; yy <= 1; yy++)
+                    for (int xx = -1; xx <= 1; xx++)
+                    {
+                        int2 p = pixelPos + int2(xx, yy);
+                        if (xx == 0 && yy == 0) continue;
+                        if (p.x < 0 || p.y < 0 || p.x >= c.gRectSize[0] || p.y >= c.gRectSize[1]) continue;
+                        float luminance = Color::Luminance(in.load(p).xyz());
+                        if (P.CompareMaterials(material(p), centerMaterialID, minMaterial))
+                        {
+                            if (luminance > maxLuminance) { maxLuminance = luminance; maxCoords = p; }
+                            if (luminance < minLuminance) { minLuminance = luminance; minCoords = p; }
+                        }
+                    }
+                int2 coords = pixelPos;
+                if (centerLuminance > maxLuminance) coords = maxCoords;
+                if (centerLuminance < minLuminance) coords = minCoords;
+                return float4(in.load(coords).xyz(), center.w);
+            };
+            gOut_Spec.store(pixelPos, rcrs(gIn_Spec, c.gSpecMinMaterial));
+            gOut_Diff.store(pixelPos, rcrs(gIn_Diff, c.gDiffMinMaterial));
+        }
+}
+
 void AtrousSmem(const Pass& P, Tex* t, int gridW, int gridH)
 {
     const CB& c = P.c;
     const Tex &gIn_Tiles = t[0], &gIn_Spec = t[1], &gIn_Diff = t[2], &gIn_HistoryLength = t[3], &gIn_SpecReprojectionConfidence = t[4], &gIn_Normal_Roughness = t[5], &gIn_ViewZ = t[6];
+    const Tex &gIn_SpecConfidence = t[7], &gIn_DiffConfidence = t[8];
     Tex &gOut_Spec = t[9], &gOut_Diff = t[10], &gOut_NormalRoughness = t[11], &gOut_MaterialID = t[12], &gOut_ViewZ = t[13];
     const int2 rectMax(c.gRectSize[0] - 1, c.gRectSize[1] - 1);
     const float gk[2] = {0.44198f, 0.27901f};
@@ -1058,14 +1126,35 @@ void AtrousSmem(const Pass& P, Tex* t, int gridW, int gridH)
                 float2 roughnessWeightParams = Pass::GetRoughnessWeightParams(centerRoughness, c.gRoughnessFraction);
                 float specularReprojectionConfidence = gIn_SpecReprojectionConfidence.load(pixelPos).x;
                 float specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, c.gLuminanceEdgeStoppingRelaxation);
-                float specularNormalWeightParamSimplified = Pass::GetNormalWeightParam2(1.0f, diffuseLobeAngleFraction);
+                // confidence-driven relaxation (:189-201, :226-238)
+                float diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = diffuseLobeAngleFraction;
+                float specularLobeAngleFraction = c.gLobeAngleFraction;
+                if (c.gHasHistoryConfidence)
+                {
+                    float specConfidenceDrivenRelaxation = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - gIn_SpecConfidence.load(pixelPos).x));
+                    float r = saturate(specConfidenceDrivenRelaxation * c.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+                    diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = lerp(diffuseLobeAngleFraction, 1.0f, r);
+                    specularLobeAngleFraction = lerp(specularLobeAngleFraction, 1.0f, r);
+                    r = saturate(specConfidenceDrivenRelaxation * c.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+                    specularLuminanceWeightRelaxation *= 1.0f - r;
+                }
+                float specularNormalWeightParamSimplified = Pass::GetNormalWeightParam2(1.0f, diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight);
                 float2 specularNormalWeightParams = Pass::GetNormalWeightParams_ATrous(centerRoughness, historyLength, specularReprojectionConfidence, c.gNormalEdgeStoppingRelaxation,
-                                                                                       c.gLobeAngleFraction, c.gSpecLobeAngleSlack);
+                                                                                       specularLobeAngleFraction, c.gSpecLobeAngleSlack);
                 float sumWSpecular = 0.0f, sumWDiffuse = 0.0f;
                 float4 sumSpecular(0.0f), sumDiffuse(0.0f);
                 float3 centerV = -normalize(centerWorldPos);
                 float centerDiffuseLuminance = Color::Luminance(sDiff(0, 0).xyz());
                 float diffusePhiLIlluminationInv = 1.0f / max(1.0e-4f, c.gDiffPhiLuminance * sqrt(centerDiffuseVar));
+                float diffuseLuminanceWeightRelaxation = 1.0f;
+                if (c.gHasHistoryConfidence)
+                {
+                    float diffConfidenceDrivenRelaxation = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - gIn_DiffConfidence.load(pixelPos).x));
+                    float r = saturate(diffConfidenceDrivenRelaxation * c.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+                    diffuseLobeAngleFraction = lerp(diffuseLobeAngleFraction, 1.0f, r);
+                    r = saturate(diffConfidenceDrivenRelaxation * c.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+                    diffuseLuminanceWeightRelaxation = 1.0f - r;
+                }
                 float diffuseNormalWeightParam = Pass::GetNormalWeightParam2(1.0f, diffuseLobeAngleFraction);
                 float depthThreshold = c.gDepthThreshold * (c.gOrthoMode == 0.0f ? centerViewZ : 1.0f);
 
@@ -1104,6 +1193,7 @@ void AtrousSmem(const Pass& P, Tex* t, int gridW, int gridH)
                         float4 sd = sDiff(cx, cy);
                         float diffuseLuminanceW = abs(centerDiffuseLuminance - Color::Luminance(sd.xyz())) * diffusePhiLIlluminationInv;
                         diffuseLuminanceW = min(c.gDiffMaxLuminanceRelativeDifference, diffuseLuminanceW);
+                        diffuseLuminanceW *= diffuseLuminanceWeightRelaxation;
                         float wDiffuse = geometryW * normalWDiffuse * exp(-diffuseLuminanceW);
                         wDiffuse = isCenter ? kernelW : wDiffuse;
                         wDiffuse *= float(P.CompareMaterials(sampleMaterialID, centerMaterialID, c.gDiffMinMaterial));
@@ -1163,6 +1253,7 @@ void Atrous(const Pass& P, Tex* t, int gridW, int gridH)
 {
     const CB& c = P.c;
     const Tex &gIn_Tiles = t[0], &gIn_Spec = t[1], &gIn_Diff = t[2], &gIn_HistoryLength = t[3], &gIn_SpecReprojectionConfidence = t[4], &gIn_Normal_Roughness = t[5], &gIn_ViewZ = t[6];
+    const Tex &gIn_SpecConfidence = t[7], &gIn_DiffConfidence = t[8];
     Tex &gOut_Spec = t[9], &gOut_Diff = t[10];
     const float gk[2] = {0.44198f, 0.27901f};
     const int step = (int)c.gStepSize;
@@ -1192,15 +1283,36 @@ void Atrous(const Pass& P, Tex* t, int gridW, int gridH)
             float specularReprojectionConfidence = gIn_SpecReprojectionConfidence.load(pixelPos).x;
             float specularLuminanceWeightRelaxation = 1.0f;
             if (c.gStepSize <= 4) specularLuminanceWeightRelaxation = lerp(1.0f, specularReprojectionConfidence, c.gLuminanceEdgeStoppingRelaxation);
-            float specularNormalWeightParamSimplified = Pass::GetNormalWeightParam2(1.0f, diffuseLobeAngleFraction);
+            // confidence-driven relaxation (:55-67, :95-106)
+            float diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = diffuseLobeAngleFraction;
+            float specularLobeAngleFraction = c.gLobeAngleFraction;
+            if (c.gHasHistoryConfidence)
+            {
+                float specConfidenceDrivenRelaxation = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - gIn_SpecConfidence.load(pixelPos).x));
+                float r = saturate(specConfidenceDrivenRelaxation * c.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+                diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight = lerp(diffuseLobeAngleFraction, 1.0f, r);
+                specularLobeAngleFraction = lerp(specularLobeAngleFraction, 1.0f, r);
+                r = saturate(specConfidenceDrivenRelaxation * c.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+                specularLuminanceWeightRelaxation *= 1.0f - r;
+            }
+            float specularNormalWeightParamSimplified = Pass::GetNormalWeightParam2(1.0f, diffuseLobeAngleFractionForSimplifiedSpecularNormalWeight);
             float2 specularNormalWeightParams = Pass::GetNormalWeightParams_ATrous(centerRoughness, historyLength, specularReprojectionConfidence, c.gNormalEdgeStoppingRelaxation,
-                                                                                   c.gLobeAngleFraction, c.gSpecLobeAngleSlack);
+                                                                                   specularLobeAngleFraction, c.gSpecLobeAngleSlack);
             float sumWSpecular = 0.44198f * 0.44198f;
             float4 sumSpecular = centerSpec * float4(sumWSpecular, sumWSpecular, sumWSpecular, sumWSpecular * sumWSpecular);
 
             float4 centerDiff = gIn_Diff.load(pixelPos);
             float centerDiffuseLuminance = Color::Luminance(centerDiff.xyz());
             float diffusePhiLIlluminationInv = 1.0f / max(1.0e-4f, c.gDiffPhiLuminance * sqrt(centerDiff.w));
+            float diffuseLuminanceWeightRelaxation = 1.0f;
+            if (c.gHasHistoryConfidence)
+            {
+                float diffConfidenceDrivenRelaxation = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - gIn_DiffConfidence.load(pixelPos).x));
+                float r = saturate(diffConfidenceDrivenRelaxation * c.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+                diffuseLobeAngleFraction = lerp(diffuseLobeAngleFraction, 1.0f, r);
+                r = saturate(diffConfidenceDrivenRelaxation * c.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+                diffuseLuminanceWeightRelaxation = 1.0f - r;
+            }
             float diffuseNormalWeightParam = Pass::GetNormalWeightParam2(1.0f, diffuseLobeAngleFraction);
             float sumWDiffuse = 0.44198f * 0.44198f;
             float4 sumDiffuse = centerDiff * float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse);
@@ -1260,6 +1372,7 @@ void Atrous(const Pass& P, Tex* t, int gridW, int gridH)
                         float4 sd = gIn_Diff.load(p);
                         float lw = abs(centerDiffuseLuminance - Color::Luminance(sd.xyz())) * diffusePhiLIlluminationInv;
                         lw = min(c.gDiffMaxLuminanceRelativeDifference, lw);
+                        lw *= diffuseLuminanceWeightRelaxation;
                         wDiffuse *= exp(-lw);
                         sumWDiffuse += wDiffuse;
                         sumDiffuse += float4(wDiffuse, wDiffuse, wDiffuse, wDiffuse * wDiffuse) * sd;
@@ -1283,6 +1396,8 @@ int relax_dispatch_impl(const char* shaderName, const void* constants, int const
     else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_TemporalAccumulation.cs")) TemporalAccumulation(P, tex, gridW, gridH);
     else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_HistoryFix.cs")) HistoryFix(P, tex, gridW, gridH);
     else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_HistoryClamping.cs")) HistoryClamping(P, tex, gridW, gridH);
+    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_Copy.cs")) Copy(P, tex, gridW, gridH);
+    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_AntiFirefly.cs")) AntiFirefly(P, tex, gridW, gridH);
     else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_AtrousSmem.cs")) AtrousSmem(P, tex, gridW, gridH);
     else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_Atrous.cs")) Atrous(P, tex, gridW, gridH);
     else return -1;

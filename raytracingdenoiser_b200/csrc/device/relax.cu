@@ -391,6 +391,7 @@ struct RxTaArgs
 {
     RC c;
     Surf tiles, spec, diff, mv, nr, z, histSpecFast, histDiffFast, histSpec, histDiff, prevNr, prevZ, prevHitDist, prevLength, prevMaterial;
+    Surf specConfidence, diffConfidence, mix; // optional R8_UNORM inputs, read only when the constants say so
     Surf outSpec, outDiff, outSpecFast, outDiffFast, outHitDist, outLength, outConfidence;
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
 
     float disocclusionThresholdMix = 0.0f;
     if (currentMaterialID == c.gStrandMaterialID) disocclusionThresholdMix = pixelSize / (pixelSize + c.gStrandThickness);
+    if (c.gHasDisocclusionThresholdMix) disocclusionThresholdMix = LoadR8Unorm(Near(a.mix), x, y);
     const float disocclusionThreshold = lerpf(c.gDisocclusionThreshold, c.gDisocclusionThresholdAlternate, disocclusionThresholdMix);
 
     // ================= surface motion based history (:35-229)
@@ -579,8 +581,15 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
 
     // ---- diffuse (:579-617)
     {
-        float alpha = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (c.gDiffMaxAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
-        float alphaResponsive = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (c.gDiffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+        float diffMaxAccumulatedFrameNum = c.gDiffMaxAccumulatedFrameNum, diffMaxFastAccumulatedFrameNum = c.gDiffMaxFastAccumulatedFrameNum;
+        if (c.gHasHistoryConfidence)
+        {
+            const float conf = LoadR8Unorm(Near(a.diffConfidence), x, y);
+            diffMaxAccumulatedFrameNum *= conf;
+            diffMaxFastAccumulatedFrameNum *= conf;
+        }
+        float alpha = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (diffMaxAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+        float alphaResponsive = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (diffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
         f4 acc = lerp4(prevDiffSMB, mk4(diffuseIllumination, diffuse2ndMoment), alpha);
         f3 accResponsive = lerp3(prevDiffSMBResponsive, diffuseIllumination, alphaResponsive);
         StoreRGBA16F(a.outDiff, x, y, acc);
@@ -589,8 +598,15 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
     StoreR8Unorm(a.outLength, x, y, __fdiv_rn(historyLength, 255.0f));
 
     // ---- specular (:625-928)
-    const float specHistoryFrames = fminf(c.gSpecMaxAccumulatedFrameNum, historyLength);
-    const float specHistoryResponsiveFrames = fminf(c.gSpecMaxFastAccumulatedFrameNum, historyLength);
+    float specMaxAccumulatedFrameNum = c.gSpecMaxAccumulatedFrameNum, specMaxFastAccumulatedFrameNum = c.gSpecMaxFastAccumulatedFrameNum;
+    if (c.gHasHistoryConfidence)
+    {
+        const float conf = LoadR8Unorm(Near(a.specConfidence), x, y);
+        specMaxAccumulatedFrameNum *= conf;
+        specMaxFastAccumulatedFrameNum *= conf;
+    }
+    const float specHistoryFrames = fminf(specMaxAccumulatedFrameNum, historyLength);
+    const float specHistoryResponsiveFrames = fminf(specMaxFastAccumulatedFrameNum, historyLength);
     const float hitDist = minHitDist3x3 == kInf ? 0.0f : minHitDist3x3;
 
     float curvature;
@@ -967,12 +983,142 @@ __global__ void __launch_bounds__(256) RelaxHistoryClampingKernel(const __grid_c
 }
 
 // =============================================================================================
+// Copy (RELAX_Copy.hlsli:11-24) and anti-firefly (RELAX_AntiFirefly.hlsli:11-222): RelaxSettings::enableAntiFirefly
+// =============================================================================================
+struct RxCopyArgs
+{
+    Surf inSpec, inDiff, outSpec, outDiff;
+    int gridW, gridH; // texels the reference's 8x8 groups cover (stores beyond the texture are dropped)
+    int rowBegin, rowEnd;
+};
+__global__ void __launch_bounds__(256) RelaxCopyKernel(const __grid_constant__ RxCopyArgs a)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.gridW || y >= a.gridH || y >= a.rowEnd || !Inside(a.outSpec, x, y)) return;
+    *TexelPtrRW<uint2>(a.outSpec, x, y) = __ldg(TexelPtr<uint2>(Near(a.inSpec), x, y));
+    *TexelPtrRW<uint2>(a.outDiff, x, y) = __ldg(TexelPtr<uint2>(Near(a.inDiff), x, y));
+}
+
+struct RxAfArgs
+{
+    RC c;
+    Surf tiles, spec, diff, nr, z, outSpec, outDiff;
+    int rowBegin, rowEnd;
+};
+// Cross-bilateral rank-conditioned rank-selection: a centre whose luminance is outside the [min, max] of its same-material 3x3
+// neighbours is replaced by that extreme neighbour.  The CTA stages the (32 + 2) x (8 + 2) tile of both signals' luminance and
+// colour and the material ids in shared memory once (the reference's Preload, :22-38: clamped coordinates); the 8 neighbours are
+// LDS.  Visiting order and strict comparisons are the reference's (ties keep the first extreme met, rows first).
+constexpr int kAfW = 32 + 2, kAfH = 8 + 2;
+__global__ void __launch_bounds__(256) RelaxAntiFireflyKernel(const __grid_constant__ RxAfArgs a)
+{
+    const RC& c = a.c;
+    __shared__ uint2 sSpec[kAfH][kAfW], sDiff[kAfH][kAfW];
+    __shared__ float sSpecLuma[kAfH][kAfW], sDiffLuma[kAfH][kAfW];
+    __shared__ unsigned char sMaterial[kAfH][kAfW];
+    const int W = c.gRectSize[0], H = c.gRectSize[1];
+    const int x0 = blockIdx.x * 32 - 1, y0 = a.rowBegin + blockIdx.y * 8 - 1;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int tileY = min(a.rowBegin + (int)blockIdx.y * 8, H - 1);
+    const bool skyTile = IsSkyTile(a.tiles, min((int)blockIdx.x * 32, W - 1), tileY) && IsSkyTile(a.tiles, min((int)blockIdx.x * 32 + 31, W - 1), tileY);
+    if (skyTile) return; // both 16x16 tiles this CTA covers are sky: nothing to do (uniform, before any barrier)
+    for (int i = tid; i < kAfW * kAfH; i += 256)
+    {
+        const int lx = i % kAfW, ly = i / kAfW;
+        const int px = clampi(x0 + lx, 0, W - 1), py = clampi(y0 + ly, 0, H - 1);
+        const uint2 sp = __ldg(TexelPtr<uint2>(a.spec, px, py)), df = __ldg(TexelPtr<uint2>(a.diff, px, py));
+        sSpec[ly][lx] = sp;
+        sDiff[ly][lx] = df;
+        // rank selection compares luminances: evaluated in the oracle's operation order, so that near-ties select the same texel
+        const f4 sf = UnpackHalf4(sp), dfv = UnpackHalf4(df);
+        sSpecLuma[ly][lx] = __fadd_rn(__fadd_rn(__fmul_rn(sf.x, 0.2126f), __fmul_rn(sf.y, 0.7152f)), __fmul_rn(sf.z, 0.0722f));
+        sDiffLuma[ly][lx] = __fadd_rn(__fadd_rn(__fmul_rn(dfv.x, 0.2126f), __fmul_rn(dfv.y, 0.7152f)), __fmul_rn(dfv.z, 0.0722f));
+        sMaterial[ly][lx] = (unsigned char)(LoadU32(a.nr, px, py) >> 30);
+    }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H || y >= a.rowEnd) return;
+    if (IsSkyTile(a.tiles, x, y)) return;
+    if (UnpackViewZ(c, LoadR32F(Near(a.z), x, y)) > c.gDenoisingRange) return;
+
+    const int cx = threadIdx.x + 1, cy = threadIdx.y + 1;
+    const float centerMaterialID = (float)sMaterial[cy][cx];
+    float maxS = -1.0f, minS = 1.0e6f, maxD = -1.0f, minD = 1.0e6f;
+    int maxSAt = cy * kAfW + cx, minSAt = maxSAt, maxDAt = maxSAt, minDAt = maxSAt;
+#pragma unroll
+    for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+        for (int xx = -1; xx <= 1; xx++)
+        {
+            if (xx == 0 && yy == 0) continue;
+            if (x + xx < 0 || y + yy < 0 || x + xx >= W || y + yy >= H) continue;
+            const int at = (cy + yy) * kAfW + cx + xx;
+            const float m = (float)sMaterial[cy + yy][cx + xx];
+            if (SameMaterial(m, centerMaterialID, c.gSpecMinMaterial))
+            {
+                const float l = sSpecLuma[cy + yy][cx + xx];
+                if (l > maxS) { maxS = l; maxSAt = at; }
+                if (l < minS) { minS = l; minSAt = at; }
+            }
+            if (SameMaterial(m, centerMaterialID, c.gDiffMinMaterial))
+            {
+                const float l = sDiffLuma[cy + yy][cx + xx];
+                if (l > maxD) { maxD = l; maxDAt = at; }
+                if (l < minD) { minD = l; minDAt = at; }
+            }
+        }
+    int sAt = cy * kAfW + cx, dAt = sAt;
+    const float ls = sSpecLuma[cy][cx], ld = sDiffLuma[cy][cx];
+    if (ls > maxS) sAt = maxSAt;
+    if (ls < minS) sAt = minSAt;
+    if (ld > maxD) dAt = maxDAt;
+    if (ld < minD) dAt = minDAt;
+    // colour of the selected texel, second moment of the centre: the .w half is spliced in without a float round trip
+    uint2 so = (&sSpec[0][0])[sAt], dn = (&sDiff[0][0])[dAt];
+    so.y = (so.y & 0xffffu) | (sSpec[cy][cx].y & 0xffff0000u);
+    dn.y = (dn.y & 0xffffu) | (sDiff[cy][cx].y & 0xffff0000u);
+    *TexelPtrRW<uint2>(a.outSpec, x, y) = so;
+    *TexelPtrRW<uint2>(a.outDiff, x, y) = dn;
+}
+
+// confidence-driven relaxation of the A-trous edge stopping (RELAX_Atrous.hlsli:55-67, :95-106; RELAX_AtrousSmem.hlsli:189-201, :226-238)
+struct ConfidenceRelaxation
+{
+    float simplifiedSpecularLobeAngleFraction, specularLobeAngleFraction, diffuseLobeAngleFraction;
+    float specularLuminanceScale, diffuseLuminanceScale; // multiply the luminance weight exponents
+};
+template <class ARGS>
+__device__ __forceinline__ ConfidenceRelaxation RelaxByConfidence(const ARGS& a, int x, int y, float diffuseLobeAngleFraction)
+{
+    const RC& c = a.c;
+    ConfidenceRelaxation r;
+    r.simplifiedSpecularLobeAngleFraction = diffuseLobeAngleFraction;
+    r.specularLobeAngleFraction = c.gLobeAngleFraction;
+    r.diffuseLobeAngleFraction = diffuseLobeAngleFraction;
+    r.specularLuminanceScale = r.diffuseLuminanceScale = 1.0f;
+    if (c.gHasHistoryConfidence)
+    {
+        const float sr = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - LoadR8Unorm(a.specConfidence, x, y)));
+        float t = saturate(sr * c.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+        r.simplifiedSpecularLobeAngleFraction = lerpf(diffuseLobeAngleFraction, 1.0f, t);
+        r.specularLobeAngleFraction = lerpf(c.gLobeAngleFraction, 1.0f, t);
+        r.specularLuminanceScale = 1.0f - saturate(sr * c.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+        const float dr = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - LoadR8Unorm(a.diffConfidence, x, y)));
+        t = saturate(dr * c.gConfidenceDrivenNormalEdgeStoppingRelaxation);
+        r.diffuseLobeAngleFraction = lerpf(diffuseLobeAngleFraction, 1.0f, t);
+        r.diffuseLuminanceScale = 1.0f - saturate(dr * c.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
+    }
+    return r;
+}
+
+// =============================================================================================
 // A-trous, first iteration with spatial variance estimation (RELAX_AtrousSmem.hlsli:11-472)
 // =============================================================================================
 struct RxAtrousArgs
 {
     RC c;
     Surf tiles, spec, diff, length, confidence, nr, z, outSpec, outDiff, outNr, outMaterial, outZ;
+    Surf specConfidence, diffConfidence; // optional R8_UNORM inputs (confidence-driven relaxation), read only when gHasHistoryConfidence
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
@@ -1026,9 +1172,11 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
         const float specularPhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, c.gSpecPhiLuminance * sqrtf(centerSpecularVar));
         const f2 rwp = RoughnessWeightParams(centerRoughness, c.gRoughnessFraction);
         const float specularReprojectionConfidence = LoadR8Unorm(a.confidence, x, y);
-        const float specularLuminanceWeightRelaxation = lerpf(1.0f, specularReprojectionConfidence, c.gLuminanceEdgeStoppingRelaxation);
-        const float diffuseNormalWeightParam = NormalWeightParam2(1.0f, c.gLobeAngleFraction);
-        const f2 snwp = NormalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, c.gNormalEdgeStoppingRelaxation, c.gLobeAngleFraction, c.gSpecLobeAngleSlack);
+        const ConfidenceRelaxation cr = RelaxByConfidence(a, x, y, c.gLobeAngleFraction);
+        const float specularLuminanceWeightRelaxation = lerpf(1.0f, specularReprojectionConfidence, c.gLuminanceEdgeStoppingRelaxation) * cr.specularLuminanceScale;
+        const float diffuseNormalWeightParam = NormalWeightParam2(1.0f, cr.diffuseLobeAngleFraction);
+        const float simplifiedSpecularNormalWeightParam = NormalWeightParam2(1.0f, cr.simplifiedSpecularLobeAngleFraction);
+        const f2 snwp = NormalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, c.gNormalEdgeStoppingRelaxation, cr.specularLobeAngleFraction, c.gSpecLobeAngleSlack);
         const f3 centerV = -normalize(centerWorldPos);
         const float centerDiffuseLuminance = Luma(xyz(LoadRGBA16F(a.diff, x, y)));
         const float diffusePhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, c.gDiffPhiLuminance * sqrtf(centerDiffuseVar));
@@ -1050,20 +1198,21 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
                 const float angles = AcosApprox(dot(centerNormal, sg.N));
                 const f3 sampleV = -normalize(sw + centerWorldPos * c.gRoughnessEdgeStoppingRelaxation);
                 const float normalWSimplified = NonExpWeight(angles, diffuseNormalWeightParam, 0.0f);
+                const float normalWSpecularSimplified = NonExpWeight(angles, simplifiedSpecularNormalWeightParam, 0.0f);
                 const float normalWSpecular = SpecularNormalWeightAtrous(snwp, centerNormal, sg.N, centerV, sampleV);
                 const float roughnessW = NonExpWeight(sg.roughness, rwp.x, rwp.y);
                 const f4 ss = LoadRGBA16F(a.spec, px, py);
                 float lw = fabsf(centerSpecularLuminance - Luma(xyz(ss))) * specularPhiLIlluminationInv;
                 lw = fminf(c.gSpecMaxLuminanceRelativeDifference, lw) * specularLuminanceWeightRelaxation;
                 float wSpecular = geometryW * expf(-lw);
-                wSpecular *= c.gRoughnessEdgeStoppingEnabled ? normalWSpecular * roughnessW : normalWSimplified;
+                wSpecular *= c.gRoughnessEdgeStoppingEnabled ? normalWSpecular * roughnessW : normalWSpecularSimplified;
                 wSpecular = isCenter ? kernelW : wSpecular;
                 wSpecular *= SameMaterial(sg.materialID, centerMaterialID, c.gSpecMinMaterial) ? 1.0f : 0.0f;
                 sumWSpecular += wSpecular;
                 sumSpecular = sumSpecular + ss * wSpecular;
 
                 const f4 sd = LoadRGBA16F(a.diff, px, py);
-                float dlw = fminf(c.gDiffMaxLuminanceRelativeDifference, fabsf(centerDiffuseLuminance - Luma(xyz(sd))) * diffusePhiLIlluminationInv);
+                float dlw = fminf(c.gDiffMaxLuminanceRelativeDifference, fabsf(centerDiffuseLuminance - Luma(xyz(sd))) * diffusePhiLIlluminationInv) * cr.diffuseLuminanceScale;
                 float wDiffuse = geometryW * normalWSimplified * expf(-dlw);
                 wDiffuse = isCenter ? kernelW : wDiffuse;
                 wDiffuse *= SameMaterial(sg.materialID, centerMaterialID, c.gDiffMinMaterial) ? 1.0f : 0.0f;
@@ -1145,8 +1294,11 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
     const float specularReprojectionConfidence = LoadR8Unorm(a.confidence, x, y);
     float specularLuminanceWeightRelaxation = 1.0f;
     if (c.gStepSize <= 4) specularLuminanceWeightRelaxation = lerpf(1.0f, specularReprojectionConfidence, c.gLuminanceEdgeStoppingRelaxation);
-    const float normalWeightParam = NormalWeightParam2(1.0f, diffuseLobeAngleFraction);
-    const f2 snwp = NormalWeightParamsAtrous(g.roughness, historyLength, specularReprojectionConfidence, c.gNormalEdgeStoppingRelaxation, c.gLobeAngleFraction, c.gSpecLobeAngleSlack);
+    const ConfidenceRelaxation cr = RelaxByConfidence(a, x, y, diffuseLobeAngleFraction);
+    specularLuminanceWeightRelaxation *= cr.specularLuminanceScale;
+    const float normalWeightParam = NormalWeightParam2(1.0f, cr.diffuseLobeAngleFraction);
+    const float simplifiedSpecularNormalWeightParam = NormalWeightParam2(1.0f, cr.simplifiedSpecularLobeAngleFraction);
+    const f2 snwp = NormalWeightParamsAtrous(g.roughness, historyLength, specularReprojectionConfidence, c.gNormalEdgeStoppingRelaxation, cr.specularLobeAngleFraction, c.gSpecLobeAngleSlack);
     const float w0 = 0.44198f * 0.44198f;
     float sumWSpecular = w0, sumWDiffuse = w0;
     f4 sumSpecular = mk4(centerSpec.x * w0, centerSpec.y * w0, centerSpec.z * w0, centerSpec.w * (w0 * w0));
@@ -1186,9 +1338,10 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
             const f3 sampleV = -normalize(sw + centerWorldPos * c.gRoughnessEdgeStoppingRelaxation);
             const float angles = AcosApprox(dot(centerNormal, sg.N));
             const float normalWSimplified = NonExpWeight(angles, normalWeightParam, 0.0f);
+            const float normalWSpecularSimplified = NonExpWeight(angles, simplifiedSpecularNormalWeightParam, 0.0f);
             const float normalWSpecular = SpecularNormalWeightAtrous(snwp, centerNormal, sg.N, centerV, sampleV);
             const float roughnessW = NonExpWeight(sg.roughness, rwp.x, rwp.y);
-            float wSpecular = geometryW * (c.gRoughnessEdgeStoppingEnabled ? normalWSpecular * roughnessW : normalWSimplified);
+            float wSpecular = geometryW * (c.gRoughnessEdgeStoppingEnabled ? normalWSpecular * roughnessW : normalWSpecularSimplified);
             wSpecular *= SameMaterial(sg.materialID, g.materialID, c.gSpecMinMaterial) ? 1.0f : 0.0f;
             if (wSpecular > 1e-4f)
             {
@@ -1204,7 +1357,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
             if (wDiffuse > 1e-4f)
             {
                 const f4 sd = LoadRGBA16F(a.diff, px, py);
-                float lw = fminf(c.gDiffMaxLuminanceRelativeDifference, fabsf(centerDiffuseLuminance - Luma(xyz(sd))) * diffusePhiLIlluminationInv);
+                float lw = fminf(c.gDiffMaxLuminanceRelativeDifference, fabsf(centerDiffuseLuminance - Luma(xyz(sd))) * diffusePhiLIlluminationInv) * cr.diffuseLuminanceScale;
                 wDiffuse *= expf(-lw);
                 sumWDiffuse += wDiffuse;
                 sumDiffuse = sumDiffuse + mk4(sd.x * wDiffuse, sd.y * wDiffuse, sd.z * wDiffuse, sd.w * (wDiffuse * wDiffuse));
@@ -1225,7 +1378,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
     const int W = c.gRectSize[0];
     const int rows = p.rowEnd - p.rowBegin;
     if (rows <= 0) return cudaSuccess;
-    if (c.gDiffCheckerboard != 2 || c.gSpecCheckerboard != 2 || c.gHasHistoryConfidence || c.gHasDisocclusionThresholdMix) return cudaErrorNotSupported;
+    if (c.gDiffCheckerboard != 2 || c.gSpecCheckerboard != 2) return cudaErrorNotSupported;
     const dim3 block(32, 8), grid((W + 31) / 32, (rows + 7) / 8);
 
     if (!strcmp(shader, "RELAX_ClassifyTiles.cs"))
@@ -1254,6 +1407,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.mv = p.tex[3]; a.nr = p.tex[4]; a.z = p.tex[5];
         a.histSpecFast = p.tex[6]; a.histDiffFast = p.tex[7]; a.histSpec = p.tex[8]; a.histDiff = p.tex[9];
         a.prevNr = p.tex[10]; a.prevZ = p.tex[11]; a.prevHitDist = p.tex[12]; a.prevLength = p.tex[13]; a.prevMaterial = p.tex[14];
+        a.specConfidence = p.tex[15]; a.diffConfidence = p.tex[16]; a.mix = p.tex[17]; // bound to IN_VIEWZ when absent, never read then
         a.outSpec = p.tex[18]; a.outDiff = p.tex[19]; a.outSpecFast = p.tex[20]; a.outDiffFast = p.tex[21]; a.outHitDist = p.tex[22]; a.outLength = p.tex[23];
         a.outConfidence = p.tex[24];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
@@ -1278,6 +1432,22 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
         NRD_B200_LAUNCH(p, grid, block, a, RelaxHistoryClampingKernel);
     }
+    else if (!strcmp(shader, "RELAX_DiffuseSpecular_Copy.cs"))
+    {
+        RxCopyArgs a;
+        a.inSpec = p.tex[0]; a.inDiff = p.tex[1]; a.outSpec = p.tex[2]; a.outDiff = p.tex[3];
+        a.gridW = p.gridW * 8; a.gridH = p.gridH * 8;
+        a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
+        NRD_B200_LAUNCH(p, dim3((a.outSpec.w + 31) / 32, grid.y), block, a, RelaxCopyKernel);
+    }
+    else if (!strcmp(shader, "RELAX_DiffuseSpecular_AntiFirefly.cs"))
+    {
+        RxAfArgs a;
+        a.c = c;
+        a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.nr = p.tex[3]; a.z = p.tex[4]; a.outSpec = p.tex[5]; a.outDiff = p.tex[6];
+        a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
+        NRD_B200_LAUNCH(p, grid, block, a, RelaxAntiFireflyKernel);
+    }
     else if (!strcmp(shader, "RELAX_DiffuseSpecular_AtrousSmem.cs") || !strcmp(shader, "RELAX_DiffuseSpecular_Atrous.cs"))
     {
         const bool smem = !strcmp(shader, "RELAX_DiffuseSpecular_AtrousSmem.cs");
@@ -1285,6 +1455,7 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.c = c;
         a.guide = p.guide;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.length = p.tex[3]; a.confidence = p.tex[4]; a.nr = p.tex[5]; a.z = p.tex[6];
+        a.specConfidence = p.tex[7]; a.diffConfidence = p.tex[8];
         a.outSpec = p.tex[9]; a.outDiff = p.tex[10];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
         if (smem)

@@ -18,6 +18,9 @@ USER_FORMATS = {
     "OUT_DIFF_RADIANCE_HITDIST": (nrd.Format.RGBA16_SFLOAT, torch.float16, 4),
     "OUT_SPEC_RADIANCE_HITDIST": (nrd.Format.RGBA16_SFLOAT, torch.float16, 4),
     "IN_PENUMBRA": (nrd.Format.R16_SFLOAT, torch.float16, 1),
+    "IN_DIFF_CONFIDENCE": (nrd.Format.R8_UNORM, torch.uint8, 1),
+    "IN_SPEC_CONFIDENCE": (nrd.Format.R8_UNORM, torch.uint8, 1),
+    "IN_DISOCCLUSION_THRESHOLD_MIX": (nrd.Format.R8_UNORM, torch.uint8, 1),
     "OUT_SHADOW_TRANSLUCENCY": (nrd.Format.R8_UNORM, torch.uint8, 1),
     "IN_TRANSLUCENCY": (nrd.Format.RGBA8_UNORM, torch.uint8, 4),
     "OUT_SHADOW_TRANSLUCENCY#RGBA8": (nrd.Format.RGBA8_UNORM, torch.uint8, 4),   # SIGMA_SHADOW_TRANSLUCENCY writes float4
@@ -43,12 +46,33 @@ DENOISER_RESOURCES = {
 }
 
 
+OPTIONAL_INPUTS = {  # CommonSettings flag -> the user textures it makes the passes read, per signal
+    "isHistoryConfidenceAvailable": {"diff": "IN_DIFF_CONFIDENCE", "spec": "IN_SPEC_CONFIDENCE"},
+    "isDisocclusionThresholdMixAvailable": {"any": "IN_DISOCCLUSION_THRESHOLD_MIX"},
+}
+
+
+def denoiser_resources(denoiser, common=None):
+    """User textures of a denoiser, plus the optional inputs the CommonSettings overrides in `common` switch on."""
+    names = list(DENOISER_RESOURCES[denoiser])
+    for flag, extra in OPTIONAL_INPUTS.items():
+        if common and common.get(flag):
+            if "any" in extra:
+                names.append(extra["any"])
+            if "diff" in extra and "IN_DIFF_RADIANCE_HITDIST" in names:
+                names.append(extra["diff"])
+            if "spec" in extra and "IN_SPEC_RADIANCE_HITDIST" in names:
+                names.append(extra["spec"])
+    return names
+
+
 def radiance_mode(denoiser):
     return "relax" if denoiser == nrd.Denoiser.RELAX_DIFFUSE_SPECULAR else "reblur"
 
 
-def make_common_settings(frame, width, height, frame_index, time_delta_ms=16.6667):
-    """CommonSettings for one synthetic frame: 2.5D motion vectors in pixels, deterministic frame time."""
+def make_common_settings(frame, width, height, frame_index, time_delta_ms=16.6667, common=None):
+    """CommonSettings for one synthetic frame: 2.5D motion vectors in pixels, deterministic frame time.  `common` = dict of
+    CommonSettings fields to override (optional inputs, accumulation mode, ...)."""
     cs = nrd.CommonSettings()
     for k, m in (("viewToClipMatrix", frame["viewToClip"]), ("viewToClipMatrixPrev", frame["viewToClip"]),
                  ("worldToViewMatrix", frame["worldToView"]), ("worldToViewMatrixPrev", frame["worldToViewPrev"])):
@@ -60,19 +84,21 @@ def make_common_settings(frame, width, height, frame_index, time_delta_ms=16.666
         getattr(cs, k)[0], getattr(cs, k)[1] = width, height
     cs.timeDeltaBetweenFrames = time_delta_ms
     cs.frameIndex = frame_index
+    for k, v in (common or {}).items():
+        setattr(cs, k, v)
     return cs
 
 
 class GpuDenoiser(object):
     """One denoiser instance + CUDA context + user textures on one GPU (optionally one strip of the frame)."""
 
-    def __init__(self, denoiser, width, height, device=0, identifier=0, settings=None):
-        self.denoiser, self.width, self.height, self.identifier = denoiser, width, height, identifier
+    def __init__(self, denoiser, width, height, device=0, identifier=0, settings=None, common=None):
+        self.denoiser, self.width, self.height, self.identifier, self.common = denoiser, width, height, identifier, common
         self.device = torch.device("cuda", device)
         self.instance = nrd.Instance([(identifier, denoiser)])
         self.ctx = nrd.CudaContext(self.instance, width, height, device=device)
         self.tex = {}
-        for name in DENOISER_RESOURCES[denoiser]:
+        for name in denoiser_resources(denoiser, common):
             fmt, dtype, ch = user_format(denoiser, name)
             shape = (height, width, ch) if ch > 1 else (height, width)
             t = torch.zeros(shape, dtype=dtype, device=self.device)

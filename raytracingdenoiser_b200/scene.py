@@ -246,7 +246,16 @@ class Scene(object):
         transl = torch.cat([((dist_occ >= 65504.0) | sky).to(torch.float32)[..., None], torch.clamp(tcol, 0.0, 1.0)], -1)
         transl = torch.floor(transl * 255.0 + 0.5).to(torch.uint8).contiguous()
 
+        # optional inputs (CommonSettings::isHistoryConfidenceAvailable / isDisocclusionThresholdMixAvailable): smooth screen-space
+        # patterns that move with the frame index, R8_UNORM
+        fu, fv = u * 6.0 + 0.37 * frame_index, v * 4.0 - 0.21 * frame_index
+        diff_conf = 0.5 + 0.5 * torch.sin(fu) * torch.cos(fv)
+        spec_conf = 0.5 + 0.5 * torch.cos(fu * 1.3 + 1.0) * torch.sin(fv * 0.7)
+        mix = torch.clamp(0.5 + 0.5 * torch.sin(fu * 0.5 + fv), 0.0, 1.0)
+        unorm8 = lambda x: torch.floor(torch.clamp(x, 0.0, 1.0) * 255.0 + 0.5).to(torch.uint8).contiguous()
+
         out = {
+            "IN_DIFF_CONFIDENCE": unorm8(diff_conf), "IN_SPEC_CONFIDENCE": unorm8(spec_conf), "IN_DISOCCLUSION_THRESHOLD_MIX": unorm8(mix),
             "IN_TRANSLUCENCY": transl,
             "IN_VIEWZ": viewz.to(torch.float32).contiguous(),
             "IN_NORMAL_ROUGHNESS": pack_normal_roughness(n, rough, mat),

@@ -54,7 +54,7 @@ def alloc(fmt, w, h):
 class CpuDenoiser(object):
     """Mirror of harness.GpuDenoiser on the CPU: same scheduler (the product's), oracle passes, numpy textures."""
 
-    def __init__(self, denoiser, width, height, identifier=0, settings=None, user_formats=None, instance=None, variant=""):
+    def __init__(self, denoiser, width, height, identifier=0, settings=None, user_formats=None, instance=None, variant="", common=None):
         from raytracingdenoiser_b200 import harness
         self.width, self.height, self.identifier = width, height, identifier
         self.lib = oracle_lib(variant)
@@ -67,7 +67,7 @@ class CpuDenoiser(object):
         self.formats = {"permanent": [f for f, _ in desc["permanentPool"]], "transient": [f for f, _ in desc["transientPool"]]}
         self.user = {}
         self.user_fmt = {}
-        for name in harness.DENOISER_RESOURCES[denoiser]:
+        for name in harness.denoiser_resources(denoiser, common):
             fmt = harness.user_format(denoiser, name)[0]
             self.user[name] = alloc(fmt, width, height)
             self.user_fmt[name] = fmt

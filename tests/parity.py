@@ -30,7 +30,7 @@ def _scene_device(width, height, device):
 
 
 class SideBySide(object):
-    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",)):
+    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",), common=None):
         """noise_floor=True: the dispatches whose shader name contains one of `floor_passes` are also run, on the same re-synchronised
         inputs, by two perturbed builds of the oracle -- "fma" (FMA contraction allowed: a second IEEE-legal evaluation of the same
         expressions) and "uv" (the uv of every bilinear fetch moved by one float ulp: the sub-texel position a shader hands to the
@@ -40,15 +40,15 @@ class SideBySide(object):
         of the second moment across a contrast edge) is held to its floor instead -- the kernel must agree with the oracle at
         least as well as the oracle agrees with itself."""
         import torch
-        self.denoiser, self.w, self.h, self.identifier = denoiser, width, height, identifier
-        self.cpu = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, settings=settings)
+        self.denoiser, self.w, self.h, self.identifier, self.common = denoiser, width, height, identifier, common
+        self.cpu = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, settings=settings, common=common)
         self.instance = self.cpu.instance
         self.floor_passes = tuple(floor_passes)
-        self.cpu_alt = [orr.CpuDenoiser(denoiser, width, height, identifier=identifier, instance=self.instance, variant=v) for v in ("fma", "uv")] if noise_floor else []
+        self.cpu_alt = [orr.CpuDenoiser(denoiser, width, height, identifier=identifier, instance=self.instance, variant=v, common=common) for v in ("fma", "uv")] if noise_floor else []
         self.ctx = nrd.CudaContext(self.instance, width, height, device=device)
         self.torch = torch
         self.dev_user = {}
-        for name in harness.DENOISER_RESOURCES[denoiser]:
+        for name in harness.denoiser_resources(denoiser, common):
             fmt, dtype, ch = harness.user_format(denoiser, name)
             t = torch.zeros((height, width, ch) if ch > 1 else (height, width), dtype=dtype, device="cuda:%d" % device)
             self.dev_user[name] = t
@@ -95,14 +95,14 @@ class SideBySide(object):
         for f in range(first_frame, first_frame + warmup):
             fr = self.scene.frame(f, harness.radiance_mode(self.denoiser))
             self.cpu.set_inputs(fr)
-            self.cpu.denoise(harness.make_common_settings(fr, self.w, self.h, f))
+            self.cpu.denoise(harness.make_common_settings(fr, self.w, self.h, f, common=self.common))
             if f == first_frame:
                 self.cpu.set_inputs(fr)
         first_frame += warmup
         for f in range(first_frame, first_frame + frames):
             fr = self.scene.frame(f, harness.radiance_mode(self.denoiser))
             self.cpu.set_inputs(fr)
-            cs = harness.make_common_settings(fr, self.w, self.h, f)
+            cs = harness.make_common_settings(fr, self.w, self.h, f, common=self.common)
             self.instance.set_common_settings(cs)
             r, raw, n = self.instance.get_compute_dispatches_raw([self.identifier])
             assert r == nrd.Result.SUCCESS

@@ -67,3 +67,18 @@ def test_reblur_hit_distance_reconstruction_per_pass(denoiser_name, mode, width,
     assert any("HitDistReconstruction" in r["shader"] for r in report)
     _dump("parity_hitdist_%s_%s.json" % (denoiser_name, mode), report)
     assert not sbs.failures(), sbs.describe_failures()
+
+
+@pytest.mark.parametrize("denoiser_name", ["REBLUR_DIFFUSE_SPECULAR", "REBLUR_SPECULAR"])
+def test_reblur_optional_inputs_per_pass(denoiser_name):
+    """CommonSettings::isHistoryConfidenceAvailable / isDisocclusionThresholdMixAvailable: temporal accumulation reads IN_DIFF_CONFIDENCE /
+    IN_SPEC_CONFIDENCE / IN_DISOCCLUSION_THRESHOLD_MIX (REBLUR_TemporalAccumulation.hlsli:220-221, :327-328, :830-831)."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    common = {"isHistoryConfidenceAvailable": True, "isDisocclusionThresholdMixAvailable": True}
+    sbs = parity.SideBySide(getattr(nrd.Denoiser, denoiser_name), 250, 141, common=common)
+    report = sbs.run_per_pass(4)
+    bound = {res for r in report for res in [r["resource"]]}
+    assert any("TemporalAccumulation" in r["shader"] for r in report), bound
+    _dump("parity_optional_inputs_%s.json" % denoiser_name, report)
+    assert not sbs.failures(), sbs.describe_failures()

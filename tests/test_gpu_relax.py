@@ -71,3 +71,33 @@ def test_relax_against_golden_vector():
         got = t.cpu().numpy().view(ref[name].dtype).reshape(ref[name].shape)
         frac, _ = orr.compare(ref[name], got, nrd.Format.RGBA16_SFLOAT, 1e-3, 1e-4)
         assert frac >= 0.99, (name, frac)
+
+
+def test_relax_optional_inputs_per_pass():
+    """History confidence (temporal accumulation caps + confidence-driven relaxation of the A-trous edge stopping,
+    RELAX_TemporalAccumulation.hlsli:585-632, RELAX_Atrous.hlsli:55-106) and the disocclusion-threshold mix (:483-484)."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    common = {"isHistoryConfidenceAvailable": True, "isDisocclusionThresholdMixAvailable": True}
+    s = nrd.RelaxSettings()
+    s.confidenceDrivenRelaxationMultiplier = 0.7
+    s.confidenceDrivenLuminanceEdgeStoppingRelaxation = 0.4
+    s.confidenceDrivenNormalEdgeStoppingRelaxation = 0.5
+    sbs = parity.SideBySide(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, 250, 141, settings=s, common=common, noise_floor=True)
+    report = sbs.run_per_pass(4)
+    _dump("parity_RELAX_optional_inputs.json", report)
+    assert not sbs.failures(), sbs.describe_failures()
+
+
+def test_relax_anti_firefly_per_pass():
+    """RelaxSettings::enableAntiFirefly: the Copy pass and the 3x3 rank-conditioned rank-selection (RELAX_Copy.hlsli, RELAX_AntiFirefly.hlsli)."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    s = nrd.RelaxSettings()
+    s.enableAntiFirefly = True
+    sbs = parity.SideBySide(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, 250, 141, settings=s, noise_floor=True)
+    report = sbs.run_per_pass(4)
+    names = {r["shader"] for r in report}
+    assert "RELAX_DiffuseSpecular_AntiFirefly.cs" in names and "RELAX_DiffuseSpecular_Copy.cs" in names
+    _dump("parity_RELAX_antifirefly.json", report)
+    assert not sbs.failures(), sbs.describe_failures()

@@ -257,3 +257,47 @@ def test_subtexel_noise_floor_of_relax_temporal_accumulation():
     assert ta > 0.99, worst              # ... mildly (the effect grows with the frame size: ulp(uv) * size)
     # passes that only point-sample are untouched
     assert worst["RELAX_DiffuseSpecular_HistoryClamping.cs"] == 1.0, worst
+
+
+def test_optional_inputs_reach_the_oracle():
+    """History confidence and the disocclusion-threshold mix are bound and read: switching them on changes the temporal result."""
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h = 96, 64
+    sc = scene.Scene(w, h)
+    outs = []
+    for common in (None, {"isHistoryConfidenceAvailable": True}, {"isDisocclusionThresholdMixAvailable": True}):
+        cpu = orr.CpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, w, h, common=common)
+        for f in range(3):
+            fr = sc.frame(f)
+            cpu.set_inputs(fr)
+            cpu.denoise(harness.make_common_settings(fr, w, h, f, common=common))
+            if f == 0:
+                cpu.set_inputs(fr)
+        outs.append(cpu.user["OUT_DIFF_RADIANCE_HITDIST"].copy())
+    assert (outs[0] != outs[1]).any() and (outs[0] != outs[2]).any()
+
+
+def test_relax_anti_firefly_removes_fireflies_in_the_oracle():
+    """The synthetic scene plants 50x fireflies on 0.1 % of the pixels: with enableAntiFirefly the brightest output texel drops."""
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h = 96, 64
+    sc = scene.Scene(w, h)
+    peak = []
+    for af in (False, True):
+        s = nrd.RelaxSettings()
+        s.enableAntiFirefly = af
+        cpu = orr.CpuDenoiser(nrd.Denoiser.RELAX_DIFFUSE_SPECULAR, w, h, settings=s)
+        names = set()
+        for f in range(3):
+            fr = sc.frame(f, "relax")
+            cpu.set_inputs(fr)
+            names |= {d.shaderFileName for d in cpu.denoise(harness.make_common_settings(fr, w, h, f))}
+            if f == 0:
+                cpu.set_inputs(fr)
+        assert ("RELAX_DiffuseSpecular_AntiFirefly.cs" in names) == af
+        out = cpu.user["OUT_DIFF_RADIANCE_HITDIST"].view(np.float16).astype(np.float32)[..., :3]
+        assert np.isfinite(out).all()
+        peak.append(float(out.max()))
+    assert peak[1] <= peak[0]
