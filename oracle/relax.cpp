@@ -399,7 +399,7 @@ void PrePass(const Pass& P, Tex* t, int gridW, int gridH)
         }
 }
 
-void TemporalAccumulation(const Pass& P, Tex* t, int gridW, int gridH)
+void TemporalAccumulation(const Pass& P, Tex* t, int gridW, int gridH, bool hasDiff, bool hasSpec)
 {
     const CB& c = P.c;
     const Tex &gIn_Tiles = t[0], &gIn_Spec = t[1], &gIn_Diff = t[2], &gIn_Mv = t[3], &gIn_Normal_Roughness = t[4], &gIn_ViewZ = t[5], &gHistory_SpecFast = t[6],
@@ -567,7 +567,9 @@ void TemporalAccumulation(const Pass& P, Tex* t, int gridW, int gridH)
                 historyLength = max(historyLength, 1.0f);
             }
             historyLength = c.gResetHistory != 0 ? 1.0f : historyLength;
-            float maxAccumulatedFrameNum = 1.0f + max(c.gDiffMaxAccumulatedFrameNum, c.gSpecMaxAccumulatedFrameNum);
+            // :568-574: only the signals the shader was compiled for take part
+            float maxAccumulatedFrameNum = 1.0f + (hasDiff && hasSpec ? max(c.gDiffMaxAccumulatedFrameNum, c.gSpecMaxAccumulatedFrameNum)
+                                                                     : (hasDiff ? c.gDiffMaxAccumulatedFrameNum : c.gSpecMaxAccumulatedFrameNum));
             historyLength = min(historyLength, maxAccumulatedFrameNum);
 
             uint checkerboard = Sequence::CheckerBoard(pixelPos, c.gFrameIndex);
@@ -1384,28 +1386,80 @@ void Atrous(const Pass& P, Tex* t, int gridW, int gridH)
 }
 } // namespace
 
-int relax_dispatch_impl(const char* shaderName, const void* constants, int constantsSize, Tex* tex, int gridW, int gridH)
+// RELAX_Diffuse_* / RELAX_Specular_* are the RELAX_DiffuseSpecular_* shaders compiled without the other signal (RELAX_DIFFUSE /
+// RELAX_SPECULAR defines): the bindings of the absent signal do not exist (Source/Denoisers/Relax_Diffuse.hpp, Relax_Specular.hpp
+// list the same passes minus those resources).  The passes above are written for both signals; a one-signal dispatch is expanded to
+// that layout with NULL textures (0 x 0: every load reads 0, every store is dropped) in the places of the absent signal.  Per pass:
+// the binding layout of the two-signal shader, c = common, s = specular only, d = diffuse only.
+struct PassLayout
+{
+    const char* pass;
+    const char* layout;
+};
+const PassLayout kLayouts[] = {
+    {"PrePass.cs", "csdccsd"},
+    {"TemporalAccumulation.cs", "csdcccsdsdccsccsdcsdsdscs"},
+    {"HistoryFix.cs", "csdcccsd"},
+    {"HistoryClamping.cs", "ccsdsdsdcsdsdc"},
+    {"Copy.cs", "sdsd"},
+    {"AntiFirefly.cs", "csdccsd"},
+    {"AtrousSmem.cs", "csdcsccsdsdccc"},
+    {"Atrous.cs", "csdcsccsdsd"},
+};
+
+int relax_dispatch_impl(const char* shaderName, const void* constants, int constantsSize, Tex* tex, int texNum, int gridW, int gridH)
 {
     if (constantsSize < 704) return -2;
     CB cb;
     memset(&cb, 0, sizeof(cb));
     memcpy(&cb, constants, constantsSize < (int)sizeof(CB) ? constantsSize : (int)sizeof(CB));
     Pass P(cb);
-    if (!strcmp(shaderName, "RELAX_ClassifyTiles.cs")) ClassifyTiles(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_PrePass.cs")) PrePass(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_TemporalAccumulation.cs")) TemporalAccumulation(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_HistoryFix.cs")) HistoryFix(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_HistoryClamping.cs")) HistoryClamping(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_Copy.cs")) Copy(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_AntiFirefly.cs")) AntiFirefly(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_AtrousSmem.cs")) AtrousSmem(P, tex, gridW, gridH);
-    else if (!strcmp(shaderName, "RELAX_DiffuseSpecular_Atrous.cs")) Atrous(P, tex, gridW, gridH);
+    if (!strcmp(shaderName, "RELAX_ClassifyTiles.cs"))
+    {
+        ClassifyTiles(P, tex, gridW, gridH);
+        return 0;
+    }
+    if (strncmp(shaderName, "RELAX_", 6) != 0) return -1;
+    const char* p = shaderName + 6;
+    bool hasDiff = false, hasSpec = false;
+    if (!strncmp(p, "DiffuseSpecular_", 16)) { hasDiff = hasSpec = true; p += 16; }
+    else if (!strncmp(p, "Diffuse_", 8)) { hasDiff = true; p += 8; }
+    else if (!strncmp(p, "Specular_", 9)) { hasSpec = true; p += 9; }
+    else return -1;
+
+    const PassLayout* layout = nullptr;
+    for (const PassLayout& l : kLayouts)
+        if (!strcmp(p, l.pass)) layout = &l;
+    if (!layout) return -1;
+    Tex t[32];
+    int k = 0;
+    const int n = (int)strlen(layout->layout);
+    for (int i = 0; i < n; i++)
+    {
+        const char kind = layout->layout[i];
+        const bool present = kind == 'c' || (kind == 's' && hasSpec) || (kind == 'd' && hasDiff);
+        if (present)
+        {
+            if (k >= texNum) return -3;
+            t[i] = tex[k++];
+        }
+    }
+    if (k != texNum) return -3;
+
+    if (!strcmp(p, "PrePass.cs")) PrePass(P, t, gridW, gridH);
+    else if (!strcmp(p, "TemporalAccumulation.cs")) TemporalAccumulation(P, t, gridW, gridH, hasDiff, hasSpec);
+    else if (!strcmp(p, "HistoryFix.cs")) HistoryFix(P, t, gridW, gridH);
+    else if (!strcmp(p, "HistoryClamping.cs")) HistoryClamping(P, t, gridW, gridH);
+    else if (!strcmp(p, "Copy.cs")) Copy(P, t, gridW, gridH);
+    else if (!strcmp(p, "AntiFirefly.cs")) AntiFirefly(P, t, gridW, gridH);
+    else if (!strcmp(p, "AtrousSmem.cs")) AtrousSmem(P, t, gridW, gridH);
+    else if (!strcmp(p, "Atrous.cs")) Atrous(P, t, gridW, gridH);
     else return -1;
     return 0;
 }
 } // namespace hlsl
 
-int oracle_relax_dispatch(const char* shaderName, const void* constants, int constantsSize, hlsl::Tex* tex, int, int gridW, int gridH)
+int oracle_relax_dispatch(const char* shaderName, const void* constants, int constantsSize, hlsl::Tex* tex, int texNum, int gridW, int gridH)
 {
-    return hlsl::relax_dispatch_impl(shaderName, constants, constantsSize, tex, gridW, gridH);
+    return hlsl::relax_dispatch_impl(shaderName, constants, constantsSize, tex, texNum, gridW, gridH);
 }

@@ -253,7 +253,7 @@ struct RxPrePassArgs
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
-__global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant__ RxPrePassArgs a)
+template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant__ RxPrePassArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant_
     };
 
     // ---- diffuse
+    if (DIFF)
     {
         f4 diff = LoadRGBA16F(a.diff, x, y);
         if (c.gDiffBlurRadius > 0.0f)
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant_
         StoreRGBA16F(a.outDiff, x, y, min4(max4(diff, 0.0f), kFp16MaxRx));
     }
     // ---- specular
+    if (SPEC)
     {
         f4 spec = LoadRGBA16F(a.spec, x, y);
         spec.w = fmaxf(0.0f, fminf(c.gDenoisingRange, spec.w));
@@ -396,7 +398,7 @@ struct RxTaArgs
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
-__global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const __grid_constant__ RxTaArgs a)
+template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const __grid_constant__ RxTaArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 4 + threadIdx.y;
@@ -438,8 +440,8 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
         prevUVSMB = GetScreenUv(c.gWorldToClipPrev, prevWorldPos);
     }
 
-    const f3 diffuseIllumination = xyz(LoadRGBA16F(a.diff, x, y));
-    const f4 specularIllumination = LoadRGBA16F(a.spec, x, y);
+    const f3 diffuseIllumination = DIFF ? xyz(LoadRGBA16F(a.diff, x, y)) : mk3(0.0f);
+    const f4 specularIllumination = SPEC ? LoadRGBA16F(a.spec, x, y) : mk4(0.0f);
 
     // ---- 3x3: min hit distance and average normal (shared-memory preload in the reference, :360-374)
     float minHitDist3x3 = specularIllumination.w == 0.0f ? kInf : specularIllumination.w;
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
             if (i == 0 && j == 0) continue;
             int px = clampi(x + i, 0, W - 1), py = clampi(y + j, 0, H - 1);
             f3 n = RX_GUIDE(a, px, py).N;
-            float h = LoadRGBA16F(a.spec, px, py).w;
+            const float h = SPEC ? LoadRGBA16F(a.spec, px, py).w : 0.0f;
             minHitDist3x3 = fminf(minHitDist3x3, h == 0.0f ? kInf : h);
             currentNormalAveraged = currentNormalAveraged + n;
             if (i == 1 && j == 0) n10 = n;
@@ -536,10 +538,10 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
         const f4 bcw = mk4(tapsValid.x * (omx * omy), tapsValid.y * (bwx * omy), tapsValid.z * (omx * bwy), tapsValid.w * (bwx * bwy));
         const bool useBicubic = bicubicFootprintValid > 0.0f;
         const CatRomSetup cr = SetupCatRom(prevPixelPos, c.gResourceSizeInvPrev, bcw, useBicubic);
-        prevDiffSMB = max4(ResolveCatRom4(cr, a.histDiff), 0.0f);
-        prevSpecSMB = max4(ResolveCatRom4(cr, a.histSpec), 0.0f);
-        prevDiffSMBResponsive = xyz(max4(ResolveCatRom4(cr, a.histDiffFast), 0.0f));
-        prevSpecSMBResponsive = xyz(max4(ResolveCatRom4(cr, a.histSpecFast), 0.0f));
+        prevDiffSMB = DIFF ? max4(ResolveCatRom4(cr, a.histDiff), 0.0f) : mk4(0.0f);
+        prevSpecSMB = SPEC ? max4(ResolveCatRom4(cr, a.histSpec), 0.0f) : mk4(0.0f);
+        prevDiffSMBResponsive = DIFF ? xyz(max4(ResolveCatRom4(cr, a.histDiffFast), 0.0f)) : mk3(0.0f);
+        prevSpecSMBResponsive = SPEC ? xyz(max4(ResolveCatRom4(cr, a.histSpecFast), 0.0f)) : mk3(0.0f);
 
         const float wsum = bcw.x + bcw.y + bcw.z + bcw.w;
         {
@@ -549,6 +551,8 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
             float o = s00 * bcw.x + s10 * bcw.y + s01 * bcw.z + s11 * bcw.w;
             historyLength = 255.0f * (wsum < 0.0001f ? 0.0f : o / wsum);
         }
+        prevReflectionHitTSMB = 0.0f;
+        if (SPEC)
         {
             float s00 = FetchClamped1(a.prevHitDist, bx, by), s10 = FetchClamped1(a.prevHitDist, bx + 1, by);
             float s01 = FetchClamped1(a.prevHitDist, bx, by + 1), s11 = FetchClamped1(a.prevHitDist, bx + 1, by + 1);
@@ -577,9 +581,11 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
         historyLength = fmaxf(historyLength, 1.0f);
     }
     historyLength = c.gResetHistory != 0 ? 1.0f : historyLength;
-    historyLength = fminf(historyLength, 1.0f + fmaxf(c.gDiffMaxAccumulatedFrameNum, c.gSpecMaxAccumulatedFrameNum));
+    // (:568-574) only the signals this kernel was compiled for take part
+    historyLength = fminf(historyLength, 1.0f + (DIFF && SPEC ? fmaxf(c.gDiffMaxAccumulatedFrameNum, c.gSpecMaxAccumulatedFrameNum) : (DIFF ? c.gDiffMaxAccumulatedFrameNum : c.gSpecMaxAccumulatedFrameNum)));
 
     // ---- diffuse (:579-617)
+    if (DIFF)
     {
         float diffMaxAccumulatedFrameNum = c.gDiffMaxAccumulatedFrameNum, diffMaxFastAccumulatedFrameNum = c.gDiffMaxFastAccumulatedFrameNum;
         if (c.gHasHistoryConfidence)
@@ -596,6 +602,7 @@ __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const 
         StoreRGBA16F(a.outDiffFast, x, y, mk4(accResponsive, 0.0f));
     }
     StoreR8Unorm(a.outLength, x, y, __fdiv_rn(historyLength, 255.0f));
+    if (!SPEC) return;
 
     // ---- specular (:625-928)
     float specMaxAccumulatedFrameNum = c.gSpecMaxAccumulatedFrameNum, specMaxFastAccumulatedFrameNum = c.gSpecMaxFastAccumulatedFrameNum;
@@ -816,7 +823,7 @@ struct RxHfArgs
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
-__global__ void __launch_bounds__(256) RelaxHistoryFixKernel(const __grid_constant__ RxHfArgs a)
+template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxHistoryFixKernel(const __grid_constant__ RxHfArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
@@ -832,7 +839,7 @@ __global__ void __launch_bounds__(256) RelaxHistoryFixKernel(const __grid_consta
     const f3 centerWorldPos = PinnedCurWorldPos(c, x, y, centerViewZ);
     const f3 centerV = -PinnedNormalize(centerWorldPos);
     const float depthThreshold = __fmul_rn(c.gDepthThreshold, c.gOrthoMode == 0.0f ? centerViewZ : 1.0f);
-    f4 diffSum = LoadRGBA16F(a.diff, x, y), specSum = LoadRGBA16F(a.spec, x, y);
+    f4 diffSum = DIFF ? LoadRGBA16F(a.diff, x, y) : mk4(0.0f), specSum = SPEC ? LoadRGBA16F(a.spec, x, y) : mk4(0.0f);
     float diffWSum = 1.0f, specWSum = 1.0f;
     const f2 snwp = NormalWeightParamsAtrous(g.roughness, 5.0f, 1.0f, 0.0f, c.gLobeAngleFraction, c.gSpecLobeAngleSlack);
     const float normalPower = fmaxf(c.gHistoryFixEdgeStoppingNormalPower, 0.01f);
@@ -850,9 +857,9 @@ __global__ void __launch_bounds__(256) RelaxHistoryFixKernel(const __grid_consta
             f3 sw = PinnedCurWorldPos(c, sx, sy, sz);
             f3 dv = PinnedSub(sw, centerWorldPos);
             float geometryWeight = fabsf(PinnedDot3(dv.x, dv.y, dv.z, g.N)) < depthThreshold ? 1.0f : 0.0f;
-            float dw = geometryWeight * powf(fmaxf(0.01f, dot(g.N, sg.N)), normalPower);
+            float dw = DIFF ? geometryWeight * powf(fmaxf(0.01f, dot(g.N, sg.N)), normalPower) : 0.0f;
             dw *= SameMaterial(sg.materialID, g.materialID, c.gDiffMinMaterial) ? 1.0f : 0.0f;
-            if (dw > 1e-4f)
+            if (DIFF && dw > 1e-4f)
             {
                 diffSum = diffSum + LoadRGBA16F(a.diff, sx, sy) * dw;
                 diffWSum += dw;
@@ -862,14 +869,14 @@ __global__ void __launch_bounds__(256) RelaxHistoryFixKernel(const __grid_consta
             float cosa = fminf(PinnedDot3(g.N.x, g.N.y, g.N.z, sg.N), PinnedDot3(centerV.x, centerV.y, centerV.z, sampleV));
             float swt = geometryWeight * saturate(1.0f - SmoothStep(0.0f, snwp.x, AcosApprox(cosa)) * snwp.y);
             swt *= SameMaterial(sg.materialID, g.materialID, c.gSpecMinMaterial) ? 1.0f : 0.0f;
-            if (swt > 1e-4f)
+            if (SPEC && swt > 1e-4f)
             {
                 specSum = specSum + LoadRGBA16F(a.spec, sx, sy) * swt;
                 specWSum += swt;
             }
         }
-    StoreRGBA16F(a.outDiff, x, y, mk4(diffSum.x / diffWSum, diffSum.y / diffWSum, diffSum.z / diffWSum, diffSum.w / diffWSum));
-    StoreRGBA16F(a.outSpec, x, y, mk4(specSum.x / specWSum, specSum.y / specWSum, specSum.z / specWSum, specSum.w / specWSum));
+    if (DIFF) StoreRGBA16F(a.outDiff, x, y, mk4(diffSum.x / diffWSum, diffSum.y / diffWSum, diffSum.z / diffWSum, diffSum.w / diffWSum));
+    if (SPEC) StoreRGBA16F(a.outSpec, x, y, mk4(specSum.x / specWSum, specSum.y / specWSum, specSum.z / specWSum, specSum.w / specWSum));
 }
 
 // =============================================================================================
@@ -969,7 +976,7 @@ __device__ __forceinline__ void ClampSignal(const RC& c, const Surf& zSurf, int 
     StoreRGBA16F(outSlow, x, y, outS);
     StoreRGBA16F(outFast, x, y, outR);
 }
-__global__ void __launch_bounds__(256) RelaxHistoryClampingKernel(const __grid_constant__ RxHcArgs a)
+template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxHistoryClampingKernel(const __grid_constant__ RxHcArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
@@ -977,8 +984,8 @@ __global__ void __launch_bounds__(256) RelaxHistoryClampingKernel(const __grid_c
     if (IsSkyTile(a.tiles, x, y)) return;
     if (!(LoadR32F(a.z, x, y) < c.gDenoisingRange)) return;
     const float historyLength = LoadR8Times255(a.length, x, y);
-    ClampSignal<true>(c, a.z, x, y, historyLength, a.specNoisy, a.spec, a.specFast, a.outSpec, a.outSpecFast);
-    ClampSignal<false>(c, a.z, x, y, historyLength, a.diffNoisy, a.diff, a.diffFast, a.outDiff, a.outDiffFast);
+    if (SPEC) ClampSignal<true>(c, a.z, x, y, historyLength, a.specNoisy, a.spec, a.specFast, a.outSpec, a.outSpecFast);
+    if (DIFF) ClampSignal<false>(c, a.z, x, y, historyLength, a.diffNoisy, a.diff, a.diffFast, a.outDiff, a.outDiffFast);
     StoreU8(a.outLength, x, y, LoadU8(a.length, x, y));
 }
 
@@ -991,12 +998,12 @@ struct RxCopyArgs
     int gridW, gridH; // texels the reference's 8x8 groups cover (stores beyond the texture are dropped)
     int rowBegin, rowEnd;
 };
-__global__ void __launch_bounds__(256) RelaxCopyKernel(const __grid_constant__ RxCopyArgs a)
+template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxCopyKernel(const __grid_constant__ RxCopyArgs a)
 {
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
-    if (x >= a.gridW || y >= a.gridH || y >= a.rowEnd || !Inside(a.outSpec, x, y)) return;
-    *TexelPtrRW<uint2>(a.outSpec, x, y) = __ldg(TexelPtr<uint2>(Near(a.inSpec), x, y));
-    *TexelPtrRW<uint2>(a.outDiff, x, y) = __ldg(TexelPtr<uint2>(Near(a.inDiff), x, y));
+    if (x >= a.gridW || y >= a.gridH || y >= a.rowEnd || !Inside(SPEC ? a.outSpec : a.outDiff, x, y)) return;
+    if (SPEC) *TexelPtrRW<uint2>(a.outSpec, x, y) = __ldg(TexelPtr<uint2>(Near(a.inSpec), x, y));
+    if (DIFF) *TexelPtrRW<uint2>(a.outDiff, x, y) = __ldg(TexelPtr<uint2>(Near(a.inDiff), x, y));
 }
 
 struct RxAfArgs
@@ -1010,7 +1017,7 @@ struct RxAfArgs
 // colour and the material ids in shared memory once (the reference's Preload, :22-38: clamped coordinates); the 8 neighbours are
 // LDS.  Visiting order and strict comparisons are the reference's (ties keep the first extreme met, rows first).
 constexpr int kAfW = 32 + 2, kAfH = 8 + 2;
-__global__ void __launch_bounds__(256) RelaxAntiFireflyKernel(const __grid_constant__ RxAfArgs a)
+template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAntiFireflyKernel(const __grid_constant__ RxAfArgs a)
 {
     const RC& c = a.c;
     __shared__ uint2 sSpec[kAfH][kAfW], sDiff[kAfH][kAfW];
@@ -1026,7 +1033,7 @@ __global__ void __launch_bounds__(256) RelaxAntiFireflyKernel(const __grid_const
     {
         const int lx = i % kAfW, ly = i / kAfW;
         const int px = clampi(x0 + lx, 0, W - 1), py = clampi(y0 + ly, 0, H - 1);
-        const uint2 sp = __ldg(TexelPtr<uint2>(a.spec, px, py)), df = __ldg(TexelPtr<uint2>(a.diff, px, py));
+        const uint2 sp = SPEC ? __ldg(TexelPtr<uint2>(a.spec, px, py)) : make_uint2(0u, 0u), df = DIFF ? __ldg(TexelPtr<uint2>(a.diff, px, py)) : make_uint2(0u, 0u);
         sSpec[ly][lx] = sp;
         sDiff[ly][lx] = df;
         // rank selection compares luminances: evaluated in the oracle's operation order, so that near-ties select the same texel
@@ -1077,9 +1084,12 @@ __global__ void __launch_bounds__(256) RelaxAntiFireflyKernel(const __grid_const
     uint2 so = (&sSpec[0][0])[sAt], dn = (&sDiff[0][0])[dAt];
     so.y = (so.y & 0xffffu) | (sSpec[cy][cx].y & 0xffff0000u);
     dn.y = (dn.y & 0xffffu) | (sDiff[cy][cx].y & 0xffff0000u);
-    *TexelPtrRW<uint2>(a.outSpec, x, y) = so;
-    *TexelPtrRW<uint2>(a.outDiff, x, y) = dn;
+    if (SPEC) *TexelPtrRW<uint2>(a.outSpec, x, y) = so;
+    if (DIFF) *TexelPtrRW<uint2>(a.outDiff, x, y) = dn;
 }
+
+// signal load of a kernel compiled for one or both signals: the absent signal reads as zero and its arithmetic is dead code
+template <bool PRESENT> __device__ __forceinline__ f4 LoadSignal(const Surf& s, int x, int y) { return PRESENT ? LoadRGBA16F(s, x, y) : mk4(0.0f); }
 
 // confidence-driven relaxation of the A-trous edge stopping (RELAX_Atrous.hlsli:55-67, :95-106; RELAX_AtrousSmem.hlsli:189-201, :226-238)
 struct ConfidenceRelaxation
@@ -1087,7 +1097,7 @@ struct ConfidenceRelaxation
     float simplifiedSpecularLobeAngleFraction, specularLobeAngleFraction, diffuseLobeAngleFraction;
     float specularLuminanceScale, diffuseLuminanceScale; // multiply the luminance weight exponents
 };
-template <class ARGS>
+template <bool DIFF, bool SPEC, class ARGS>
 __device__ __forceinline__ ConfidenceRelaxation RelaxByConfidence(const ARGS& a, int x, int y, float diffuseLobeAngleFraction)
 {
     const RC& c = a.c;
@@ -1098,12 +1108,12 @@ __device__ __forceinline__ ConfidenceRelaxation RelaxByConfidence(const ARGS& a,
     r.specularLuminanceScale = r.diffuseLuminanceScale = 1.0f;
     if (c.gHasHistoryConfidence)
     {
-        const float sr = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - LoadR8Unorm(a.specConfidence, x, y)));
+        const float sr = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - (SPEC ? LoadR8Unorm(a.specConfidence, x, y) : 1.0f)));
         float t = saturate(sr * c.gConfidenceDrivenNormalEdgeStoppingRelaxation);
         r.simplifiedSpecularLobeAngleFraction = lerpf(diffuseLobeAngleFraction, 1.0f, t);
         r.specularLobeAngleFraction = lerpf(c.gLobeAngleFraction, 1.0f, t);
         r.specularLuminanceScale = 1.0f - saturate(sr * c.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
-        const float dr = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - LoadR8Unorm(a.diffConfidence, x, y)));
+        const float dr = saturate(c.gConfidenceDrivenRelaxationMultiplier * (1.0f - (DIFF ? LoadR8Unorm(a.diffConfidence, x, y) : 1.0f)));
         t = saturate(dr * c.gConfidenceDrivenNormalEdgeStoppingRelaxation);
         r.diffuseLobeAngleFraction = lerpf(diffuseLobeAngleFraction, 1.0f, t);
         r.diffuseLuminanceScale = 1.0f - saturate(dr * c.gConfidenceDrivenLuminanceEdgeStoppingRelaxation);
@@ -1122,7 +1132,7 @@ struct RxAtrousArgs
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
-__global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_constant__ RxAtrousArgs a)
+template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_constant__ RxAtrousArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
@@ -1162,23 +1172,23 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
             {
                 int px = clampi(x + dx, 0, W - 1), py = clampi(y + dy, 0, H - 1);
                 float k = (dx == 0 ? 0.5f : 0.25f) * (dy == 0 ? 0.5f : 0.25f);
-                specSum = specSum + LoadRGBA16F(a.spec, px, py) * k;
-                diffSum = diffSum + LoadRGBA16F(a.diff, px, py) * k;
+                specSum = specSum + LoadSignal<SPEC>(a.spec, px, py) * k;
+                diffSum = diffSum + LoadSignal<DIFF>(a.diff, px, py) * k;
             }
         const float s1 = Luma(xyz(specSum)), d1 = Luma(xyz(diffSum));
         const float centerSpecularVar = fmaxf(0.0f, specSum.w - s1 * s1), centerDiffuseVar = fmaxf(0.0f, diffSum.w - d1 * d1);
 
-        const float centerSpecularLuminance = Luma(xyz(LoadRGBA16F(a.spec, x, y)));
+        const float centerSpecularLuminance = Luma(xyz(LoadSignal<SPEC>(a.spec, x, y)));
         const float specularPhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, c.gSpecPhiLuminance * sqrtf(centerSpecularVar));
         const f2 rwp = RoughnessWeightParams(centerRoughness, c.gRoughnessFraction);
-        const float specularReprojectionConfidence = LoadR8Unorm(a.confidence, x, y);
-        const ConfidenceRelaxation cr = RelaxByConfidence(a, x, y, c.gLobeAngleFraction);
+        const float specularReprojectionConfidence = (SPEC ? LoadR8Unorm(a.confidence, x, y) : 1.0f);
+        const ConfidenceRelaxation cr = RelaxByConfidence<DIFF, SPEC>(a, x, y, c.gLobeAngleFraction);
         const float specularLuminanceWeightRelaxation = lerpf(1.0f, specularReprojectionConfidence, c.gLuminanceEdgeStoppingRelaxation) * cr.specularLuminanceScale;
         const float diffuseNormalWeightParam = NormalWeightParam2(1.0f, cr.diffuseLobeAngleFraction);
         const float simplifiedSpecularNormalWeightParam = NormalWeightParam2(1.0f, cr.simplifiedSpecularLobeAngleFraction);
         const f2 snwp = NormalWeightParamsAtrous(centerRoughness, historyLength, specularReprojectionConfidence, c.gNormalEdgeStoppingRelaxation, cr.specularLobeAngleFraction, c.gSpecLobeAngleSlack);
         const f3 centerV = -normalize(centerWorldPos);
-        const float centerDiffuseLuminance = Luma(xyz(LoadRGBA16F(a.diff, x, y)));
+        const float centerDiffuseLuminance = Luma(xyz(LoadSignal<DIFF>(a.diff, x, y)));
         const float diffusePhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, c.gDiffPhiLuminance * sqrtf(centerDiffuseVar));
         const float depthThreshold = c.gDepthThreshold * (c.gOrthoMode == 0.0f ? centerViewZ : 1.0f);
         float sumWSpecular = 0.0f, sumWDiffuse = 0.0f;
@@ -1201,7 +1211,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
                 const float normalWSpecularSimplified = NonExpWeight(angles, simplifiedSpecularNormalWeightParam, 0.0f);
                 const float normalWSpecular = SpecularNormalWeightAtrous(snwp, centerNormal, sg.N, centerV, sampleV);
                 const float roughnessW = NonExpWeight(sg.roughness, rwp.x, rwp.y);
-                const f4 ss = LoadRGBA16F(a.spec, px, py);
+                const f4 ss = LoadSignal<SPEC>(a.spec, px, py);
                 float lw = fabsf(centerSpecularLuminance - Luma(xyz(ss))) * specularPhiLIlluminationInv;
                 lw = fminf(c.gSpecMaxLuminanceRelativeDifference, lw) * specularLuminanceWeightRelaxation;
                 float wSpecular = geometryW * expf(-lw);
@@ -1211,7 +1221,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
                 sumWSpecular += wSpecular;
                 sumSpecular = sumSpecular + ss * wSpecular;
 
-                const f4 sd = LoadRGBA16F(a.diff, px, py);
+                const f4 sd = LoadSignal<DIFF>(a.diff, px, py);
                 float dlw = fminf(c.gDiffMaxLuminanceRelativeDifference, fabsf(centerDiffuseLuminance - Luma(xyz(sd))) * diffusePhiLIlluminationInv) * cr.diffuseLuminanceScale;
                 float wDiffuse = geometryW * normalWSimplified * expf(-dlw);
                 wDiffuse = isCenter ? kernelW : wDiffuse;
@@ -1222,11 +1232,11 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
         sumWSpecular = fmaxf(sumWSpecular, 1e-6f);
         sumSpecular = mk4(sumSpecular.x / sumWSpecular, sumSpecular.y / sumWSpecular, sumSpecular.z / sumWSpecular, sumSpecular.w / sumWSpecular);
         const float sp1 = Luma(xyz(sumSpecular));
-        StoreRGBA16F(a.outSpec, x, y, mk4(xyz(sumSpecular), fmaxf(0.0f, sumSpecular.w - sp1 * sp1)));
+        if (SPEC) StoreRGBA16F(a.outSpec, x, y, mk4(xyz(sumSpecular), fmaxf(0.0f, sumSpecular.w - sp1 * sp1)));
         sumWDiffuse = fmaxf(sumWDiffuse, 1e-6f);
         sumDiffuse = mk4(sumDiffuse.x / sumWDiffuse, sumDiffuse.y / sumWDiffuse, sumDiffuse.z / sumWDiffuse, sumDiffuse.w / sumWDiffuse);
         const float dp1 = Luma(xyz(sumDiffuse));
-        StoreRGBA16F(a.outDiff, x, y, mk4(xyz(sumDiffuse), fmaxf(0.0f, sumDiffuse.w - dp1 * dp1)));
+        if (DIFF) StoreRGBA16F(a.outDiff, x, y, mk4(xyz(sumDiffuse), fmaxf(0.0f, sumDiffuse.w - dp1 * dp1)));
     }
     else
     {
@@ -1242,13 +1252,13 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
                 const int px = clampi(x + cx, 0, W - 1), py = clampi(y + cy, 0, H - 1);
                 const Guide sg = RX_GUIDE(a, px, py);
                 const float normalW = NonExpWeight(AcosApprox(dot(centerNormal, sg.N)), normalWeightParam, 0.0f);
-                const f4 ss = LoadRGBA16F(a.spec, px, py);
+                const f4 ss = LoadSignal<SPEC>(a.spec, px, py);
                 const float specularW = normalW * (SameMaterial(sg.materialID, centerMaterialID, c.gSpecMinMaterial) ? 1.0f : 0.0f);
                 sumWS += specularW;
                 sumS = sumS + xyz(ss) * specularW;
                 sumS1 += Luma(xyz(ss)) * specularW;
                 sumS2 += ss.w * specularW;
-                const f4 sd = LoadRGBA16F(a.diff, px, py);
+                const f4 sd = LoadSignal<DIFF>(a.diff, px, py);
                 const float diffuseW = normalW * (SameMaterial(sg.materialID, centerMaterialID, c.gDiffMinMaterial) ? 1.0f : 0.0f);
                 sumWD += diffuseW;
                 sumD = sumD + xyz(sd) * diffuseW;
@@ -1259,18 +1269,18 @@ __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_consta
         sumWS = fmaxf(sumWS, 1e-6f);
         sumS1 /= sumWS;
         sumS2 /= sumWS;
-        StoreRGBA16F(a.outSpec, x, y, mk4(sumS.x / sumWS, sumS.y / sumWS, sumS.z / sumWS, fmaxf(0.0f, sumS2 - sumS1 * sumS1) * boost));
+        if (SPEC) StoreRGBA16F(a.outSpec, x, y, mk4(sumS.x / sumWS, sumS.y / sumWS, sumS.z / sumWS, fmaxf(0.0f, sumS2 - sumS1 * sumS1) * boost));
         sumWD = fmaxf(sumWD, 1e-6f);
         sumD1 /= sumWD;
         sumD2 /= sumWD;
-        StoreRGBA16F(a.outDiff, x, y, mk4(sumD.x / sumWD, sumD.y / sumWD, sumD.z / sumWD, fmaxf(0.0f, sumD2 - sumD1 * sumD1) * boost));
+        if (DIFF) StoreRGBA16F(a.outDiff, x, y, mk4(sumD.x / sumWD, sumD.y / sumWD, sumD.z / sumWD, fmaxf(0.0f, sumD2 - sumD1 * sumD1) * boost));
     }
 }
 
 // =============================================================================================
 // A-trous (RELAX_Atrous.hlsli:11-243)
 // =============================================================================================
-__global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__ RxAtrousArgs a)
+template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__ RxAtrousArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
@@ -1287,14 +1297,14 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
     float diffuseLobeAngleFraction = c.gLobeAngleFraction / sqrtf((float)c.gStepSize);
     diffuseLobeAngleFraction = lerpf(0.99f, diffuseLobeAngleFraction, saturate(historyLength / 5.0f));
 
-    const f4 centerSpec = LoadRGBA16F(a.spec, x, y);
+    const f4 centerSpec = LoadSignal<SPEC>(a.spec, x, y);
     const float centerSpecularLuminance = Luma(xyz(centerSpec));
     const float specularPhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, c.gSpecPhiLuminance * sqrtf(centerSpec.w));
     const f2 rwp = RoughnessWeightParams(g.roughness, c.gRoughnessFraction);
-    const float specularReprojectionConfidence = LoadR8Unorm(a.confidence, x, y);
+    const float specularReprojectionConfidence = (SPEC ? LoadR8Unorm(a.confidence, x, y) : 1.0f);
     float specularLuminanceWeightRelaxation = 1.0f;
     if (c.gStepSize <= 4) specularLuminanceWeightRelaxation = lerpf(1.0f, specularReprojectionConfidence, c.gLuminanceEdgeStoppingRelaxation);
-    const ConfidenceRelaxation cr = RelaxByConfidence(a, x, y, diffuseLobeAngleFraction);
+    const ConfidenceRelaxation cr = RelaxByConfidence<DIFF, SPEC>(a, x, y, diffuseLobeAngleFraction);
     specularLuminanceWeightRelaxation *= cr.specularLuminanceScale;
     const float normalWeightParam = NormalWeightParam2(1.0f, cr.diffuseLobeAngleFraction);
     const float simplifiedSpecularNormalWeightParam = NormalWeightParam2(1.0f, cr.simplifiedSpecularLobeAngleFraction);
@@ -1302,7 +1312,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
     const float w0 = 0.44198f * 0.44198f;
     float sumWSpecular = w0, sumWDiffuse = w0;
     f4 sumSpecular = mk4(centerSpec.x * w0, centerSpec.y * w0, centerSpec.z * w0, centerSpec.w * (w0 * w0));
-    const f4 centerDiff = LoadRGBA16F(a.diff, x, y);
+    const f4 centerDiff = LoadSignal<DIFF>(a.diff, x, y);
     const float centerDiffuseLuminance = Luma(xyz(centerDiff));
     const float diffusePhiLIlluminationInv = 1.0f / fmaxf(1.0e-4f, c.gDiffPhiLuminance * sqrtf(centerDiff.w));
     f4 sumDiffuse = mk4(centerDiff.x * w0, centerDiff.y * w0, centerDiff.z * w0, centerDiff.w * (w0 * w0));
@@ -1345,7 +1355,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
             wSpecular *= SameMaterial(sg.materialID, g.materialID, c.gSpecMinMaterial) ? 1.0f : 0.0f;
             if (wSpecular > 1e-4f)
             {
-                const f4 ss = LoadRGBA16F(a.spec, px, py);
+                const f4 ss = LoadSignal<SPEC>(a.spec, px, py);
                 float lw = fminf(c.gSpecMaxLuminanceRelativeDifference, fabsf(centerSpecularLuminance - Luma(xyz(ss))) * specularPhiLIlluminationInv);
                 lw *= specularLuminanceWeightRelaxation;
                 wSpecular *= expf(-lw);
@@ -1356,7 +1366,7 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
             wDiffuse *= SameMaterial(sg.materialID, g.materialID, c.gDiffMinMaterial) ? 1.0f : 0.0f;
             if (wDiffuse > 1e-4f)
             {
-                const f4 sd = LoadRGBA16F(a.diff, px, py);
+                const f4 sd = LoadSignal<DIFF>(a.diff, px, py);
                 float lw = fminf(c.gDiffMaxLuminanceRelativeDifference, fabsf(centerDiffuseLuminance - Luma(xyz(sd))) * diffusePhiLIlluminationInv) * cr.diffuseLuminanceScale;
                 wDiffuse *= expf(-lw);
                 sumWDiffuse += wDiffuse;
@@ -1364,42 +1374,46 @@ __global__ void __launch_bounds__(256) RelaxAtrousKernel(const __grid_constant__
             }
         }
     const float s2 = sumWSpecular * sumWSpecular, d2 = sumWDiffuse * sumWDiffuse;
-    StoreRGBA16F(a.outSpec, x, y, mk4(sumSpecular.x / sumWSpecular, sumSpecular.y / sumWSpecular, sumSpecular.z / sumWSpecular, sumSpecular.w / s2));
-    StoreRGBA16F(a.outDiff, x, y, mk4(sumDiffuse.x / sumWDiffuse, sumDiffuse.y / sumWDiffuse, sumDiffuse.z / sumWDiffuse, sumDiffuse.w / d2));
+    if (SPEC) StoreRGBA16F(a.outSpec, x, y, mk4(sumSpecular.x / sumWSpecular, sumSpecular.y / sumWSpecular, sumSpecular.z / sumWSpecular, sumSpecular.w / s2));
+    if (DIFF) StoreRGBA16F(a.outDiff, x, y, mk4(sumDiffuse.x / sumWDiffuse, sumDiffuse.y / sumWDiffuse, sumDiffuse.z / sumWDiffuse, sumDiffuse.w / d2));
 }
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
-cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
+// RELAX_Diffuse_* / RELAX_Specular_* are the two-signal passes without the other signal's bindings (Source/Denoisers/Relax_Diffuse.hpp,
+// Relax_Specular.hpp): a one-signal dispatch is expanded to the two-signal binding layout below (c = common, s = specular only,
+// d = diffuse only; absent bindings stay null surfaces, the kernels are compiled without every access to them).
+struct RelaxPassLayout
 {
-    RC c;
-    memset(&c, 0, sizeof(c));
-    memcpy(&c, p.constants, p.constantsSize < sizeof(RC) ? p.constantsSize : sizeof(RC));
+    const char* pass;
+    const char* layout;
+};
+static const RelaxPassLayout kRelaxLayouts[] = {
+    {"PrePass.cs", "csdccsd"},
+    {"TemporalAccumulation.cs", "csdcccsdsdccsccsdcsdsdscs"},
+    {"HistoryFix.cs", "csdcccsd"},
+    {"HistoryClamping.cs", "ccsdsdsdcsdsdc"},
+    {"Copy.cs", "sdsd"},
+    {"AntiFirefly.cs", "csdccsd"},
+    {"AtrousSmem.cs", "csdcsccsdsdccc"},
+    {"Atrous.cs", "csdcsccsdsd"},
+};
+
+template <bool DIFF, bool SPEC> static cudaError_t LaunchRelaxSignals(const PassLaunch& p, const char* shader, const RC& c)
+{
     const int W = c.gRectSize[0];
     const int rows = p.rowEnd - p.rowBegin;
-    if (rows <= 0) return cudaSuccess;
-    if (c.gDiffCheckerboard != 2 || c.gSpecCheckerboard != 2) return cudaErrorNotSupported;
     const dim3 block(32, 8), grid((W + 31) / 32, (rows + 7) / 8);
-
-    if (!strcmp(shader, "RELAX_ClassifyTiles.cs"))
-    {
-        RxTilesArgs a;
-        a.nr = p.guideNr; a.guide = p.guide; a.buildGuide = p.guideMode == 1 ? 1 : 0;
-        a.z = p.tex[0]; a.tiles = p.tex[1];
-        a.denoisingRange = c.gDenoisingRange; a.tilesW = p.gridW; a.tilesH = p.gridH;
-        int warps = a.tilesW * a.tilesH;
-        NRD_B200_LAUNCH(p, (warps * 32 + 255) / 256, 256, a, RelaxClassifyTilesKernel);
-    }
-    else if (!strcmp(shader, "RELAX_DiffuseSpecular_PrePass.cs"))
+    if (!strcmp(shader, "PrePass.cs"))
     {
         RxPrePassArgs a;
         a.c = c;
         a.guide = p.guide;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.nr = p.tex[3]; a.z = p.tex[4]; a.outSpec = p.tex[5]; a.outDiff = p.tex[6];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, grid, block, a, RelaxPrePassKernel);
+        NRD_B200_LAUNCH(p, grid, block, a, RelaxPrePassKernel<DIFF, SPEC>);
     }
-    else if (!strcmp(shader, "RELAX_DiffuseSpecular_TemporalAccumulation.cs"))
+    else if (!strcmp(shader, "TemporalAccumulation.cs"))
     {
         RxTaArgs a;
         a.c = c;
@@ -1411,18 +1425,18 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.outSpec = p.tex[18]; a.outDiff = p.tex[19]; a.outSpecFast = p.tex[20]; a.outDiffFast = p.tex[21]; a.outHitDist = p.tex[22]; a.outLength = p.tex[23];
         a.outConfidence = p.tex[24];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, dim3((W + 31) / 32, (rows + 3) / 4), dim3(32, 4), a, RelaxTemporalAccumulationKernel);
+        NRD_B200_LAUNCH(p, dim3((W + 31) / 32, (rows + 3) / 4), dim3(32, 4), a, RelaxTemporalAccumulationKernel<DIFF, SPEC>);
     }
-    else if (!strcmp(shader, "RELAX_DiffuseSpecular_HistoryFix.cs"))
+    else if (!strcmp(shader, "HistoryFix.cs"))
     {
         RxHfArgs a;
         a.c = c;
         a.guide = p.guide;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.length = p.tex[3]; a.nr = p.tex[4]; a.z = p.tex[5]; a.outSpec = p.tex[6]; a.outDiff = p.tex[7];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, grid, block, a, RelaxHistoryFixKernel);
+        NRD_B200_LAUNCH(p, grid, block, a, RelaxHistoryFixKernel<DIFF, SPEC>);
     }
-    else if (!strcmp(shader, "RELAX_DiffuseSpecular_HistoryClamping.cs"))
+    else if (!strcmp(shader, "HistoryClamping.cs"))
     {
         RxHcArgs a;
         a.c = c;
@@ -1430,27 +1444,27 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         a.length = p.tex[8];
         a.outSpec = p.tex[9]; a.outDiff = p.tex[10]; a.outSpecFast = p.tex[11]; a.outDiffFast = p.tex[12]; a.outLength = p.tex[13];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, grid, block, a, RelaxHistoryClampingKernel);
+        NRD_B200_LAUNCH(p, grid, block, a, RelaxHistoryClampingKernel<DIFF, SPEC>);
     }
-    else if (!strcmp(shader, "RELAX_DiffuseSpecular_Copy.cs"))
+    else if (!strcmp(shader, "Copy.cs"))
     {
         RxCopyArgs a;
         a.inSpec = p.tex[0]; a.inDiff = p.tex[1]; a.outSpec = p.tex[2]; a.outDiff = p.tex[3];
         a.gridW = p.gridW * 8; a.gridH = p.gridH * 8;
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, dim3((a.outSpec.w + 31) / 32, grid.y), block, a, RelaxCopyKernel);
+        NRD_B200_LAUNCH(p, dim3(((SPEC ? a.outSpec.w : a.outDiff.w) + 31) / 32, grid.y), block, a, RelaxCopyKernel<DIFF, SPEC>);
     }
-    else if (!strcmp(shader, "RELAX_DiffuseSpecular_AntiFirefly.cs"))
+    else if (!strcmp(shader, "AntiFirefly.cs"))
     {
         RxAfArgs a;
         a.c = c;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.nr = p.tex[3]; a.z = p.tex[4]; a.outSpec = p.tex[5]; a.outDiff = p.tex[6];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, grid, block, a, RelaxAntiFireflyKernel);
+        NRD_B200_LAUNCH(p, grid, block, a, RelaxAntiFireflyKernel<DIFF, SPEC>);
     }
-    else if (!strcmp(shader, "RELAX_DiffuseSpecular_AtrousSmem.cs") || !strcmp(shader, "RELAX_DiffuseSpecular_Atrous.cs"))
+    else if (!strcmp(shader, "AtrousSmem.cs") || !strcmp(shader, "Atrous.cs"))
     {
-        const bool smem = !strcmp(shader, "RELAX_DiffuseSpecular_AtrousSmem.cs");
+        const bool smem = !strcmp(shader, "AtrousSmem.cs");
         RxAtrousArgs a;
         a.c = c;
         a.guide = p.guide;
@@ -1461,17 +1475,63 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
         if (smem)
         {
             a.outNr = p.tex[11]; a.outMaterial = p.tex[12]; a.outZ = p.tex[13];
-            NRD_B200_LAUNCH(p, dim3((a.z.w + 31) / 32, grid.y), block, a, RelaxAtrousSmemKernel);
+            NRD_B200_LAUNCH(p, dim3((a.z.w + 31) / 32, grid.y), block, a, RelaxAtrousSmemKernel<DIFF, SPEC>);
         }
         else
         {
             a.outNr = a.outMaterial = a.outZ = a.z;
-            NRD_B200_LAUNCH(p, grid, block, a, RelaxAtrousKernel);
+            NRD_B200_LAUNCH(p, grid, block, a, RelaxAtrousKernel<DIFF, SPEC>);
         }
     }
     else
         return cudaErrorNotSupported;
     return cudaGetLastError();
+}
+
+cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
+{
+    RC c;
+    memset(&c, 0, sizeof(c));
+    memcpy(&c, p.constants, p.constantsSize < sizeof(RC) ? p.constantsSize : sizeof(RC));
+    if (p.rowEnd - p.rowBegin <= 0) return cudaSuccess;
+    if (c.gDiffCheckerboard != 2 || c.gSpecCheckerboard != 2) return cudaErrorNotSupported;
+
+    if (!strcmp(shader, "RELAX_ClassifyTiles.cs"))
+    {
+        RxTilesArgs a;
+        a.nr = p.guideNr; a.guide = p.guide; a.buildGuide = p.guideMode == 1 ? 1 : 0;
+        a.z = p.tex[0]; a.tiles = p.tex[1];
+        a.denoisingRange = c.gDenoisingRange; a.tilesW = p.gridW; a.tilesH = p.gridH;
+        int warps = a.tilesW * a.tilesH;
+        NRD_B200_LAUNCH(p, (warps * 32 + 255) / 256, 256, a, RelaxClassifyTilesKernel);
+        return cudaGetLastError();
+    }
+    if (strncmp(shader, "RELAX_", 6) != 0) return cudaErrorNotSupported;
+    const char* pass = shader + 6;
+    bool hasDiff = false, hasSpec = false;
+    if (!strncmp(pass, "DiffuseSpecular_", 16)) { hasDiff = hasSpec = true; pass += 16; }
+    else if (!strncmp(pass, "Diffuse_", 8)) { hasDiff = true; pass += 8; }
+    else if (!strncmp(pass, "Specular_", 9)) { hasSpec = true; pass += 9; }
+    else return cudaErrorNotSupported;
+    const RelaxPassLayout* layout = nullptr;
+    for (const RelaxPassLayout& l : kRelaxLayouts)
+        if (!strcmp(pass, l.pass)) layout = &l;
+    if (!layout) return cudaErrorNotSupported;
+    PassLaunch q = p;
+    for (Surf& t : q.tex) t = Surf{};
+    uint32_t k = 0;
+    for (uint32_t i = 0; layout->layout[i]; i++)
+    {
+        const char kind = layout->layout[i];
+        if (kind == 'c' || (kind == 's' && hasSpec) || (kind == 'd' && hasDiff))
+        {
+            if (k >= p.texNum && !p.preloadOnly) return cudaErrorInvalidValue;
+            q.tex[i] = p.tex[k++];
+        }
+    }
+    if (k != p.texNum && !p.preloadOnly) return cudaErrorInvalidValue;
+    if (hasDiff && hasSpec) return LaunchRelaxSignals<true, true>(q, pass, c);
+    return hasDiff ? LaunchRelaxSignals<true, false>(q, pass, c) : LaunchRelaxSignals<false, true>(q, pass, c);
 }
 
 #if !defined(NRD_B200_NO_STRIPS)

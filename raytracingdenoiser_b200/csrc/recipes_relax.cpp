@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 using namespace nrd;
@@ -36,39 +37,68 @@ enum RelaxPass : uint32_t
 const uint32_t kSharedSize = offsetof(RelaxConstants, gStepSize); // 704
 } // namespace
 
-void Scheduler::AddRelaxDiffuseSpecular(DenoiserSlot& slot)
+// shader file names are "RELAX_<Diffuse|Specular|DiffuseSpecular>_<Pass>.cs"; they have to outlive the instance, so they are
+// interned once per process
+static const char* RelaxShaderName(int signal, const char* pass)
+{
+    static char table[3][16][80];
+    static int used[3];
+    static const char* signalNames[3] = {"Diffuse", "Specular", "DiffuseSpecular"};
+    char tmp[80];
+    snprintf(tmp, sizeof(tmp), "RELAX_%s_%s.cs", signalNames[signal], pass);
+    for (int i = 0; i < used[signal]; i++)
+        if (!strcmp(table[signal][i], tmp)) return table[signal][i];
+    char* dst = table[signal][used[signal]++];
+    strcpy(dst, tmp);
+    return dst;
+}
+
+// One builder for Source/Denoisers/Relax_Diffuse.hpp, Relax_Specular.hpp and Relax_DiffuseSpecular.hpp: the one-signal graphs are
+// the two-signal graph without the other signal's textures and bindings (pool order: Relax_Diffuse.hpp:17-44, Relax_Specular.hpp:17-52,
+// Relax_DiffuseSpecular.hpp:17-62).
+void Scheduler::AddRelax(DenoiserSlot& slot, bool hasDiff, bool hasSpec)
 {
     new (&slot.settings.relax) RelaxSettings();
     slot.settingsSize = sizeof(RelaxSettings);
-    const char* dn = "RELAX_DiffuseSpecular";
+    const int signal = hasDiff && hasSpec ? 2 : (hasSpec ? 1 : 0);
+    const char* dn = signal == 2 ? "RELAX_DiffuseSpecular" : (signal == 1 ? "RELAX_Specular" : "RELAX_Diffuse");
     const uint32_t cb = kSharedSize;
     const uint32_t cbAtrous = offsetof(RelaxConstants, gIsLastPass) + sizeof(uint32_t); // 712: sizeof() of the reference struct, no register padding
 
-    enum : uint16_t
+    uint16_t next = kPermanentBase;
+    uint16_t P_SPEC_ILLUM_PREV = 0, P_DIFF_ILLUM_PREV = 0, P_SPEC_ILLUM_RESPONSIVE_PREV = 0, P_DIFF_ILLUM_RESPONSIVE_PREV = 0, P_REFLECTION_HIT_T_CURR = 0, P_REFLECTION_HIT_T_PREV = 0;
+    if (hasSpec) { P_SPEC_ILLUM_PREV = next++; AddPermanent(Format::RGBA16_SFLOAT); }
+    if (hasDiff) { P_DIFF_ILLUM_PREV = next++; AddPermanent(Format::RGBA16_SFLOAT); }
+    if (hasSpec) { P_SPEC_ILLUM_RESPONSIVE_PREV = next++; AddPermanent(Format::RGBA16_SFLOAT); }
+    if (hasDiff) { P_DIFF_ILLUM_RESPONSIVE_PREV = next++; AddPermanent(Format::RGBA16_SFLOAT); }
+    if (hasSpec)
     {
-        P_SPEC_ILLUM_PREV = kPermanentBase, P_DIFF_ILLUM_PREV, P_SPEC_ILLUM_RESPONSIVE_PREV, P_DIFF_ILLUM_RESPONSIVE_PREV,
-        P_REFLECTION_HIT_T_CURR, P_REFLECTION_HIT_T_PREV, P_HISTORY_LENGTH_PREV, P_NORMAL_ROUGHNESS_PREV, P_MATERIAL_ID_PREV, P_VIEWZ_PREV,
-    };
-    for (int i = 0; i < 4; i++) AddPermanent(Format::RGBA16_SFLOAT);
-    AddPermanent(Format::R16_SFLOAT);
-    AddPermanent(Format::R16_SFLOAT);
+        P_REFLECTION_HIT_T_CURR = next++; P_REFLECTION_HIT_T_PREV = next++;
+        AddPermanent(Format::R16_SFLOAT); AddPermanent(Format::R16_SFLOAT);
+    }
+    const uint16_t P_HISTORY_LENGTH_PREV = next++, P_NORMAL_ROUGHNESS_PREV = next++, P_MATERIAL_ID_PREV = next++, P_VIEWZ_PREV = next++;
     AddPermanent(Format::R8_UNORM);
     AddPermanent(Format::RGBA8_UNORM);
     AddPermanent(Format::R8_UNORM);
     AddPermanent(Format::R32_SFLOAT);
 
-    enum : uint16_t
-    {
-        T_SPEC_ILLUM_PING = kTransientBase, T_SPEC_ILLUM_PONG, T_DIFF_ILLUM_PING, T_DIFF_ILLUM_PONG, T_SPEC_REPROJECTION_CONFIDENCE, T_TILES, T_HISTORY_LENGTH,
-    };
-    for (int i = 0; i < 4; i++) AddTransient(Format::RGBA16_SFLOAT);
-    AddTransient(Format::R8_UNORM);
+    next = kTransientBase;
+    uint16_t T_SPEC_ILLUM_PING = 0, T_SPEC_ILLUM_PONG = 0, T_DIFF_ILLUM_PING = 0, T_DIFF_ILLUM_PONG = 0, T_SPEC_REPROJECTION_CONFIDENCE = 0;
+    if (hasSpec) { T_SPEC_ILLUM_PING = next++; T_SPEC_ILLUM_PONG = next++; AddTransient(Format::RGBA16_SFLOAT); AddTransient(Format::RGBA16_SFLOAT); }
+    if (hasDiff) { T_DIFF_ILLUM_PING = next++; T_DIFF_ILLUM_PONG = next++; AddTransient(Format::RGBA16_SFLOAT); AddTransient(Format::RGBA16_SFLOAT); }
+    if (hasSpec) { T_SPEC_REPROJECTION_CONFIDENCE = next++; AddTransient(Format::R8_UNORM); }
+    const uint16_t T_TILES = next++, T_HISTORY_LENGTH = next++;
     AddTransient(Format::R8_UNORM, 16);
     AddTransient(Format::R8_UNORM);
 
     const uint16_t IN_SPEC = R(ResourceType::IN_SPEC_RADIANCE_HITDIST), IN_DIFF = R(ResourceType::IN_DIFF_RADIANCE_HITDIST);
     const uint16_t OUT_SPEC = R(ResourceType::OUT_SPEC_RADIANCE_HITDIST), OUT_DIFF = R(ResourceType::OUT_DIFF_RADIANCE_HITDIST);
     const uint16_t NR = R(ResourceType::IN_NORMAL_ROUGHNESS), VZ = R(ResourceType::IN_VIEWZ);
+    // bindings of a signal that the denoiser does not have are simply not pushed
+    auto InS = [&](uint16_t r, uint16_t swapWith = kNoSwap) { if (hasSpec) In(r, swapWith); };
+    auto InD = [&](uint16_t r) { if (hasDiff) In(r); };
+    auto OutS = [&](uint16_t r, uint16_t swapWith = kNoSwap) { if (hasSpec) Out(r, swapWith); };
+    auto OutD = [&](uint16_t r) { if (hasDiff) Out(r); };
 
     BeginPass(dn, "Classify tiles");
     In(VZ);
@@ -78,54 +108,54 @@ void Scheduler::AddRelaxDiffuseSpecular(DenoiserSlot& slot)
     for (int i = 0; i < 2; i++)
     {
         BeginPass(dn, "Hit distance reconstruction");
-        In(T_TILES); In(IN_SPEC); In(IN_DIFF); In(NR); In(VZ);
-        Out(T_SPEC_ILLUM_PING); Out(T_DIFF_ILLUM_PING);
-        Emit(i ? "RELAX_DiffuseSpecular_HitDistReconstruction_5x5.cs" : "RELAX_DiffuseSpecular_HitDistReconstruction.cs", 8, 8, cb);
+        In(T_TILES); InS(IN_SPEC); InD(IN_DIFF); In(NR); In(VZ);
+        OutS(T_SPEC_ILLUM_PING); OutD(T_DIFF_ILLUM_PING);
+        Emit(RelaxShaderName(signal, i ? "HitDistReconstruction_5x5" : "HitDistReconstruction"), 8, 8, cb);
     }
 
     for (int i = 0; i < 2; i++)
     {
         BeginPass(dn, "Pre-pass");
-        In(T_TILES); In(i ? (uint16_t)T_SPEC_ILLUM_PING : IN_SPEC); In(i ? (uint16_t)T_DIFF_ILLUM_PING : IN_DIFF); In(NR); In(VZ);
-        Out(OUT_SPEC); Out(OUT_DIFF);
-        Emit("RELAX_DiffuseSpecular_PrePass.cs", 16, 16, cb);
+        In(T_TILES); InS(i ? T_SPEC_ILLUM_PING : IN_SPEC); InD(i ? T_DIFF_ILLUM_PING : IN_DIFF); In(NR); In(VZ);
+        OutS(OUT_SPEC); OutD(OUT_DIFF);
+        Emit(RelaxShaderName(signal, "PrePass"), 16, 16, cb);
     }
 
     for (int i = 0; i < 4; i++)
     {
         const bool hasMix = (i >> 1) & 1, hasConfidence = i & 1;
         BeginPass(dn, "Temporal accumulation");
-        In(T_TILES); In(OUT_SPEC); In(OUT_DIFF); In(R(ResourceType::IN_MV)); In(NR); In(VZ);
-        In(P_SPEC_ILLUM_RESPONSIVE_PREV); In(P_DIFF_ILLUM_RESPONSIVE_PREV); In(P_SPEC_ILLUM_PREV); In(P_DIFF_ILLUM_PREV);
-        In(P_NORMAL_ROUGHNESS_PREV); In(P_VIEWZ_PREV); In(P_REFLECTION_HIT_T_PREV, P_REFLECTION_HIT_T_CURR);
+        In(T_TILES); InS(OUT_SPEC); InD(OUT_DIFF); In(R(ResourceType::IN_MV)); In(NR); In(VZ);
+        InS(P_SPEC_ILLUM_RESPONSIVE_PREV); InD(P_DIFF_ILLUM_RESPONSIVE_PREV); InS(P_SPEC_ILLUM_PREV); InD(P_DIFF_ILLUM_PREV);
+        In(P_NORMAL_ROUGHNESS_PREV); In(P_VIEWZ_PREV); InS(P_REFLECTION_HIT_T_PREV, P_REFLECTION_HIT_T_CURR);
         In(P_HISTORY_LENGTH_PREV); In(P_MATERIAL_ID_PREV);
-        In(hasConfidence ? R(ResourceType::IN_SPEC_CONFIDENCE) : kDummy);
-        In(hasConfidence ? R(ResourceType::IN_DIFF_CONFIDENCE) : kDummy);
+        InS(hasConfidence ? R(ResourceType::IN_SPEC_CONFIDENCE) : kDummy);
+        InD(hasConfidence ? R(ResourceType::IN_DIFF_CONFIDENCE) : kDummy);
         In(hasMix ? R(ResourceType::IN_DISOCCLUSION_THRESHOLD_MIX) : kDummy);
-        Out(T_SPEC_ILLUM_PING); Out(T_DIFF_ILLUM_PING); Out(T_SPEC_ILLUM_PONG); Out(T_DIFF_ILLUM_PONG);
-        Out(P_REFLECTION_HIT_T_CURR, P_REFLECTION_HIT_T_PREV); Out(T_HISTORY_LENGTH); Out(T_SPEC_REPROJECTION_CONFIDENCE);
-        Emit("RELAX_DiffuseSpecular_TemporalAccumulation.cs", 8, 16, cb);
+        OutS(T_SPEC_ILLUM_PING); OutD(T_DIFF_ILLUM_PING); OutS(T_SPEC_ILLUM_PONG); OutD(T_DIFF_ILLUM_PONG);
+        OutS(P_REFLECTION_HIT_T_CURR, P_REFLECTION_HIT_T_PREV); Out(T_HISTORY_LENGTH); OutS(T_SPEC_REPROJECTION_CONFIDENCE);
+        Emit(RelaxShaderName(signal, "TemporalAccumulation"), 8, 16, cb);
     }
 
     BeginPass(dn, "History fix");
-    In(T_TILES); In(T_SPEC_ILLUM_PING); In(T_DIFF_ILLUM_PING); In(T_HISTORY_LENGTH); In(NR); In(VZ);
-    Out(T_SPEC_ILLUM_PONG); Out(T_DIFF_ILLUM_PONG);
-    Emit("RELAX_DiffuseSpecular_HistoryFix.cs", 8, 8, cb);
+    In(T_TILES); InS(T_SPEC_ILLUM_PING); InD(T_DIFF_ILLUM_PING); In(T_HISTORY_LENGTH); In(NR); In(VZ);
+    OutS(T_SPEC_ILLUM_PONG); OutD(T_DIFF_ILLUM_PONG);
+    Emit(RelaxShaderName(signal, "HistoryFix"), 8, 8, cb);
 
     BeginPass(dn, "History clamping");
-    In(T_TILES); In(VZ); In(OUT_SPEC); In(OUT_DIFF); In(T_SPEC_ILLUM_PING); In(T_DIFF_ILLUM_PING); In(T_SPEC_ILLUM_PONG); In(T_DIFF_ILLUM_PONG); In(T_HISTORY_LENGTH);
-    Out(P_SPEC_ILLUM_PREV); Out(P_DIFF_ILLUM_PREV); Out(P_SPEC_ILLUM_RESPONSIVE_PREV); Out(P_DIFF_ILLUM_RESPONSIVE_PREV); Out(P_HISTORY_LENGTH_PREV);
-    Emit("RELAX_DiffuseSpecular_HistoryClamping.cs", 8, 8, cb);
+    In(T_TILES); In(VZ); InS(OUT_SPEC); InD(OUT_DIFF); InS(T_SPEC_ILLUM_PING); InD(T_DIFF_ILLUM_PING); InS(T_SPEC_ILLUM_PONG); InD(T_DIFF_ILLUM_PONG); In(T_HISTORY_LENGTH);
+    OutS(P_SPEC_ILLUM_PREV); OutD(P_DIFF_ILLUM_PREV); OutS(P_SPEC_ILLUM_RESPONSIVE_PREV); OutD(P_DIFF_ILLUM_RESPONSIVE_PREV); Out(P_HISTORY_LENGTH_PREV);
+    Emit(RelaxShaderName(signal, "HistoryClamping"), 8, 8, cb);
 
     BeginPass(dn, "Copy");
-    In(P_SPEC_ILLUM_PREV); In(P_DIFF_ILLUM_PREV);
-    Out(OUT_SPEC); Out(OUT_DIFF);
-    Emit("RELAX_DiffuseSpecular_Copy.cs", 8, 8, cb);
+    InS(P_SPEC_ILLUM_PREV); InD(P_DIFF_ILLUM_PREV);
+    OutS(OUT_SPEC); OutD(OUT_DIFF);
+    Emit(RelaxShaderName(signal, "Copy"), 8, 8, cb);
 
     BeginPass(dn, "Anti-firefly");
-    In(T_TILES); In(OUT_SPEC); In(OUT_DIFF); In(NR); In(VZ);
-    Out(P_SPEC_ILLUM_PREV); Out(P_DIFF_ILLUM_PREV);
-    Emit("RELAX_DiffuseSpecular_AntiFirefly.cs", 8, 8, cb);
+    In(T_TILES); InS(OUT_SPEC); InD(OUT_DIFF); In(NR); In(VZ);
+    OutS(P_SPEC_ILLUM_PREV); OutD(P_DIFF_ILLUM_PREV);
+    Emit(RelaxShaderName(signal, "AntiFirefly"), 8, 8, cb);
 
     for (int i = 0; i < 2; i++)
     {
@@ -135,24 +165,24 @@ void Scheduler::AddRelaxDiffuseSpecular(DenoiserSlot& slot)
             const bool isSmem = j == 0, isEven = (j % 2) == 0, isLast = j > 2;
             BeginPass(dn, isSmem ? "A-trous (SMEM)" : "A-trous");
             In(T_TILES);
-            if (isSmem) { In(P_SPEC_ILLUM_PREV); In(P_DIFF_ILLUM_PREV); }
-            else { In(isEven ? T_SPEC_ILLUM_PONG : T_SPEC_ILLUM_PING); In(isEven ? T_DIFF_ILLUM_PONG : T_DIFF_ILLUM_PING); }
-            In(T_HISTORY_LENGTH); In(T_SPEC_REPROJECTION_CONFIDENCE); In(NR); In(VZ);
-            In(hasConfidence ? R(ResourceType::IN_SPEC_CONFIDENCE) : kDummy);
-            In(hasConfidence ? R(ResourceType::IN_DIFF_CONFIDENCE) : kDummy);
-            if (isLast) { Out(OUT_SPEC); Out(OUT_DIFF); }
-            else { Out(isEven ? T_SPEC_ILLUM_PING : T_SPEC_ILLUM_PONG); Out(isEven ? T_DIFF_ILLUM_PING : T_DIFF_ILLUM_PONG); }
+            if (isSmem) { InS(P_SPEC_ILLUM_PREV); InD(P_DIFF_ILLUM_PREV); }
+            else { InS(isEven ? T_SPEC_ILLUM_PONG : T_SPEC_ILLUM_PING); InD(isEven ? T_DIFF_ILLUM_PONG : T_DIFF_ILLUM_PING); }
+            In(T_HISTORY_LENGTH); InS(T_SPEC_REPROJECTION_CONFIDENCE); In(NR); In(VZ);
+            InS(hasConfidence ? R(ResourceType::IN_SPEC_CONFIDENCE) : kDummy);
+            InD(hasConfidence ? R(ResourceType::IN_DIFF_CONFIDENCE) : kDummy);
+            if (isLast) { OutS(OUT_SPEC); OutD(OUT_DIFF); }
+            else { OutS(isEven ? T_SPEC_ILLUM_PING : T_SPEC_ILLUM_PONG); OutD(isEven ? T_DIFF_ILLUM_PING : T_DIFF_ILLUM_PONG); }
             if (isSmem) { Out(P_NORMAL_ROUGHNESS_PREV); Out(P_MATERIAL_ID_PREV); Out(P_VIEWZ_PREV); }
             const uint16_t repeats = isLast ? 1 : (kMaxAtrousPasses - 2 + 1) / 2;
-            if (isSmem) Emit("RELAX_DiffuseSpecular_AtrousSmem.cs", 8, 8, cbAtrous);
-            else Emit("RELAX_DiffuseSpecular_Atrous.cs", 16, 16, cbAtrous, 1, repeats);
+            if (isSmem) Emit(RelaxShaderName(signal, "AtrousSmem"), 8, 8, cbAtrous);
+            else Emit(RelaxShaderName(signal, "Atrous"), 16, 16, cbAtrous, 1, repeats);
         }
     }
 
     BeginPass(dn, "Split screen");
-    In(VZ); In(IN_DIFF); In(IN_SPEC);
-    Out(OUT_DIFF); Out(OUT_SPEC);
-    Emit("RELAX_DiffuseSpecular_SplitScreen.cs", 8, 16, cb);
+    In(VZ); InD(IN_DIFF); InS(IN_SPEC);
+    OutD(OUT_DIFF); OutS(OUT_SPEC);
+    Emit(RelaxShaderName(signal, "SplitScreen"), 8, 16, cb);
 
     BeginPass(dn, "Validation");
     In(NR); In(VZ); In(R(ResourceType::IN_MV)); In(T_HISTORY_LENGTH);

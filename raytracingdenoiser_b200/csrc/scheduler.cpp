@@ -84,7 +84,9 @@ Result Scheduler::Create(const InstanceCreationDesc& creation)
             case Denoiser::REBLUR_DIFFUSE: AddReblur(slot, true, false); break;
             case Denoiser::REBLUR_SPECULAR: AddReblur(slot, false, true); break;
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: AddReblur(slot, true, true); break;
-            case Denoiser::RELAX_DIFFUSE_SPECULAR: AddRelaxDiffuseSpecular(slot); break;
+            case Denoiser::RELAX_DIFFUSE: AddRelax(slot, true, false); break;
+            case Denoiser::RELAX_SPECULAR: AddRelax(slot, false, true); break;
+            case Denoiser::RELAX_DIFFUSE_SPECULAR: AddRelax(slot, true, true); break;
             case Denoiser::SIGMA_SHADOW: AddSigmaShadow(slot, false); break;
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: AddSigmaShadow(slot, true); break;
             default: return Result::INVALID_ARGUMENT;
@@ -464,6 +466,8 @@ Result Scheduler::GetComputeDispatches(const Identifier* ids, uint32_t idsNum, c
             case Denoiser::REBLUR_DIFFUSE:
             case Denoiser::REBLUR_SPECULAR:
             case Denoiser::REBLUR_DIFFUSE_SPECULAR: UpdateReblur(slot); break;
+            case Denoiser::RELAX_DIFFUSE:
+            case Denoiser::RELAX_SPECULAR:
             case Denoiser::RELAX_DIFFUSE_SPECULAR: UpdateRelax(slot); break;
             case Denoiser::SIGMA_SHADOW:
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: UpdateSigma(slot); break;

@@ -137,7 +137,7 @@ private:
     void AddReblur(DenoiserSlot& slot, bool hasDiffuse, bool hasSpecular);
     void UpdateReblur(const DenoiserSlot& slot);
     void FillReblurConstants(const nrd::ReblurSettings& s, void* data);
-    void AddRelaxDiffuseSpecular(DenoiserSlot& slot);
+    void AddRelax(DenoiserSlot& slot, bool hasDiff, bool hasSpec);
     void UpdateRelax(const DenoiserSlot& slot);
     void FillRelaxConstants(const nrd::RelaxSettings& s, void* data);
     void AddSigmaShadow(DenoiserSlot& slot, bool translucent);

@@ -41,6 +41,8 @@ DENOISER_RESOURCES = {
                                            "OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"],
     nrd.Denoiser.RELAX_DIFFUSE_SPECULAR: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_DIFF_RADIANCE_HITDIST", "IN_SPEC_RADIANCE_HITDIST",
                                           "OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"],
+    nrd.Denoiser.RELAX_DIFFUSE: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_DIFF_RADIANCE_HITDIST", "OUT_DIFF_RADIANCE_HITDIST"],
+    nrd.Denoiser.RELAX_SPECULAR: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_SPEC_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"],
     nrd.Denoiser.SIGMA_SHADOW: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_PENUMBRA", "OUT_SHADOW_TRANSLUCENCY"],
     nrd.Denoiser.SIGMA_SHADOW_TRANSLUCENCY: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_PENUMBRA", "IN_TRANSLUCENCY", "OUT_SHADOW_TRANSLUCENCY"],
 }
@@ -67,7 +69,7 @@ def denoiser_resources(denoiser, common=None):
 
 
 def radiance_mode(denoiser):
-    return "relax" if denoiser == nrd.Denoiser.RELAX_DIFFUSE_SPECULAR else "reblur"
+    return "relax" if nrd.Denoiser(denoiser).name.startswith("RELAX") else "reblur"
 
 
 def make_common_settings(frame, width, height, frame_index, time_delta_ms=16.6667, common=None):

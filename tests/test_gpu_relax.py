@@ -101,3 +101,27 @@ def test_relax_anti_firefly_per_pass():
     assert "RELAX_DiffuseSpecular_AntiFirefly.cs" in names and "RELAX_DiffuseSpecular_Copy.cs" in names
     _dump("parity_RELAX_antifirefly.json", report)
     assert not sbs.failures(), sbs.describe_failures()
+
+
+@pytest.mark.parametrize("denoiser_name", ["RELAX_DIFFUSE", "RELAX_SPECULAR"])
+def test_relax_one_signal_per_pass_parity(denoiser_name):
+    """RELAX_DIFFUSE / RELAX_SPECULAR: the same kernels compiled without the other signal (Source/Denoisers/Relax_Diffuse.hpp,
+    Relax_Specular.hpp), anti-firefly on so that Copy / AntiFirefly are covered too."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    s = nrd.RelaxSettings()
+    s.enableAntiFirefly = True
+    sbs = parity.SideBySide(getattr(nrd.Denoiser, denoiser_name), 250, 141, settings=s, noise_floor=True)
+    report = sbs.run_per_pass(4)
+    _dump("parity_%s.json" % denoiser_name, report)
+    assert not sbs.failures(), sbs.describe_failures()
+
+
+@pytest.mark.parametrize("denoiser_name", ["RELAX_DIFFUSE", "RELAX_SPECULAR"])
+def test_relax_one_signal_sequence_parity(denoiser_name):
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    res = parity.run_sequence(getattr(nrd.Denoiser, denoiser_name), 320, 180, 8)
+    _dump("sequence_%s.json" % denoiser_name.lower(), res)
+    for name, (frac, psnr) in res.items():
+        assert frac >= 0.99 and psnr >= 60.0, (name, frac, psnr)

@@ -301,3 +301,26 @@ def test_relax_anti_firefly_removes_fireflies_in_the_oracle():
         assert np.isfinite(out).all()
         peak.append(float(out.max()))
     assert peak[1] <= peak[0]
+
+
+@pytest.mark.parametrize("single,signal", [("RELAX_DIFFUSE", "DIFF"), ("RELAX_SPECULAR", "SPEC")])
+def test_relax_one_signal_denoisers_equal_the_two_signal_denoiser_per_signal(single, signal):
+    """RELAX_DIFFUSE / RELAX_SPECULAR run the two-signal passes without the other signal's bindings: with equal accumulation caps
+    (the defaults) each must reproduce its signal of RELAX_DIFFUSE_SPECULAR bit for bit -- checks the one-signal binding layouts."""
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h = 96, 64
+    sc = scene.Scene(w, h)
+    s = nrd.RelaxSettings()
+    s.enableAntiFirefly = True
+    outs = []
+    for den in (getattr(nrd.Denoiser, single), nrd.Denoiser.RELAX_DIFFUSE_SPECULAR):
+        cpu = orr.CpuDenoiser(den, w, h, settings=s)
+        for f in range(4):
+            fr = sc.frame(f, "relax")
+            cpu.set_inputs(fr)
+            cpu.denoise(harness.make_common_settings(fr, w, h, f))
+            if f == 0:
+                cpu.set_inputs(fr)
+        outs.append(cpu.user["OUT_%s_RADIANCE_HITDIST" % signal].copy())
+    assert outs[0].any() and (outs[0] == outs[1]).all()

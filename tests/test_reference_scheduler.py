@@ -183,7 +183,7 @@ def _compare_streams(ref_lib, den, settings, variant, frames=3, w=1920, h=1080):
     return checked
 
 
-SUPPORTED = ["REBLUR_DIFFUSE", "REBLUR_SPECULAR", "REBLUR_DIFFUSE_SPECULAR", "RELAX_DIFFUSE_SPECULAR", "SIGMA_SHADOW", "SIGMA_SHADOW_TRANSLUCENCY"]
+SUPPORTED = ["REBLUR_DIFFUSE", "REBLUR_SPECULAR", "REBLUR_DIFFUSE_SPECULAR", "RELAX_DIFFUSE", "RELAX_SPECULAR", "RELAX_DIFFUSE_SPECULAR", "SIGMA_SHADOW", "SIGMA_SHADOW_TRANSLUCENCY"]
 
 
 @pytest.mark.parametrize("denoiser_name", SUPPORTED)

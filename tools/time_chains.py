@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--only", default="")
     args = ap.parse_args()
     import torch
     from raytracingdenoiser_b200 import build
@@ -28,7 +29,9 @@ def main():
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream(dev)
     for den in (nrd.Denoiser.REBLUR_DIFFUSE, nrd.Denoiser.REBLUR_SPECULAR, nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, nrd.Denoiser.RELAX_DIFFUSE_SPECULAR,
-                nrd.Denoiser.SIGMA_SHADOW):
+                nrd.Denoiser.SIGMA_SHADOW, nrd.Denoiser.SIGMA_SHADOW_TRANSLUCENCY):
+        if args.only and den.name != args.only:
+            continue
         sc = scene.Scene(W, H, device="cuda:0")
         mode = harness.radiance_mode(den)
         frames = [sc.frame(f, mode) for f in range(args.warmup + args.frames)]
