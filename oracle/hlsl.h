@@ -158,7 +158,7 @@ inline float asfloat(uint u) { float f; memcpy(&f, &u, 4); return f; }
 enum Fmt : int
 {
     R8_UNORM = 0, R8_UINT = 2, RG8_UNORM = 4, RGBA8_UNORM = 8, R16_UNORM = 13, R16_UINT = 15, R16_SFLOAT = 17, RGBA16_SFLOAT = 27,
-    R32_UINT = 28, R32_SFLOAT = 30, R10_G10_B10_A2_UNORM = 40,
+    R32_UINT = 28, R32_SFLOAT = 30, RGBA32_SFLOAT = 39, R10_G10_B10_A2_UNORM = 40,
 };
 
 inline uint unormEncode(float v, float maxv)
@@ -185,6 +185,7 @@ struct Tex
             case RG8_UNORM: case R16_UNORM: case R16_UINT: case R16_SFLOAT: return 2;
             case RGBA8_UNORM: case R32_UINT: case R32_SFLOAT: case R10_G10_B10_A2_UNORM: return 4;
             case RGBA16_SFLOAT: return 8;
+            case RGBA32_SFLOAT: return 16;
         }
         return 0;
     }
@@ -203,6 +204,7 @@ struct Tex
             case R16_SFLOAT: { uint16_t v; memcpy(&v, p, 2); return float4(f16tof32(v), 0, 0, 0); }
             case RGBA16_SFLOAT: { uint16_t v[4]; memcpy(v, p, 8); return float4(f16tof32(v[0]), f16tof32(v[1]), f16tof32(v[2]), f16tof32(v[3])); }
             case R32_SFLOAT: { float v; memcpy(&v, p, 4); return float4(v, 0, 0, 0); }
+            case RGBA32_SFLOAT: { float v[4]; memcpy(v, p, 16); return float4(v[0], v[1], v[2], v[3]); }
             case R10_G10_B10_A2_UNORM:
             {
                 uint v; memcpy(&v, p, 4);
@@ -239,6 +241,7 @@ struct Tex
             case R16_SFLOAT: { uint16_t q = f32tof16(v.x); memcpy(p, &q, 2); break; }
             case RGBA16_SFLOAT: { uint16_t q[4] = {f32tof16(v.x), f32tof16(v.y), f32tof16(v.z), f32tof16(v.w)}; memcpy(p, q, 8); break; }
             case R32_SFLOAT: memcpy(p, &v.x, 4); break;
+            case RGBA32_SFLOAT: { float q[4] = {v.x, v.y, v.z, v.w}; memcpy(p, q, 16); break; }
             case R10_G10_B10_A2_UNORM:
             {
                 uint q = unormEncode(v.x, 1023.0f) | (unormEncode(v.y, 1023.0f) << 10) | (unormEncode(v.z, 1023.0f) << 20) | (unormEncode(v.w, 3.0f) << 30);

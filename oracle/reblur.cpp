@@ -1884,6 +1884,29 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
             gOut_InternalData.storeu(pixelPos, Pass::PackInternalData(data1.x, data1.y, materialID));
         }
 }
+// REBLUR_SplitScreen.hlsli:11-47: the part of the screen left of gSplitScreen shows the noisy input (checkerboard off)
+void SplitScreen(const Pass& P, Signals sg, Tex* t, int W, int H)
+{
+    const CB& c = P.c;
+    int k = 0;
+    const Tex& gIn_ViewZ = t[k++];
+    const Tex* gIn_Diff = sg.diff ? &t[k++] : nullptr;
+    const Tex* gIn_Spec = sg.spec ? &t[k++] : nullptr;
+    Tex* gOut_Diff = sg.diff ? &t[k++] : nullptr;
+    Tex* gOut_Spec = sg.spec ? &t[k++] : nullptr;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++)
+        {
+            const int2 pixelPos(x, y);
+            float2 pixelUv = (float2(float(x), float(y)) + float2(0.5f)) * c.gRectSizeInv;
+            if (pixelUv.x > c.gSplitScreen || x > c.gRectSizeMinusOne[0] || y > c.gRectSizeMinusOne[1]) continue;
+            float viewZ = P.UnpackViewZ(gIn_ViewZ.load(pixelPos).x);
+            float keep = float(viewZ < c.gDenoisingRange);
+            if (sg.diff) gOut_Diff->store(pixelPos, gIn_Diff->load(pixelPos) * float4(keep));
+            if (sg.spec) gOut_Spec->store(pixelPos, gIn_Spec->load(pixelPos) * float4(keep));
+        }
+}
 } // namespace
 
 int reblur_dispatch_impl(const char* shaderName, const void* constants, int constantsSize, hlsl::Tex* tex, int texNum, int gridW, int gridH);
@@ -1926,6 +1949,7 @@ int hlsl::reblur_dispatch_impl(const char* shaderName, const void* constants, in
     else if (!strcmp(p, "PostBlur.cs")) PostBlur(P, sg, false, tex, W, H);
     else if (!strcmp(p, "PostBlur_NoTemporalStabilization.cs")) PostBlur(P, sg, true, tex, W, H);
     else if (!strcmp(p, "TemporalStabilization.cs")) TemporalStabilization(P, sg, tex, W, H);
+    else if (!strcmp(p, "SplitScreen.cs")) SplitScreen(P, sg, tex, W, H);
     else return -1;
     return 0;
 }

@@ -1384,6 +1384,26 @@ void Atrous(const Pass& P, Tex* t, int gridW, int gridH)
             gOut_Diff.store(pixelPos, sumDiffuse / float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse));
         }
 }
+// RELAX_SplitScreen.hlsli:11-50 (checkerboard off, no SH): binding layout of the two-signal shader is viewZ, diff, spec | diff, spec
+void SplitScreen(const Pass& P, Tex* t, int gridW, int gridH)
+{
+    const CB& c = P.c;
+    const Tex &gIn_ViewZ = t[0], &gIn_Diff = t[1], &gIn_Spec = t[2];
+    Tex &gOut_Diff = t[3], &gOut_Spec = t[4];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < gridH * 16; y++)
+        for (int x = 0; x < gridW * 8; x++)
+        {
+            const int2 pixelPos(x, y);
+            float2 pixelUv = (float2(float(x), float(y)) + float2(0.5f)) * c.gRectSizeInv;
+            if (pixelUv.x > c.gSplitScreen || x >= c.gRectSize[0] || y >= c.gRectSize[1]) continue;
+            float viewZ = P.UnpackViewZ(gIn_ViewZ.load(pixelPos).x);
+            float keep = float(viewZ < c.gDenoisingRange);
+            gOut_Diff.store(pixelPos, gIn_Diff.load(pixelPos) * float4(keep));
+            gOut_Spec.store(pixelPos, gIn_Spec.load(pixelPos) * float4(keep));
+        }
+}
+
 } // namespace
 
 // RELAX_Diffuse_* / RELAX_Specular_* are the RELAX_DiffuseSpecular_* shaders compiled without the other signal (RELAX_DIFFUSE /
@@ -1405,6 +1425,7 @@ const PassLayout kLayouts[] = {
     {"AntiFirefly.cs", "csdccsd"},
     {"AtrousSmem.cs", "csdcsccsdsdccc"},
     {"Atrous.cs", "csdcsccsdsd"},
+    {"SplitScreen.cs", "cdsds"},
 };
 
 int relax_dispatch_impl(const char* shaderName, const void* constants, int constantsSize, Tex* tex, int texNum, int gridW, int gridH)
@@ -1454,6 +1475,7 @@ int relax_dispatch_impl(const char* shaderName, const void* constants, int const
     else if (!strcmp(p, "AntiFirefly.cs")) AntiFirefly(P, t, gridW, gridH);
     else if (!strcmp(p, "AtrousSmem.cs")) AtrousSmem(P, t, gridW, gridH);
     else if (!strcmp(p, "Atrous.cs")) Atrous(P, t, gridW, gridH);
+    else if (!strcmp(p, "SplitScreen.cs")) SplitScreen(P, t, gridW, gridH);
     else return -1;
     return 0;
 }

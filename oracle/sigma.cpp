@@ -434,6 +434,26 @@ void TemporalStabilization(const Pass& P, Tex* t, int gridW, int gridH)
             gOut_HistoryLength.storeu(pixelPos, PackViewZAndHistoryLength(viewZ, historyLength));
         }
 }
+// SIGMA_SplitScreen.hlsli:11-36
+void SplitScreen(const Pass& P, bool translucent, Tex* t, int gridW, int gridH)
+{
+    const CB& c = P.c;
+    int k = 0;
+    const Tex &gIn_ViewZ = t[k++], &gIn_Penumbra = t[k++];
+    const Tex* gIn_Shadow_Translucency = translucent ? &t[k++] : nullptr;
+    Tex& gOut_Shadow_Translucency = t[k++];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < gridH * 16; y++)
+        for (int x = 0; x < gridW * 8; x++)
+        {
+            const int2 pixelPos(x, y);
+            float2 pixelUv = (float2(float(x), float(y)) + float2(0.5f)) * c.gRectSizeInv;
+            if (pixelUv.x > c.gSplitScreen || x > c.gRectSizeMinusOne[0] || y > c.gRectSizeMinusOne[1]) continue;
+            float viewZ = abs(gIn_ViewZ.load(pixelPos).x * c.gViewZScale);
+            float4 s = translucent ? gIn_Shadow_Translucency->load(pixelPos) : float4(float(IsLit(gIn_Penumbra.load(pixelPos).x)));
+            gOut_Shadow_Translucency.store(pixelPos, s * float4(float(viewZ < c.gDenoisingRange)));
+        }
+}
 } // namespace
 
 int sigma_dispatch_impl(const char* shaderName, const void* constants, int constantsSize, Tex* tex, int gridW, int gridH)
@@ -454,6 +474,7 @@ int sigma_dispatch_impl(const char* shaderName, const void* constants, int const
         else if (!strcmp(pass, "Blur.cs")) Blur(P, true, translucent, tex, gridW, gridH);
         else if (!strcmp(pass, "PostBlur.cs")) Blur(P, false, translucent, tex, gridW, gridH);
         else if (!strcmp(pass, "TemporalStabilization.cs")) TemporalStabilization(P, tex, gridW, gridH);
+        else if (!strcmp(pass, "SplitScreen.cs")) SplitScreen(P, translucent, tex, gridW, gridH);
         else return -1;
     }
     return 0;

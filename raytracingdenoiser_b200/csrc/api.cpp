@@ -34,7 +34,7 @@ void DefaultFree(void*, void* memory) { free(memory); }
 // Only the denoisers whose whole pass chain exists as CUDA kernels are advertised; CreateInstance returns
 // Result::UNSUPPORTED for the rest exactly like the reference does for an unknown denoiser (InstanceImpl.cpp:110-117).
 const Denoiser kSupported[] = {Denoiser::REBLUR_DIFFUSE, Denoiser::REBLUR_SPECULAR, Denoiser::REBLUR_DIFFUSE_SPECULAR,
-                               Denoiser::RELAX_DIFFUSE, Denoiser::RELAX_SPECULAR, Denoiser::RELAX_DIFFUSE_SPECULAR, Denoiser::SIGMA_SHADOW, Denoiser::SIGMA_SHADOW_TRANSLUCENCY};
+                               Denoiser::RELAX_DIFFUSE, Denoiser::RELAX_SPECULAR, Denoiser::RELAX_DIFFUSE_SPECULAR, Denoiser::SIGMA_SHADOW, Denoiser::SIGMA_SHADOW_TRANSLUCENCY, Denoiser::REFERENCE};
 
 const LibraryDesc kLibraryDesc = {{100, 200, 300, 400},
                                   kSupported,

@@ -213,4 +213,21 @@ struct alignas(16) SigmaConstants
     uint32_t gIsRectChanged;
 };
 static_assert(sizeof(SigmaConstants) == 528, "SIGMA constant block must be 528 bytes");
+
+// REFERENCE_TemporalAccumulation.resources.hlsli:11-16 / REFERENCE_Copy.resources.hlsli:11-16 (20 bytes each in the reference)
+struct ReferenceAccumulateConstants
+{
+    uint32_t gRectOrigin[2];
+    float gAccumSpeed;
+    float gDebug;
+    float gViewZScale;
+};
+struct ReferenceCopyConstants
+{
+    float gRectSizeInv[2];
+    float gSplitScreen;
+    float gDebug;
+    float gViewZScale;
+};
+static_assert(sizeof(ReferenceAccumulateConstants) == 20 && sizeof(ReferenceCopyConstants) == 20, "REFERENCE constant blocks are 20 bytes");
 } // namespace nrdb200

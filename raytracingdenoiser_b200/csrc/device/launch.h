@@ -17,6 +17,7 @@
     cudaError_t LaunchReblurTemporalStabilization(const nrdb200_abi::PassLaunch& p, int signal);                \
     cudaError_t LaunchSigma(const nrdb200_abi::PassLaunch& p, const char* shaderName);                          \
     cudaError_t LaunchRelax(const nrdb200_abi::PassLaunch& p, const char* shaderName);                          \
+    cudaError_t LaunchAux(const nrdb200_abi::PassLaunch& p, const char* shaderName);                            \
     }
 
 NRD_B200_DECLARE_LAUNCHERS(nrdb200)
@@ -30,5 +31,6 @@ cudaError_t SetPeerTableReblurHitDist(int slot, const nrdb200_abi::PeerTable* ta
 cudaError_t SetPeerTableReblurTemporal(int slot, const nrdb200_abi::PeerTable* table);
 cudaError_t SetPeerTableSigma(int slot, const nrdb200_abi::PeerTable* table);
 cudaError_t SetPeerTableRelax(int slot, const nrdb200_abi::PeerTable* table);
+cudaError_t SetPeerTableAux(int slot, const nrdb200_abi::PeerTable* table);
 } // namespace nrdb200
 #endif

@@ -43,13 +43,14 @@ struct Launchers
     cudaError_t (*temporalStabilization)(const PassLaunch&, int);
     cudaError_t (*sigma)(const PassLaunch&, const char*);
     cudaError_t (*relax)(const PassLaunch&, const char*);
+    cudaError_t (*aux)(const PassLaunch&, const char*); // split-screen passes, REFERENCE denoiser
 };
 const Launchers kStripLaunchers = {nrdb200::LaunchReblurClassifyTiles, nrdb200::LaunchReblurHitDistReconstruction, nrdb200::LaunchReblurPrePass, nrdb200::LaunchReblurTemporalAccumulation,
                                    nrdb200::LaunchReblurHistoryFix, nrdb200::LaunchReblurBlur, nrdb200::LaunchReblurPostBlur,
-                                   nrdb200::LaunchReblurTemporalStabilization, nrdb200::LaunchSigma, nrdb200::LaunchRelax};
+                                   nrdb200::LaunchReblurTemporalStabilization, nrdb200::LaunchSigma, nrdb200::LaunchRelax, nrdb200::LaunchAux};
 const Launchers kSingleLaunchers = {nrdb200_single::LaunchReblurClassifyTiles, nrdb200_single::LaunchReblurHitDistReconstruction, nrdb200_single::LaunchReblurPrePass, nrdb200_single::LaunchReblurTemporalAccumulation,
                                     nrdb200_single::LaunchReblurHistoryFix, nrdb200_single::LaunchReblurBlur, nrdb200_single::LaunchReblurPostBlur,
-                                    nrdb200_single::LaunchReblurTemporalStabilization, nrdb200_single::LaunchSigma, nrdb200_single::LaunchRelax};
+                                    nrdb200_single::LaunchReblurTemporalStabilization, nrdb200_single::LaunchSigma, nrdb200_single::LaunchRelax, nrdb200_single::LaunchAux};
 
 std::atomic<uint64_t> g_launchCount{0};
 std::mutex g_slotMutex;
@@ -96,6 +97,8 @@ bool ExpectedUserFormat(ResourceType type, Format& expected, bool translucent = 
         case ResourceType::OUT_DIFF_RADIANCE_HITDIST:
         case ResourceType::OUT_SPEC_RADIANCE_HITDIST: expected = Format::RGBA16_SFLOAT; return true;
         case ResourceType::IN_PENUMBRA: expected = Format::R16_SFLOAT; return true;
+        case ResourceType::IN_SIGNAL:
+        case ResourceType::OUT_SIGNAL: expected = Format::RGBA16_SFLOAT; return true; // REFERENCE denoiser
         // optional inputs (CommonSettings::isHistoryConfidenceAvailable / isDisocclusionThresholdMixAvailable)
         case ResourceType::IN_DIFF_CONFIDENCE:
         case ResourceType::IN_SPEC_CONFIDENCE:
@@ -269,6 +272,7 @@ cudaError_t LaunchByName(const Launchers& L, const PassLaunch& p, const char* sh
     const char* pass = nullptr;
     if (!strncmp(shader, "Clear_", 6)) return p.preloadOnly ? cudaSuccess : LaunchClear(p);
     if (p.rowEnd <= p.rowBegin) return cudaSuccess; // a rank without rows still takes part in the barriers
+    if (strstr(shader, "_SplitScreen.cs") || !strncmp(shader, "REFERENCE_", 10)) return L.aux(p, shader);
     if (!strcmp(shader, "REBLUR_ClassifyTiles.cs")) return L.classifyTiles(p);
     if (ParseReblur(shader, signal, pass))
     {
@@ -704,6 +708,7 @@ NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t 
     if (e == cudaSuccess) e = SetPeerTableReblurTemporal(ctx->peerSlot, &table);
     if (e == cudaSuccess) e = SetPeerTableSigma(ctx->peerSlot, &table);
     if (e == cudaSuccess) e = SetPeerTableRelax(ctx->peerSlot, &table);
+    if (e == cudaSuccess) e = SetPeerTableAux(ctx->peerSlot, &table);
     if (e != cudaSuccess) return Fail(ctx, Result::FAILURE, std::string("peer table: ") + cudaGetErrorString(e));
     ctx->rank = rank;
     ctx->world = worldSize;
@@ -759,7 +764,8 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     // decoded-guide surface: ClassifyTiles (first pass of every REBLUR frame) fills it, all later passes of the frame read it
     const bool isReblur = !strncmp(shader, "REBLUR_", 7), isRelax = !strncmp(shader, "RELAX_", 6);
     const bool buildsGuide = !strcmp(shader, "REBLUR_ClassifyTiles.cs") || !strcmp(shader, "RELAX_ClassifyTiles.cs");
-    const bool readsGuide = (isReblur || isRelax) && !buildsGuide; // every other REBLUR / RELAX pass reads it (REBLUR: and the roughness table)
+    const bool isSplitScreen = strstr(shader, "_SplitScreen.cs") != nullptr; // may be the only pass of the frame (splitScreen >= 1)
+    const bool readsGuide = (isReblur || isRelax) && !buildsGuide && !isSplitScreen; // every other REBLUR / RELAX pass reads it (REBLUR: and the roughness table)
     p.guide = ToSurf(ctx, ctx->guide);
     if (buildsGuide)
     {

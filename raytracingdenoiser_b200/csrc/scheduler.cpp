@@ -89,6 +89,7 @@ Result Scheduler::Create(const InstanceCreationDesc& creation)
             case Denoiser::RELAX_DIFFUSE_SPECULAR: AddRelax(slot, true, true); break;
             case Denoiser::SIGMA_SHADOW: AddSigmaShadow(slot, false); break;
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: AddSigmaShadow(slot, true); break;
+            case Denoiser::REFERENCE: AddReference(slot); break;
             default: return Result::INVALID_ARGUMENT;
         }
 
@@ -471,6 +472,7 @@ Result Scheduler::GetComputeDispatches(const Identifier* ids, uint32_t idsNum, c
             case Denoiser::RELAX_DIFFUSE_SPECULAR: UpdateRelax(slot); break;
             case Denoiser::SIGMA_SHADOW:
             case Denoiser::SIGMA_SHADOW_TRANSLUCENCY: UpdateSigma(slot); break;
+            case Denoiser::REFERENCE: UpdateReference(slot); break;
             default: break;
         }
     }

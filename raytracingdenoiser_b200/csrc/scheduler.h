@@ -143,6 +143,8 @@ private:
     void AddSigmaShadow(DenoiserSlot& slot, bool translucent);
     void UpdateSigma(const DenoiserSlot& slot);
     void FillSigmaConstants(const nrd::SigmaSettings& s, void* data);
+    void AddReference(DenoiserSlot& slot);
+    void UpdateReference(const DenoiserSlot& slot);
 
     MemoryHooks hooks_;
     Vec<DenoiserSlot> slots_;
@@ -170,5 +172,6 @@ private:
     bool hasPrevTime_ = false;
     std::chrono::steady_clock::time_point prevTime_;
     float smoothedTimeDelta_ = 16.6667f;
+    uint32_t accumulatedFrameNum_ = 0; // REFERENCE denoiser: frames accumulated so far (one counter per instance, like the reference)
 };
 } // namespace nrdb200

@@ -18,6 +18,8 @@ USER_FORMATS = {
     "OUT_DIFF_RADIANCE_HITDIST": (nrd.Format.RGBA16_SFLOAT, torch.float16, 4),
     "OUT_SPEC_RADIANCE_HITDIST": (nrd.Format.RGBA16_SFLOAT, torch.float16, 4),
     "IN_PENUMBRA": (nrd.Format.R16_SFLOAT, torch.float16, 1),
+    "IN_SIGNAL": (nrd.Format.RGBA16_SFLOAT, torch.float16, 4),
+    "OUT_SIGNAL": (nrd.Format.RGBA16_SFLOAT, torch.float16, 4),
     "IN_DIFF_CONFIDENCE": (nrd.Format.R8_UNORM, torch.uint8, 1),
     "IN_SPEC_CONFIDENCE": (nrd.Format.R8_UNORM, torch.uint8, 1),
     "IN_DISOCCLUSION_THRESHOLD_MIX": (nrd.Format.R8_UNORM, torch.uint8, 1),
@@ -43,6 +45,7 @@ DENOISER_RESOURCES = {
                                           "OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"],
     nrd.Denoiser.RELAX_DIFFUSE: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_DIFF_RADIANCE_HITDIST", "OUT_DIFF_RADIANCE_HITDIST"],
     nrd.Denoiser.RELAX_SPECULAR: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_SPEC_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"],
+    nrd.Denoiser.REFERENCE: ["IN_SIGNAL", "OUT_SIGNAL"],
     nrd.Denoiser.SIGMA_SHADOW: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_PENUMBRA", "OUT_SHADOW_TRANSLUCENCY"],
     nrd.Denoiser.SIGMA_SHADOW_TRANSLUCENCY: ["IN_MV", "IN_NORMAL_ROUGHNESS", "IN_VIEWZ", "IN_PENUMBRA", "IN_TRANSLUCENCY", "OUT_SHADOW_TRANSLUCENCY"],
 }

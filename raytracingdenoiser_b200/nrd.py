@@ -180,6 +180,8 @@ RelaxSettings = _struct("RelaxSettings", [
 SigmaSettings = _struct("SigmaSettings", [("lightDirection", f32 * 3), ("planeDistanceSensitivity", f32), ("maxStabilizedFrameNum", u32)],
                         dict(planeDistanceSensitivity=0.02, maxStabilizedFrameNum=5))
 
+ReferenceSettings = _struct("ReferenceSettings", [("maxAccumulatedFrameNum", u32)], dict(maxAccumulatedFrameNum=1020))
+
 NrdCudaContextDesc = _struct("NrdCudaContextDesc", [("resourceWidth", u16), ("resourceHeight", u16), ("stripY0", u16), ("stripY1", u16), ("stripHeight", u16), ("haloRows", u16), ("device", C.c_int32)])
 NrdCudaTextureInfo = _struct("NrdCudaTextureInfo", [("devicePtr", C.c_void_p), ("pitchBytes", C.c_size_t), ("format", u32), ("width", u16), ("height", u16),
                                                     ("firstRow", u16), ("rowsNum", u16)])

@@ -269,6 +269,7 @@ class Scene(object):
         else:
             out["IN_DIFF_RADIANCE_HITDIST"] = pack_relax(ld, diff_hit, sky)
             out["IN_SPEC_RADIANCE_HITDIST"] = pack_relax(ls, spec_hit, sky)
+        out["IN_SIGNAL"] = out["IN_DIFF_RADIANCE_HITDIST"]  # REFERENCE denoiser: any RGBA16F signal
         return out
 
 

@@ -43,7 +43,7 @@ def oracle_lib(variant=""):
 
 _NP = {nrd.Format.R8_UNORM: (np.uint8, 1), nrd.Format.R8_UINT: (np.uint8, 1), nrd.Format.RG8_UNORM: (np.uint8, 2), nrd.Format.RGBA8_UNORM: (np.uint8, 4),
        nrd.Format.R16_UINT: (np.uint16, 1), nrd.Format.R16_SFLOAT: (np.float16, 1), nrd.Format.RGBA16_SFLOAT: (np.float16, 4), nrd.Format.R32_UINT: (np.uint32, 1),
-       nrd.Format.R32_SFLOAT: (np.float32, 1), nrd.Format.R10_G10_B10_A2_UNORM: (np.uint32, 1)}
+       nrd.Format.R32_SFLOAT: (np.float32, 1), nrd.Format.R10_G10_B10_A2_UNORM: (np.uint32, 1), nrd.Format.RGBA32_SFLOAT: (np.float32, 4)}
 
 
 def alloc(fmt, w, h):
@@ -132,7 +132,7 @@ def compare(a, b, fmt, rel=1e-3, abs_tol=1e-4, layout=None):
         err, tol = np.abs(ca - cb), 2e-3 * np.maximum(np.abs(ca), np.abs(cb)) + abs_tol
         ok &= err <= tol
         return float(ok.mean()), float((err / tol).max())
-    if fmt in (nrd.Format.RGBA16_SFLOAT, nrd.Format.R16_SFLOAT, nrd.Format.R32_SFLOAT):
+    if fmt in (nrd.Format.RGBA16_SFLOAT, nrd.Format.R16_SFLOAT, nrd.Format.R32_SFLOAT, nrd.Format.RGBA32_SFLOAT):
         x, y = a.astype(np.float64), b.astype(np.float64)
         x = np.nan_to_num(x, nan=1e30, posinf=1e30, neginf=-1e30)
         y = np.nan_to_num(y, nan=1e30, posinf=1e30, neginf=-1e30)
@@ -178,7 +178,7 @@ def _excess_map(a, b, fmt, rel, abs_tol, layout=None):
         ca, cb = np.nan_to_num(ca, nan=1e30, posinf=1e30, neginf=-1e30), np.nan_to_num(cb, nan=1e30, posinf=1e30, neginf=-1e30)
         ex = np.maximum(ex, np.abs(ca - cb) / (2e-3 * np.maximum(np.abs(ca), np.abs(cb)) + abs_tol))
         return ex, bad
-    if fmt in (nrd.Format.RGBA16_SFLOAT, nrd.Format.R16_SFLOAT, nrd.Format.R32_SFLOAT):
+    if fmt in (nrd.Format.RGBA16_SFLOAT, nrd.Format.R16_SFLOAT, nrd.Format.R32_SFLOAT, nrd.Format.RGBA32_SFLOAT):
         x, y = a.astype(np.float64), b.astype(np.float64)
         bad = np.isfinite(x) & ~np.isfinite(y)
         x = np.nan_to_num(x, nan=1e30, posinf=1e30, neginf=-1e30)

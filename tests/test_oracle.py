@@ -324,3 +324,44 @@ def test_relax_one_signal_denoisers_equal_the_two_signal_denoiser_per_signal(sin
                 cpu.set_inputs(fr)
         outs.append(cpu.user["OUT_%s_RADIANCE_HITDIST" % signal].copy())
     assert outs[0].any() and (outs[0] == outs[1]).all()
+
+
+def test_reference_denoiser_accumulates_a_running_average_in_the_oracle():
+    """Static camera: after n frames OUT_SIGNAL is the mean of the n inputs (accumSpeed = 1 / (1 + n), Reference.hpp:60-73)."""
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h = 64, 48
+    sc = scene.Scene(w, h)
+    cpu = orr.CpuDenoiser(nrd.Denoiser.REFERENCE, w, h)
+    fr0 = sc.frame(0)
+    acc = np.zeros((h, w, 4), dtype=np.float64)
+    for f in range(4):
+        fr = dict(fr0)  # frame-0 camera for every frame: worldToClip == worldToClipPrev after the first one
+        fr["IN_SIGNAL"] = sc.frame(f)["IN_SIGNAL"]
+        fr["worldToViewPrev"] = fr["worldToView"]
+        cpu.set_inputs(fr)
+        cpu.denoise(harness.make_common_settings(fr, w, h, f))
+        acc += cpu.user["IN_SIGNAL"].view(np.float16).astype(np.float64)
+    out = cpu.user["OUT_SIGNAL"].view(np.float16).astype(np.float64)
+    assert np.allclose(out, acc / 4.0, rtol=2e-3, atol=1e-3)
+
+
+def test_split_screen_shows_the_input_left_of_the_split_in_the_oracle():
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h = 96, 64
+    sc = scene.Scene(w, h)
+    common = {"splitScreen": 0.5}
+    cpu = orr.CpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE, w, h, common=common)
+    names = set()
+    for f in range(2):
+        fr = sc.frame(f)
+        cpu.set_inputs(fr)
+        names |= {d.shaderFileName for d in cpu.denoise(harness.make_common_settings(fr, w, h, f, common=common))}
+    assert "REBLUR_Diffuse_SplitScreen.cs" in names
+    out = cpu.user["OUT_DIFF_RADIANCE_HITDIST"].view(np.float16).astype(np.float32)
+    inp = cpu.user["IN_DIFF_RADIANCE_HITDIST"].view(np.float16).astype(np.float32)
+    z = np.abs(cpu.user["IN_VIEWZ"]) < 500000.0
+    left = slice(0, w // 2 - 1)
+    assert np.array_equal(out[:, left][z[:, left]], inp[:, left][z[:, left]])
+    assert not np.array_equal(out[:, w // 2 + 1:], inp[:, w // 2 + 1:])
