@@ -22,6 +22,26 @@ class OracleTexture(C.Structure):
 _oracle = {}
 
 
+def host_threads():
+    """Threads the oracle may really use: the affinity mask capped by the cgroup CPU quota.  A container that sees 128 cores through
+    sched_getaffinity may be throttled to 16 of them; an OpenMP team of 128 then thrashes (measured: 3-8x slower oracle passes)."""
+    import math
+    affinity = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        parts = open("/sys/fs/cgroup/cpu.max").read().split()  # cgroup v2: "<quota|max> <period>"
+        if parts and parts[0] != "max":
+            quota = float(parts[0]) / float(parts[1])
+    except Exception:
+        try:
+            q, per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()), float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    return affinity if quota is None else max(1, min(affinity, int(math.ceil(quota))))
+
+
 def oracle_lib(variant=""):
     """variant "": the oracle (no FMA contraction); "fma": the same sources compiled with contraction allowed -- a second
     IEEE-legal evaluation; "uv": the same sources with the uv of every bilinear fetch moved by one float ulp (oracle/hlsl.h).
@@ -37,6 +57,8 @@ def oracle_lib(variant=""):
         lib.oracle_num_threads.restype = C.c_int
         lib.oracle_set_num_threads.argtypes = [C.c_int]
         lib.oracle_set_num_threads.restype = None
+        if not os.environ.get("OMP_NUM_THREADS"):
+            lib.oracle_set_num_threads(host_threads())  # (each library build carries its own OpenMP setting)
         _oracle[variant] = lib
     return _oracle[variant]
 

@@ -26,10 +26,12 @@ def _dump(name, report):
 
 def _all_cores():
     import oracle_runner as orr
-    orr.oracle_lib().oracle_set_num_threads(len(os.sched_getaffinity(0)))
+    for v in ("", "fma", "uv"):
+        orr.oracle_lib(v).oracle_set_num_threads(orr.host_threads())  # also under launchers that export OMP_NUM_THREADS=1
 
 
-def test_config2_reblur_diffuse_1080p_spatial_only():
+def test_config2_reblur_diffuse_1080p_spatial_only(gpu_time_budget):
+    gpu_time_budget(20)
     import parity
     from raytracingdenoiser_b200 import nrd
     _all_cores()
@@ -42,7 +44,8 @@ def test_config2_reblur_diffuse_1080p_spatial_only():
     assert not sbs.failures(), sbs.describe_failures()
 
 
-def test_config5_reblur_diffuse_specular_4k_per_pass():
+def test_config5_reblur_diffuse_specular_4k_per_pass(gpu_time_budget):
+    gpu_time_budget(130)
     import parity
     from raytracingdenoiser_b200 import nrd
     _all_cores()
@@ -53,7 +56,8 @@ def test_config5_reblur_diffuse_specular_4k_per_pass():
     assert not sbs.failures(), sbs.describe_failures()
 
 
-def test_config4_relax_4k_per_pass_steady_state():
+def test_config4_relax_4k_per_pass_steady_state(gpu_time_budget):
+    gpu_time_budget(280)
     import parity
     from raytracingdenoiser_b200 import nrd
     _all_cores()
@@ -65,7 +69,7 @@ def test_config4_relax_4k_per_pass_steady_state():
     assert not sbs.failures(), sbs.describe_failures()
 
 
-def test_config3_reblur_1440p_64_frame_sequence():
+def test_config3_reblur_1440p_64_frame_sequence(gpu_time_budget):
     """Statistical gate of SURVEY.md 8(d) at the stated size and length, read against the chain's own rounding-noise floor.
 
     SURVEY asked for >= 99 % of texels within 1e-3 relative after 64 frames.  That is not a property any independent evaluation of
@@ -78,6 +82,7 @@ def test_config3_reblur_1440p_64_frame_sequence():
     The 12-frame gates of test_gpu_reblur.py / test_gpu_relax.py stay at 99 %."""
     import parity
     from raytracingdenoiser_b200 import nrd
+    gpu_time_budget(320)
     _all_cores()
     res = parity.run_sequence(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, 2560, 1440, 64, noise_floor=True)
     _dump("sequence_config3_1440p_64.json", {k: {"fraction_within_tolerance": v[0], "psnr_db": v[1], "oracle_vs_oracle_fma_fraction": v[2]} for k, v in res.items()})
