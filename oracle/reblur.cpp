@@ -78,6 +78,10 @@ const float3 g_Special8[8] = {
     float3(-0.25f * std::sqrt(2.0f), 0.25f * std::sqrt(2.0f), 0.5f), float3(0.25f * std::sqrt(2.0f), 0.25f * std::sqrt(2.0f), 0.5f),
     float3(0.25f * std::sqrt(2.0f), -0.25f * std::sqrt(2.0f), 0.5f), float3(-0.25f * std::sqrt(2.0f), -0.25f * std::sqrt(2.0f), 0.5f)};
 
+// Common.hlsli:170-179
+const float3 g_Special6[6] = {float3(-0.5f * std::sqrt(3.0f), -0.5f, 1.0f), float3(0.0f, 1.0f, 1.0f), float3(0.5f * std::sqrt(3.0f), -0.5f, 1.0f),
+                              float3(0.0f, -0.3f, 0.3f), float3(0.15f * std::sqrt(3.0f), 0.15f, 0.3f), float3(-0.15f * std::sqrt(3.0f), 0.15f, 0.3f)};
+
 // ---- NRD.hlsli helpers ----------------------------------------------------------------------------
 float3 _NRD_SafeNormalize(float3 v) { return v * float3(rsqrt(dot(v, v) + 1e-9f)); }              // NRD.hlsli:321-324
 float3 _NRD_DecodeUnitVector(float2 p)                                                            // NRD.hlsli:337-347 (unsigned, no normalize)
@@ -122,7 +126,10 @@ float NRD_GetNormalizedStrandThickness(float strandThickness, float pixelSize) {
 struct Pass
 {
     const CB& c;
-    explicit Pass(const CB& cb) : c(cb) {}
+    // REBLUR_PERFORMANCE_MODE (REBLUR_Config.hlsli:196-238, the "REBLUR_Perf_*" shader permutations): no CatRom history filters,
+    // screen-space sampling for both signals, 6 taps of g_Special6, anti-firefly radius 3, cheaper history fix / reconstruction
+    bool perf = false;
+    explicit Pass(const CB& cb, bool performanceMode = false) : c(cb), perf(performanceMode) {}
 
     float UnpackViewZ(float z) const { return abs(z * c.gViewZScale); }                                                   // :235
     float PixelRadiusToWorld(float unproject, float orthoMode, float pixelRadius, float viewZ) const                     // :237-240
@@ -510,9 +517,9 @@ void DiffuseSpatialFilter(const Pass& P, const SpatialCtx& s, float sum, float4 
         skew *= float2(blurRadius); // in pixels: uv * rectSize is evaluated directly (Pass::TapTexelScreen)
         float4 scaledRotator = Geometry::ScaleRotator(s.rotator, skew);
 
-        for (uint n = 0; n < 8; n++)
+        for (uint n = 0; n < (P.perf ? 6u : 8u); n++)
         {
-            float3 offset = g_Special8[n];
+            float3 offset = P.perf ? g_Special6[n] : g_Special8[n];
             float2 uv = floor(Pass::TapTexelScreen(s.pixelPos, scaledRotator, offset.xy())) + float2(0.5f);
             if (pre) uv = Pass::ApplyCheckerboardShift(uv, c.gDiffCheckerboard, n, c.gFrameIndex);
             uv *= c.gRectSizeInv;
@@ -618,7 +625,8 @@ void SpecularSpatialFilter(const Pass& P, const SpatialCtx& s, float sum, float4
 
         float4 scaledRotator(0.0f);
         float3 Tv(0.0f), Bv(0.0f);
-        if (pre)
+        const bool screenSpace = pre || P.perf; // REBLUR_USE_SCREEN_SPACE_SAMPLING_FOR_SPECULAR = 1 in performance mode
+        if (screenSpace)
         {
             float2 skew(1.0f);
             skew *= float2(blurRadius); // in pixels (Pass::TapTexelScreen)
@@ -639,11 +647,11 @@ void SpecularSpatialFilter(const Pass& P, const SpatialCtx& s, float sum, float4
         }
         const Pass::KernelProjection kernelProjection = Pass::ProjectKernel(c.gViewToClip, c.gRectSize, s.Xv, Tv, Bv);
 
-        for (uint n = 0; n < 8; n++)
+        for (uint n = 0; n < (P.perf ? 6u : 8u); n++)
         {
-            float3 offset = g_Special8[n];
+            float3 offset = P.perf ? g_Special6[n] : g_Special8[n];
             float2 uv;
-            if (pre) uv = Pass::TapTexelScreen(s.pixelPos, scaledRotator, offset.xy());
+            if (screenSpace) uv = Pass::TapTexelScreen(s.pixelPos, scaledRotator, offset.xy());
             else uv = Pass::TapTexelWorld(kernelProjection, offset, s.rotator);
             uv = floor(uv) + float2(0.5f);
             if (pre) uv = Pass::ApplyCheckerboardShift(uv, c.gSpecCheckerboard, n, c.gFrameIndex);
@@ -809,11 +817,14 @@ void HitDistReconstruction(const Pass& P, Signals sg, int border, Tex* t, int W,
                     float3 Xvs = Geometry::ReconstructViewPosition(uv, c.gFrustum, data.z, c.gOrthoMode);
                     w *= Pass::ComputeWeight(dot(Nv, Xvs), geometryWeightParams.x, geometryWeightParams.y);
                     float2 ww(w);
-                    float cosa = dot(N, nr.xyz());
-                    float angle = Math::AcosApprox(cosa);
-                    ww.x *= Pass::ComputeExponentialWeight(angle, diffNormalWeightParam, 0.0f);
-                    ww.y *= Pass::ComputeExponentialWeight(angle, specNormalWeightParam, 0.0f);
-                    ww.y *= Pass::ComputeExponentialWeight(nr.w * nr.w, relaxedRoughnessWeightParams.x, relaxedRoughnessWeightParams.y);
+                    if (!P.perf) // :106-119
+                    {
+                        float cosa = dot(N, nr.xyz());
+                        float angle = Math::AcosApprox(cosa);
+                        ww.x *= Pass::ComputeExponentialWeight(angle, diffNormalWeightParam, 0.0f);
+                        ww.y *= Pass::ComputeExponentialWeight(angle, specNormalWeightParam, 0.0f);
+                        ww.y *= Pass::ComputeExponentialWeight(nr.w * nr.w, relaxedRoughnessWeightParams.x, relaxedRoughnessWeightParams.y);
+                    }
                     data.x = ww.x == 0.0f ? 0.0f : data.x; // Denanify
                     data.y = ww.y == 0.0f ? 0.0f : data.y;
                     ww *= float2(float(data.x != 0.0f), float(data.y != 0.0f));
@@ -1180,7 +1191,7 @@ void TemporalAccumulation(const Pass& P, Signals sg, Tex* t, int W, int H)
 
             // 2x2 occlusion weights (:271-279)
             float4 smbOcclusionWeights = Filtering::GetBilinearCustomWeights(smbBilinearFilter, float4(smbOcclusion0.z, smbOcclusion1.y, smbOcclusion2.y, smbOcclusion3.x));
-            bool smbAllowCatRom = dot(smbOcclusion0 + smbOcclusion1 + smbOcclusion2 + smbOcclusion3, float3(1.0f)) > 11.5f;
+            bool smbAllowCatRom = dot(smbOcclusion0 + smbOcclusion1 + smbOcclusion2 + smbOcclusion3, float3(1.0f)) > 11.5f && !P.perf;
             float fbits = smbOcclusion0.z * 1.0f;
             fbits += smbOcclusion1.y * 2.0f;
             fbits += smbOcclusion2.y * 4.0f;
@@ -1337,7 +1348,7 @@ void TemporalAccumulation(const Pass& P, Signals sg, Tex* t, int W, int H)
                 float vmbFootprintQuality = Filtering::ApplyBilinearFilter(vmbOcclusion.x, vmbOcclusion.y, vmbOcclusion.z, vmbOcclusion.w, vmbBilinearFilter);
                 vmbFootprintQuality = Math::Sqrt01(vmbFootprintQuality);
                 vmbSpecAccumSpeed *= lerp(vmbFootprintQuality, 1.0f, 1.0f / (1.0f + vmbSpecAccumSpeed));
-                bool vmbAllowCatRom = dot(vmbOcclusion, float4(1.0f)) > 3.5f;
+                bool vmbAllowCatRom = dot(vmbOcclusion, float4(1.0f)) > 3.5f && !P.perf;
                 vmbAllowCatRom = vmbAllowCatRom && smbAllowCatRom;
 
                 // (:533-556)
@@ -1606,6 +1617,7 @@ void HistoryFix(const Pass& P, Signals sg, Tex* t, int W, int H)
                     float hitDistFactor = Pass::GetHitDistFactor(hitDist, frustumSize);
                     float2 hitDistanceWeightParams = Pass::GetHitDistanceWeightParams(hitDistFactor, nonLinearAccumSpeed, isSpec ? roughness : 1.0f);
                     float sum = 1.0f + fn;
+                    if (P.perf) sum = 1.0f + 1.0f / (1.0f + c.gMaxAccumulatedFrameNum) - nonLinearAccumSpeed; // :88-90
                     sig *= float4(sum);
 
                     for (int j = -2; j <= 2; j++)
@@ -1625,8 +1637,11 @@ void HistoryFix(const Pass& P, Signals sg, Tex* t, int W, int H)
                             w *= float(max(materialID, minMaterial) == max(materialIDs, minMaterial));
                             w *= Pass::ComputeExponentialWeight(angle, normalWeightParam, 0.0f);
                             if (isSpec) w *= Pass::ComputeExponentialWeight(Ns.w * Ns.w, relaxedRoughnessWeightParams.x, relaxedRoughnessWeightParams.y);
-                            float2 d1 = unpackData1(gIn_Data1.load(pos));
-                            w *= 1.0f + (isSpec ? d1.y : d1.x);
+                            if (!P.perf) // :139-141
+                            {
+                                float2 d1 = unpackData1(gIn_Data1.load(pos));
+                                w *= 1.0f + (isSpec ? d1.y : d1.x);
+                            }
                             float4 sv = gIn_Sig.load(pos);
                             sv = w == 0.0f ? float4(0.0f) : sv;
                             float hs = sv.w * hitDistScale;
@@ -1668,6 +1683,7 @@ void HistoryFix(const Pass& P, Signals sg, Tex* t, int W, int H)
                 if (c.gAntiFirefly != 0.0f)
                 {
                     float am1 = 0, am2 = 0;
+                    const int REBLUR_ANTI_FIREFLY_FILTER_RADIUS = P.perf ? 3 : 4; // REBLUR_Config.hlsli:87, :236-237
                     for (int j = -REBLUR_ANTI_FIREFLY_FILTER_RADIUS; j <= REBLUR_ANTI_FIREFLY_FILTER_RADIUS; j++)
                         for (int i = -REBLUR_ANTI_FIREFLY_FILTER_RADIUS; i <= REBLUR_ANTI_FIREFLY_FILTER_RADIUS; i++)
                         {
@@ -1763,7 +1779,7 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
             Filtering::Bilinear smbBilinearFilter = Filtering::GetBilinearFilter(smbPixelUv, c.gRectSizePrev);
             float4 smbOcclusion = float4(float((bits & 1) != 0), float((bits & 2) != 0), float((bits & 4) != 0), float((bits & 8) != 0));
             float4 smbOcclusionWeights = Filtering::GetBilinearCustomWeights(smbBilinearFilter, smbOcclusion);
-            bool smbAllowCatRom = dot(smbOcclusion, float4(1.0f)) > 3.5f;
+            bool smbAllowCatRom = dot(smbOcclusion, float4(1.0f)) > 3.5f && !P.perf;
             float smbFootprintQuality = Filtering::ApplyBilinearFilter(smbOcclusion.x, smbOcclusion.y, smbOcclusion.z, smbOcclusion.w, smbBilinearFilter);
             smbFootprintQuality = Math::Sqrt01(smbFootprintQuality);
 
@@ -1794,7 +1810,7 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
                 float diffLuma, diffLumaM1, diffLumaM2, diffMin, diffMax;
                 stats(*gIn_Diff, diffLuma, diffLumaM1, diffLumaM2, diffMin, diffMax);
                 float diffLumaSigma = Pass::GetStdDev(diffLumaM1, diffLumaM2);
-                if (c.gMaxBlurRadius != 0.0f) diffLuma = clamp(diffLuma, diffMin, diffMax);
+                if (c.gMaxBlurRadius != 0.0f && !P.perf) diffLuma = clamp(diffLuma, diffMin, diffMax); // RCRS: not in performance mode (:131-135)
 
                 float4 h4;
                 P.BicubicFilter(saturate(smbPixelUv) * c.gRectSizePrev, c.gResourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom, *gHistory_DiffLumaStabilized, h4, nullptr, nullptr);
@@ -1824,7 +1840,7 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
                 float specLuma, specLumaM1, specLumaM2, specMin, specMax;
                 stats(*gIn_Spec, specLuma, specLumaM1, specLumaM2, specMin, specMax);
                 float specLumaSigma = Pass::GetStdDev(specLumaM1, specLumaM2);
-                if (c.gMaxBlurRadius != 0.0f) specLuma = clamp(specLuma, specMin, specMax);
+                if (c.gMaxBlurRadius != 0.0f && !P.perf) specLuma = clamp(specLuma, specMin, specMax);
 
                 float virtualHistoryAmount = data2.x;
                 float curvature = data2.y;
@@ -1845,7 +1861,7 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
                 Filtering::Bilinear vmbBilinearFilter = Filtering::GetBilinearFilter(vmbPixelUv, c.gRectSizePrev);
                 float4 vmbOcclusion = float4(float((bits & 16) != 0), float((bits & 32) != 0), float((bits & 64) != 0), float((bits & 128) != 0));
                 float4 vmbOcclusionWeights = Filtering::GetBilinearCustomWeights(vmbBilinearFilter, vmbOcclusion);
-                bool vmbAllowCatRom = dot(vmbOcclusion, float4(1.0f)) > 3.5f;
+                bool vmbAllowCatRom = dot(vmbOcclusion, float4(1.0f)) > 3.5f && !P.perf;
                 float vmbFootprintQuality = Filtering::ApplyBilinearFilter(vmbOcclusion.x, vmbOcclusion.y, vmbOcclusion.z, vmbOcclusion.w, vmbBilinearFilter);
                 vmbFootprintQuality = Math::Sqrt01(vmbFootprintQuality);
 
@@ -1924,15 +1940,16 @@ int hlsl::reblur_dispatch_impl(const char* shaderName, const void* constants, in
     if (constantsSize < (int)sizeof(CB)) return -2;
     CB cb;
     memcpy(&cb, constants, sizeof(CB));
-    Pass P(cb);
+    const bool perf = !strncmp(shaderName, "REBLUR_Perf_", 12);
+    Pass P(cb, perf);
 
     if (!strcmp(shaderName, "REBLUR_ClassifyTiles.cs"))
     {
         ClassifyTiles(P, tex, gridW, gridH);
         return 0;
     }
-    if (strncmp(shaderName, "REBLUR_", 7) != 0 || !strncmp(shaderName, "REBLUR_Perf_", 12)) return -1;
-    const char* p = shaderName + 7;
+    if (strncmp(shaderName, "REBLUR_", 7) != 0) return -1;
+    const char* p = shaderName + (perf ? 12 : 7);
     Signals sg{false, false};
     if (!strncmp(p, "DiffuseSpecular_", 16)) { sg = {true, true}; p += 16; }
     else if (!strncmp(p, "Diffuse_", 8)) { sg = {true, false}; p += 8; }

@@ -23,6 +23,7 @@ struct HitDistArgs
     const float4* lut;
     int rowBegin, rowEnd;
     int useTma; // the guide window is staged by TMA (else by clamped loads)
+    int perf;   // REBLUR_PERFORMANCE_MODE: no normal / roughness weights (REBLUR_HitDistReconstruction.hlsli:106-119)
 };
 
 constexpr int kHdTileW = 32, kHdTileH = 8;
@@ -101,12 +102,16 @@ __global__ void __launch_bounds__(kHdTileW* kHdTileH) ReblurHitDistReconstructio
             const f3 Xvs = ReconstructViewPosition(uv, c.gFrustum, zs, c.gOrthoMode);
             float w = __expf(-0.66f * 0.25f * (float)(i * i + j * j)); // GetGaussianWeight(length(o) * 0.5)
             w *= NonExpWeight(dot(Nv, Xvs), geoA, geoB);
-            const float angle = AcosApprox(N.x * g.x + N.y * g.y + N.z * g.z);
-            f2 ww = mk2(w * ExpWeight(angle, diffNormalParam, 0.0f), w * ExpWeight(angle, specNormalParam, 0.0f));
-            if (SPEC)
+            f2 ww = mk2(w, w);
+            if (!a.perf)
             {
-                const float r = sRough[sy][sx];
-                ww.y *= ExpWeight(r * r, rrp.x, rrp.y);
+                const float angle = AcosApprox(N.x * g.x + N.y * g.y + N.z * g.z);
+                ww = mk2(w * ExpWeight(angle, diffNormalParam, 0.0f), w * ExpWeight(angle, specNormalParam, 0.0f));
+                if (SPEC)
+                {
+                    const float r = sRough[sy][sx];
+                    ww.y *= ExpWeight(r * r, rrp.x, rrp.y);
+                }
             }
             const float2 h = sHit[sy][sx];
             // Denanify + "valid sample" test: a neighbour takes part iff its weight and its hit distance are non-zero
@@ -149,6 +154,7 @@ template <bool DIFF, bool SPEC, int BORDER> static cudaError_t LaunchHitDist(con
     if (DIFF) a.outDiff = p.tex[k++];
     if (SPEC) a.outSpec = p.tex[k++];
     a.guide = p.guide;
+    a.perf = p.performanceMode ? 1 : 0;
     a.lut = (const float4*)p.roughnessLut;
     a.rowBegin = p.rowBegin;
     a.rowEnd = p.rowEnd;

@@ -230,6 +230,7 @@ struct TaArgs
     Surf guide;          // decoded guides of the current frame (surf.h PassLaunch::guide)
     const float4* lut;   // roughness table (surf.h PassLaunch::roughnessLut)
     int rowBegin, rowEnd;
+    int perf;            // REBLUR_PERFORMANCE_MODE: no CatRom history filters (REBLUR_Config.hlsli:196-202)
 };
 
 template <bool DIFF, bool SPEC>
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         }
     const f4 smbOcclusion = mk4(occ[1][1], occ[1][2], occ[2][1], occ[2][2]);
     const f4 smbOcclusionWeights = CustomWeights(smbF, smbOcclusion);
-    const bool smbAllowCatRom = occSum > 11.5f;
+    const bool smbAllowCatRom = occSum > 11.5f && !a.perf;
     float fbits = smbOcclusion.x + smbOcclusion.y * 2.0f + smbOcclusion.z * 4.0f + smbOcclusion.w * 8.0f;
 
     const f3 id00 = UnpackInternalData(pid[1][1]), id10 = UnpackInternalData(pid[1][2]), id01 = UnpackInternalData(pid[2][1]), id11 = UnpackInternalData(pid[2][2]);
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         float vmbSpecAccumSpeed = ApplyCustomWeights(v00.y, v10.y, v01.y, v11.y, vmbOcclusionWeights);
         float vmbFootprintQuality = Sqrt01(ApplyBilinear(vmbOcclusion.x, vmbOcclusion.y, vmbOcclusion.z, vmbOcclusion.w, vmbF));
         vmbSpecAccumSpeed *= lerpf(vmbFootprintQuality, 1.0f, 1.0f / (1.0f + vmbSpecAccumSpeed));
-        const bool vmbAllowCatRom = (vmbOcclusion.x + vmbOcclusion.y + vmbOcclusion.z + vmbOcclusion.w > 3.5f) && smbAllowCatRom;
+        const bool vmbAllowCatRom = (vmbOcclusion.x + vmbOcclusion.y + vmbOcclusion.z + vmbOcclusion.w > 3.5f) && smbAllowCatRom; // (smbAllowCatRom is false in performance mode)
 
         // how far (in angle) the virtual motion may have travelled
         float curvatureAngleTan = pixelSize * fabsf(curvature) * fmaxf(vmbPixelsTraveled / fmaxf(NoV, 0.01f), 1.0f) * 2.0f;
@@ -756,6 +757,7 @@ struct HfArgs
     const float4* lut;
     int rowBegin, rowEnd;
     int useTma; // the fast-history window is staged by TMA (else by clamped loads)
+    int perf;   // REBLUR_PERFORMANCE_MODE (REBLUR_HistoryFix.hlsli:88-90, :139-141; anti-firefly radius 3)
 };
 
 template <bool BOTH> __device__ __forceinline__ f2 LoadFrames(const Surf& s, int x, int y)
@@ -783,7 +785,7 @@ constexpr int kHfBorder = 2, kHfPad = 8, kHfBoxW = 32 + 2 * kHfPad, kHfBoxH = 8 
 // where every pixel is young and no lane idles) keep the per-pixel loop.
 struct HfItem
 {
-    int x, y, stridei, isSpec;
+    int x, y, stridei, isSpec, perf;
     float stride, u, v;                  // pixelUv
     float Nvx, Nvy, Nvz, geoA, geoB;     // plane-distance weight
     float Nx, Ny, Nz, material;          // material = max(materialID, minMaterial)
@@ -817,6 +819,7 @@ __device__ __forceinline__ HfItem HfMakeItem(const HfArgs& a, int x, int y, floa
     it.y = y;
     it.stridei = (int)(stride + 0.5f);
     it.isSpec = IS_SPEC ? 1 : 0;
+    it.perf = a.perf;
     it.stride = stride;
     it.u = pixelUv.x;
     it.v = pixelUv.y;
@@ -859,8 +862,11 @@ __device__ __forceinline__ HfTap HfEvalTap(const ReblurConstants& c, const HfIte
     w *= it.material == fmaxf(gs.materialID, it.minMaterial) ? 1.0f : 0.0f;
     w *= ExpWeight(AcosApprox(gs.N.x * it.Nx + gs.N.y * it.Ny + gs.N.z * it.Nz), it.normalParam, 0.0f);
     if (isSpec) w *= ExpWeight(gs.roughness * gs.roughness, it.rrpx, it.rrpy);
-    const f2 fr = LoadFrames<BOTH>(data1S, px, py);
-    w *= 1.0f + (isSpec ? fr.y : fr.x);
+    if (!it.perf)
+    {
+        const f2 fr = LoadFrames<BOTH>(data1S, px, py);
+        w *= 1.0f + (isSpec ? fr.y : fr.x);
+    }
     HfTap t;
     t.lo = t.hi = 0u;
     if (w != 0.0f)
@@ -903,6 +909,7 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
     if (stride != 0.0f)
     {
         float sum = 1.0f + fn;
+        if (a.perf) sum = 1.0f + 1.0f / (1.0f + c.gMaxAccumulatedFrameNum) - 1.0f / (1.0f + fn);
         const float sigW = sig.w;
         sig = sig * sum;
         if (taps)
@@ -955,16 +962,18 @@ __device__ __forceinline__ void HistoryFixSignal(const HfArgs& a, int x, int y, 
     if (c.gAntiFirefly != 0.0f)
     {
         float am1 = 0.0f, am2 = 0.0f;
-        for (int j = -4; j <= 4; j++)
-            for (int i = -4; i <= 4; i++)
+        const int R = a.perf ? 3 : 4; // REBLUR_ANTI_FIREFLY_FILTER_RADIUS
+        for (int j = -R; j <= R; j++)
+            for (int i = -R; i <= R; i++)
             {
                 if (abs(i) <= 1 && abs(j) <= 1) continue;
                 float d = LoadR16F(Near(inFast), clampi(x + i, 0, maxX), clampi(y + j, 0, maxY)); // +-4 rows
                 am1 += d;
                 am2 += d * d;
             }
-        am1 *= 1.0f / 72.0f;
-        am2 *= 1.0f / 72.0f;
+        const float invNorm = a.perf ? 1.0f / 40.0f : 1.0f / 72.0f; // (2R + 1)^2 - 9 texels
+        am1 *= invNorm;
+        am2 *= invNorm;
         float sigma = GetStdDev(am1, am2) * 2.0f;
         luma = clampf(luma, am1 - sigma, am1 + sigma);
     }
@@ -1099,6 +1108,7 @@ struct TsArgs
     const float4* lut;
     int rowBegin, rowEnd;
     int useTma; // the signal tiles are staged by TMA (else by clamped loads)
+    int perf;   // REBLUR_PERFORMANCE_MODE: no CatRom, no rank clamp of the centre luma (REBLUR_TemporalStabilization.hlsli:118, :131-135)
 };
 
 __device__ __forceinline__ float Antilag(const ReblurConstants& c, float history, float avg, float sigma, float accumSpeed) // REBLUR_Common.hlsli:244-274, mode 2
@@ -1223,7 +1233,7 @@ __global__ void __launch_bounds__(256)
     const Bilinear smbF = GetBilinear(smbPixelUv, c.gRectSizePrev);
     const f4 smbOcclusion = mk4((bits & 1u) ? 1.0f : 0.0f, (bits & 2u) ? 1.0f : 0.0f, (bits & 4u) ? 1.0f : 0.0f, (bits & 8u) ? 1.0f : 0.0f);
     const f4 smbOcclusionWeights = CustomWeights(smbF, smbOcclusion);
-    const bool smbAllowCatRom = (bits & 15u) == 15u;
+    const bool smbAllowCatRom = (bits & 15u) == 15u && !a.perf;
     const float smbFootprintQuality = Sqrt01(ApplyBilinear(smbOcclusion.x, smbOcclusion.y, smbOcclusion.z, smbOcclusion.w, smbF));
     const f2 smbSamplePos = mk2(saturate(smbPixelUv.x) * c.gRectSizePrev[0], saturate(smbPixelUv.y) * c.gRectSizePrev[1]);
     const CatRomSetup smbSetup = SetupCatRom(smbSamplePos, c.gResourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom);
@@ -1233,7 +1243,7 @@ __global__ void __launch_bounds__(256)
         float luma, m1, m2, mn, mx;
         LumaStats3x3(sDiff, luma, m1, m2, mn, mx);
         const float sigma = PinnedStdDev(m1, m2);
-        if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
+        if (c.gMaxBlurRadius != 0.0f && !a.perf) luma = clampf(luma, mn, mx);
         float history = fmaxf(ResolveCatRom1(smbSetup, a.histDiffStab), 0.0f);
         const float antilag = Antilag(c, history, m1, sigma, smbFootprintQuality * data1.x);
         const float tw = smbFootprintQuality * (data1.x / (1.0f + data1.x));
@@ -1254,7 +1264,7 @@ __global__ void __launch_bounds__(256)
         float luma, m1, m2, mn, mx;
         LumaStats3x3(sSpec, luma, m1, m2, mn, mx);
         const float sigma = PinnedStdDev(m1, m2);
-        if (c.gMaxBlurRadius != 0.0f) luma = clampf(luma, mn, mx);
+        if (c.gMaxBlurRadius != 0.0f && !a.perf) luma = clampf(luma, mn, mx);
 
         f4 spec = UnpackHalf4(sSpec[threadIdx.y + 1][threadIdx.x + kTsPad]);
         float hitDistForTracking = spec.w * ((c.gHitDistParams[0] + viewZ * c.gHitDistParams[1]) * g0.hitK);
@@ -1270,7 +1280,7 @@ __global__ void __launch_bounds__(256)
         const Bilinear vmbF = GetBilinear(vmbPixelUv, c.gRectSizePrev);
         const f4 vmbOcclusion = mk4((bits & 16u) ? 1.0f : 0.0f, (bits & 32u) ? 1.0f : 0.0f, (bits & 64u) ? 1.0f : 0.0f, (bits & 128u) ? 1.0f : 0.0f);
         const f4 vmbOcclusionWeights = CustomWeights(vmbF, vmbOcclusion);
-        const bool vmbAllowCatRom = (bits & 240u) == 240u;
+        const bool vmbAllowCatRom = (bits & 240u) == 240u && !a.perf;
         const float vmbFootprintQuality = Sqrt01(ApplyBilinear(vmbOcclusion.x, vmbOcclusion.y, vmbOcclusion.z, vmbOcclusion.w, vmbF));
         const f2 vmbSamplePos = mk2(saturate(vmbPixelUv.x) * c.gRectSizePrev[0], saturate(vmbPixelUv.y) * c.gRectSizePrev[1]);
         const CatRomSetup vmbSetup = SetupCatRom(vmbSamplePos, c.gResourceSizeInvPrev, vmbOcclusionWeights, vmbAllowCatRom);
@@ -1335,6 +1345,7 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchTa(const PassLaunch& p)
     a.outData2 = p.tex[k++];
     a.rowBegin = p.rowBegin;
     a.rowEnd = p.rowEnd;
+    a.perf = p.performanceMode ? 1 : 0;
     const int W = (int)a.c.gRectSize[0];
     dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 3) / 4), block(32, 4);
     NRD_B200_LAUNCH(p, grid, block, a, ReblurTemporalAccumulationKernel<DIFF, SPEC>);
@@ -1366,6 +1377,7 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchHf(const PassLaunch& p)
     if (SPEC) a.outSpecFast = p.tex[k++];
     a.rowBegin = p.rowBegin;
     a.rowEnd = p.rowEnd;
+    a.perf = p.performanceMode ? 1 : 0;
     const int W = (int)a.c.gRectSize[0];
     dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
     if (p.preloadOnly)
@@ -1412,6 +1424,7 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchTs(const PassLaunch& p)
     if (SPEC) a.outSpecStab = p.tex[k++];
     a.rowBegin = p.rowBegin;
     a.rowEnd = p.rowEnd;
+    a.perf = p.performanceMode ? 1 : 0;
     const int W = (int)a.c.gRectSize[0];
     dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 7) / 8), block(32, 8);
     if (p.preloadOnly)

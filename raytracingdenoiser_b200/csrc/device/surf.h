@@ -48,6 +48,7 @@ struct PassLaunch
     int rowBegin, rowEnd;  // rows this launch must produce, in the pass's own pixel units
     cudaStream_t stream;
     bool preloadOnly;      // do not launch: only make the driver load the kernel this pass maps to (see NRD_B200_LAUNCH)
+    bool performanceMode;  // REBLUR: the pass is the "REBLUR_Perf_*" permutation (ReblurSettings::enablePerformanceMode)
     // Decoded-guide surface (executor-owned RGBA32F, not part of the DispatchDesc): {N.x, N.y, N.z, viewZ (REBLUR: unpacked |z * gViewZScale|, RELAX: raw)} of the current
     // frame's IN_NORMAL_ROUGHNESS / IN_VIEWZ.  guideMode 1 = this pass writes it (REBLUR ClassifyTiles, the first pass of every
     // frame; guideNr = IN_NORMAL_ROUGHNESS, which that dispatch does not bind itself), 2 = it is complete and the filter passes

@@ -253,10 +253,11 @@ Result UpdateRoughnessLut(NrdCudaContext* ctx, const float* hitDistParams, cudaS
 }
 
 // "REBLUR_DiffuseSpecular_Blur.cs" -> family REBLUR, signal 2, pass "Blur"
-bool ParseReblur(const char* name, int& signal, const char*& pass)
+bool ParseReblur(const char* name, int& signal, const char*& pass, bool& perf)
 {
     if (strncmp(name, "REBLUR_", 7) != 0) return false;
-    const char* p = name + 7;
+    perf = !strncmp(name, "REBLUR_Perf_", 12); // ReblurSettings::enablePerformanceMode permutations (Source/Reblur.cpp:106-118)
+    const char* p = name + (perf ? 12 : 7);
     if (!strncmp(p, "DiffuseSpecular_", 16)) { signal = 2; p += 16; }
     else if (!strncmp(p, "Diffuse_", 8)) { signal = 0; p += 8; }
     else if (!strncmp(p, "Specular_", 9)) { signal = 1; p += 9; }
@@ -266,16 +267,19 @@ bool ParseReblur(const char* name, int& signal, const char*& pass)
 }
 
 // pass (shader file name) -> kernel launcher of one build
-cudaError_t LaunchByName(const Launchers& L, const PassLaunch& p, const char* shader)
+cudaError_t LaunchByName(const Launchers& L, const PassLaunch& launch, const char* shader)
 {
     int signal = 0;
     const char* pass = nullptr;
+    bool perf = false;
+    PassLaunch p = launch;
     if (!strncmp(shader, "Clear_", 6)) return p.preloadOnly ? cudaSuccess : LaunchClear(p);
     if (p.rowEnd <= p.rowBegin) return cudaSuccess; // a rank without rows still takes part in the barriers
     if (strstr(shader, "_SplitScreen.cs") || !strncmp(shader, "REFERENCE_", 10)) return L.aux(p, shader);
     if (!strcmp(shader, "REBLUR_ClassifyTiles.cs")) return L.classifyTiles(p);
-    if (ParseReblur(shader, signal, pass))
+    if (ParseReblur(shader, signal, pass, perf))
     {
+        p.performanceMode = perf;
         if (!strcmp(pass, "HitDistReconstruction.cs")) return L.hitDistReconstruction(p, signal, false);
         if (!strcmp(pass, "HitDistReconstruction_5x5.cs")) return L.hitDistReconstruction(p, signal, true);
         if (!strcmp(pass, "PrePass.cs")) return L.prePass(p, signal);

@@ -82,3 +82,28 @@ def test_reblur_optional_inputs_per_pass(denoiser_name):
     assert any("TemporalAccumulation" in r["shader"] for r in report), bound
     _dump("parity_optional_inputs_%s.json" % denoiser_name, report)
     assert not sbs.failures(), sbs.describe_failures()
+
+
+@pytest.mark.parametrize("denoiser_name,hitdist", [("REBLUR_DIFFUSE_SPECULAR", "OFF"), ("REBLUR_DIFFUSE_SPECULAR", "AREA_3X3"), ("REBLUR_DIFFUSE", "OFF"), ("REBLUR_SPECULAR", "AREA_5X5")])
+def test_reblur_performance_mode_per_pass(denoiser_name, hitdist):
+    """ReblurSettings::enablePerformanceMode: the REBLUR_Perf_* permutations (6 taps of g_Special6, screen-space sampling for both
+    signals, bilinear instead of CatRom history filters, no rank clamp in temporal stabilization, anti-firefly radius 3;
+    REBLUR_Config.hlsli:196-238, Source/Reblur.cpp:106-118)."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    s = nrd.ReblurSettings(enablePerformanceMode=True, enableAntiFirefly=True, hitDistanceReconstructionMode=int(getattr(nrd.HitDistanceReconstructionMode, hitdist)))
+    sbs = parity.SideBySide(getattr(nrd.Denoiser, denoiser_name), 250, 141, settings=s)
+    report = sbs.run_per_pass(5)
+    shaders = {r["shader"] for r in report if not r["shader"].startswith("Clear_")}
+    assert all(x.startswith("REBLUR_Perf_") or x == "REBLUR_ClassifyTiles.cs" for x in shaders), shaders
+    _dump("parity_perf_%s_%s.json" % (denoiser_name, hitdist), report)
+    assert not sbs.failures(), sbs.describe_failures()
+
+
+def test_reblur_performance_mode_sequence_parity():
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    res = parity.run_sequence(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, 320, 180, 10, settings=nrd.ReblurSettings(enablePerformanceMode=True))
+    _dump("sequence_reblur_perf.json", res)
+    for name, (frac, psnr) in res.items():
+        assert frac >= 0.99 and psnr >= 60.0, (name, frac, psnr)

@@ -365,3 +365,25 @@ def test_split_screen_shows_the_input_left_of_the_split_in_the_oracle():
     left = slice(0, w // 2 - 1)
     assert np.array_equal(out[:, left][z[:, left]], inp[:, left][z[:, left]])
     assert not np.array_equal(out[:, w // 2 + 1:], inp[:, w // 2 + 1:])
+
+
+def test_reblur_performance_mode_runs_the_perf_permutations_in_the_oracle():
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h = 96, 64
+    sc = scene.Scene(w, h)
+    outs = []
+    for perf in (False, True):
+        cpu = orr.CpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, w, h, settings=nrd.ReblurSettings(enablePerformanceMode=perf, enableAntiFirefly=True))
+        names = set()
+        for f in range(4):
+            fr = sc.frame(f)
+            cpu.set_inputs(fr)
+            names |= {d.shaderFileName for d in cpu.denoise(harness.make_common_settings(fr, w, h, f))}
+            if f == 0:
+                cpu.set_inputs(fr)
+        assert any(n.startswith("REBLUR_Perf_") for n in names) == perf
+        out = cpu.user["OUT_SPEC_RADIANCE_HITDIST"].view(np.float16).astype(np.float32)
+        assert np.isfinite(out).all() and out.any()
+        outs.append(out)
+    assert not np.array_equal(outs[0], outs[1])
