@@ -134,6 +134,14 @@ __device__ __forceinline__ float SpecularNormalWeightAtrous(f2 p0, f3 n0, f3 n, 
     a = SmoothStep(0.0f, p0.x, a);
     return saturate(1.0f - a * p0.y);
 }
+// the same with the sample's view vector given un-normalised (v = -s / |s|): dot(v0, v) = -dot(v0, s) * rsqrt(dot(s, s))
+__device__ __forceinline__ float SpecularNormalWeightAtrousRaw(f2 p0, f3 n0, f3 n, f3 v0, f3 s)
+{
+    float cosa = fminf(dot(n0, n), -dot(v0, s) * rsqrtf(dot(s, s)));
+    float a = AcosApprox(cosa);
+    a = SmoothStep(0.0f, p0.x, a);
+    return saturate(1.0f - a * p0.y);
+}
 __device__ __forceinline__ float NormalWeightParam2(float roughness, float angleFraction) // :158-165
 {
     return 1.0f / fmaxf(atanf(RelaxLobeTanHalfAngle(roughness, angleFraction)), kNormalUlp);
@@ -1193,9 +1201,9 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAtro
         const float depthThreshold = c.gDepthThreshold * (c.gOrthoMode == 0.0f ? centerViewZ : 1.0f);
         float sumWSpecular = 0.0f, sumWDiffuse = 0.0f;
         f4 sumSpecular = mk4(0.0f), sumDiffuse = mk4(0.0f);
-#pragma unroll 1
+#pragma unroll
         for (int cx = -1; cx <= 1; cx++)
-#pragma unroll 1
+#pragma unroll
             for (int cy = -1; cy <= 1; cy++)
             {
                 const bool isCenter = cx == 0 && cy == 0;
@@ -1206,15 +1214,15 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAtro
                 const f3 sw = CurWorldPos(c, px, py, UnpackViewZ(c, LoadR32F(a.z, px, py)));
                 float geometryW = PlaneDistWeightAtrous(centerWorldPos, centerNormal, sw, depthThreshold) * kernelW;
                 const float angles = AcosApprox(dot(centerNormal, sg.N));
-                const f3 sampleV = -normalize(sw + centerWorldPos * c.gRoughnessEdgeStoppingRelaxation);
+                const f3 sampleRay = sw + centerWorldPos * c.gRoughnessEdgeStoppingRelaxation; // sampleV = -normalize(sampleRay)
                 const float normalWSimplified = NonExpWeight(angles, diffuseNormalWeightParam, 0.0f);
                 const float normalWSpecularSimplified = NonExpWeight(angles, simplifiedSpecularNormalWeightParam, 0.0f);
-                const float normalWSpecular = SpecularNormalWeightAtrous(snwp, centerNormal, sg.N, centerV, sampleV);
+                const float normalWSpecular = SpecularNormalWeightAtrousRaw(snwp, centerNormal, sg.N, centerV, sampleRay);
                 const float roughnessW = NonExpWeight(sg.roughness, rwp.x, rwp.y);
                 const f4 ss = LoadSignal<SPEC>(a.spec, px, py);
                 float lw = fabsf(centerSpecularLuminance - Luma(xyz(ss))) * specularPhiLIlluminationInv;
                 lw = fminf(c.gSpecMaxLuminanceRelativeDifference, lw) * specularLuminanceWeightRelaxation;
-                float wSpecular = geometryW * expf(-lw);
+                float wSpecular = geometryW * __expf(-lw);
                 wSpecular *= c.gRoughnessEdgeStoppingEnabled ? normalWSpecular * roughnessW : normalWSpecularSimplified;
                 wSpecular = isCenter ? kernelW : wSpecular;
                 wSpecular *= SameMaterial(sg.materialID, centerMaterialID, c.gSpecMinMaterial) ? 1.0f : 0.0f;
@@ -1223,7 +1231,7 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAtro
 
                 const f4 sd = LoadSignal<DIFF>(a.diff, px, py);
                 float dlw = fminf(c.gDiffMaxLuminanceRelativeDifference, fabsf(centerDiffuseLuminance - Luma(xyz(sd))) * diffusePhiLIlluminationInv) * cr.diffuseLuminanceScale;
-                float wDiffuse = geometryW * normalWSimplified * expf(-dlw);
+                float wDiffuse = geometryW * normalWSimplified * __expf(-dlw);
                 wDiffuse = isCenter ? kernelW : wDiffuse;
                 wDiffuse *= SameMaterial(sg.materialID, centerMaterialID, c.gDiffMinMaterial) ? 1.0f : 0.0f;
                 sumWDiffuse += wDiffuse;
@@ -1331,44 +1339,80 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAtro
         offx = (int)__fmul_rn(half, __fadd_rn(r0, -0.5f));
         offy = (int)__fmul_rn(half, __fadd_rn(r1, -0.5f));
     }
-#pragma unroll 1
+    // Per-tap work is kept to what depends on the tap (these kernels are issue-bound, ~8 taps x 5 iterations per pixel):
+    //  * the pixel ray F + R * csx - U * csy is affine in the pixel position: the ray of the centre tap position (x + off) and the
+    //    two per-step increments are evaluated once, a tap adds them with compile-time signs (perspective: world position = ray * viewZ);
+    //  * the plane distance dot(sw - cw, cn) is viewZ * dot(ray, cn) - dot(cw, cn);
+    //  * the tap's view vector is never normalised: dot(v0, -s / |s|) = -dot(v0, s) * rsqrt(dot(s, s));
+    //  * viewZ comes with the guide texel (RELAX_ClassifyTiles stores the raw viewZ in its .w), the luminance weights use ex2.approx.
+    const bool perspective = c.gOrthoMode == 0.0f;
+    const float kx = 2.0f * c.gRectSizeInv[0], ky = 2.0f * c.gRectSizeInv[1];
+    const float csx0 = ((float)(x + offx) + 0.5f) * kx - 1.0f, csy0 = ((float)(y + offy) + 0.5f) * ky - 1.0f;
+    const f3 R = ld3(c.gFrustumRight), U = ld3(c.gFrustumUp), F = ld3(c.gFrustumForward);
+    const f3 d0 = R * csx0 - U * csy0;                     // offset of the ray from the forward axis at the (jittered) centre
+    const f3 dX = R * ((float)step * kx), dY = U * (-(float)step * ky); // increments per step in x / y
+    const float planeC = dot(centerWorldPos, centerNormal);
+    const f3 relaxedCenter = centerWorldPos * c.gRoughnessEdgeStoppingRelaxation;
+    const float invSpecAngle = 1.0f / snwp.x;
+    const float rwpx = rwp.x * (1.0f / 1023.0f);           // applied to the tap's 10-bit roughness code
+    const bool roughnessEdgeStopping = c.gRoughnessEdgeStoppingEnabled != 0;
+    const bool compareSpecMaterial = c.gSpecMinMaterial < 3.0f, compareDiffMaterial = c.gDiffMinMaterial < 3.0f; // material ids are 0..3
+    const unsigned centerPacked = LoadU32(a.nr, x, y);
+    const float centerMaterial = (float)(centerPacked >> 30);
+#pragma unroll
     for (int yy = -1; yy <= 1; yy++)
-#pragma unroll 1
+#pragma unroll
         for (int xx = -1; xx <= 1; xx++)
         {
             if (xx == 0 && yy == 0) continue;
             const int px = x + offx + xx * step, py = y + offy + yy * step;
-            if (px < 0 || py < 0 || px >= W || py >= H) continue; // geometry weight is zero outside
+            if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) continue; // geometry weight is zero outside
             const float kernelW = (xx == 0 ? 0.44198f : 0.27901f) * (yy == 0 ? 0.44198f : 0.27901f);
-            const Guide sg = RX_GUIDE(a, px, py);
-            const float sz = UnpackViewZ(c, LoadR32F(a.z, px, py));
-            const f3 sw = CurWorldPos(c, px, py, sz);
-            float geometryW = PlaneDistWeightAtrous(centerWorldPos, centerNormal, sw, depthThreshold) * kernelW;
-            geometryW *= sz < c.gDenoisingRange ? 1.0f : 0.0f;
-            const f3 sampleV = -normalize(sw + centerWorldPos * c.gRoughnessEdgeStoppingRelaxation);
-            const float angles = AcosApprox(dot(centerNormal, sg.N));
+            const float4 q = __ldg(TexelPtr<float4>(a.guide, px, py)); // {N.xyz, raw viewZ}
+            const unsigned packed = LoadU32(a.nr, px, py);
+            const float sz = fabsf(q.w * c.gViewZScale);
+            f3 d = d0;
+            if (xx != 0) d = xx > 0 ? d + dX : d - dX;
+            if (yy != 0) d = yy > 0 ? d + dY : d - dY;
+            const f3 sw = perspective ? (F + d) * sz : F * sz + d;
+            float geometryW = fabsf(dot(sw, centerNormal) - planeC) < depthThreshold ? kernelW : 0.0f;
+            geometryW = sz < c.gDenoisingRange ? geometryW : 0.0f;
+            const float cosn = centerNormal.x * q.x + centerNormal.y * q.y + centerNormal.z * q.z;
+            const float angles = AcosApprox(cosn);
             const float normalWSimplified = NonExpWeight(angles, normalWeightParam, 0.0f);
-            const float normalWSpecularSimplified = NonExpWeight(angles, simplifiedSpecularNormalWeightParam, 0.0f);
-            const float normalWSpecular = SpecularNormalWeightAtrous(snwp, centerNormal, sg.N, centerV, sampleV);
-            const float roughnessW = NonExpWeight(sg.roughness, rwp.x, rwp.y);
-            float wSpecular = geometryW * (c.gRoughnessEdgeStoppingEnabled ? normalWSpecular * roughnessW : normalWSpecularSimplified);
-            wSpecular *= SameMaterial(sg.materialID, g.materialID, c.gSpecMinMaterial) ? 1.0f : 0.0f;
-            if (wSpecular > 1e-4f)
+            float wSpecular = 0.0f;
+            if (SPEC)
+            {
+                if (roughnessEdgeStopping)
+                {
+                    // GetSpecularNormalWeight_ATrous (RELAX_Common.hlsli:147-156) with sampleV = -normalize(sw + relaxation * cw)
+                    const f3 sr = sw + relaxedCenter;
+                    const float cosa = fminf(cosn, -dot(centerV, sr) * rsqrtf(dot(sr, sr)));
+                    const float t = SatMul(AcosApprox(cosa), invSpecAngle);
+                    const float normalWSpecular = saturate(1.0f - t * t * fmaf(-2.0f, t, 3.0f) * snwp.y);
+                    const float roughnessW = NonExpWeight((float)((packed >> 20) & 1023u), rwpx, rwp.y);
+                    wSpecular = geometryW * (normalWSpecular * roughnessW);
+                }
+                else
+                    wSpecular = geometryW * NonExpWeight(angles, simplifiedSpecularNormalWeightParam, 0.0f);
+                if (compareSpecMaterial) wSpecular = SameMaterial((float)(packed >> 30), centerMaterial, c.gSpecMinMaterial) ? wSpecular : 0.0f;
+            }
+            if (SPEC && wSpecular > 1e-4f)
             {
                 const f4 ss = LoadSignal<SPEC>(a.spec, px, py);
                 float lw = fminf(c.gSpecMaxLuminanceRelativeDifference, fabsf(centerSpecularLuminance - Luma(xyz(ss))) * specularPhiLIlluminationInv);
                 lw *= specularLuminanceWeightRelaxation;
-                wSpecular *= expf(-lw);
+                wSpecular *= __expf(-lw); // a weight in (0, 1]
                 sumWSpecular += wSpecular;
                 sumSpecular = sumSpecular + mk4(ss.x * wSpecular, ss.y * wSpecular, ss.z * wSpecular, ss.w * (wSpecular * wSpecular));
             }
             float wDiffuse = geometryW * normalWSimplified;
-            wDiffuse *= SameMaterial(sg.materialID, g.materialID, c.gDiffMinMaterial) ? 1.0f : 0.0f;
-            if (wDiffuse > 1e-4f)
+            if (compareDiffMaterial) wDiffuse = SameMaterial((float)(packed >> 30), centerMaterial, c.gDiffMinMaterial) ? wDiffuse : 0.0f;
+            if (DIFF && wDiffuse > 1e-4f)
             {
                 const f4 sd = LoadSignal<DIFF>(a.diff, px, py);
                 float lw = fminf(c.gDiffMaxLuminanceRelativeDifference, fabsf(centerDiffuseLuminance - Luma(xyz(sd))) * diffusePhiLIlluminationInv) * cr.diffuseLuminanceScale;
-                wDiffuse *= expf(-lw);
+                wDiffuse *= __expf(-lw);
                 sumWDiffuse += wDiffuse;
                 sumDiffuse = sumDiffuse + mk4(sd.x * wDiffuse, sd.y * wDiffuse, sd.z * wDiffuse, sd.w * (wDiffuse * wDiffuse));
             }
