@@ -174,6 +174,10 @@ struct Tex
     int pitch = 0;
     int fmt = 0;
     int yoff = 0; // first row physically present (strips); always 0 in the oracle's own tests
+    // WithRectOrigin / WithRectOffset (Common.hlsli:200-205): the guide inputs of an application are addressed at rectOrigin + pixelPos.
+    // Every access below takes rect-relative coordinates and adds the origin; w / h stay the size of the whole resource (samplers
+    // scale uv by it).
+    int ox = 0, oy = 0;
 
     const uint8_t* at(int x, int y) const { return data + size_t(y - yoff) * pitch + size_t(x) * bpp(); }
     uint8_t* at(int x, int y) { return data + size_t(y - yoff) * pitch + size_t(x) * bpp(); }
@@ -193,6 +197,8 @@ struct Tex
 
     float4 load(int x, int y) const
     {
+        x += ox;
+        y += oy;
         if (!inside(x, y)) return float4(0.0f);
         const uint8_t* p = at(x, y);
         switch (fmt)
@@ -216,6 +222,8 @@ struct Tex
     float4 load(int2 p) const { return load(p.x, p.y); }
     uint loadu(int x, int y) const
     {
+        x += ox;
+        y += oy;
         if (!inside(x, y)) return 0;
         const uint8_t* p = at(x, y);
         switch (fmt)
@@ -230,6 +238,8 @@ struct Tex
 
     void store(int x, int y, float4 v)
     {
+        x += ox;
+        y += oy;
         if (!inside(x, y)) return;
         uint8_t* p = at(x, y);
         switch (fmt)
@@ -254,6 +264,8 @@ struct Tex
     void store(int2 p, float v) { store(p.x, p.y, float4(v, 0, 0, 0)); }
     void storeu(int x, int y, uint v)
     {
+        x += ox;
+        y += oy;
         if (!inside(x, y)) return;
         uint8_t* p = at(x, y);
         switch (fmt)
@@ -266,8 +278,8 @@ struct Tex
     void storeu(int2 p, uint v) { storeu(p.x, p.y, v); }
 
     // clamp-to-edge texel fetch used by the samplers
-    float4 texel(int x, int y) const { return load(clamp(x, 0, w - 1), clamp(y, 0, h - 1)); }
-    uint texelu(int x, int y) const { return loadu(clamp(x, 0, w - 1), clamp(y, 0, h - 1)); }
+    float4 texel(int x, int y) const { return load(clamp(x, -ox, w - 1 - ox), clamp(y, -oy, h - 1 - oy)); }
+    uint texelu(int x, int y) const { return loadu(clamp(x, -ox, w - 1 - ox), clamp(y, -oy, h - 1 - oy)); }
 
     float4 sampleNearest(float2 uv) const { return texel((int)std::floor(uv.x * w), (int)std::floor(uv.y * h)); }
     float4 sampleLinear(float2 uv) const

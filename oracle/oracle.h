@@ -13,6 +13,7 @@ struct OracleTexture
     int32_t pitchBytes;
     int32_t format;   // nrd::Format
     int32_t firstRow; // 0 unless the caller holds a strip
+    int32_t originX, originY; // CommonSettings::rectOrigin for the inputs the shaders read through WithRectOrigin, else 0
 };
 // Executes one DispatchDesc on the CPU.  shaderName = PipelineDesc::shaderFileName of the dispatch's pipeline.
 // Returns 0 on success, -1 unknown pass, -2 bad constants.

@@ -55,6 +55,8 @@ extern "C" int oracle_dispatch(const char* shaderName, const void* constants, in
         tex[i].pitch = textures[i].pitchBytes;
         tex[i].fmt = textures[i].format;
         tex[i].yoff = textures[i].firstRow;
+        tex[i].ox = textures[i].originX;
+        tex[i].oy = textures[i].originY;
     }
     if (!strncmp(shaderName, "Clear_", 6))
     {

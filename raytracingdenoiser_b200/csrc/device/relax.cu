@@ -1139,23 +1139,24 @@ struct RxAtrousArgs
     Surf specConfidence, diffConfidence; // optional R8_UNORM inputs (confidence-driven relaxation), read only when gHasHistoryConfidence
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
+    int gridW, gridH; // texels the reference's thread groups cover (first iteration: the previous-frame guides are refreshed for all of them)
 };
 template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAtrousSmemKernel(const __grid_constant__ RxAtrousArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
     const int W = c.gRectSize[0], H = c.gRectSize[1];
-    if (y >= a.rowEnd || !Inside(a.z, x, y)) return;
+    if (y >= a.rowEnd || x >= a.gridW || y >= a.gridH || !Inside(a.outZ, x, y)) return;
     const bool isSky = IsSkyTile(a.tiles, x, y);
 
-    // previous-frame guides are refreshed for every pixel (:252-266)
-    const float viewZpacked = LoadR32F(a.z, x, y);
+    // previous-frame guides are refreshed for every pixel the thread groups cover (:252-266); IN_VIEWZ reads 0 beyond its (rect-origin) view
+    const float viewZpacked = Inside(a.z, x, y) ? LoadR32F(a.z, x, y) : 0.0f;
     StoreR32F(a.outZ, x, y, viewZpacked);
     Guide g;
     g.N = mk3(0.0f);
     g.roughness = 0.0f;
     g.materialID = 0.0f;
-    if (!isSky) g = RX_GUIDE(a, x, y);
+    if (!isSky) g = RX_GUIDE(a, min(x, W - 1), min(y, H - 1)); // threads of a group that overhang the rect see the clamped texel (the reference's Preload clamps)
     const float centerViewZ = UnpackViewZ(c, viewZpacked);
     f4 nr = mk4(g.N, g.roughness);
     if (centerViewZ > c.gDenoisingRange) nr = mk4(1.0f / 255.0f);
@@ -1519,7 +1520,9 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchRelaxSignals(const Pass
         if (smem)
         {
             a.outNr = p.tex[11]; a.outMaterial = p.tex[12]; a.outZ = p.tex[13];
-            NRD_B200_LAUNCH(p, dim3((a.z.w + 31) / 32, grid.y), block, a, RelaxAtrousSmemKernel<DIFF, SPEC>);
+            a.gridW = p.gridW * 8; a.gridH = p.gridH * 8;
+            const int coverW = min(a.gridW, p.preloadOnly ? 32 : a.outZ.w), coverRows = min(p.rowEnd, a.gridH) - p.rowBegin;
+            NRD_B200_LAUNCH(p, dim3((coverW + 31) / 32, (max(coverRows, 1) + 7) / 8), block, a, RelaxAtrousSmemKernel<DIFF, SPEC>);
         }
         else
         {

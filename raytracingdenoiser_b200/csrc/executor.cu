@@ -210,6 +210,32 @@ Surf ToSurf(const NrdCudaContext* ctx, const Texture& t)
     return s;
 }
 
+// WithRectOrigin (Common.hlsli:200-205): the guide inputs an application binds from its full-size G-buffer -- IN_VIEWZ, IN_NORMAL_ROUGHNESS,
+// IN_MV, the confidence / disocclusion-mix / base-colour inputs -- are read at rectOrigin + pixelPos; the kernels get a view of the
+// texture that starts at rectOrigin.  Noisy signals, outputs and pool textures are addressed at pixelPos itself.
+Surf WithRectOrigin(Surf s, ResourceType type, const Texture& t, const CommonSettings& cs)
+{
+    const uint32_t ox = cs.rectOrigin[0], oy = cs.rectOrigin[1];
+    if (!ox && !oy) return s;
+    switch (type)
+    {
+        case ResourceType::IN_VIEWZ:
+        case ResourceType::IN_NORMAL_ROUGHNESS:
+        case ResourceType::IN_MV:
+        case ResourceType::IN_DIFF_CONFIDENCE:
+        case ResourceType::IN_SPEC_CONFIDENCE:
+        case ResourceType::IN_DISOCCLUSION_THRESHOLD_MIX:
+        case ResourceType::IN_BASECOLOR_METALNESS: break;
+        default: return s;
+    }
+    s.base += (size_t)oy * s.pitch + (size_t)ox * BytesPerTexel(t.format);
+    s.w -= (int)ox;
+    s.h -= (int)oy;
+    s.y1 -= (int)oy;
+    s.lrows -= oy;
+    return s;
+}
+
 // Roughness table: every function of the 10-bit roughness code alone that the REBLUR spatial filters need, evaluated with the
 // host libm in the reference's operation order (Common.hlsli:311-317 GetSpecMagicCurve, NRD.hlsli:520-523
 // _REBLUR_GetHitDistanceNormalization, NRD.hlsli:386-392 _NRD_GetSpecularDominantFactor).  `volatile` keeps every intermediate a
@@ -734,9 +760,15 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     if (d->pipelineIndex >= id.pipelinesNum) return Result::INVALID_ARGUMENT;
     const char* shader = id.pipelines[d->pipelineIndex].shaderFileName;
     const CommonSettings& cs = ((Scheduler*)ctx->instance)->Common();
-    if (cs.rectSize[0] != cs.resourceSize[0] || cs.rectSize[1] != cs.resourceSize[1] || cs.rectOrigin[0] || cs.rectOrigin[1] ||
-        cs.resourceSize[0] != ctx->desc.resourceWidth || cs.resourceSize[1] != ctx->desc.resourceHeight)
-        return Fail(ctx, Result::UNSUPPORTED, "dynamic resolution (rectSize != resourceSize) is not implemented by the CUDA executor");
+    // Dynamic resolution (Source/InstanceImpl.cpp:834-856, Shaders/Include/Common.hlsli:200-222): the passes run over rectSize <= resourceSize;
+    // the application's guide inputs are addressed at rectOrigin + pixel (WithRectOrigin), everything else at the pixel itself.
+    if (cs.resourceSize[0] != ctx->desc.resourceWidth || cs.resourceSize[1] != ctx->desc.resourceHeight)
+        return Fail(ctx, Result::INVALID_ARGUMENT, "CommonSettings::resourceSize differs from the size the context was created for");
+    if (cs.rectOrigin[0] + (uint32_t)cs.rectSize[0] > cs.resourceSize[0] || cs.rectOrigin[1] + (uint32_t)cs.rectSize[1] > cs.resourceSize[1])
+        return Fail(ctx, Result::INVALID_ARGUMENT, "rectOrigin + rectSize exceeds resourceSize");
+    const bool subRect = cs.rectSize[0] != cs.resourceSize[0] || cs.rectSize[1] != cs.resourceSize[1] || cs.rectOrigin[0] || cs.rectOrigin[1];
+    if (subRect && StripMode(ctx) && ctx->world > 1)
+        return Fail(ctx, Result::UNSUPPORTED, "dynamic resolution (rectSize != resourceSize) is not implemented for multi-GPU strips");
     if (cs.isBaseColorMetalnessAvailable)
         return Fail(ctx, Result::UNSUPPORTED, "the base-colour / metalness input (specular motion-vector patch) is not implemented by the CUDA executor");
     if (StripMode(ctx) && !ctx->connected && (ctx->desc.stripY0 != 0 || ctx->desc.stripY1 != ctx->desc.resourceHeight))
@@ -755,7 +787,7 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         const ResourceDesc& r = d->resources[i];
         const Texture* t = Resolve(ctx, r.type, r.indexInPool);
         if (!t) return Fail(ctx, Result::INVALID_ARGUMENT, std::string("unbound resource ") + GetResourceTypeString(r.type) + " for " + d->name);
-        p.tex[i] = ToSurf(ctx, *t);
+        p.tex[i] = WithRectOrigin(ToSurf(ctx, *t), r.type, *t, cs);
         p.texBytes[i] = (uint8_t)BytesPerTexel(t->format);
     }
     // checkerboarded inputs bind the same passes (no separate shader name), so they have to be rejected here, loudly
@@ -775,7 +807,7 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     {
         const Texture* nr = Resolve(ctx, ResourceType::IN_NORMAL_ROUGHNESS, 0);
         if (!nr) return Fail(ctx, Result::INVALID_ARGUMENT, "unbound resource IN_NORMAL_ROUGHNESS for ClassifyTiles (it also builds the guide surface)");
-        p.guideNr = ToSurf(ctx, *nr);
+        p.guideNr = WithRectOrigin(ToSurf(ctx, *nr), ResourceType::IN_NORMAL_ROUGHNESS, *nr, cs);
         p.guideMode = 1;
     }
     else if (readsGuide)

@@ -51,6 +51,9 @@ DENOISER_RESOURCES = {
 }
 
 
+# inputs an application binds from its full-size G-buffer: read at rectOrigin + pixel (Common.hlsli:200-205 WithRectOrigin)
+RECT_ORIGIN_INPUTS = ("IN_VIEWZ", "IN_NORMAL_ROUGHNESS", "IN_MV", "IN_DIFF_CONFIDENCE", "IN_SPEC_CONFIDENCE", "IN_DISOCCLUSION_THRESHOLD_MIX", "IN_BASECOLOR_METALNESS")
+
 OPTIONAL_INPUTS = {  # CommonSettings flag -> the user textures it makes the passes read, per signal
     "isHistoryConfidenceAvailable": {"diff": "IN_DIFF_CONFIDENCE", "spec": "IN_SPEC_CONFIDENCE"},
     "isDisocclusionThresholdMixAvailable": {"any": "IN_DISOCCLUSION_THRESHOLD_MIX"},
@@ -87,6 +90,11 @@ def make_common_settings(frame, width, height, frame_index, time_delta_ms=16.666
     cs.motionVectorScale[0], cs.motionVectorScale[1], cs.motionVectorScale[2] = 1.0 / width, 1.0 / height, 1.0
     for k in ("resourceSize", "resourceSizePrev", "rectSize", "rectSizePrev"):
         getattr(cs, k)[0], getattr(cs, k)[1] = width, height
+    common = dict(common or {})
+    for k in ("resourceSize", "resourceSizePrev", "rectSize", "rectSizePrev", "rectOrigin"):  # array fields (dynamic resolution)
+        if k in common:
+            v = common.pop(k)
+            getattr(cs, k)[0], getattr(cs, k)[1] = int(v[0]), int(v[1])
     cs.timeDeltaBetweenFrames = time_delta_ms
     cs.frameIndex = frame_index
     for k, v in (common or {}).items():

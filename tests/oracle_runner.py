@@ -16,7 +16,8 @@ _ORACLE_PATH = os.path.join(_ROOT, "oracle", "liboracle.so")
 
 
 class OracleTexture(C.Structure):
-    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pitchBytes", C.c_int32), ("format", C.c_int32), ("firstRow", C.c_int32)]
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pitchBytes", C.c_int32), ("format", C.c_int32), ("firstRow", C.c_int32),
+                ("originX", C.c_int32), ("originY", C.c_int32)]
 
 
 _oracle = {}
@@ -89,6 +90,7 @@ class CpuDenoiser(object):
         self.formats = {"permanent": [f for f, _ in desc["permanentPool"]], "transient": [f for f, _ in desc["transientPool"]]}
         self.user = {}
         self.user_fmt = {}
+        self.rect_origin = (0, 0)  # CommonSettings::rectOrigin of the frame being run (set by denoise() / the parity harness)
         for name in harness.denoiser_resources(denoiser, common):
             fmt = harness.user_format(denoiser, name)[0]
             self.user[name] = alloc(fmt, width, height)
@@ -102,20 +104,29 @@ class CpuDenoiser(object):
         name = nrd.ResourceType(rtype).name
         return self.user[name], self.user_fmt[name]
 
-    def set_inputs(self, frame):
+    def set_inputs(self, frame, rect_origin=(0, 0)):
+        """Writes the frame's inputs into the user textures.  A frame smaller than the textures (dynamic resolution) goes to the
+        top-left corner -- or, for the guide inputs an application binds from its G-buffer, to rect_origin (WithRectOrigin)."""
+        from raytracingdenoiser_b200 import harness
         for name, arr in self.user.items():
             if name.startswith("IN_"):
                 src = frame[name]
                 src = src.cpu().numpy() if hasattr(src, "cpu") else np.asarray(src)
-                arr[...] = src.view(arr.dtype).reshape(arr.shape)
+                src = src.view(arr.dtype).reshape((src.shape[0], src.shape[1]) + arr.shape[2:])
+                ox, oy = rect_origin if name in harness.RECT_ORIGIN_INPUTS else (0, 0)
+                arr[oy:oy + src.shape[0], ox:ox + src.shape[1]] = src
 
     def run_dispatch(self, d):
         lib = self.lib
         texs = (OracleTexture * len(d.resources))()
         keep = []
+        from raytracingdenoiser_b200 import harness
         for i, (_, rtype, index) in enumerate(d.resources):
             arr, fmt = self.resolve(rtype, index)
             keep.append(arr)
+            texs[i].originX = texs[i].originY = 0
+            if nrd.ResourceType(rtype).name in harness.RECT_ORIGIN_INPUTS:
+                texs[i].originX, texs[i].originY = self.rect_origin  # WithRectOrigin (Common.hlsli:200-205)
             texs[i].data = arr.ctypes.data
             texs[i].height, texs[i].width = arr.shape[0], arr.shape[1]
             texs[i].pitchBytes = arr.strides[0]
@@ -128,6 +139,7 @@ class CpuDenoiser(object):
             raise RuntimeError("oracle_dispatch(%s) failed with %d" % (d.shaderFileName, r))
 
     def denoise(self, common_settings, on_dispatch=None):
+        self.rect_origin = (int(common_settings.rectOrigin[0]), int(common_settings.rectOrigin[1]))
         self.instance.set_common_settings(common_settings)
         dispatches = self.instance.get_compute_dispatches([self.identifier])
         for i, d in enumerate(dispatches):

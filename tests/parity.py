@@ -89,9 +89,27 @@ class SideBySide(object):
                 rec["outlier_budget"] = max(rec["outlier_budget"], rec["floor_outliers"])
             self.report.append(rec)
 
-    def run_per_pass(self, frames, first_frame=0, warmup=0):
+    def _frame(self, f, rect_fn):
+        """(scene frame, CommonSettings, rectOrigin) of frame f.  rect_fn(f) -> (originX, originY, width, height): dynamic resolution,
+        the scene is rendered at the rect size into textures of the context's (resource) size."""
+        if rect_fn is None:
+            fr = self.scene.frame(f, harness.radiance_mode(self.denoiser))
+            return fr, harness.make_common_settings(fr, self.w, self.h, f, common=self.common), (0, 0)
+        ox, oy, rw, rh = rect_fn(f)
+        prev = rect_fn(f - 1) if f > 0 else (ox, oy, rw, rh)
+        if (rw, rh) not in self._scenes:
+            self._scenes[(rw, rh)] = scene.Scene(rw, rh, device=_scene_device(rw, rh, 0))
+        fr = self._scenes[(rw, rh)].frame(f, harness.radiance_mode(self.denoiser))
+        common = dict(self.common or {})
+        common.update(resourceSize=(self.w, self.h), resourceSizePrev=(self.w, self.h), rectSizePrev=(prev[2], prev[3]), rectOrigin=(ox, oy))
+        return fr, harness.make_common_settings(fr, rw, rh, f, common=common), (ox, oy)
+
+    def run_per_pass(self, frames, first_frame=0, warmup=0, rect_fn=None):
         """Hard gate.  Returns the list of per-(frame, pass, output) comparison records.  `warmup` frames are run by the oracle
         alone first (histories long enough for the steady-state branches); the kernels start from the oracle's state anyway."""
+        self._scenes = {}
+        if rect_fn is not None:
+            return self._run_per_pass_rects(frames, rect_fn)
         for f in range(first_frame, first_frame + warmup):
             fr = self.scene.frame(f, harness.radiance_mode(self.denoiser))
             self.cpu.set_inputs(fr)
@@ -129,6 +147,30 @@ class SideBySide(object):
                 self._compare_outputs(f, d)
             if f == 0:
                 self.cpu.set_inputs(fr)  # the frame-0 clears also zero IN_MV (reference quirk), restore it
+        return self.report
+
+    def _run_per_pass_rects(self, frames, rect_fn):
+        for f in range(frames):
+            fr, cs, origin = self._frame(f, rect_fn)
+            for c in [self.cpu] + self.cpu_alt:
+                c.rect_origin = origin
+            self.cpu.set_inputs(fr, rect_origin=origin)
+            self.instance.set_common_settings(cs)
+            r, raw, n = self.instance.get_compute_dispatches_raw([self.identifier])
+            assert r == nrd.Result.SUCCESS
+            pipelines = self.instance.get_instance_desc()["pipelines"]
+            for name, arr in self.cpu.user.items():
+                if name.startswith("IN_"):
+                    self.ctx.upload(getattr(nrd.ResourceType, name), 0, np.ascontiguousarray(arr))
+            for i in range(n):
+                d = nrd.Dispatch(raw[i], pipelines)
+                self._sync_to_gpu(d)
+                self.ctx.execute_raw(C.byref(raw[i]))
+                self.torch.cuda.synchronize()
+                self.cpu.run_dispatch(d)
+                self._compare_outputs(f, d)
+            if f == 0:
+                self.cpu.set_inputs(fr, rect_origin=origin)  # the frame-0 clears also zero IN_MV (reference quirk), restore it
         return self.report
 
     def failures(self):

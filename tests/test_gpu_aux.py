@@ -47,3 +47,20 @@ def test_reference_denoiser_per_pass_and_sequence():
     res = parity.run_sequence(nrd.Denoiser.REFERENCE, 320, 180, 6)
     for name, (frac, psnr) in res.items():
         assert frac >= 0.999 and psnr >= 60.0, (name, frac, psnr)
+
+
+def _rects(f):
+    """Dynamic resolution: the rect changes size after two frames and sits at a non-zero origin of the G-buffer inputs."""
+    return (16, 8, 250, 141) if f < 2 else (24, 16, 280, 158)
+
+
+@pytest.mark.parametrize("denoiser_name", ["REBLUR_DIFFUSE_SPECULAR", "RELAX_DIFFUSE_SPECULAR", "SIGMA_SHADOW"])
+def test_dynamic_resolution_per_pass(denoiser_name):
+    """rectSize < resourceSize, rectOrigin != 0, rectSizePrev != rectSize (Source/InstanceImpl.cpp:834-856, Common.hlsli:200-222):
+    textures are 320x192, the passes run over a 250x141 rect and then over a 280x158 one."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    sbs = parity.SideBySide(getattr(nrd.Denoiser, denoiser_name), 320, 192, noise_floor=denoiser_name.startswith("RELAX"))
+    report = sbs.run_per_pass(4, rect_fn=_rects)
+    _dump("parity_dynres_%s.json" % denoiser_name, report)
+    assert not sbs.failures(), sbs.describe_failures()

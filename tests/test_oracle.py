@@ -387,3 +387,26 @@ def test_reblur_performance_mode_runs_the_perf_permutations_in_the_oracle():
         assert np.isfinite(out).all() and out.any()
         outs.append(out)
     assert not np.array_equal(outs[0], outs[1])
+
+
+def test_dynamic_resolution_rect_origin_does_not_change_the_result_in_the_oracle():
+    """A 96x64 rect of 160x96 textures: the guide inputs (viewZ, normals, motion) sit at rectOrigin of their textures (WithRectOrigin,
+    Common.hlsli:200-205), everything else at (0, 0).  Moving the origin -- with garbage around the rect -- must not change a texel."""
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h, RW, RH = 96, 64, 160, 96
+    sc = scene.Scene(w, h)
+    outs = []
+    for ox, oy in ((0, 0), (16, 8), (64, 32)):
+        cpu = orr.CpuDenoiser(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, RW, RH)
+        for f in range(3):
+            fr = sc.frame(f)
+            for name in harness.RECT_ORIGIN_INPUTS:
+                if name in cpu.user:
+                    cpu.user[name][...] = np.random.RandomState(f).randint(0, 200, cpu.user[name].shape).astype(cpu.user[name].dtype)  # garbage around the rect
+            cpu.set_inputs(fr, rect_origin=(ox, oy))
+            cpu.denoise(harness.make_common_settings(fr, w, h, f, common=dict(resourceSize=(RW, RH), resourceSizePrev=(RW, RH), rectOrigin=(ox, oy))))
+        outs.append({k: v[:h, :w].copy() for k, v in cpu.user.items() if k.startswith("OUT_")})
+    for k in outs[0]:
+        assert outs[0][k].any()
+        assert np.array_equal(outs[0][k].view(np.uint16), outs[1][k].view(np.uint16)) and np.array_equal(outs[0][k].view(np.uint16), outs[2][k].view(np.uint16)), k
