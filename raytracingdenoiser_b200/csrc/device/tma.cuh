@@ -97,7 +97,8 @@ template <class T, int BW, int BH> __device__ __forceinline__ void PatchClampToE
     {
         const int lx = i % BW, ly = i / BW, gx = boxX0 + lx, gy = boxY0 + ly;
         const int cx = min(max(gx, 0), maxX), cy = min(max(gy, 0), maxY);
-        if ((cx != gx || cy != gy) && cx - boxX0 < BW && cy - boxY0 < BH) tile[ly][lx] = tile[cy - boxY0][cx - boxX0];
+        // (a box that lies entirely beyond the frame -- a CTA past the rect under dynamic resolution -- has no clamped texel inside it: skipped)
+        if ((cx != gx || cy != gy) && (unsigned)(cx - boxX0) < (unsigned)BW && (unsigned)(cy - boxY0) < (unsigned)BH) tile[ly][lx] = tile[cy - boxY0][cx - boxX0];
     }
 }
 // every thread that reads the tile

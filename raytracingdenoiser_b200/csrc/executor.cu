@@ -826,6 +826,12 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     // rows to produce: the context's strip (the full frame on one GPU)
     p.rowBegin = ctx->desc.stripY0;
     p.rowEnd = ctx->desc.stripY1;
+    if (subRect)
+    {
+        // dynamic resolution: no pass produces rows beyond max(rect, previous rect) (the grids of USE_MAX_DIMS passes), whole tiles
+        const uint32_t rows = ((uint32_t)std::max(cs.rectSize[1], cs.rectSizePrev[1]) + 15u) & ~15u;
+        p.rowEnd = (int)std::min<uint32_t>((uint32_t)p.rowEnd, rows);
+    }
     {
         // profiling aid (one GPU only): NRD_B200_DEBUG_ROWS="y0,y1" restricts every pass to a row range, to cost a strip in isolation
         static const char* dbg = getenv("NRD_B200_DEBUG_ROWS");
