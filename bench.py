@@ -45,6 +45,18 @@ def measured_peaks():
     return FALLBACK_HBM_GBS, "fallback"
 
 
+def measured_traffic(width, height, world):
+    """DRAM bytes of the Blur + PostBlur launch pair from the committed ncu capture of this workload (profiles/r2_reblur_traffic.json,
+    written from an `ncu --set full` report; ncu cannot run inside a timed bench).  None when no capture matches the workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_reblur_traffic.json")))
+        if world == 1 and list(t["size"]) == [width, height]:
+            return float(t["bytes_per_launch"]["Blur"] + t["bytes_per_launch"]["Post-blur"])
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(object):
     """nvidia-smi SM clock / throttle-reason sampler running beside the timed region."""
 
@@ -349,7 +361,7 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum of one Blur + one PostBlur launch at 3840x2160, from the ncu --set full
                 # capture summarised in profiles/r1_reblur_ncu_summary.txt (304.9 MB + 305.6 MB); below the algorithmic bytes
                 # because sky tiles are skipped
-                "frac": achieved / peak, "traffic": 610.5e6 if (W, H, world) == (3840, 2160, 1) else None, "algorithmic_bytes_per_launch_pair": algo_bytes,
+                "frac": achieved / peak, "traffic": measured_traffic(W, H, world), "algorithmic_bytes_per_launch_pair": algo_bytes,
                 "per_pass_ms": pass_ms,
                 "per_pass_frac": {k: (ALGO_BYTES_PER_PIXEL[k] * W * H / (v * 1e-3) / 1e9 / peak) for k, v in pass_ms.items() if k in ALGO_BYTES_PER_PIXEL and v > 0}}
 

@@ -156,6 +156,12 @@ struct Pass
         float a = 1.0f / lerp(sensitivity, 1.0f, saturate(roughness * fraction));
         return float2(a, -roughness * a);
     }
+    static float GetNormalWeightParam(float nonLinearAccumSpeed, float lobeAngleFraction, float roughness = 1.0f) // Common.hlsli:486-500
+    {
+        float percentOfVolume = 0.75f * lerp(lobeAngleFraction, 1.0f, nonLinearAccumSpeed); // NRD_MAX_PERCENT_OF_LOBE_VOLUME
+        float angle = atan(ImportanceSampling::GetSpecularLobeTanHalfAngle(roughness, percentOfVolume));
+        return 1.0f / max(angle, NRD_NORMAL_ENCODING_ERROR);
+    }
     static float2 GetRelaxedRoughnessWeightParams(float m, float fraction = 1.0f, float sensitivity = 0.01f)
     {
         float a = 1.0f / lerp(sensitivity, 1.0f, lerp(m * m, m, fraction));
@@ -215,6 +221,83 @@ void ClassifyTiles(const Pass& P, Tex* t, int gridW, int gridH)
             for (int j = 0; j < 16; j++)
                 for (int i = 0; i < 16; i++) n += abs(gIn_ViewZ.load(tx * 16 + i, ty * 16 + j).x) > P.c.gDenoisingRange ? 1 : 0;
             gOut_Tiles.store(tx, ty, float4(n == 256 ? 1.0f : 0.0f, 0, 0, 0));
+        }
+}
+
+// RELAX_HitDistReconstruction.hlsli:10-155 (3x3: border 1, 5x5: border 2); two-signal binding layout: tiles, spec, diff, normal-roughness,
+// viewZ | spec, diff
+void HitDistReconstruction(const Pass& P, int border, Tex* t, int gridW, int gridH)
+{
+    const CB& c = P.c;
+    const Tex &gIn_Tiles = t[0], &gIn_Spec = t[1], &gIn_Diff = t[2], &gIn_Normal_Roughness = t[3], &gIn_ViewZ = t[4];
+    Tex &gOut_Spec = t[5], &gOut_Diff = t[6];
+    const int2 rectMax(c.gRectSize[0] - 1, c.gRectSize[1] - 1);
+    const bool hasSpec = gIn_Spec.w != 0, hasDiff = gIn_Diff.w != 0; // absent signal = NULL texture (see kLayouts)
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < gridH * 8; y++)
+        for (int x = 0; x < gridW * 8; x++)
+        {
+            const int2 pixelPos(x, y);
+            float2 pixelUv = (float2(float(x), float(y)) + float2(0.5f)) * c.gRectSizeInv;
+            float isSky = gIn_Tiles.load(x >> 4, y >> 4).x;
+            if (isSky != 0.0f || x >= c.gRectSize[0] || y >= c.gRectSize[1]) continue;
+            // the shared-memory tile of the reference holds clamped texels (Preload :13-32); an absent signal reads gDenoisingRange
+            auto hitDistViewZ = [&](int2 p) {
+                p = clamp(p, int2(0), rectMax);
+                return float3(hasSpec ? gIn_Spec.load(p).w : c.gDenoisingRange, hasDiff ? gIn_Diff.load(p).w : c.gDenoisingRange, P.UnpackViewZ(gIn_ViewZ.load(p).x));
+            };
+            float3 centerHitdistViewZ = hitDistViewZ(pixelPos);
+            float centerViewZ = centerHitdistViewZ.z;
+            if (centerViewZ > c.gDenoisingRange) continue;
+            float4 normalAndRoughness = NRD_FrontEnd_UnpackNormalAndRoughness(gIn_Normal_Roughness.load(pixelPos));
+            float3 centerNormal = normalAndRoughness.xyz();
+            float centerRoughness = normalAndRoughness.w;
+
+            float centerSpecularHitDist = centerHitdistViewZ.x;
+            float2 relaxedRoughnessWeightParams = Pass::GetRelaxedRoughnessWeightParams(centerRoughness * centerRoughness);
+            float specularNormalWeightParam = Pass::GetNormalWeightParam(1.0f, 1.0f, centerRoughness);
+            float sumSpecularWeight = 1000.0f * float(centerSpecularHitDist != 0.0f);
+            float sumSpecularHitDist = centerSpecularHitDist * sumSpecularWeight;
+            float centerDiffuseHitDist = centerHitdistViewZ.y;
+            float diffuseNormalWeightParam = Pass::GetNormalWeightParam(1.0f, 1.0f);
+            float sumDiffuseWeight = 1000.0f * float(centerDiffuseHitDist != 0.0f);
+            float sumDiffuseHitDist = centerDiffuseHitDist * sumDiffuseWeight;
+
+            for (int dy = 0; dy <= border * 2; dy++)
+                for (int dx = 0; dx <= border * 2; dx++)
+                {
+                    int2 o = int2(dx, dy) - int2(border);
+                    if (o.x == 0 && o.y == 0) continue;
+                    int2 pos = clamp(pixelPos + o, int2(0), rectMax);
+                    float3 sampleNormal = NRD_FrontEnd_UnpackNormalAndRoughness(gIn_Normal_Roughness.load(pos)).xyz();
+                    float3 sampleHitdistViewZ = hitDistViewZ(pixelPos + o);
+                    float sampleViewZ = sampleHitdistViewZ.z;
+                    float angle = Math::AcosApprox(dot(centerNormal, sampleNormal));
+                    float w = IsInScreenNearest(pixelUv + float2(float(o.x), float(o.y)) * c.gRectSizeInv);
+                    w *= float(sampleViewZ < c.gDenoisingRange);
+                    w *= GetGaussianWeight(length(float2(float(o.x), float(o.y))) * 0.5f);
+                    w *= Pass::GetBilateralWeight(sampleViewZ, centerViewZ);
+
+                    float specularWeight = w;
+                    specularWeight *= ComputeExponentialWeight(angle, specularNormalWeightParam, 0.0f);
+                    // (sic: the reference feeds the CENTRE roughness here, :117 -- the weight is exp(0) = 1)
+                    specularWeight *= ComputeExponentialWeight(normalAndRoughness.w * normalAndRoughness.w, relaxedRoughnessWeightParams.x, relaxedRoughnessWeightParams.y);
+                    float sampleSpecularHitDist = specularWeight == 0.0f ? 0.0f : sampleHitdistViewZ.x; // Denanify
+                    specularWeight *= float(sampleSpecularHitDist != 0.0f);
+                    sumSpecularHitDist += sampleSpecularHitDist * specularWeight;
+                    sumSpecularWeight += specularWeight;
+
+                    float diffuseWeight = w;
+                    diffuseWeight *= ComputeExponentialWeight(angle, diffuseNormalWeightParam, 0.0f);
+                    float sampleDiffuseHitDist = diffuseWeight == 0.0f ? 0.0f : sampleHitdistViewZ.y;
+                    diffuseWeight *= float(sampleDiffuseHitDist != 0.0f);
+                    sumDiffuseHitDist += diffuseWeight == 0.0f ? 0.0f : sampleDiffuseHitDist * diffuseWeight;
+                    sumDiffuseWeight += diffuseWeight;
+                }
+            sumSpecularHitDist /= max(sumSpecularWeight, 1e-6f);
+            gOut_Spec.store(pixelPos, float4(gIn_Spec.load(pixelPos).xyz(), sumSpecularHitDist));
+            sumDiffuseHitDist /= max(sumDiffuseWeight, 1e-6f);
+            gOut_Diff.store(pixelPos, float4(gIn_Diff.load(pixelPos).xyz(), sumDiffuseHitDist));
         }
 }
 
@@ -1417,6 +1500,8 @@ struct PassLayout
     const char* layout;
 };
 const PassLayout kLayouts[] = {
+    {"HitDistReconstruction.cs", "csdccsd"},
+    {"HitDistReconstruction_5x5.cs", "csdccsd"},
     {"PrePass.cs", "csdccsd"},
     {"TemporalAccumulation.cs", "csdcccsdsdccsccsdcsdsdscs"},
     {"HistoryFix.cs", "csdcccsd"},
@@ -1467,7 +1552,9 @@ int relax_dispatch_impl(const char* shaderName, const void* constants, int const
     }
     if (k != texNum) return -3;
 
-    if (!strcmp(p, "PrePass.cs")) PrePass(P, t, gridW, gridH);
+    if (!strcmp(p, "HitDistReconstruction.cs")) HitDistReconstruction(P, 1, t, gridW, gridH);
+    else if (!strcmp(p, "HitDistReconstruction_5x5.cs")) HitDistReconstruction(P, 2, t, gridW, gridH);
+    else if (!strcmp(p, "PrePass.cs")) PrePass(P, t, gridW, gridH);
     else if (!strcmp(p, "TemporalAccumulation.cs")) TemporalAccumulation(P, t, gridW, gridH, hasDiff, hasSpec);
     else if (!strcmp(p, "HistoryFix.cs")) HistoryFix(P, t, gridW, gridH);
     else if (!strcmp(p, "HistoryClamping.cs")) HistoryClamping(P, t, gridW, gridH);

@@ -47,6 +47,9 @@ __device__ __forceinline__ float LoadR8UnormExactClamped(const Surf& s, int x, i
 // octahedral decode at every tap of every A-trous iteration), roughness / material from the packed bits
 #define RX_GUIDE(a, x, y) rb::LoadGuide((a).guide, (a).nr, x, y)
 __device__ __forceinline__ bool IsSkyTile(const Surf& tiles, int x, int y) { return LoadU8(tiles, x >> 4, y >> 4) != 0; }
+// signal load of a kernel compiled for one or both signals: the absent signal reads as zero and its arithmetic is dead code
+template <bool PRESENT> __device__ __forceinline__ f4 LoadSignal(const Surf& s, int x, int y) { return PRESENT ? LoadRGBA16F(s, x, y) : mk4(0.0f); }
+
 
 // RELAX_Common.hlsli:66-96
 __device__ __forceinline__ f3 WorldPosFromClip(const float* R, const float* U, const float* F, float ortho, float csx, float csy, float viewZ)
@@ -249,6 +252,71 @@ __global__ void __launch_bounds__(256) RelaxClassifyTilesKernel(const __grid_con
     }
     allSky = __all_sync(0xffffffffu, allSky);
     if (lane == 0 && ownTile) StoreU8(a.tiles, tx, ty, allSky ? 255u : 0u);
+}
+
+// =============================================================================================
+// Hit-distance reconstruction (RELAX_HitDistReconstruction.hlsli:10-155): RelaxSettings::hitDistanceReconstructionMode 3x3 / 5x5.
+// A dense (2 BORDER + 1)^2 stencil over guides and hit distances; the neighbourhood of a 32x8 CTA is read through L1 (every texel
+// is shared by up to 25 threads of the CTA).
+// =============================================================================================
+struct RxHitDistArgs
+{
+    RC c;
+    Surf tiles, spec, diff, nr, z, outSpec, outDiff;
+    Surf guide;
+    int rowBegin, rowEnd;
+};
+template <bool DIFF, bool SPEC, int BORDER> __global__ void __launch_bounds__(256) RelaxHitDistReconstructionKernel(const __grid_constant__ RxHitDistArgs a)
+{
+    const RC& c = a.c;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
+    const int W = c.gRectSize[0], H = c.gRectSize[1];
+    if (x >= W || y >= H || y >= a.rowEnd) return;
+    if (IsSkyTile(a.tiles, x, y)) return;
+    const float centerViewZ = UnpackViewZ(c, LoadR32F(a.z, x, y));
+    if (centerViewZ > c.gDenoisingRange) return;
+    const Guide g = RX_GUIDE(a, x, y);
+    const f4 centerSpec = LoadSignal<SPEC>(a.spec, x, y), centerDiff = LoadSignal<DIFF>(a.diff, x, y);
+    // GetNormalWeightParam(1, 1, roughness) (Common.hlsli:486-500): 1 / max(atan(lobe tan half angle at 75 % of the volume), encoding error)
+    const float specularNormalWeightParam = 1.0f / fmaxf(atanf(LobeTanHalfAngle(g.roughness, kLobeVolume)), kNormalEncodingError);
+    const float diffuseNormalWeightParam = 1.0f / fmaxf(atanf(LobeTanHalfAngle(1.0f, kLobeVolume)), kNormalEncodingError);
+    // (sic) the reference weighs every tap by the roughness of the CENTRE against itself (:117): one factor for all taps
+    const f2 rrp = RelaxedRoughnessWeightParams(g.roughness * g.roughness, 1.0f);
+    const float roughnessWeight = ExpWeight(g.roughness * g.roughness, rrp.x, rrp.y);
+    float sumSpecularWeight = centerSpec.w != 0.0f ? 1000.0f : 0.0f, sumDiffuseWeight = centerDiff.w != 0.0f ? 1000.0f : 0.0f;
+    float sumSpecularHitDist = centerSpec.w * sumSpecularWeight, sumDiffuseHitDist = centerDiff.w * sumDiffuseWeight;
+#pragma unroll
+    for (int dy = -BORDER; dy <= BORDER; dy++)
+#pragma unroll
+        for (int dx = -BORDER; dx <= BORDER; dx++)
+        {
+            if (dx == 0 && dy == 0) continue;
+            const int px = x + dx, py = y + dy;
+            if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) continue; // IsInScreenNearest of the neighbour's centre
+            const float4 q = __ldg(TexelPtr<float4>(a.guide, px, py)); // {N.xyz, raw viewZ}
+            const float sampleViewZ = fabsf(q.w * c.gViewZScale);
+            float w = sampleViewZ < c.gDenoisingRange ? __expf(-0.66f * 0.25f * (float)(dx * dx + dy * dy)) : 0.0f; // GetGaussianWeight(length(o) / 2)
+            w *= BilateralWeight(sampleViewZ, centerViewZ);
+            const float angle = AcosApprox(g.N.x * q.x + g.N.y * q.y + g.N.z * q.z);
+            if (SPEC)
+            {
+                float ws = w * ExpWeight(angle, specularNormalWeightParam, 0.0f) * roughnessWeight;
+                const float h = ws == 0.0f ? 0.0f : LoadSignal<SPEC>(a.spec, px, py).w;
+                ws = h != 0.0f ? ws : 0.0f;
+                sumSpecularHitDist = fmaf(h, ws, sumSpecularHitDist);
+                sumSpecularWeight += ws;
+            }
+            if (DIFF)
+            {
+                float wd = w * ExpWeight(angle, diffuseNormalWeightParam, 0.0f);
+                const float h = wd == 0.0f ? 0.0f : LoadSignal<DIFF>(a.diff, px, py).w;
+                wd = h != 0.0f ? wd : 0.0f;
+                sumDiffuseHitDist = fmaf(h, wd, sumDiffuseHitDist);
+                sumDiffuseWeight += wd;
+            }
+        }
+    if (SPEC) StoreRGBA16F(a.outSpec, x, y, mk4(xyz(centerSpec), sumSpecularHitDist / fmaxf(sumSpecularWeight, 1e-6f)));
+    if (DIFF) StoreRGBA16F(a.outDiff, x, y, mk4(xyz(centerDiff), sumDiffuseHitDist / fmaxf(sumDiffuseWeight, 1e-6f)));
 }
 
 // =============================================================================================
@@ -1096,9 +1164,6 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxAnti
     if (DIFF) *TexelPtrRW<uint2>(a.outDiff, x, y) = dn;
 }
 
-// signal load of a kernel compiled for one or both signals: the absent signal reads as zero and its arithmetic is dead code
-template <bool PRESENT> __device__ __forceinline__ f4 LoadSignal(const Surf& s, int x, int y) { return PRESENT ? LoadRGBA16F(s, x, y) : mk4(0.0f); }
-
 // confidence-driven relaxation of the A-trous edge stopping (RELAX_Atrous.hlsli:55-67, :95-106; RELAX_AtrousSmem.hlsli:189-201, :226-238)
 struct ConfidenceRelaxation
 {
@@ -1434,6 +1499,8 @@ struct RelaxPassLayout
     const char* layout;
 };
 static const RelaxPassLayout kRelaxLayouts[] = {
+    {"HitDistReconstruction.cs", "csdccsd"},
+    {"HitDistReconstruction_5x5.cs", "csdccsd"},
     {"PrePass.cs", "csdccsd"},
     {"TemporalAccumulation.cs", "csdcccsdsdccsccsdcsdsdscs"},
     {"HistoryFix.cs", "csdcccsd"},
@@ -1449,7 +1516,17 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchRelaxSignals(const Pass
     const int W = c.gRectSize[0];
     const int rows = p.rowEnd - p.rowBegin;
     const dim3 block(32, 8), grid((W + 31) / 32, (rows + 7) / 8);
-    if (!strcmp(shader, "PrePass.cs"))
+    if (!strcmp(shader, "HitDistReconstruction.cs") || !strcmp(shader, "HitDistReconstruction_5x5.cs"))
+    {
+        RxHitDistArgs a;
+        a.c = c;
+        a.guide = p.guide;
+        a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.nr = p.tex[3]; a.z = p.tex[4]; a.outSpec = p.tex[5]; a.outDiff = p.tex[6];
+        a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
+        if (!strcmp(shader, "HitDistReconstruction.cs")) NRD_B200_LAUNCH(p, grid, block, a, RelaxHitDistReconstructionKernel<DIFF, SPEC, 1>);
+        else NRD_B200_LAUNCH(p, grid, block, a, RelaxHitDistReconstructionKernel<DIFF, SPEC, 2>);
+    }
+    else if (!strcmp(shader, "PrePass.cs"))
     {
         RxPrePassArgs a;
         a.c = c;

@@ -125,3 +125,17 @@ def test_relax_one_signal_sequence_parity(denoiser_name):
     _dump("sequence_%s.json" % denoiser_name.lower(), res)
     for name, (frac, psnr) in res.items():
         assert frac >= 0.99 and psnr >= 60.0, (name, frac, psnr)
+
+
+@pytest.mark.parametrize("denoiser_name,mode", [("RELAX_DIFFUSE_SPECULAR", "AREA_3X3"), ("RELAX_DIFFUSE_SPECULAR", "AREA_5X5"), ("RELAX_SPECULAR", "AREA_5X5"), ("RELAX_DIFFUSE", "AREA_3X3")])
+def test_relax_hit_distance_reconstruction_per_pass(denoiser_name, mode):
+    """RelaxSettings::hitDistanceReconstructionMode: the extra 3x3 / 5x5 pass (RELAX_HitDistReconstruction.hlsli) and the chain behind it."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    s = nrd.RelaxSettings()
+    s.hitDistanceReconstructionMode = int(getattr(nrd.HitDistanceReconstructionMode, mode))
+    sbs = parity.SideBySide(getattr(nrd.Denoiser, denoiser_name), 250, 141, settings=s, noise_floor=True)
+    report = sbs.run_per_pass(3)
+    assert any("HitDistReconstruction" in r["shader"] for r in report)
+    _dump("parity_hitdist_%s_%s.json" % (denoiser_name, mode), report)
+    assert not sbs.failures(), sbs.describe_failures()
