@@ -379,6 +379,9 @@ NRD_API nrd::Result nrdCudaExecuteDispatch(NrdCudaContext* context, const nrd::D
 NRD_API nrd::Result nrdCudaDenoise(NrdCudaContext* context, const nrd::Identifier* identifiers, uint32_t identifiersNum, void* stream, uint32_t* launches);
 // Synchronous copies between tightly described host buffers and a texture (pool or user) of the context: the rows
 // physically present in the context are transferred.  Used to checkpoint / restore the permanent pool and by the tests.
+// Strip mode: only the context's own rows are written -- the neighbours' ghost copies of those rows are NOT refreshed (a ghost
+// refresh is a collective step of all ranks).  After restoring history textures into connected strip contexts, run one frame with
+// AccumulationMode::RESTART or restore every rank's full ghost range through nrdCudaGetTexture / nrdCudaCopyTexture.
 NRD_API nrd::Result nrdCudaUploadTexture(NrdCudaContext* context, uint32_t resourceType, uint32_t indexInPool, const void* hostPtr, size_t hostPitchBytes);
 NRD_API nrd::Result nrdCudaDownloadTexture(NrdCudaContext* context, uint32_t resourceType, uint32_t indexInPool, void* hostPtr, size_t hostPitchBytes);
 // Asynchronous 2D copy (cudaMemcpyDefault: pinned host or device memory) between an application buffer holding the rows

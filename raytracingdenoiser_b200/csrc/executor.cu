@@ -58,7 +58,7 @@ bool g_slotUsed[kMaxPeerSlots] = {};
 
 constexpr size_t kArenaHeader = 256;           // barrier flags: kMaxPeers x u32 (slot s = last epoch signalled by rank s), then the error word
 constexpr unsigned kPushCounterWord = 16;      // u32 index in the header: ticket counter of the fused ghost push + barrier kernel
-constexpr long long kBarrierTimeoutCycles = 4000000000ll; // ~2 s: a missing peer turns into an error instead of a hung GPU
+constexpr long long kBarrierTimeoutNs = 2000000000ll; // 2 s of %globaltimer (independent of the SM clock): a missing peer turns into an error instead of a hung GPU
 
 uint32_t BytesPerTexel(Format f)
 {
@@ -125,6 +125,7 @@ struct NrdCudaContext
     float* roughnessLut = nullptr;     // device, 1024 x float4 (allocated with the context: no cudaMalloc -- an implicit device
     float* roughnessLutStaging = nullptr; // synchronisation -- may happen while a strip barrier spins); pinned staging copy
     cudaEvent_t lutUploaded = nullptr;
+    unsigned* hostError = nullptr;        // pinned + mapped: a strip barrier that timed out writes its epoch here (strip mode)
     bool timing = false;                  // nrdCudaSetTiming: three events per dispatch (before the kernel, after it, after push + barrier)
     cudaEvent_t timingEvents[3 * 64] = {};
     uint32_t timingCount = 0;
@@ -346,7 +347,8 @@ struct BarrierArgs
     unsigned* flags; // local arena header
     long long delta[kMaxPeers];
     unsigned rank, world, epoch;
-    long long timeout;
+    long long timeout;        // nanoseconds of %globaltimer
+    unsigned* hostError;      // pinned, device-mapped word of the context: a timed-out barrier reports here, the host sees it without a sync
 };
 
 struct PushItem
@@ -387,6 +389,12 @@ cudaError_t LaunchClear(const PassLaunch& p)
     return cudaGetLastError();
 }
 
+__device__ __forceinline__ unsigned long long GlobalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void StripBarrierBody(const BarrierArgs& a, unsigned t)
 {
     if (t >= a.world) return;
@@ -394,12 +402,14 @@ __device__ __forceinline__ void StripBarrierBody(const BarrierArgs& a, unsigned 
     volatile unsigned* remote = (volatile unsigned*)((uint8_t*)a.flags + a.delta[t]) + a.rank;
     *remote = a.epoch;
     volatile unsigned* mine = a.flags + t;
-    const long long start = clock64();
+    if (((volatile unsigned*)a.flags)[kMaxPeers] != 0) return; // an earlier barrier of this context timed out: do not wait 2 s per pass again
+    const unsigned long long start = GlobalTimerNs();
     while ((int)(*mine - a.epoch) < 0)
     {
-        if (clock64() - start > a.timeout)
+        if ((long long)(GlobalTimerNs() - start) > a.timeout)
         {
-            a.flags[kMaxPeers] = a.epoch; // error word
+            a.flags[kMaxPeers] = a.epoch; // sticky error word (device side) ...
+            if (a.hostError) *(volatile unsigned*)a.hostError = a.epoch; // ... and its host-visible twin: the next API call fails
             break;
         }
         __nanosleep(64);
@@ -460,7 +470,8 @@ BarrierArgs NextBarrier(NrdCudaContext* ctx)
     a.rank = ctx->rank;
     a.world = ctx->world;
     a.epoch = ++ctx->epoch;
-    a.timeout = kBarrierTimeoutCycles;
+    a.timeout = kBarrierTimeoutNs;
+    a.hostError = ctx->hostError;
     return a;
 }
 
@@ -595,6 +606,15 @@ NRD_API Result nrdCudaCreateContext(Instance* instance, const NrdCudaContextDesc
         nrdCudaDestroyContext(ctx);
         return Result::FAILURE;
     }
+    if (StripMode(ctx))
+    {
+        if (cudaHostAlloc((void**)&ctx->hostError, sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+        {
+            nrdCudaDestroyContext(ctx);
+            return Result::FAILURE;
+        }
+        *ctx->hostError = 0;
+    }
     cudaMemset(ctx->arena, 0, ctx->arenaBytes);
     // the memset runs on the legacy default stream, the context is used on the caller's (non-blocking) streams and by peers:
     // nothing may touch the arena (barrier flags included) before it is zero
@@ -626,6 +646,7 @@ NRD_API void nrdCudaDestroyContext(NrdCudaContext* ctx)
     if (ctx->roughnessLut) cudaFree(ctx->roughnessLut);
     if (ctx->roughnessLutStaging) cudaFreeHost(ctx->roughnessLutStaging);
     if (ctx->lutUploaded) cudaEventDestroy(ctx->lutUploaded);
+    if (ctx->hostError) cudaFreeHost(ctx->hostError);
     for (cudaEvent_t ev : ctx->timingEvents)
         if (ev) cudaEventDestroy(ev);
     delete ctx;
@@ -756,6 +777,8 @@ namespace
 Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream, uint32_t pushMask)
 {
     if (!ctx || !d) return Result::INVALID_ARGUMENT;
+    if (ctx->hostError && *(volatile unsigned*)ctx->hostError)
+        return Fail(ctx, Result::FAILURE, "a strip barrier of this context timed out waiting for a peer (epoch " + std::to_string(*(volatile unsigned*)ctx->hostError) + "): its outputs since then are not valid");
     const InstanceDesc& id = GetInstanceDesc(*ctx->instance);
     if (d->pipelineIndex >= id.pipelinesNum) return Result::INVALID_ARGUMENT;
     const char* shader = id.pipelines[d->pipelineIndex].shaderFileName;
