@@ -26,6 +26,10 @@ constexpr float kFp16MaxRx = 65504.0f;
 __constant__ float kPoisson8[8][3] = {{-0.4706069f, -0.4427112f, +0.6461146f}, {-0.9057375f, +0.3003471f, +0.9542373f}, {-0.3487388f, +0.4037880f, +0.5335386f},
                                       {+0.1023042f, +0.6439373f, +0.6520134f}, {+0.5699277f, +0.3513750f, +0.6695386f}, {+0.2939128f, -0.1131226f, +0.3149309f},
                                       {+0.7836658f, -0.4208784f, +0.8895339f}, {+0.1564120f, -0.8198990f, +0.8346850f}};
+// GetGaussianWeight(length) = exp(-0.66 length^2) of the eight taps
+#define NRD_B200_POISSON8_X(i) ((i) == 0 ? -0.4706069f : (i) == 1 ? -0.9057375f : (i) == 2 ? -0.3487388f : (i) == 3 ? 0.1023042f : (i) == 4 ? 0.5699277f : (i) == 5 ? 0.2939128f : (i) == 6 ? 0.7836658f : 0.1564120f)
+#define NRD_B200_POISSON8_Y(i) ((i) == 0 ? -0.4427112f : (i) == 1 ? 0.3003471f : (i) == 2 ? 0.4037880f : (i) == 3 ? 0.6439373f : (i) == 4 ? 0.3513750f : (i) == 5 ? -0.1131226f : (i) == 6 ? -0.4208784f : -0.8198990f)
+#define NRD_B200_POISSON8_GAUSS(i) ((i) == 0 ? 0.7591725f : (i) == 1 ? 0.5482766f : (i) == 2 ? 0.82871586f : (i) == 3 ? 0.75534534f : (i) == 4 ? 0.743887f : (i) == 5 ? 0.9366368f : (i) == 6 ? 0.5931912f : 0.6313964f)
 __constant__ unsigned kBayerRx[16] = {0, 8, 2, 10, 12, 4, 14, 6, 3, 11, 1, 9, 15, 7, 13, 5};
 
 typedef RelaxConstants RC;
@@ -47,6 +51,14 @@ __device__ __forceinline__ float LoadR8UnormExactClamped(const Surf& s, int x, i
 // octahedral decode at every tap of every A-trous iteration), roughness / material from the packed bits
 #define RX_GUIDE(a, x, y) rb::LoadGuide((a).guide, (a).nr, x, y)
 __device__ __forceinline__ bool IsSkyTile(const Surf& tiles, int x, int y) { return LoadU8(tiles, x >> 4, y >> 4) != 0; }
+// floor(x) for |x| < 2^22 without the conversion pipe (x + 1.5 * 2^23 rounded towards -inf keeps floor(x) in its low mantissa bits);
+// anything outside that range comes out as an index far outside any screen
+__device__ __forceinline__ float FloorIndexRx(float x, int& i)
+{
+    const float t = __fadd_rd(x, 12582912.0f);
+    i = __float_as_int(t) - 0x4B400000;
+    return __fadd_rn(t, -12582912.0f);
+}
 // signal load of a kernel compiled for one or both signals: the absent signal reads as zero and its arithmetic is dead code
 template <bool PRESENT> __device__ __forceinline__ f4 LoadSignal(const Surf& s, int x, int y) { return PRESENT ? LoadRGBA16F(s, x, y) : mk4(0.0f); }
 
@@ -350,15 +362,19 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
     const float frustumSize = PixelRadiusToWorld(c, (float)min(W, H), centerViewZ);
 
     // tap position in pixels (pinned: selects the texel), returns the in-screen flag
+    // (the rotated offsets are per-frame uniforms: with the tap index a compile-time constant of the unrolled loops they fold into
+    // uniform-datapath arithmetic; floor() is the FADD.RM trick of the REBLUR filters -- same value for |x| < 2^22, off screen otherwise)
+    const float kx2 = 2.0f * c.gRectSizeInv[0], ky2 = 2.0f * c.gRectSizeInv[1];
     auto tapPos = [&](int i, float blurRadius, int& tx, int& ty, float& csx, float& csy) {
-        float ox = kPoisson8[i][0], oy = kPoisson8[i][1];
-        float rxv = __fadd_rn(__fmul_rn(ox, rx0), __fmul_rn(oy, rx1)), ryv = __fadd_rn(__fmul_rn(ox, rx2), __fmul_rn(oy, rx3));
-        float fx = floorf(__fadd_rn(posX, __fmul_rn(rxv, blurRadius))), fy = floorf(__fadd_rn(posY, __fmul_rn(ryv, blurRadius)));
-        bool inScreen = fx >= 0.0f && fy >= 0.0f && fx < (float)W && fy < (float)H;
-        tx = (int)fminf(fmaxf(fx, 0.0f), (float)(W - 1));
-        ty = (int)fminf(fmaxf(fy, 0.0f), (float)(H - 1));
-        csx = (fx + 0.5f) * c.gRectSizeInv[0] * 2.0f - 1.0f;
-        csy = (fy + 0.5f) * c.gRectSizeInv[1] * 2.0f - 1.0f;
+        const float ox = NRD_B200_POISSON8_X(i), oy = NRD_B200_POISSON8_Y(i);
+        const float rxv = __fadd_rn(__fmul_rn(ox, rx0), __fmul_rn(oy, rx1)), ryv = __fadd_rn(__fmul_rn(ox, rx2), __fmul_rn(oy, rx3));
+        int ix, iy;
+        const float fx = FloorIndexRx(__fadd_rn(posX, __fmul_rn(rxv, blurRadius)), ix), fy = FloorIndexRx(__fadd_rn(posY, __fmul_rn(ryv, blurRadius)), iy);
+        const bool inScreen = (unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H;
+        tx = clampi(ix, 0, W - 1);
+        ty = clampi(iy, 0, H - 1);
+        csx = fmaf(fx + 0.5f, kx2, -1.0f);
+        csy = fmaf(fy + 0.5f, ky2, -1.0f);
         return inScreen;
     };
 
@@ -374,26 +390,27 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
             const float normalWeightParam = NormalWeightParam2(1.0f, 0.25f * c.gLobeAngleFraction);
             const f2 hdp = HitDistanceWeightParams(diff.w, 1.0f / 9.0f, SpecMagicCurve(1.0f));
             float weightSum = 1.0f;
-#pragma unroll 1
+            const float planeThreshold = c.gDepthThreshold * planeZ, planeC = dot(centerWorldPos, centerNormal);
+#pragma unroll
             for (int i = 0; i < 8; i++)
             {
                 int tx, ty;
                 float csx, csy;
-                bool inScreen = tapPos(i, blurRadius, tx, ty, csx, csy);
-                Guide sg = RX_GUIDE(a, tx, ty);
-                float sz = UnpackViewZ(c, LoadR32F(a.z, tx, ty));
-                f3 sw = CurWorldPosFromClip(c, csx, csy, sz);
-                float w = inScreen ? 1.0f : 0.0f;
-                w *= sz < c.gDenoisingRange ? 1.0f : 0.0f;
-                w *= SameMaterial(g.materialID, sg.materialID, c.gDiffMinMaterial) ? 1.0f : 0.0f;
-                w *= fabsf(dot(sw - centerWorldPos, centerNormal)) / planeZ > c.gDepthThreshold ? 0.0f : 1.0f;
-                w *= NonExpWeight(AcosApprox(dot(centerNormal, sg.N)), normalWeightParam, 0.0f);
-                f4 s = LoadRGBA16F(a.diff, tx, ty);
-                if (w == 0.0f) s = mk4(0.0f);
-                w *= lerpf(c.gMinHitDistanceWeight, 1.0f, ExpWeight(s.w, hdp.x, hdp.y));
-                w *= expf(-0.66f * kPoisson8[i][2] * kPoisson8[i][2]);
-                weightSum += w;
-                diff = diff + s * w;
+                const bool inScreen = tapPos(i, blurRadius, tx, ty, csx, csy);
+                const float4 q = __ldg(TexelPtr<float4>(a.guide, tx, ty)); // {N.xyz, raw viewZ}
+                const float sz = fabsf(q.w * c.gViewZScale);
+                const f3 sw = CurWorldPosFromClip(c, csx, csy, sz);
+                float w = inScreen && sz < c.gDenoisingRange ? NRD_B200_POISSON8_GAUSS(i) : 0.0f;
+                if (c.gDiffMinMaterial < 3.0f) w = SameMaterial(g.materialID, (float)(LoadU32(a.nr, tx, ty) >> 30), c.gDiffMinMaterial) ? w : 0.0f;
+                w = fabsf(dot(sw, centerNormal) - planeC) > planeThreshold ? 0.0f : w;
+                w *= NonExpWeight(AcosApprox(centerNormal.x * q.x + centerNormal.y * q.y + centerNormal.z * q.z), normalWeightParam, 0.0f);
+                if (w != 0.0f)
+                {
+                    const f4 s = LoadRGBA16F(a.diff, tx, ty);
+                    w *= lerpf(c.gMinHitDistanceWeight, 1.0f, ExpWeight(s.w, hdp.x, hdp.y));
+                    weightSum += w;
+                    diff = diff + s * w;
+                }
             }
             diff = mk4(diff.x / weightSum, diff.y / weightSum, diff.z / weightSum, diff.w / weightSum);
         }
@@ -425,33 +442,35 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
             float minHitT = specularHitT == 0.0f ? kInf : specularHitT;
             const float roughnessLerp = LinearStep(0.5f, 1.0f, centerRoughness);
             float weightSum = 1.0f;
-#pragma unroll 1
+            const float planeThreshold = c.gDepthThreshold * planeZ, planeC = dot(centerWorldPos, centerNormal);
+            const float rwpx = rwp.x * (1.0f / 1023.0f); // applied to the tap's 10-bit roughness code
+#pragma unroll
             for (int i = 0; i < 8; i++)
             {
                 int tx, ty;
                 float csx, csy;
-                bool inScreen = tapPos(i, blurRadius, tx, ty, csx, csy);
-                Guide sg = RX_GUIDE(a, tx, ty);
-                float sz = UnpackViewZ(c, LoadR32F(a.z, tx, ty));
-                float w = inScreen ? 1.0f : 0.0f;
-                w *= sz < c.gDenoisingRange ? 1.0f : 0.0f;
-                w *= SameMaterial(g.materialID, sg.materialID, c.gSpecMinMaterial) ? 1.0f : 0.0f;
-                w *= NonExpWeight(sg.roughness, rwp.x, rwp.y);
-                w *= NonExpWeight(AcosApprox(dot(centerNormal, sg.N)), normalWeightParam, 0.0f);
-                f3 sw = CurWorldPosFromClip(c, csx, csy, sz);
-                w *= fabsf(dot(sw - centerWorldPos, centerNormal)) / planeZ > c.gDepthThreshold ? 0.0f : 1.0f;
-                f4 s = LoadRGBA16F(a.spec, tx, ty);
-                if (w == 0.0f) s = mk4(0.0f);
-                w *= lerpf(minHitDistWeight, 1.0f, ExpWeight(s.w, hdp.x, hdp.y));
-                w *= expf(-0.66f * kPoisson8[i][2] * kPoisson8[i][2]);
-                float d = length(sw - centerWorldPos);
-                float t = s.w / (spec.w + d);
-                w *= lerpf(saturate(t), 1.0f, roughnessLerp);
-                weightSum += w;
-                spec.x += s.x * w;
-                spec.y += s.y * w;
-                spec.z += s.z * w;
-                if (w != 0.0f) minHitT = fminf(minHitT, s.w == 0.0f ? kInf : s.w);
+                const bool inScreen = tapPos(i, blurRadius, tx, ty, csx, csy);
+                const float4 q = __ldg(TexelPtr<float4>(a.guide, tx, ty)); // {N.xyz, raw viewZ}
+                const unsigned packed = LoadU32(a.nr, tx, ty);
+                const float sz = fabsf(q.w * c.gViewZScale);
+                float w = inScreen && sz < c.gDenoisingRange ? NRD_B200_POISSON8_GAUSS(i) : 0.0f;
+                if (c.gSpecMinMaterial < 3.0f) w = SameMaterial(g.materialID, (float)(packed >> 30), c.gSpecMinMaterial) ? w : 0.0f;
+                w *= NonExpWeight((float)((packed >> 20) & 1023u), rwpx, rwp.y);
+                w *= NonExpWeight(AcosApprox(centerNormal.x * q.x + centerNormal.y * q.y + centerNormal.z * q.z), normalWeightParam, 0.0f);
+                const f3 sw = CurWorldPosFromClip(c, csx, csy, sz);
+                w = fabsf(dot(sw, centerNormal) - planeC) > planeThreshold ? 0.0f : w;
+                if (w != 0.0f)
+                {
+                    const f4 s = LoadRGBA16F(a.spec, tx, ty);
+                    w *= lerpf(minHitDistWeight, 1.0f, ExpWeight(s.w, hdp.x, hdp.y));
+                    const float d = length(sw - centerWorldPos);
+                    w *= lerpf(SatMul(s.w, __fdividef(1.0f, spec.w + d)), 1.0f, roughnessLerp);
+                    weightSum += w;
+                    spec.x += s.x * w;
+                    spec.y += s.y * w;
+                    spec.z += s.z * w;
+                    if (w != 0.0f) minHitT = fminf(minHitT, s.w == 0.0f ? kInf : s.w);
+                }
             }
             spec.x /= weightSum;
             spec.y /= weightSum;
@@ -965,31 +984,51 @@ struct RxHcArgs
     Surf outSpec, outDiff, outSpecFast, outDiffFast, outLength;
     int rowBegin, rowEnd;
 };
-template <bool IS_SPEC>
-__device__ __forceinline__ void ClampSignal(const RC& c, const Surf& zSurf, int x, int y, float historyLength, const Surf& inNoisy, const Surf& inSlow, const Surf& inFast,
-                                            const Surf& outSlow, const Surf& outFast)
+// The 5x5 window of a pixel is shared by up to 25 threads of the CTA: the CTA stages, once, for its (32 + 4) x (8 + 4) texels (clamped
+// coordinates, like the reference's Preload, RELAX_HistoryClamping.hlsli:12-60) the responsive history already converted to YCoCg with the
+// "inside the denoising range" flag, and the noisy input with its luminance.  The 25 taps are then LDS.128 pairs; the moments are summed
+// in the oracle's order (window scan order, individually rounded) because sigma = sqrt(m2 - m1^2) is rounding noise on flat regions.
+constexpr int kHcW = 32 + 4, kHcH = 8 + 4;
+struct HcTile
+{
+    float4 fast[kHcH][kHcW];  // {Y, Co, Cg, viewZ < denoisingRange ? 1 : 0}
+    float4 noisy[kHcH][kHcW]; // {r, g, b, luminance}
+};
+__device__ __forceinline__ void StageHcTile(HcTile& tile, const RC& c, const Surf& zSurf, const Surf& inNoisy, const Surf& inFast, int x0, int y0, int tid)
 {
     const int W = c.gRectSize[0], H = c.gRectSize[1];
-    // moments in the oracle's operation order: sigma = sqrt(m2 - m1^2) is rounding noise on flat regions (see LumaStats3x3)
+    for (int i = tid; i < kHcW * kHcH; i += 256)
+    {
+        const int lx = i % kHcW, ly = i / kHcW;
+        const int px = clampi(x0 + lx, 0, W - 1), py = clampi(y0 + ly, 0, H - 1);
+        // texels beyond the denoising range take no part in the moments: they are staged as zeros (adding +0 is exact) with a zero count
+        const bool valid = LoadR32F(zSurf, px, py) < c.gDenoisingRange;
+        const f3 sy = valid ? RgbToYCoCg(xyz(LoadRGBA16F(inFast, px, py))) : mk3(0.0f); // exact: power-of-two coefficients
+        const f3 n = valid ? xyz(LoadRGBA16F(inNoisy, px, py)) : mk3(0.0f);
+        tile.fast[ly][lx] = make_float4(sy.x, sy.y, sy.z, valid ? 1.0f : 0.0f);
+        tile.noisy[ly][lx] = make_float4(n.x, n.y, n.z, valid ? PinnedLuma(n) : 0.0f);
+    }
+}
+template <bool IS_SPEC>
+__device__ __forceinline__ void ClampSignal(const RC& c, const HcTile& tile, int x, int y, float historyLength, const Surf& inNoisy, const Surf& inSlow, const Surf& inFast,
+                                            const Surf& outSlow, const Surf& outFast)
+{
     f3 m1 = mk3(0.0f), m2 = mk3(0.0f), noisyM1 = mk3(0.0f);
     float noisyM2 = 0.0f, sum = 0.0f;
-#pragma unroll 1
+    const int cx = threadIdx.x + 2, cy = threadIdx.y + 2;
+#pragma unroll
     for (int dx = -2; dx <= 2; dx++)
 #pragma unroll
         for (int dy = -2; dy <= 2; dy++)
         {
-            int px = clampi(x + dx, 0, W - 1), py = clampi(y + dy, 0, H - 1);
-            if (LoadR32F(zSurf, px, py) < c.gDenoisingRange)
-            {
-                f3 sy = RgbToYCoCg(xyz(LoadRGBA16F(inFast, px, py))); // exact: power-of-two coefficients
-                m1 = PinnedAdd(m1, sy);
-                m2 = PinnedAdd(m2, mk3(__fmul_rn(sy.x, sy.x), __fmul_rn(sy.y, sy.y), __fmul_rn(sy.z, sy.z)));
-                f3 n = xyz(LoadRGBA16F(inNoisy, px, py));
-                float l = PinnedLuma(n);
-                noisyM1 = PinnedAdd(noisyM1, n);
-                noisyM2 = __fadd_rn(noisyM2, __fmul_rn(l, l));
-                sum += 1.0f;
-            }
+            const float4 f = tile.fast[cy + dy][cx + dx];
+            const float4 nl = tile.noisy[cy + dy][cx + dx];
+            const f3 sy = mk3(f.x, f.y, f.z), n = mk3(nl.x, nl.y, nl.z);
+            m1 = PinnedAdd(m1, sy);
+            m2 = PinnedAdd(m2, mk3(__fmul_rn(sy.x, sy.x), __fmul_rn(sy.y, sy.y), __fmul_rn(sy.z, sy.z)));
+            noisyM1 = PinnedAdd(noisyM1, n);
+            noisyM2 = __fadd_rn(noisyM2, __fmul_rn(nl.w, nl.w));
+            sum += f.w;
         }
     m1 = mk3(__fdiv_rn(m1.x, sum), __fdiv_rn(m1.y, sum), __fdiv_rn(m1.z, sum));
     m2 = mk3(__fdiv_rn(m2.x, sum), __fdiv_rn(m2.y, sum), __fdiv_rn(m2.z, sum));
@@ -1055,13 +1094,24 @@ __device__ __forceinline__ void ClampSignal(const RC& c, const Surf& zSurf, int 
 template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxHistoryClampingKernel(const __grid_constant__ RxHcArgs a)
 {
     const RC& c = a.c;
+    __shared__ HcTile sTiles[(SPEC ? 1 : 0) + (DIFF ? 1 : 0)]; // specular first
+    HcTile& sSpecTile = sTiles[0];
+    HcTile& sDiffTile = sTiles[SPEC && DIFF ? 1 : 0];
+    const int W = c.gRectSize[0], H = c.gRectSize[1];
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
-    if (x >= c.gRectSize[0] || y >= c.gRectSize[1] || y >= a.rowEnd) return;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int tileY = min(a.rowBegin + (int)blockIdx.y * 8, H - 1);
+    if ((int)blockIdx.x * 32 >= W || a.rowBegin + (int)blockIdx.y * 8 >= H) return; // CTA beyond the rect (uniform)
+    if (IsSkyTile(a.tiles, min((int)blockIdx.x * 32, W - 1), tileY) && IsSkyTile(a.tiles, min((int)blockIdx.x * 32 + 31, W - 1), tileY)) return; // both tiles sky (uniform)
+    if (SPEC) StageHcTile(sSpecTile, c, a.z, a.specNoisy, a.specFast, (int)blockIdx.x * 32 - 2, a.rowBegin + (int)blockIdx.y * 8 - 2, tid);
+    if (DIFF) StageHcTile(sDiffTile, c, a.z, a.diffNoisy, a.diffFast, (int)blockIdx.x * 32 - 2, a.rowBegin + (int)blockIdx.y * 8 - 2, tid);
+    __syncthreads();
+    if (x >= W || y >= H || y >= a.rowEnd) return;
     if (IsSkyTile(a.tiles, x, y)) return;
     if (!(LoadR32F(a.z, x, y) < c.gDenoisingRange)) return;
     const float historyLength = LoadR8Times255(a.length, x, y);
-    if (SPEC) ClampSignal<true>(c, a.z, x, y, historyLength, a.specNoisy, a.spec, a.specFast, a.outSpec, a.outSpecFast);
-    if (DIFF) ClampSignal<false>(c, a.z, x, y, historyLength, a.diffNoisy, a.diff, a.diffFast, a.outDiff, a.outDiffFast);
+    if (SPEC) ClampSignal<true>(c, sSpecTile, x, y, historyLength, a.specNoisy, a.spec, a.specFast, a.outSpec, a.outSpecFast);
+    if (DIFF) ClampSignal<false>(c, sDiffTile, x, y, historyLength, a.diffNoisy, a.diff, a.diffFast, a.outDiff, a.outDiffFast);
     StoreU8(a.outLength, x, y, LoadU8(a.length, x, y));
 }
 
