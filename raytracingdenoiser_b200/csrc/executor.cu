@@ -109,6 +109,68 @@ bool ExpectedUserFormat(ResourceType type, Format& expected, bool translucent = 
 }
 } // namespace
 
+// ---- user textures in a format above the minimum (Include/NRDDescs.h:43-137 lists MINIMUM formats) -----------------------------------
+// The kernels are written for one format per user texture (ExpectedUserFormat).  A texture bound in a wider format of the same kind
+// (e.g. RGBA32_SFLOAT radiance, R16_SFLOAT viewZ, RG16_SFLOAT motion) gets a shadow copy in the kernels' format: inputs are converted
+// into it before the passes that read them, outputs out of it after the passes that wrote them (one streaming kernel per texture).
+struct FormatInfo
+{
+    int channels;
+    int kind; // 0 = UNORM8, 1 = SFLOAT16, 2 = SFLOAT32
+};
+bool ConvertibleFormat(Format f, FormatInfo& info)
+{
+    switch (f)
+    {
+        case Format::R8_UNORM: info = {1, 0}; return true;
+        case Format::RGBA8_UNORM: info = {4, 0}; return true;
+        case Format::R16_SFLOAT: info = {1, 1}; return true;
+        case Format::RG16_SFLOAT: info = {2, 1}; return true;
+        case Format::RGBA16_SFLOAT: info = {4, 1}; return true;
+        case Format::R32_SFLOAT: info = {1, 2}; return true;
+        case Format::RG32_SFLOAT: info = {2, 2}; return true;
+        case Format::RGBA32_SFLOAT: info = {4, 2}; return true;
+        default: return false;
+    }
+}
+struct ConvertArgs
+{
+    const uint8_t* src;
+    uint8_t* dst;
+    size_t srcPitch, dstPitch;
+    int width, height;
+    int srcChannels, srcKind, dstChannels, dstKind;
+};
+__device__ __forceinline__ float LoadChannel(const uint8_t* texel, int kind, int ch)
+{
+    if (kind == 0) return (float)texel[ch] / 255.0f;
+    if (kind == 1) return __half2float(__ushort_as_half(((const unsigned short*)texel)[ch]));
+    return ((const float*)texel)[ch];
+}
+__device__ __forceinline__ void StoreChannel(uint8_t* texel, int kind, int ch, float v)
+{
+    if (kind == 0) texel[ch] = (unsigned char)__fadd_rn(__fmul_rn(__saturatef(v), 255.0f), 0.5f); // D3D float -> UNORM
+    else if (kind == 1) ((unsigned short*)texel)[ch] = __half_as_ushort(__float2half_rn(v));
+    else ((float*)texel)[ch] = v;
+}
+// channels the source does not have read 0 (a two-channel motion vector has no z / w), extra source channels are dropped
+__global__ void __launch_bounds__(256) ConvertFormatKernel(const __grid_constant__ ConvertArgs a)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= a.width || y >= a.height) return;
+    const int srcBytes = a.srcChannels * (a.srcKind == 0 ? 1 : (a.srcKind == 1 ? 2 : 4)), dstBytes = a.dstChannels * (a.dstKind == 0 ? 1 : (a.dstKind == 1 ? 2 : 4));
+    const uint8_t* s = a.src + (size_t)y * a.srcPitch + (size_t)x * srcBytes;
+    uint8_t* d = a.dst + (size_t)y * a.dstPitch + (size_t)x * dstBytes;
+    for (int ch = 0; ch < a.dstChannels; ch++) StoreChannel(d, a.dstKind, ch, ch < a.srcChannels ? LoadChannel(s, a.srcKind, ch) : 0.0f);
+}
+struct ForeignTexture
+{
+    void* ptr = nullptr;     // the application's texture
+    size_t pitch = 0;
+    Format format = Format::R8_UNORM;
+    void* shadow = nullptr;  // cudaMalloc'ed copy in the kernels' format (NrdCudaContext::user[] points at it)
+};
+
 struct NrdCudaContext
 {
     Instance* instance = nullptr;
@@ -117,6 +179,7 @@ struct NrdCudaContext
     size_t arenaBytes = 0;
     std::vector<Texture> permanent, transient;
     Texture user[(size_t)ResourceType::MAX_NUM];
+    ForeignTexture foreign[(size_t)ResourceType::MAX_NUM]; // user textures bound in a wider format than the kernels' (see ConvertFormatKernel)
     // decoded-guide surface of the REBLUR spatial passes (surf.h PassLaunch::guide): written by ClassifyTiles, the first pass
     // of every REBLUR frame, read by PrePass / Blur / PostBlur of the same frame
     Texture guide;
@@ -647,6 +710,8 @@ NRD_API void nrdCudaDestroyContext(NrdCudaContext* ctx)
     if (ctx->roughnessLutStaging) cudaFreeHost(ctx->roughnessLutStaging);
     if (ctx->lutUploaded) cudaEventDestroy(ctx->lutUploaded);
     if (ctx->hostError) cudaFreeHost(ctx->hostError);
+    for (ForeignTexture& f : ctx->foreign)
+        if (f.shadow) cudaFree(f.shadow);
     for (cudaEvent_t ev : ctx->timingEvents)
         if (ev) cudaEventDestroy(ev);
     delete ctx;
@@ -659,7 +724,36 @@ NRD_API Result nrdCudaSetUserTexture(NrdCudaContext* ctx, uint32_t resourceType,
     Format expected;
     if (!ExpectedUserFormat((ResourceType)resourceType, expected, ((Scheduler*)ctx->instance)->HasDenoiser(Denoiser::SIGMA_SHADOW_TRANSLUCENCY)))
         return Fail(ctx, Result::UNSUPPORTED, "resource type not consumed by the supported denoisers");
-    if ((Format)format != expected) return Fail(ctx, Result::UNSUPPORTED, "unsupported format for this resource type (see nrd_b200.h)");
+    ForeignTexture& foreign = ctx->foreign[resourceType];
+    const bool wider = (Format)format != expected;
+    if (wider)
+    {
+        // a wider format of the same kind: bind a shadow texture in the kernels' format, converted around the passes
+        FormatInfo have, want;
+        const bool packedNormals = expected == Format::R10_G10_B10_A2_UNORM; // the normal encoding is a property of the library build (LibraryDesc)
+        if (packedNormals || !ConvertibleFormat((Format)format, have) || !ConvertibleFormat(expected, want) ||
+            (have.channels < want.channels && (ResourceType)resourceType != ResourceType::IN_MV) || have.kind < want.kind)
+            return Fail(ctx, Result::UNSUPPORTED, "unsupported format for this resource type (see nrd_b200.h: the listed format, or a float format with at least its channels and precision)");
+    }
+    if (foreign.shadow) cudaFree(foreign.shadow); // (the previous binding of this resource type is replaced from here on)
+    foreign = ForeignTexture{};
+    if (wider)
+    {
+        const size_t shadowPitch = ((size_t)ctx->desc.resourceWidth * BytesPerTexel(expected) + 255) & ~(size_t)255;
+        if (cudaMalloc(&foreign.shadow, shadowPitch * ctx->desc.resourceHeight) != cudaSuccess)
+        {
+            foreign.shadow = nullptr;
+            ctx->user[resourceType] = Texture{};
+            return Fail(ctx, Result::FAILURE, "cudaMalloc of the format-conversion shadow texture failed");
+        }
+        cudaMemset(foreign.shadow, 0, shadowPitch * ctx->desc.resourceHeight);
+        foreign.ptr = devicePtr;
+        foreign.pitch = pitchBytes;
+        foreign.format = (Format)format;
+        devicePtr = foreign.shadow;
+        pitchBytes = shadowPitch;
+        format = (uint32_t)expected;
+    }
     Texture& t = ctx->user[resourceType];
     t.ptr = devicePtr;
     t.pitch = pitchBytes;
@@ -773,6 +867,45 @@ NRD_API Result nrdCudaConnectPeers(NrdCudaContext* ctx, uint32_t rank, uint32_t 
 
 namespace
 {
+// converts one user texture that is bound in a wider format between the application's copy and the shadow the kernels use
+Result ConvertForeign(NrdCudaContext* ctx, uint32_t type, bool toNative, cudaStream_t stream)
+{
+    const ForeignTexture& f = ctx->foreign[type];
+    if (!f.shadow) return Result::SUCCESS;
+    const Texture& t = ctx->user[type];
+    FormatInfo app, native;
+    ConvertibleFormat(f.format, app);
+    ConvertibleFormat(t.format, native);
+    ConvertArgs a{};
+    a.width = t.width;
+    a.height = t.height;
+    if (toNative)
+    {
+        a.src = (const uint8_t*)f.ptr; a.srcPitch = f.pitch; a.srcChannels = app.channels; a.srcKind = app.kind;
+        a.dst = (uint8_t*)t.ptr; a.dstPitch = t.pitch; a.dstChannels = native.channels; a.dstKind = native.kind;
+    }
+    else
+    {
+        a.src = (const uint8_t*)t.ptr; a.srcPitch = t.pitch; a.srcChannels = native.channels; a.srcKind = native.kind;
+        a.dst = (uint8_t*)f.ptr; a.dstPitch = f.pitch; a.dstChannels = app.channels; a.dstKind = app.kind;
+    }
+    ConvertFormatKernel<<<dim3((a.width + 31) / 32, (a.height + 7) / 8), dim3(32, 8), 0, stream>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? Result::SUCCESS : Fail(ctx, Result::FAILURE, std::string("format conversion: ") + cudaGetErrorString(e));
+}
+Result ConvertForeignAll(NrdCudaContext* ctx, bool inputs, cudaStream_t stream)
+{
+    for (uint32_t t = 0; t < (uint32_t)ResourceType::MAX_NUM; t++)
+    {
+        if (!ctx->foreign[t].shadow) continue;
+        const char* name = GetResourceTypeString((ResourceType)t);
+        if (!name || (strncmp(name, "IN_", 3) == 0) != inputs) continue;
+        const Result r = ConvertForeign(ctx, t, inputs, stream);
+        if (r != Result::SUCCESS) return r;
+    }
+    return Result::SUCCESS;
+}
+
 // pushMask: bit i set = the ghost rows of resource i must be refreshed after this pass (it is read by a later pass)
 Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream, uint32_t pushMask)
 {
@@ -938,7 +1071,22 @@ extern "C" {
 NRD_API Result nrdCudaExecuteDispatch(NrdCudaContext* ctx, const DispatchDesc* d, void* stream)
 {
     if (!ctx || !d) return Result::INVALID_ARGUMENT;
-    return ExecuteInternal(ctx, d, stream, StorageMask(d)); // no look-ahead here: refresh the ghosts of every output
+    // textures bound in a wider format: convert what this pass reads before it and what it writes after it (nrdCudaDenoise does it per frame)
+    for (uint32_t i = 0; i < d->resourcesNum; i++)
+        if (d->resources[i].descriptorType == DescriptorType::TEXTURE && (uint32_t)d->resources[i].type < (uint32_t)ResourceType::TRANSIENT_POOL)
+        {
+            const Result cr = ConvertForeign(ctx, (uint32_t)d->resources[i].type, true, (cudaStream_t)stream);
+            if (cr != Result::SUCCESS) return cr;
+        }
+    const Result r = ExecuteInternal(ctx, d, stream, StorageMask(d)); // no look-ahead here: refresh the ghosts of every output
+    if (r != Result::SUCCESS) return r;
+    for (uint32_t i = 0; i < d->resourcesNum; i++)
+        if (d->resources[i].descriptorType == DescriptorType::STORAGE_TEXTURE && (uint32_t)d->resources[i].type < (uint32_t)ResourceType::TRANSIENT_POOL)
+        {
+            const Result cr = ConvertForeign(ctx, (uint32_t)d->resources[i].type, false, (cudaStream_t)stream);
+            if (cr != Result::SUCCESS) return cr;
+        }
+    return Result::SUCCESS;
 }
 
 NRD_API Result nrdCudaDenoise(NrdCudaContext* ctx, const Identifier* identifiers, uint32_t identifiersNum, void* stream, uint32_t* launches)
@@ -947,6 +1095,8 @@ NRD_API Result nrdCudaDenoise(NrdCudaContext* ctx, const Identifier* identifiers
     const DispatchDesc* dispatches = nullptr;
     uint32_t n = 0;
     Result r = GetComputeDispatches(*ctx->instance, identifiers, identifiersNum, dispatches, n);
+    if (r != Result::SUCCESS) return r;
+    r = ConvertForeignAll(ctx, true, (cudaStream_t)stream); // inputs bound in a wider format -> the kernels' format
     if (r != Result::SUCCESS) return r;
     r = FrameStart(ctx, stream);
     if (r != Result::SUCCESS) return r;
@@ -980,6 +1130,8 @@ NRD_API Result nrdCudaDenoise(NrdCudaContext* ctx, const Identifier* identifiers
         r = ExecuteInternal(ctx, &d, stream, mask);
         if (r != Result::SUCCESS) return r;
     }
+    r = ConvertForeignAll(ctx, false, (cudaStream_t)stream); // outputs -> the application's wider format
+    if (r != Result::SUCCESS) return r;
     if (launches) *launches = n;
     return Result::SUCCESS;
 }

@@ -64,3 +64,57 @@ def test_dynamic_resolution_per_pass(denoiser_name):
     report = sbs.run_per_pass(4, rect_fn=_rects)
     _dump("parity_dynres_%s.json" % denoiser_name, report)
     assert not sbs.failures(), sbs.describe_failures()
+
+
+def test_user_textures_in_wider_formats_give_the_same_result():
+    """Include/NRDDescs.h lists MINIMUM formats: a user texture may be bound in a wider float format (RGBA32_SFLOAT radiance / motion /
+    outputs, R16_SFLOAT viewZ whose values fit).  The executor converts around the passes; with inputs that convert exactly, the
+    outputs must equal those of a run with the kernels' own formats, bit for bit."""
+    import torch
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h, frames = 250, 141, 4
+    den = nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR
+    sc = scene.Scene(w, h)
+    frs = []
+    for f in range(frames):
+        fr = sc.frame(f)
+        fr["IN_VIEWZ"] = fr["IN_VIEWZ"].to(torch.float16).to(torch.float32)  # values a R16_SFLOAT texture can hold
+        frs.append(fr)
+    native = harness.GpuDenoiser(den, w, h)
+    for f, fr in enumerate(frs):
+        native.set_inputs(fr)
+        native.denoise(harness.make_common_settings(fr, w, h, f))
+    torch.cuda.synchronize()
+    want = {k: v.clone() for k, v in native.outputs().items()}
+    native.destroy()
+
+    inst = nrd.Instance([(0, den)])
+    ctx = nrd.CudaContext(inst, w, h)
+    dev = torch.device("cuda", 0)
+    wide = {"IN_MV": (nrd.Format.RGBA32_SFLOAT, torch.float32, 4), "IN_VIEWZ": (nrd.Format.R16_SFLOAT, torch.float16, 1),
+            "IN_DIFF_RADIANCE_HITDIST": (nrd.Format.RGBA32_SFLOAT, torch.float32, 4), "IN_SPEC_RADIANCE_HITDIST": (nrd.Format.RGBA16_SFLOAT, torch.float16, 4),
+            "OUT_DIFF_RADIANCE_HITDIST": (nrd.Format.RGBA32_SFLOAT, torch.float32, 4), "OUT_SPEC_RADIANCE_HITDIST": (nrd.Format.RGBA32_SFLOAT, torch.float32, 4),
+            "IN_NORMAL_ROUGHNESS": harness.USER_FORMATS["IN_NORMAL_ROUGHNESS"]}
+    tex = {}
+    for name, (fmt, dtype, ch) in wide.items():
+        t = torch.zeros((h, w, ch) if ch > 1 else (h, w), dtype=dtype, device=dev)
+        tex[name] = t
+        ctx.set_user_texture(getattr(nrd.ResourceType, name), t.data_ptr(), t.stride(0) * t.element_size(), fmt)
+    with pytest.raises(nrd.NrdError):  # fewer channels / lower precision than the minimum is refused
+        bad = torch.zeros((h, w), dtype=torch.float16, device=dev)
+        ctx.set_user_texture(nrd.ResourceType.IN_DIFF_RADIANCE_HITDIST, bad.data_ptr(), bad.stride(0) * 2, nrd.Format.R16_SFLOAT)
+    ctx.set_user_texture(nrd.ResourceType.IN_DIFF_RADIANCE_HITDIST, tex["IN_DIFF_RADIANCE_HITDIST"].data_ptr(), tex["IN_DIFF_RADIANCE_HITDIST"].stride(0) * 4, nrd.Format.RGBA32_SFLOAT)
+    for f, fr in enumerate(frs):
+        for name, t in tex.items():
+            if name.startswith("IN_"):
+                src = fr[name].to(dev)
+                t.copy_(src.to(t.dtype) if t.dtype != src.dtype and t.dtype.is_floating_point else src)
+        inst.set_common_settings(harness.make_common_settings(fr, w, h, f))
+        ctx.denoise([0], stream=torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    for name in ("OUT_DIFF_RADIANCE_HITDIST", "OUT_SPEC_RADIANCE_HITDIST"):
+        got = tex[name]
+        assert got.abs().sum().item() > 0
+        assert torch.equal(got, want[name].to(torch.float32)), name
+    ctx.destroy()
+    inst.destroy()
