@@ -369,9 +369,9 @@ NRD_API void nrdCudaDestroyContext(NrdCudaContext* context);
 // Binds an application texture (IN_* / OUT_*).  Required formats: IN_MV RGBA16_SFLOAT, IN_NORMAL_ROUGHNESS
 // R10_G10_B10_A2_UNORM, IN_VIEWZ R32_SFLOAT, IN/OUT_*_RADIANCE_HITDIST RGBA16_SFLOAT, IN_PENUMBRA R16_SFLOAT,
 // IN_TRANSLUCENCY RGBA8_UNORM, OUT_SHADOW_TRANSLUCENCY R8_UNORM (SIGMA_SHADOW) / RGBA8_UNORM (SIGMA_SHADOW_TRANSLUCENCY).  `devicePtr` addresses texel (0, firstRow of the context).
-// A texture may also be bound in a wider float format than the one listed (Include/NRDDescs.h lists MINIMUM formats): at least the
-// channels (IN_MV may have two) and the precision of the listed one, e.g. RGBA32_SFLOAT radiance / outputs, R16/R32_SFLOAT where R8_UNORM
-// is listed.  The executor keeps a shadow copy in the listed format and converts around the passes (one extra streaming kernel per texture
+// A texture may also be bound in another float format than the one listed (Include/NRDDescs.h lists MINIMUM formats; the listed one is
+// what the kernels read): any 16- / 32-bit float format with at least the channels of the listed one (IN_MV may have two), e.g.
+// RGBA32_SFLOAT radiance / outputs, R16_SFLOAT viewZ, R16/R32_SFLOAT where R8_UNORM is listed.  The executor keeps a shadow copy in the listed format and converts around the passes (one extra streaming kernel per texture
 // and frame).  IN_NORMAL_ROUGHNESS must be the library's normal encoding (LibraryDesc).
 NRD_API nrd::Result nrdCudaSetUserTexture(NrdCudaContext* context, uint32_t resourceType, void* devicePtr, size_t pitchBytes, uint32_t format);
 // Looks a texture up exactly like a DispatchDesc resource would be resolved.

@@ -207,6 +207,28 @@ inline float Clamp(float m1, float sigma, float x) { return clamp(x, m1 - sigma,
 namespace BRDF
 {
 inline float Pow5(float x) { return pow(saturate(1.0f - x), 5.0f); }
+// MathLib ml.hlsli (absent from the reference tree; restated from the published MathLib / STL sources, FROZEN CHOICE like the rest of
+// this file): BRDF::ConvertBaseColorMetalnessToAlbedoRf0 and BRDF::EnvironmentTerm_Rtg ("Ray Tracing Gems", chapter 32: the
+// polynomial fit of the split-sum environment BRDF)
+inline void ConvertBaseColorMetalnessToAlbedoRf0(float3 baseColor, float metalness, float3& albedo, float3& Rf0)
+{
+    albedo = baseColor * float3(saturate(1.0f - metalness));
+    Rf0 = lerp(float3(0.04f), baseColor, metalness);
+}
+inline float3 EnvironmentTerm_Rtg(float3 Rf0, float NoV, float linearRoughness)
+{
+    float m = linearRoughness * linearRoughness;
+    float4 X(1.0f, NoV, NoV * NoV, NoV * NoV * NoV);
+    float4 Y(1.0f, m, m * m, m * m * m);
+    // mul(M, v) with row-major literals: M1 = {{0.99044, -1.28514}, {1.29678, -0.755907}} etc.
+    float2 m1 = float2(0.99044f * X.x + -1.28514f * X.y, 1.29678f * X.x + -0.755907f * X.y);
+    float3 m2 = float3(1.0f * X.x + 2.92338f * X.y + 59.4188f * X.w, 20.3225f * X.x + -27.0302f * X.y + 222.592f * X.w, 121.563f * X.x + 626.13f * X.y + 316.627f * X.w);
+    float2 m3 = float2(0.0365463f * X.x + 3.32707f * X.y, 9.0632f * X.x + -9.04756f * X.y);
+    float3 m4 = float3(1.0f * X.x + 3.59685f * X.z + -1.36772f * X.w, 9.04401f * X.x + -16.3174f * X.z + 9.22949f * X.w, 5.56589f * X.x + 19.7886f * X.z + -20.2123f * X.w);
+    float bias = dot(m1, float2(Y.x, Y.y)) * rcp(dot(m2, float3(Y.x, Y.y, Y.w)));
+    float scale = dot(m3, float2(Y.x, Y.y)) * rcp(dot(m4, float3(Y.x, Y.y, Y.w)));
+    return saturate(Rf0 * float3(scale) + float3(bias));
+}
 } // namespace BRDF
 
 namespace Sequence

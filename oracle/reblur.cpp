@@ -1717,7 +1717,7 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
     int k = 0;
     const Tex& gIn_Tiles = t[k++];
     const Tex& gIn_Normal_Roughness = t[k++];
-    if (sg.spec) k++; // gIn_BaseColor_Metalness (dummy unless the MV patch is enabled; not restated -- off by default, Reblur.cpp:359)
+    const Tex* gIn_BaseColor_Metalness = sg.spec ? &t[k++] : nullptr; // read only when the MV patch is enabled (isBaseColorMetalnessAvailable, Reblur.cpp:359)
     const Tex& gIn_ViewZ = t[k++];
     const Tex& gIn_Data1 = t[k++];
     const Tex& gIn_Data2 = t[k++];
@@ -1726,7 +1726,7 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
     const Tex* gHistory_DiffLumaStabilized = sg.diff ? &t[k++] : nullptr;
     const Tex* gHistory_SpecLumaStabilized = sg.spec ? &t[k++] : nullptr;
     const Tex* gIn_SpecHitDistForTracking = sg.spec ? &t[k++] : nullptr;
-    const Tex& gInOut_Mv = t[k++];
+    Tex& gInOut_Mv = t[k++];
     Tex& gOut_InternalData = t[k++];
     Tex* gOut_Diff = sg.diff ? &t[k++] : nullptr;
     Tex* gOut_Spec = sg.spec ? &t[k++] : nullptr;
@@ -1852,7 +1852,37 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
                 float3 Xvirtual = Pass::GetXvirtual(hitDistForTracking, curvature, X, Xprev, N, V, roughness);
                 float2 vmbPixelUv = Geometry::GetScreenUv(c.gWorldToClipPrev, Xvirtual);
                 vmbPixelUv = materialID == c.gCameraAttachedReflectionMaterialID ? pixelUv : vmbPixelUv;
-                // MV patch (:250-285) requires gSpecProbabilityThresholdsForMvModification.x < 1, i.e. base colour input: not restated
+                // modify MVs if requested (:250-285): specular-dominant pixels get the motion of their reflection
+                if (c.gSpecProbabilityThresholdsForMvModification.x < 1.0f)
+                {
+                    float NoV = abs(dot(N, V));
+                    float4 baseColorMetalness = gIn_BaseColor_Metalness->load(pixelPos);
+                    float3 albedo, Rf0;
+                    BRDF::ConvertBaseColorMetalnessToAlbedoRf0(baseColorMetalness.xyz(), baseColorMetalness.w, albedo, Rf0);
+                    float3 Fenv = BRDF::EnvironmentTerm_Rtg(Rf0, NoV, roughness);
+                    float lumSpec = Color::Luminance(Fenv);
+                    float lumDiff = Color::Luminance(albedo * (float3(1.0f) - Fenv));
+                    float specProb = lumSpec / (lumDiff + lumSpec + NRD_EPS);
+                    float f = Math::SmoothStep(c.gSpecProbabilityThresholdsForMvModification.x, c.gSpecProbabilityThresholdsForMvModification.y, specProb);
+                    f *= 1.0f - Pass::GetSpecMagicCurve(roughness);
+                    f *= 1.0f - Math::Sqrt01(abs(curvature));
+                    if (f != 0.0f)
+                    {
+                        float3 specMv = Xvirtual - X;
+                        if (c.gMvScale.w == 0.0f)
+                        {
+                            specMv.x = vmbPixelUv.x - pixelUv.x;
+                            specMv.y = vmbPixelUv.y - pixelUv.y;
+                            specMv.z = Geometry::AffineTransform(c.gWorldToViewPrev, Xvirtual).z - viewZ;
+                        }
+                        float3 newMv;
+                        newMv.x = specMv.x / c.gMvScale.x;
+                        newMv.y = specMv.y / c.gMvScale.y;
+                        newMv.z = c.gMvScale.z == 0.0f ? inMv.z : specMv.z / c.gMvScale.z;
+                        float3 patched = lerp(inMv.xyz(), newMv, f);
+                        gInOut_Mv.store(pixelPos, float4(patched, inMv.w));
+                    }
+                }
 
                 float4 h4;
                 P.BicubicFilter(saturate(smbPixelUv) * c.gRectSizePrev, c.gResourceSizeInvPrev, smbOcclusionWeights, smbAllowCatRom, *gHistory_SpecLumaStabilized, h4, nullptr, nullptr);

@@ -1103,6 +1103,7 @@ struct TsArgs
 {
     ReblurConstants c;
     Surf tiles, nr, z, data1, data2, inDiff, inSpec, histDiffStab, histSpecStab, hitDist, mv;
+    Surf baseColorMetalness; // IN_BASECOLOR_METALNESS (RGBA8), read only when the motion-vector patch is on (gSpecProbabilityThresholdsForMvModification.x < 1)
     Surf outInternal, outDiff, outSpec, outDiffStab, outSpecStab;
     Surf guide;
     const float4* lut;
@@ -1275,6 +1276,37 @@ __global__ void __launch_bounds__(256)
         f2 vmbPixelUv = GetScreenUv(c.gWorldToClipPrev, Xvirtual);
         if (g0.materialID == c.gCameraAttachedReflectionMaterialID) vmbPixelUv = pixelUv;
 
+        // modify MVs if requested (REBLUR_TemporalStabilization.hlsli:250-285): specular-dominant pixels get the motion of their reflection
+        if (c.gSpecProbabilityThresholdsForMvModification[0] < 1.0f)
+        {
+            const float NoV = fabsf(dot(g0.N, V));
+            const f4 bcm = UnpackRGBA8(LoadU32(Near(a.baseColorMetalness), x, y));
+            // BRDF::ConvertBaseColorMetalnessToAlbedoRf0 / EnvironmentTerm_Rtg (MathLib, restated in oracle/mathlib.h)
+            const float dielectric = saturate(1.0f - bcm.w);
+            const f3 albedo = mk3(bcm.x * dielectric, bcm.y * dielectric, bcm.z * dielectric);
+            const f3 Rf0 = lerp3(mk3(0.04f), xyz(bcm), bcm.w);
+            const float m = g0.roughness * g0.roughness, m2r = m * m, m3r = m * m2r, n2 = NoV * NoV, n3 = NoV * n2;
+            const float bias = ((0.99044f - 1.28514f * NoV) + (1.29678f - 0.755907f * NoV) * m) /
+                               ((1.0f + 2.92338f * NoV + 59.4188f * n3) + (20.3225f - 27.0302f * NoV + 222.592f * n3) * m + (121.563f + 626.13f * NoV + 316.627f * n3) * m3r);
+            const float scale = ((0.0365463f + 3.32707f * NoV) + (9.0632f - 9.04756f * NoV) * m) /
+                                ((1.0f + 3.59685f * n2 - 1.36772f * n3) + (9.04401f - 16.3174f * n2 + 9.22949f * n3) * m + (5.56589f + 19.7886f * n2 - 20.2123f * n3) * m3r);
+            (void)m2r;
+            const f3 Fenv = mk3(saturate(Rf0.x * scale + bias), saturate(Rf0.y * scale + bias), saturate(Rf0.z * scale + bias));
+            const float lumSpec = 0.2126f * Fenv.x + 0.7152f * Fenv.y + 0.0722f * Fenv.z;
+            const float lumDiff = 0.2126f * albedo.x * (1.0f - Fenv.x) + 0.7152f * albedo.y * (1.0f - Fenv.y) + 0.0722f * albedo.z * (1.0f - Fenv.z);
+            const float specProb = lumSpec / (lumDiff + lumSpec + kEps);
+            float f = SmoothStep(c.gSpecProbabilityThresholdsForMvModification[0], c.gSpecProbabilityThresholdsForMvModification[1], specProb);
+            f *= 1.0f - g0.smc;
+            f *= 1.0f - Sqrt01(fabsf(curvature));
+            if (f != 0.0f)
+            {
+                f3 specMv = Xvirtual - X;
+                if (c.gMvScale[3] == 0.0f) specMv = mk3(vmbPixelUv.x - pixelUv.x, vmbPixelUv.y - pixelUv.y, PinnedRow(c.gWorldToViewPrev, 2, Xvirtual.x, Xvirtual.y, Xvirtual.z) - viewZ);
+                const f3 newMv = mk3(specMv.x / c.gMvScale[0], specMv.y / c.gMvScale[1], c.gMvScale[2] == 0.0f ? mvRaw.z : specMv.z / c.gMvScale[2]);
+                StoreRGBA16F(a.mv, x, y, mk4(lerp3(xyz(mvRaw), newMv, f), mvRaw.w));
+            }
+        }
+
         float smbHistory = ResolveCatRom1(smbSetup, a.histSpecStab);
 
         const Bilinear vmbF = GetBilinear(vmbPixelUv, c.gRectSizePrev);
@@ -1410,7 +1442,7 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchTs(const PassLaunch& p)
     if (!p.preloadOnly && (p.guideMode != 2 || !p.roughnessLut)) return cudaErrorInvalidValue; // the executor always provides both
     int k = 0;
     a.tiles = p.tex[k++]; a.nr = p.tex[k++];
-    if (SPEC) k++; // gIn_BaseColor_Metalness (dummy)
+    if (SPEC) a.baseColorMetalness = p.tex[k++]; // gIn_BaseColor_Metalness (bound to IN_VIEWZ when absent, never read then)
     a.z = p.tex[k++]; a.data1 = p.tex[k++]; a.data2 = p.tex[k++];
     if (DIFF) a.inDiff = p.tex[k++];
     if (SPEC) a.inSpec = p.tex[k++];

@@ -103,6 +103,7 @@ bool ExpectedUserFormat(ResourceType type, Format& expected, bool translucent = 
         case ResourceType::IN_DIFF_CONFIDENCE:
         case ResourceType::IN_SPEC_CONFIDENCE:
         case ResourceType::IN_DISOCCLUSION_THRESHOLD_MIX: expected = Format::R8_UNORM; return true;
+        case ResourceType::IN_BASECOLOR_METALNESS: expected = Format::RGBA8_UNORM; return true; // CommonSettings::isBaseColorMetalnessAvailable
         case ResourceType::OUT_SHADOW_TRANSLUCENCY: expected = translucent ? Format::RGBA8_UNORM : Format::R8_UNORM; return true;
         default: return false;
     }
@@ -732,8 +733,8 @@ NRD_API Result nrdCudaSetUserTexture(NrdCudaContext* ctx, uint32_t resourceType,
         FormatInfo have, want;
         const bool packedNormals = expected == Format::R10_G10_B10_A2_UNORM; // the normal encoding is a property of the library build (LibraryDesc)
         if (packedNormals || !ConvertibleFormat((Format)format, have) || !ConvertibleFormat(expected, want) ||
-            (have.channels < want.channels && (ResourceType)resourceType != ResourceType::IN_MV) || have.kind < want.kind)
-            return Fail(ctx, Result::UNSUPPORTED, "unsupported format for this resource type (see nrd_b200.h: the listed format, or a float format with at least its channels and precision)");
+            (have.channels < want.channels && (ResourceType)resourceType != ResourceType::IN_MV) || (want.kind != 0 && have.kind == 0))
+            return Fail(ctx, Result::UNSUPPORTED, "unsupported format for this resource type (see nrd_b200.h: the listed format, or a 16- / 32-bit float format with at least its channels)");
     }
     if (foreign.shadow) cudaFree(foreign.shadow); // (the previous binding of this resource type is replaced from here on)
     foreign = ForeignTexture{};
@@ -925,8 +926,6 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
     const bool subRect = cs.rectSize[0] != cs.resourceSize[0] || cs.rectSize[1] != cs.resourceSize[1] || cs.rectOrigin[0] || cs.rectOrigin[1];
     if (subRect && StripMode(ctx) && ctx->world > 1)
         return Fail(ctx, Result::UNSUPPORTED, "dynamic resolution (rectSize != resourceSize) is not implemented for multi-GPU strips");
-    if (cs.isBaseColorMetalnessAvailable)
-        return Fail(ctx, Result::UNSUPPORTED, "the base-colour / metalness input (specular motion-vector patch) is not implemented by the CUDA executor");
     if (StripMode(ctx) && !ctx->connected && (ctx->desc.stripY0 != 0 || ctx->desc.stripY1 != ctx->desc.resourceHeight))
         return Fail(ctx, Result::FAILURE, "strip-mode context used before nrdCudaConnectPeers");
 

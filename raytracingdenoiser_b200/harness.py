@@ -23,6 +23,7 @@ USER_FORMATS = {
     "IN_DIFF_CONFIDENCE": (nrd.Format.R8_UNORM, torch.uint8, 1),
     "IN_SPEC_CONFIDENCE": (nrd.Format.R8_UNORM, torch.uint8, 1),
     "IN_DISOCCLUSION_THRESHOLD_MIX": (nrd.Format.R8_UNORM, torch.uint8, 1),
+    "IN_BASECOLOR_METALNESS": (nrd.Format.RGBA8_UNORM, torch.uint8, 4),
     "OUT_SHADOW_TRANSLUCENCY": (nrd.Format.R8_UNORM, torch.uint8, 1),
     "IN_TRANSLUCENCY": (nrd.Format.RGBA8_UNORM, torch.uint8, 4),
     "OUT_SHADOW_TRANSLUCENCY#RGBA8": (nrd.Format.RGBA8_UNORM, torch.uint8, 4),   # SIGMA_SHADOW_TRANSLUCENCY writes float4
@@ -57,6 +58,7 @@ RECT_ORIGIN_INPUTS = ("IN_VIEWZ", "IN_NORMAL_ROUGHNESS", "IN_MV", "IN_DIFF_CONFI
 OPTIONAL_INPUTS = {  # CommonSettings flag -> the user textures it makes the passes read, per signal
     "isHistoryConfidenceAvailable": {"diff": "IN_DIFF_CONFIDENCE", "spec": "IN_SPEC_CONFIDENCE"},
     "isDisocclusionThresholdMixAvailable": {"any": "IN_DISOCCLUSION_THRESHOLD_MIX"},
+    "isBaseColorMetalnessAvailable": {"spec": "IN_BASECOLOR_METALNESS"},
 }
 
 

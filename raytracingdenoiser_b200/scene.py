@@ -254,7 +254,13 @@ class Scene(object):
         mix = torch.clamp(0.5 + 0.5 * torch.sin(fu * 0.5 + fv), 0.0, 1.0)
         unorm8 = lambda x: torch.floor(torch.clamp(x, 0.0, 1.0) * 255.0 + 0.5).to(torch.uint8).contiguous()
 
+        # IN_BASECOLOR_METALNESS (isBaseColorMetalnessAvailable): the surface colour, every third object metallic
+        metal = ((idx % 3) == 0).to(torch.float32) * (~sky).to(torch.float32)
+        bcm = torch.cat([torch.clamp(col, 0.0, 1.0), metal[..., None]], -1)
+        bcm = torch.floor(bcm * 255.0 + 0.5).to(torch.uint8).contiguous()
+
         out = {
+            "IN_BASECOLOR_METALNESS": bcm,
             "IN_DIFF_CONFIDENCE": unorm8(diff_conf), "IN_SPEC_CONFIDENCE": unorm8(spec_conf), "IN_DISOCCLUSION_THRESHOLD_MIX": unorm8(mix),
             "IN_TRANSLUCENCY": transl,
             "IN_VIEWZ": viewz.to(torch.float32).contiguous(),

@@ -107,3 +107,18 @@ def test_reblur_performance_mode_sequence_parity():
     _dump("sequence_reblur_perf.json", res)
     for name, (frac, psnr) in res.items():
         assert frac >= 0.99 and psnr >= 60.0, (name, frac, psnr)
+
+
+def test_reblur_base_color_motion_vector_patch_per_pass():
+    """CommonSettings::isBaseColorMetalnessAvailable: temporal stabilization rewrites IN_MV of specular-dominant pixels with the motion of
+    their reflection (REBLUR_TemporalStabilization.hlsli:250-285; BRDF helpers restated from MathLib, oracle/mathlib.h)."""
+    import parity
+    from raytracingdenoiser_b200 import nrd
+    s = nrd.ReblurSettings()
+    s.specularProbabilityThresholdsForMvModification[0], s.specularProbabilityThresholdsForMvModification[1] = 0.2, 0.6
+    sbs = parity.SideBySide(nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, 250, 141, settings=s, common={"isBaseColorMetalnessAvailable": True})
+    report = sbs.run_per_pass(4)
+    mv = [r for r in report if "TemporalStabilization" in r["shader"] and r["resource"].startswith("IN_MV")]
+    assert mv, "temporal stabilization must bind IN_MV as an output"
+    _dump("parity_basecolor_mv_patch.json", report)
+    assert not sbs.failures(), sbs.describe_failures()
