@@ -89,6 +89,9 @@ enum class DescriptorType : uint32_t { TEXTURE, STORAGE_TEXTURE, MAX_NUM };
 enum class Sampler : uint32_t { NEAREST_CLAMP, LINEAR_CLAMP, MAX_NUM };
 enum class NormalEncoding : uint8_t { RGBA8_UNORM, RGBA8_SNORM, R10_G10_B10_A2_UNORM, RGBA16_UNORM, RGBA16_SNORM, MAX_NUM };
 enum class RoughnessEncoding : uint8_t { SQ_LINEAR, LINEAR, SQRT_LINEAR, MAX_NUM };
+// Checkerboarded noisy inputs (NRDSettings.h CheckerboardMode): a signal is traced for every other pixel only -- the pixels with
+// ((x ^ y ^ frameIndex) & 1) == parity -- and stored packed, pixel x at column x >> 1 of IN_DIFF_* / IN_SPEC_* (left half of the
+// texture).  BLACK: diffuse on parity 0, specular on parity 1; WHITE: the opposite.  Implemented for REBLUR and RELAX.
 enum class CheckerboardMode : uint8_t { OFF, BLACK, WHITE, MAX_NUM };
 enum class AccumulationMode : uint8_t { CONTINUE, RESTART, CLEAR_AND_RESTART, MAX_NUM };
 enum class HitDistanceReconstructionMode : uint8_t { OFF, AREA_3X3, AREA_5X5, MAX_NUM };

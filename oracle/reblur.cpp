@@ -1930,7 +1930,8 @@ void TemporalStabilization(const Pass& P, Signals sg, Tex* t, int W, int H)
             gOut_InternalData.storeu(pixelPos, Pass::PackInternalData(data1.x, data1.y, materialID));
         }
 }
-// REBLUR_SplitScreen.hlsli:11-47: the part of the screen left of gSplitScreen shows the noisy input (checkerboard off)
+// REBLUR_SplitScreen.hlsli:11-47: the part of the screen left of gSplitScreen shows the noisy input (a checkerboarded input is
+// stretched: pixel x shows packed column x >> 1)
 void SplitScreen(const Pass& P, Signals sg, Tex* t, int W, int H)
 {
     const CB& c = P.c;
@@ -1949,8 +1950,8 @@ void SplitScreen(const Pass& P, Signals sg, Tex* t, int W, int H)
             if (pixelUv.x > c.gSplitScreen || x > c.gRectSizeMinusOne[0] || y > c.gRectSizeMinusOne[1]) continue;
             float viewZ = P.UnpackViewZ(gIn_ViewZ.load(pixelPos).x);
             float keep = float(viewZ < c.gDenoisingRange);
-            if (sg.diff) gOut_Diff->store(pixelPos, gIn_Diff->load(pixelPos) * float4(keep));
-            if (sg.spec) gOut_Spec->store(pixelPos, gIn_Spec->load(pixelPos) * float4(keep));
+            if (sg.diff) gOut_Diff->store(pixelPos, gIn_Diff->load(x >> (c.gDiffCheckerboard != 2 ? 1 : 0), y) * float4(keep));
+            if (sg.spec) gOut_Spec->store(pixelPos, gIn_Spec->load(x >> (c.gSpecCheckerboard != 2 ? 1 : 0), y) * float4(keep));
         }
 }
 } // namespace

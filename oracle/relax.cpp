@@ -1467,7 +1467,7 @@ void Atrous(const Pass& P, Tex* t, int gridW, int gridH)
             gOut_Diff.store(pixelPos, sumDiffuse / float4(sumWDiffuse, sumWDiffuse, sumWDiffuse, sumWDiffuse * sumWDiffuse));
         }
 }
-// RELAX_SplitScreen.hlsli:11-50 (checkerboard off, no SH): binding layout of the two-signal shader is viewZ, diff, spec | diff, spec
+// RELAX_SplitScreen.hlsli:11-50 (no SH; a checkerboarded input is stretched: pixel x shows packed column x >> 1): binding layout of the two-signal shader is viewZ, diff, spec | diff, spec
 void SplitScreen(const Pass& P, Tex* t, int gridW, int gridH)
 {
     const CB& c = P.c;
@@ -1482,8 +1482,8 @@ void SplitScreen(const Pass& P, Tex* t, int gridW, int gridH)
             if (pixelUv.x > c.gSplitScreen || x >= c.gRectSize[0] || y >= c.gRectSize[1]) continue;
             float viewZ = P.UnpackViewZ(gIn_ViewZ.load(pixelPos).x);
             float keep = float(viewZ < c.gDenoisingRange);
-            gOut_Diff.store(pixelPos, gIn_Diff.load(pixelPos) * float4(keep));
-            gOut_Spec.store(pixelPos, gIn_Spec.load(pixelPos) * float4(keep));
+            gOut_Diff.store(pixelPos, gIn_Diff.load(x >> (c.gDiffCheckerboard != 2 ? 1 : 0), y) * float4(keep));
+            gOut_Spec.store(pixelPos, gIn_Spec.load(x >> (c.gSpecCheckerboard != 2 ? 1 : 0), y) * float4(keep));
         }
 }
 

@@ -22,6 +22,7 @@ struct SplitArgs
     float rectSizeInvX, splitScreen, viewZScale, denoisingRange;
     int rectW, rectH;
     int hasDiff, hasSpec;
+    int diffShift, specShift; // 1: checkerboarded input packed into the left half, pixel x shows column x >> 1 (REBLUR_SplitScreen.hlsli:24, :36; RELAX_SplitScreen.hlsli:24, :38)
     int rowBegin, rowEnd;
 };
 __global__ void __launch_bounds__(256) RadianceSplitScreenKernel(const __grid_constant__ SplitArgs a)
@@ -33,8 +34,8 @@ __global__ void __launch_bounds__(256) RadianceSplitScreenKernel(const __grid_co
     const float viewZ = fabsf(LoadR32F(Near(a.z), x, y) * a.viewZScale);
     const bool keep = viewZ < a.denoisingRange;
     const uint2 zero = make_uint2(0u, 0u); // x * 0 in half precision: +0 (the sign of a negative input is not preserved; NaN inputs are not expected)
-    if (a.hasDiff) *TexelPtrRW<uint2>(a.outDiff, x, y) = keep ? __ldg(TexelPtr<uint2>(Near(a.inDiff), x, y)) : zero;
-    if (a.hasSpec) *TexelPtrRW<uint2>(a.outSpec, x, y) = keep ? __ldg(TexelPtr<uint2>(Near(a.inSpec), x, y)) : zero;
+    if (a.hasDiff) *TexelPtrRW<uint2>(a.outDiff, x, y) = keep ? __ldg(TexelPtr<uint2>(Near(a.inDiff), x >> a.diffShift, y)) : zero;
+    if (a.hasSpec) *TexelPtrRW<uint2>(a.outSpec, x, y) = keep ? __ldg(TexelPtr<uint2>(Near(a.inSpec), x >> a.specShift, y)) : zero;
 }
 
 // ---- SIGMA: out = (translucent ? IN_TRANSLUCENCY : IsLit(penumbra)) * (viewZ < denoisingRange) -------------------------------
@@ -119,7 +120,8 @@ cudaError_t LaunchAux(const PassLaunch& p, const char* shader)
             a.rectW = c.gRectSize[0]; a.rectH = c.gRectSize[1];
             diffCheckerboard = c.gDiffCheckerboard; specCheckerboard = c.gSpecCheckerboard;
         }
-        if (!p.preloadOnly && (diffCheckerboard != 2 || specCheckerboard != 2)) return cudaErrorNotSupported;
+        a.diffShift = diffCheckerboard != 2 ? 1 : 0;
+        a.specShift = specCheckerboard != 2 ? 1 : 0;
         int k = 0;
         a.z = p.tex[k++];
         if (a.hasDiff) a.inDiff = p.tex[k++];

@@ -233,7 +233,8 @@ struct TaArgs
     int perf;            // REBLUR_PERFORMANCE_MODE: no CatRom history filters (REBLUR_Config.hlsli:196-202)
 };
 
-template <bool DIFF, bool SPEC>
+// CB = checkerboarded inputs (compiled out of the default kernels)
+template <bool DIFF, bool SPEC, bool CB = false>
 #ifndef NRD_B200_TA_MIN_BLOCKS
 #define NRD_B200_TA_MIN_BLOCKS 5 // <= 96 registers: 5 x 128 threads per SM instead of 3 (measured 1.7x on this kernel)
 #endif
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
     const f2 pixelUv = PixelUv(x, y, c.gRectSizeInv);
     const f3 Xv = ReconstructViewPosition(pixelUv, c.gFrustum, viewZ, c.gOrthoMode);
     const f3 X = PinnedRotate(c.gViewToWorld, Xv);
+    const unsigned checkerboard = CB ? (((unsigned)x ^ (unsigned)y) ^ c.gFrameIndex) & 1u : 0u; // Sequence::CheckerBoard
 
     // 3x3 neighbourhood: averaged normal (2x2 corner), roughness moments, min hit distance for tracking
     f3 Navg = mk3(0.0f);
@@ -674,7 +676,14 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         smbSpecHistory = ClampNegativeToZero(smbSpecHistory);
         vmbSpecHistory = ClampNegativeToZero(vmbSpecHistory);
 
-        const float smbNl = 1.0f / (1.0f + smbSpecAccumSpeed), vmbNl = 1.0f / (1.0f + vmbSpecAccumSpeed);
+        float smbNl = 1.0f / (1.0f + smbSpecAccumSpeed), vmbNl = 1.0f / (1.0f + vmbSpecAccumSpeed);
+        // checkerboarded input: a pixel whose value was resolved from its neighbours accumulates slower (:731-735)
+        const bool specHasData = !CB || c.gSpecCheckerboard == 2u || checkerboard == c.gSpecCheckerboard;
+        if (!specHasData)
+        {
+            smbNl *= lerpf(1.0f - c.gCheckerboardResolveAccumSpeed, 1.0f, smbNl);
+            vmbNl *= lerpf(1.0f - c.gCheckerboardResolveAccumSpeed, 1.0f, vmbNl);
+        }
         const float minHitNl = 1.0f / (1.0f + 0.5f * smcModified * c.gMaxAccumulatedFrameNum);
         f4 smbSpec = lerp4(smbSpecHistory, spec, smbNl);
         smbSpec.w = lerpf(smbSpecHistory.w, spec.w, fmaxf(smbNl, minHitNl));
@@ -696,6 +705,11 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         // fast history
         float smbFastNl = fmaxf(1.0f - surfaceHistoryConfidence, 1.0f / (1.0f + fminf(smbSpecAccumSpeed, c.gMaxFastAccumulatedFrameNum)));
         float vmbFastNl = fmaxf(1.0f - virtualHistoryConfidence, 1.0f / (1.0f + fminf(vmbSpecAccumSpeed, c.gMaxFastAccumulatedFrameNum)));
+        if (!specHasData)
+        {
+            smbFastNl *= lerpf(1.0f - c.gCheckerboardResolveAccumSpeed, 1.0f, smbFastNl);
+            vmbFastNl *= lerpf(1.0f - c.gCheckerboardResolveAccumSpeed, 1.0f, vmbFastNl);
+        }
         float smbSpecFast = lerpf(smbSpecFastHistory, spec.x, smbFastNl), vmbSpecFast = lerpf(vmbSpecFastHistory, spec.x, vmbFastNl);
         float specFastResult = lerpf(smbSpecFast, vmbSpecFast, virtualHistoryAmount);
         float specFastClamped = fminf(specFastResult, specHistory.x * specMaxRelativeIntensity * 4.0f);
@@ -719,7 +733,9 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         f4 smbDiffHistory = ClampNegativeToZero(ResolveCatRom4(smbSetup, a.histDiff));
         const float smbDiffFastHistory = ResolveBilinearCustom1(smbSetup, a.histDiffFast, smbOcclusionWeights);
 
-        const float nl = 1.0f / (1.0f + diffAccumSpeed);
+        float nl = 1.0f / (1.0f + diffAccumSpeed);
+        const bool diffHasData = !CB || c.gDiffCheckerboard == 2u || checkerboard == c.gDiffCheckerboard;
+        if (!diffHasData) nl *= lerpf(1.0f - c.gCheckerboardResolveAccumSpeed, 1.0f, nl);
         const float minHitNl = 1.0f / (1.0f + 0.5f * __ldg(&a.lut[1023]).x * c.gMaxAccumulatedFrameNum); // SpecMagicCurve(1)
         f4 diffResult = lerp4(smbDiffHistory, diff, nl);
         diffResult.w = lerpf(smbDiffHistory.w, diff.w, fmaxf(nl, minHitNl));
@@ -733,6 +749,7 @@ __global__ void __launch_bounds__(128, NRD_B200_TA_MIN_BLOCKS) ReblurTemporalAcc
         StoreRGBA16F(a.outDiff, x, y, diffResult);
 
         float fastNl = 1.0f / (1.0f + fminf(diffAccumSpeed, c.gMaxFastAccumulatedFrameNum));
+        if (!diffHasData) fastNl *= lerpf(1.0f - c.gCheckerboardResolveAccumSpeed, 1.0f, fastNl);
         float diffFastResult = lerpf(smbDiffFastHistory, diff.x, fastNl);
         float diffFastClamped = fminf(diffFastResult, smbDiffHistory.x * diffMaxRelativeIntensity * 4.0f);
         diffFastResult = lerpf(diffFastResult, diffFastClamped, diffAntifireflyFactor);
@@ -1380,7 +1397,9 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchTa(const PassLaunch& p)
     a.perf = p.performanceMode ? 1 : 0;
     const int W = (int)a.c.gRectSize[0];
     dim3 grid((W + 31) / 32, (p.rowEnd - p.rowBegin + 3) / 4), block(32, 4);
-    NRD_B200_LAUNCH(p, grid, block, a, ReblurTemporalAccumulationKernel<DIFF, SPEC>);
+    const bool checkerboard = (DIFF && a.c.gDiffCheckerboard != 2u) || (SPEC && a.c.gSpecCheckerboard != 2u);
+    if (checkerboard || p.preloadOnly) NRD_B200_LAUNCH(p, grid, block, a, ReblurTemporalAccumulationKernel<DIFF, SPEC, true>);
+    if (!checkerboard || p.preloadOnly) NRD_B200_LAUNCH(p, grid, block, a, ReblurTemporalAccumulationKernel<DIFF, SPEC>);
     return cudaGetLastError();
 }
 cudaError_t LaunchReblurTemporalAccumulation(const PassLaunch& p, int signal)

@@ -332,7 +332,9 @@ template <bool DIFF, bool SPEC, int BORDER> __global__ void __launch_bounds__(25
 }
 
 // =============================================================================================
-// Pre-pass (RELAX_PrePass.hlsli:13-347), checkerboard off
+// Pre-pass (RELAX_PrePass.hlsli:13-347).  CB = a checkerboarded input (RelaxSettings::checkerboardMode): the signal is packed into the
+// left half of its texture, pixels without data are resolved from their left / right neighbours before the blur (:28-58, :73-110),
+// taps that land on a pixel without data move one pixel sideways (ApplyCheckerboardShift)
 // =============================================================================================
 struct RxPrePassArgs
 {
@@ -341,7 +343,7 @@ struct RxPrePassArgs
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
-template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant__ RxPrePassArgs a)
+template <bool DIFF, bool SPEC, bool CB = false> __global__ void __launch_bounds__(256) RelaxPrePassKernel(const __grid_constant__ RxPrePassArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 8 + threadIdx.y;
@@ -361,15 +363,49 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
     const float planeZ = c.gOrthoMode == 0.0f ? centerViewZ : 1.0f;
     const float frustumSize = PixelRadiusToWorld(c, (float)min(W, H), centerViewZ);
 
+    // checkerboard resolve weights (:28-58)
+    unsigned checkerboard = 0u;
+    int cbX0 = 0, cbX1 = 0;
+    float cbW0 = 1.0f, cbW1 = 1.0f, cbMat0 = 0.0f, cbMat1 = 0.0f;
+    if (CB)
+    {
+        checkerboard = (((unsigned)x ^ (unsigned)y) ^ c.gFrameIndex) & 1u;
+        const int x0 = max(x - 1, 0), x1 = min(x + 1, W - 1);
+        const float viewZ0 = UnpackViewZ(c, LoadR32F(a.z, x0, y)), viewZ1 = UnpackViewZ(c, LoadR32F(a.z, x1, y));
+        cbMat0 = (float)(LoadU32(a.nr, x0, y) >> 30);
+        cbMat1 = (float)(LoadU32(a.nr, x1, y) >> 30);
+        cbW0 = (viewZ0 > c.gDenoisingRange || x < 1) ? 0.0f : BilateralWeight(viewZ0, centerViewZ);
+        cbW1 = (viewZ1 > c.gDenoisingRange || x > W - 2) ? 0.0f : BilateralWeight(viewZ1, centerViewZ);
+        cbX0 = x0 >> 1;
+        cbX1 = x1 >> 1;
+    }
+    auto resolve = [&](const Surf& signal, float minMaterial) {
+        float w0 = SameMaterial(g.materialID, cbMat0, minMaterial) ? cbW0 : 0.0f, w1 = SameMaterial(g.materialID, cbMat1, minMaterial) ? cbW1 : 0.0f;
+        const float norm = PositiveRcp(w0 + w1);
+        w0 *= norm;
+        w1 *= norm;
+        f4 s0 = LoadRGBA16F(signal, cbX0, y), s1 = LoadRGBA16F(signal, cbX1, y);
+        s0 = w0 == 0.0f ? mk4(0.0f) : s0;
+        s1 = w1 == 0.0f ? mk4(0.0f) : s1;
+        return s0 * w0 + s1 * w1;
+    };
+
     // tap position in pixels (pinned: selects the texel), returns the in-screen flag
     // (the rotated offsets are per-frame uniforms: with the tap index a compile-time constant of the unrolled loops they fold into
     // uniform-datapath arithmetic; floor() is the FADD.RM trick of the REBLUR filters -- same value for |x| < 2^22, off screen otherwise)
     const float kx2 = 2.0f * c.gRectSizeInv[0], ky2 = 2.0f * c.gRectSizeInv[1];
-    auto tapPos = [&](int i, float blurRadius, int& tx, int& ty, float& csx, float& csy) {
+    auto tapPos = [&](int i, float blurRadius, unsigned mode, int& tx, int& ty, float& csx, float& csy) {
         const float ox = NRD_B200_POISSON8_X(i), oy = NRD_B200_POISSON8_Y(i);
         const float rxv = __fadd_rn(__fmul_rn(ox, rx0), __fmul_rn(oy, rx1)), ryv = __fadd_rn(__fmul_rn(ox, rx2), __fmul_rn(oy, rx3));
         int ix, iy;
-        const float fx = FloorIndexRx(__fadd_rn(posX, __fmul_rn(rxv, blurRadius)), ix), fy = FloorIndexRx(__fadd_rn(posY, __fmul_rn(ryv, blurRadius)), iy);
+        float fx = FloorIndexRx(__fadd_rn(posX, __fmul_rn(rxv, blurRadius)), ix);
+        const float fy = FloorIndexRx(__fadd_rn(posY, __fmul_rn(ryv, blurRadius)), iy);
+        if (CB && mode != 2u && ((((unsigned)ix ^ (unsigned)iy) ^ c.gFrameIndex) & 1u) != mode)
+        {
+            const int d = (i & 1) == 0 ? -1 : 1; // ApplyCheckerboardShift: even taps move left, odd taps right
+            ix += d;
+            fx += (float)d;
+        }
         const bool inScreen = (unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H;
         tx = clampi(ix, 0, W - 1);
         ty = clampi(iy, 0, H - 1);
@@ -381,7 +417,9 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
     // ---- diffuse
     if (DIFF)
     {
-        f4 diff = LoadRGBA16F(a.diff, x, y);
+        const int half = CB && c.gDiffCheckerboard != 2u ? 1 : 0;
+        f4 diff = LoadRGBA16F(a.diff, x >> half, y);
+        if (CB && half && checkerboard != c.gDiffCheckerboard) diff = resolve(a.diff, c.gDiffMinMaterial);
         if (c.gDiffBlurRadius > 0.0f)
         {
             float hitDist = diff.w == 0.0f ? 1.0f : diff.w;
@@ -396,7 +434,7 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
             {
                 int tx, ty;
                 float csx, csy;
-                const bool inScreen = tapPos(i, blurRadius, tx, ty, csx, csy);
+                const bool inScreen = tapPos(i, blurRadius, c.gDiffCheckerboard, tx, ty, csx, csy);
                 const float4 q = __ldg(TexelPtr<float4>(a.guide, tx, ty)); // {N.xyz, raw viewZ}
                 const float sz = fabsf(q.w * c.gViewZScale);
                 const f3 sw = CurWorldPosFromClip(c, csx, csy, sz);
@@ -406,7 +444,7 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
                 w *= NonExpWeight(AcosApprox(centerNormal.x * q.x + centerNormal.y * q.y + centerNormal.z * q.z), normalWeightParam, 0.0f);
                 if (w != 0.0f)
                 {
-                    const f4 s = LoadRGBA16F(a.diff, tx, ty);
+                    const f4 s = LoadRGBA16F(a.diff, tx >> half, ty);
                     w *= lerpf(c.gMinHitDistanceWeight, 1.0f, ExpWeight(s.w, hdp.x, hdp.y));
                     weightSum += w;
                     diff = diff + s * w;
@@ -419,7 +457,9 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
     // ---- specular
     if (SPEC)
     {
-        f4 spec = LoadRGBA16F(a.spec, x, y);
+        const int half = CB && c.gSpecCheckerboard != 2u ? 1 : 0;
+        f4 spec = LoadRGBA16F(a.spec, x >> half, y);
+        if (CB && half && checkerboard != c.gSpecCheckerboard) spec = resolve(a.spec, c.gSpecMinMaterial);
         spec.w = fmaxf(0.0f, fminf(c.gDenoisingRange, spec.w));
         if (c.gSpecBlurRadius > 0.0f)
         {
@@ -449,7 +489,7 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
             {
                 int tx, ty;
                 float csx, csy;
-                const bool inScreen = tapPos(i, blurRadius, tx, ty, csx, csy);
+                const bool inScreen = tapPos(i, blurRadius, c.gSpecCheckerboard, tx, ty, csx, csy);
                 const float4 q = __ldg(TexelPtr<float4>(a.guide, tx, ty)); // {N.xyz, raw viewZ}
                 const unsigned packed = LoadU32(a.nr, tx, ty);
                 const float sz = fabsf(q.w * c.gViewZScale);
@@ -461,7 +501,7 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(256) RelaxPreP
                 w = fabsf(dot(sw, centerNormal) - planeC) > planeThreshold ? 0.0f : w;
                 if (w != 0.0f)
                 {
-                    const f4 s = LoadRGBA16F(a.spec, tx, ty);
+                    const f4 s = LoadRGBA16F(a.spec, tx >> half, ty);
                     w *= lerpf(minHitDistWeight, 1.0f, ExpWeight(s.w, hdp.x, hdp.y));
                     const float d = length(sw - centerWorldPos);
                     w *= lerpf(SatMul(s.w, __fdividef(1.0f, spec.w + d)), 1.0f, roughnessLerp);
@@ -493,7 +533,7 @@ struct RxTaArgs
     Surf guide; // decoded guides of the current frame (surf.h PassLaunch::guide)
     int rowBegin, rowEnd;
 };
-template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const __grid_constant__ RxTaArgs a)
+template <bool DIFF, bool SPEC, bool CB = false> __global__ void __launch_bounds__(128, 5) RelaxTemporalAccumulationKernel(const __grid_constant__ RxTaArgs a)
 {
     const RC& c = a.c;
     const int x = blockIdx.x * 32 + threadIdx.x, y = a.rowBegin + blockIdx.y * 4 + threadIdx.y;
@@ -691,6 +731,12 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(128, 5) RelaxT
         }
         float alpha = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (diffMaxAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
         float alphaResponsive = SMBReprojectionFound > 0.0f ? fmaxf(1.0f / (diffMaxFastAccumulatedFrameNum + 1.0f), 1.0f / historyLength) : 1.0f;
+        // checkerboarded input: a pixel resolved by the pre-pass accumulates slower (:597-606)
+        if (CB && c.gDiffCheckerboard != 2u && ((((unsigned)x ^ (unsigned)y) ^ c.gFrameIndex) & 1u) != c.gDiffCheckerboard && historyLength > 1.0f)
+        {
+            alpha *= 1.0f - c.gCheckerboardResolveAccumSpeed;
+            alphaResponsive *= 1.0f - c.gCheckerboardResolveAccumSpeed;
+        }
         f4 acc = lerp4(prevDiffSMB, mk4(diffuseIllumination, diffuse2ndMoment), alpha);
         f3 accResponsive = lerp3(prevDiffSMBResponsive, diffuseIllumination, alphaResponsive);
         StoreRGBA16F(a.outDiff, x, y, acc);
@@ -883,6 +929,14 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(128, 5) RelaxT
     const float specSMBConfidence = smbFound * SmoothStep01(1.0f - AcosApprox(cosVVprev) / (lobeHalfAngle * NoV / c.gFramerateScale));
     float specSMBAlpha = fmaxf(1.0f - specSMBConfidence, 1.0f / (1.0f + specHistoryFrames));
     float specSMBResponsiveAlpha = fmaxf(specSMBAlpha, 1.0f / (1.0f + specHistoryResponsiveFrames));
+    // checkerboarded input (:854-863, :881-887)
+    const bool specResolved = CB && c.gSpecCheckerboard != 2u && ((((unsigned)x ^ (unsigned)y) ^ c.gFrameIndex) & 1u) != c.gSpecCheckerboard && smbParallaxInPixelsMax < 0.5f;
+    if (specResolved)
+    {
+        const float k = 1.0f - c.gCheckerboardResolveAccumSpeed * smbFound;
+        specSMBAlpha *= k;
+        specSMBResponsiveAlpha *= k;
+    }
     f4 accSMB = mk4(lerp3(xyz(prevSpecSMB), xyz(specularIllumination), specSMBAlpha), lerpf(prevReflectionHitTSMB, specularIllumination.w, fmaxf(specSMBAlpha, 0.1f)));
     float accM2SMB = lerpf(prevSpecSMB.w, specular2ndMoment, specSMBAlpha);
     f3 accSMBResponsive = lerp3(prevSpecSMBResponsive, xyz(specularIllumination), specSMBResponsiveAlpha);
@@ -890,6 +944,13 @@ template <bool DIFF, bool SPEC> __global__ void __launch_bounds__(128, 5) RelaxT
     float specVMBAlpha = fmaxf(1.0f - specVMBConfidence, 1.0f / (1.0f + specHistoryFrames));
     float specVMBResponsiveAlpha = fmaxf(1.0f - specVMBConfidence * virtualHistoryHitDistConfidence, 1.0f / (1.0f + specHistoryResponsiveFrames));
     float specVMBHitTAlpha = fmaxf(1.0f - specVMBConfidence * virtualHistoryHitDistConfidence, 1.0f / (1.0f + specHistoryFrames));
+    if (specResolved)
+    {
+        const float k = 1.0f - c.gCheckerboardResolveAccumSpeed * (VMBReprojectionFound > 0.0f ? 1.0f : 0.0f);
+        specVMBAlpha *= k;
+        specVMBResponsiveAlpha *= k;
+        specVMBHitTAlpha *= k;
+    }
     f4 accVMB = mk4(lerp3(xyz(prevSpecVMB), xyz(specularIllumination), specVMBAlpha), lerpf(prevReflectionHitTVMB, specularIllumination.w, fmaxf(specVMBHitTAlpha, 0.1f)));
     float accM2VMB = lerpf(prevSpecVMB.w, specular2ndMoment, specVMBAlpha);
     f3 accVMBResponsive = lerp3(xyz(prevSpecVMBResponsive), xyz(specularIllumination), specVMBResponsiveAlpha);
@@ -1583,7 +1644,9 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchRelaxSignals(const Pass
         a.guide = p.guide;
         a.tiles = p.tex[0]; a.spec = p.tex[1]; a.diff = p.tex[2]; a.nr = p.tex[3]; a.z = p.tex[4]; a.outSpec = p.tex[5]; a.outDiff = p.tex[6];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, grid, block, a, RelaxPrePassKernel<DIFF, SPEC>);
+        const bool checkerboard = (DIFF && c.gDiffCheckerboard != 2u) || (SPEC && c.gSpecCheckerboard != 2u);
+        if (checkerboard || p.preloadOnly) NRD_B200_LAUNCH(p, grid, block, a, RelaxPrePassKernel<DIFF, SPEC, true>);
+        if (!checkerboard || p.preloadOnly) NRD_B200_LAUNCH(p, grid, block, a, RelaxPrePassKernel<DIFF, SPEC>);
     }
     else if (!strcmp(shader, "TemporalAccumulation.cs"))
     {
@@ -1597,7 +1660,9 @@ template <bool DIFF, bool SPEC> static cudaError_t LaunchRelaxSignals(const Pass
         a.outSpec = p.tex[18]; a.outDiff = p.tex[19]; a.outSpecFast = p.tex[20]; a.outDiffFast = p.tex[21]; a.outHitDist = p.tex[22]; a.outLength = p.tex[23];
         a.outConfidence = p.tex[24];
         a.rowBegin = p.rowBegin; a.rowEnd = p.rowEnd;
-        NRD_B200_LAUNCH(p, dim3((W + 31) / 32, (rows + 3) / 4), dim3(32, 4), a, RelaxTemporalAccumulationKernel<DIFF, SPEC>);
+        const bool checkerboard = (DIFF && c.gDiffCheckerboard != 2u) || (SPEC && c.gSpecCheckerboard != 2u);
+        if (checkerboard || p.preloadOnly) NRD_B200_LAUNCH(p, dim3((W + 31) / 32, (rows + 3) / 4), dim3(32, 4), a, RelaxTemporalAccumulationKernel<DIFF, SPEC, true>);
+        if (!checkerboard || p.preloadOnly) NRD_B200_LAUNCH(p, dim3((W + 31) / 32, (rows + 3) / 4), dim3(32, 4), a, RelaxTemporalAccumulationKernel<DIFF, SPEC>);
     }
     else if (!strcmp(shader, "HistoryFix.cs"))
     {
@@ -1668,8 +1733,6 @@ cudaError_t LaunchRelax(const PassLaunch& p, const char* shader)
     memset(&c, 0, sizeof(c));
     memcpy(&c, p.constants, p.constantsSize < sizeof(RC) ? p.constantsSize : sizeof(RC));
     if (p.rowEnd - p.rowBegin <= 0) return cudaSuccess;
-    if (c.gDiffCheckerboard != 2 || c.gSpecCheckerboard != 2) return cudaErrorNotSupported;
-
     if (!strcmp(shader, "RELAX_ClassifyTiles.cs"))
     {
         RxTilesArgs a;

@@ -391,7 +391,7 @@ cudaError_t LaunchByName(const Launchers& L, const PassLaunch& launch, const cha
 void PreloadKernels(const NrdCudaContext* ctx, const Launchers& L)
 {
     alignas(16) static unsigned char dummy[1024] = {}; // a zeroed constant block big enough for every denoiser
-    ((RelaxConstants*)dummy)->gDiffCheckerboard = ((RelaxConstants*)dummy)->gSpecCheckerboard = 2; // RELAX launchers reject other modes
+    ((RelaxConstants*)dummy)->gDiffCheckerboard = ((RelaxConstants*)dummy)->gSpecCheckerboard = 2; // (checkerboard off; in preload mode every variant is loaded anyway)
     const InstanceDesc& id = GetInstanceDesc(*ctx->instance);
     for (uint32_t i = 0; i < id.pipelinesNum; i++)
     {
@@ -945,13 +945,8 @@ Result ExecuteInternal(NrdCudaContext* ctx, const DispatchDesc* d, void* stream,
         p.tex[i] = WithRectOrigin(ToSurf(ctx, *t), r.type, *t, cs);
         p.texBytes[i] = (uint8_t)BytesPerTexel(t->format);
     }
-    // checkerboarded inputs bind the same passes (no separate shader name), so they have to be rejected here, loudly
-    if (!strncmp(shader, "REBLUR_", 7) && strcmp(shader, "REBLUR_ClassifyTiles.cs") != 0 && d->constantBufferData && d->constantBufferDataSize >= sizeof(ReblurConstants))
-    {
-        ReblurConstants rc;
-        memcpy(&rc, d->constantBufferData, sizeof(rc));
-        if (rc.gDiffCheckerboard != 2 || rc.gSpecCheckerboard != 2) return Fail(ctx, Result::UNSUPPORTED, "REBLUR checkerboard modes are not implemented by the CUDA executor");
-    }
+    // checkerboarded REBLUR inputs (ReblurSettings::checkerboardMode) bind the same passes: the pre-pass resolves them, temporal
+    // accumulation slows down on resolved pixels; RELAX and the split-screen passes reject them in their launchers
     // decoded-guide surface: ClassifyTiles (first pass of every REBLUR frame) fills it, all later passes of the frame read it
     const bool isReblur = !strncmp(shader, "REBLUR_", 7), isRelax = !strncmp(shader, "RELAX_", 6);
     const bool buildsGuide = !strcmp(shader, "REBLUR_ClassifyTiles.cs") || !strcmp(shader, "RELAX_ClassifyTiles.cs");

@@ -279,6 +279,26 @@ class Scene(object):
         return out
 
 
+def checkerboard_frame(frame, frame_index, diff_mode=2, spec_mode=2):
+    """Checkerboarded copy of a frame (ReblurSettings::checkerboardMode): only the pixels with ((x ^ y ^ frameIndex) & 1) == mode keep
+    their radiance, packed into the left half of the texture (column x >> 1); the right half is zero.  mode 2 = full resolution.
+    Reference convention: NRDSettings.h CheckerboardMode, REBLUR_PrePass.hlsli:43-100."""
+    out = dict(frame)
+    for name, mode in (("IN_DIFF_RADIANCE_HITDIST", diff_mode), ("IN_SPEC_RADIANCE_HITDIST", spec_mode)):
+        if mode == 2 or name not in frame:
+            continue
+        full = frame[name]
+        h, w = full.shape[0], full.shape[1]
+        assert w % 2 == 0
+        y = torch.arange(h, device=full.device)
+        parity = ((y ^ int(frame_index) ^ int(mode)) & 1)[:, None]            # column parity of the pixels with data in row y
+        cols = 2 * torch.arange(w // 2, device=full.device)[None, :] + parity  # (h, w/2)
+        packed = torch.zeros_like(full)
+        packed[:, : w // 2] = torch.gather(full, 1, cols[..., None].expand(h, w // 2, full.shape[2]))
+        out[name] = packed.contiguous()
+    return out
+
+
 def pack_normal_roughness(n, rough, mat):
     """NRD_FrontEnd_PackNormalAndRoughness for R10G10B10A2 / linear roughness -> int32 tensor holding the uint32 bits."""
     v = n / n.abs().sum(-1, keepdim=True)

@@ -30,8 +30,9 @@ def _scene_device(width, height, device):
 
 
 class SideBySide(object):
-    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",), common=None):
-        """noise_floor=True: the dispatches whose shader name contains one of `floor_passes` are also run, on the same re-synchronised
+    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",), common=None, frame_fn=None):
+        """frame_fn(frame, f) -> frame: transformation of the scene's frame f before either executor sees it (checkerboarded inputs).
+        noise_floor=True: the dispatches whose shader name contains one of `floor_passes` are also run, on the same re-synchronised
         inputs, by two perturbed builds of the oracle -- "fma" (FMA contraction allowed: a second IEEE-legal evaluation of the same
         expressions) and "uv" (the uv of every bilinear fetch moved by one float ulp: the sub-texel position a shader hands to the
         sampler is only known to ulp(uv) * size = 2.4e-4 texel at 4K; the kernels merge the bilinear taps of the CatRom filter with
@@ -41,6 +42,7 @@ class SideBySide(object):
         least as well as the oracle agrees with itself."""
         import torch
         self.denoiser, self.w, self.h, self.identifier, self.common = denoiser, width, height, identifier, common
+        self.frame_fn = frame_fn
         self.cpu = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, settings=settings, common=common)
         self.instance = self.cpu.instance
         self.floor_passes = tuple(floor_passes)
@@ -55,6 +57,10 @@ class SideBySide(object):
             self.ctx.set_user_texture(getattr(nrd.ResourceType, name), t.data_ptr(), t.stride(0) * t.element_size(), fmt)
         self.scene = scene.Scene(width, height, device=_scene_device(width, height, device))
         self.report = []
+
+    def _scene_frame(self, sc, f):
+        fr = sc.frame(f, harness.radiance_mode(self.denoiser))
+        return self.frame_fn(fr, f) if self.frame_fn else fr
 
     def _has_floor(self, d):
         return any(k in d.shaderFileName for k in self.floor_passes)
@@ -93,13 +99,13 @@ class SideBySide(object):
         """(scene frame, CommonSettings, rectOrigin) of frame f.  rect_fn(f) -> (originX, originY, width, height): dynamic resolution,
         the scene is rendered at the rect size into textures of the context's (resource) size."""
         if rect_fn is None:
-            fr = self.scene.frame(f, harness.radiance_mode(self.denoiser))
+            fr = self._scene_frame(self.scene, f)
             return fr, harness.make_common_settings(fr, self.w, self.h, f, common=self.common), (0, 0)
         ox, oy, rw, rh = rect_fn(f)
         prev = rect_fn(f - 1) if f > 0 else (ox, oy, rw, rh)
         if (rw, rh) not in self._scenes:
             self._scenes[(rw, rh)] = scene.Scene(rw, rh, device=_scene_device(rw, rh, 0))
-        fr = self._scenes[(rw, rh)].frame(f, harness.radiance_mode(self.denoiser))
+        fr = self._scene_frame(self._scenes[(rw, rh)], f)
         common = dict(self.common or {})
         common.update(resourceSize=(self.w, self.h), resourceSizePrev=(self.w, self.h), rectSizePrev=(prev[2], prev[3]), rectOrigin=(ox, oy))
         return fr, harness.make_common_settings(fr, rw, rh, f, common=common), (ox, oy)
@@ -111,14 +117,14 @@ class SideBySide(object):
         if rect_fn is not None:
             return self._run_per_pass_rects(frames, rect_fn)
         for f in range(first_frame, first_frame + warmup):
-            fr = self.scene.frame(f, harness.radiance_mode(self.denoiser))
+            fr = self._scene_frame(self.scene, f)
             self.cpu.set_inputs(fr)
             self.cpu.denoise(harness.make_common_settings(fr, self.w, self.h, f, common=self.common))
             if f == first_frame:
                 self.cpu.set_inputs(fr)
         first_frame += warmup
         for f in range(first_frame, first_frame + frames):
-            fr = self.scene.frame(f, harness.radiance_mode(self.denoiser))
+            fr = self._scene_frame(self.scene, f)
             self.cpu.set_inputs(fr)
             cs = harness.make_common_settings(fr, self.w, self.h, f, common=self.common)
             self.instance.set_common_settings(cs)

@@ -11,27 +11,27 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted=False):
+def _run(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted=False, settings=None, frame_fn=None):
     import os
     os.environ["NRD_B200_FORCE_STRIP_KERNELS"] = "1"  # the full-frame reference runs the strip build of the kernels
     try:
-        _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted)
+        _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted, settings, frame_fn)
     finally:
         del os.environ["NRD_B200_FORCE_STRIP_KERNELS"]
 
 
-def _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted):
+def _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call, weighted, settings=None, frame_fn=None):
     import torch
     from raytracingdenoiser_b200 import harness, nrd, scene, strips
     den = getattr(nrd.Denoiser, denoiser_name)
     mode = harness.radiance_mode(den)
-    full = harness.GpuDenoiser(den, w, h)
+    full = harness.GpuDenoiser(den, w, h, settings=settings)
     partition = None
     if weighted:  # cost-balanced, non-uniform strips from the sky mask of the first frame
         cost = strips.tile_row_cost_from_viewz(scene.Scene(w, h).frame(0, mode)["IN_VIEWZ"])
         partition = strips.partition_rows_weighted(h, world, cost, min_rows=max(halo, 16))
         assert len(set(y1 - y0 for y0, y1 in partition[1])) > 1, partition
-    parts = [strips.StripDenoiser(den, w, h, r, world, halo_rows=halo, partition=partition) for r in range(world)]
+    parts = [strips.StripDenoiser(den, w, h, r, world, halo_rows=halo, partition=partition, settings=settings) for r in range(world)]
     try:  # a failing case must not leak its strip-mode contexts (there are only kMaxPeerSlots per process)
         for p in parts:
             p.connect_local(parts)
@@ -39,6 +39,8 @@ def _run_inner(denoiser_name, w, h, world, frames, halo, whole_frame_call, weigh
         sc = scene.Scene(w, h)
         for f in range(frames):
             fr = sc.frame(f, mode)
+            if frame_fn:
+                fr = frame_fn(fr, f)
             cs = harness.make_common_settings(fr, w, h, f)
             full.set_inputs(fr)
             full.denoise(cs)

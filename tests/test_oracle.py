@@ -410,3 +410,49 @@ def test_dynamic_resolution_rect_origin_does_not_change_the_result_in_the_oracle
     for k in outs[0]:
         assert outs[0][k].any()
         assert np.array_equal(outs[0][k].view(np.uint16), outs[1][k].view(np.uint16)) and np.array_equal(outs[0][k].view(np.uint16), outs[2][k].view(np.uint16)), k
+
+
+@pytest.mark.parametrize("family,mode", [("REBLUR", "BLACK"), ("REBLUR", "WHITE"), ("RELAX", "BLACK"), ("RELAX", "WHITE")])
+def test_checkerboarded_inputs_are_resolved_by_the_pre_pass_in_the_oracle(family, mode):
+    """checkerboardMode of ReblurSettings / RelaxSettings: each signal arrives at half rate, packed into the left half of its texture
+    (scene.checkerboard_frame).  With the pre-pass radii at 0 the pre-pass only resolves (REBLUR_PrePass.hlsli:43-100,
+    RELAX_PrePass.hlsli:28-110): a pixel that has data comes out unchanged, a pixel without takes the average of its left / right
+    neighbours on the same surface."""
+    import oracle_runner as orr
+    from raytracingdenoiser_b200 import harness, nrd, scene
+    w, h = 96, 64
+    sc = scene.Scene(w, h)
+    diff_mode, spec_mode = (0, 1) if mode == "BLACK" else (1, 0)  # host code of both families: BLACK = diffuse on the 0-pixels, specular on the 1-pixels
+    Settings = nrd.ReblurSettings if family == "REBLUR" else nrd.RelaxSettings
+    settings = Settings(checkerboardMode=int(getattr(nrd.CheckerboardMode, mode)), diffusePrepassBlurRadius=0.0, specularPrepassBlurRadius=0.0)
+    den = getattr(nrd.Denoiser, family + "_DIFFUSE_SPECULAR")
+    cpu = orr.CpuDenoiser(den, w, h, settings=settings)
+    out_slots = {"diff": 5, "spec": 6} if family == "REBLUR" else {"spec": 5, "diff": 6}  # *_PrePass.resources.hlsli
+    yy, xx = np.mgrid[0:h, 0:w]
+    for f in range(3):
+        full = sc.frame(f, harness.radiance_mode(den))
+        fr = scene.checkerboard_frame(full, f, diff_mode, spec_mode)
+        grabbed = {}
+
+        def grab(i, d, when):
+            if when == "after" and d.shaderFileName.endswith("_PrePass.cs"):
+                for key, slot in out_slots.items():
+                    grabbed[key] = cpu.resolve(d.resources[slot][1], d.resources[slot][2])[0].copy()
+        cpu.set_inputs(fr)
+        cpu.denoise(harness.make_common_settings(fr, w, h, f), on_dispatch=grab)
+        if f == 0:
+            cpu.set_inputs(fr)
+        assert grabbed, "checkerboarded frames always run the pre-pass"
+        z = np.abs(cpu.user["IN_VIEWZ"]) < 500000.0
+        for key, name, m in (("diff", "IN_DIFF_RADIANCE_HITDIST", diff_mode), ("spec", "IN_SPEC_RADIANCE_HITDIST", spec_mode)):
+            want = full[name].cpu().numpy().view(np.float16).reshape(h, w, 4)
+            got = grabbed[key].view(np.float16).reshape(h, w, 4)
+            has = (((xx ^ yy ^ f) & 1) == m) & z
+            # (the RELAX pre-pass clamps the hit distance to the denoising range, the radiance passes through)
+            assert np.array_equal(got[has][:, :3].view(np.uint16), want[has][:, :3].view(np.uint16)), (key, f)
+            holes = ~(((xx ^ yy ^ f) & 1) == m) & z
+            assert np.isfinite(got[holes].astype(np.float32)).all()
+            # interior holes between two data pixels of the same surface are filled with something: not left black everywhere
+            assert (got[holes].astype(np.float32)[:, :3].sum(-1) > 0).mean() > 0.5, (key, f)
+    out = cpu.user["OUT_DIFF_RADIANCE_HITDIST"].view(np.float16).astype(np.float32)
+    assert np.isfinite(out).all() and out.any()

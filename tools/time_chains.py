@@ -30,7 +30,7 @@ def main():
     stream = torch.cuda.current_stream(dev)
     for den in (nrd.Denoiser.REBLUR_DIFFUSE, nrd.Denoiser.REBLUR_SPECULAR, nrd.Denoiser.REBLUR_DIFFUSE_SPECULAR, nrd.Denoiser.RELAX_DIFFUSE_SPECULAR,
                 nrd.Denoiser.SIGMA_SHADOW, nrd.Denoiser.SIGMA_SHADOW_TRANSLUCENCY):
-        if args.only and den.name != args.only:
+        if args.only and den.name not in args.only.split(","):
             continue
         sc = scene.Scene(W, H, device="cuda:0")
         mode = harness.radiance_mode(den)
