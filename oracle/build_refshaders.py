@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE.  Compiles the reference's OWN compute-shader sources for the CPU, from where they lie under
+/root/reference/Shaders, into oracle/_ref/shaders/<pass>.so -- so that the oracle's restatement of a pass can be checked against
+the code it restates (tests/test_reference_shaders.py).  No reference source is copied into the repository; the only outputs are
+the shared objects (and the generated vector header) under the git-ignored oracle/_ref/.
+
+Recipe per pass (one translation unit each; constants / resources / groupshared memory are globals of the shader):
+  1. gcc -E -P -x c -undef -nostdinc            the C preprocessor resolves the shader's #includes and macros where they lie
+        -include oracle/refshader/nrd_macros.h   (NRD.hlsli's "custom engine" resource macros, entry point name)
+        -I oracle/refshader                      ("ml.hlsli": MathLib is an external dependency absent from /root/reference)
+  2. fix_hlsl()                                  the HLSL constructs that are not C++ *syntax*, patched in the stream:
+        [numthreads] / [unroll] / ... attributes, ": SV_*" semantics, out / inout parameters -> references,
+        float literals get an f suffix (HLSL literals are float, C++ ones double), groupshared -> static
+  3. g++ -x c++ -include oracle/refshader/hlsl_cpp.h -shared     HLSL language semantics as a C++ header (vectors with swizzles,
+        intrinsics, textures on the oracle's hlsl::Tex, thread groups with barriers)
+The shader math itself is compiled untouched.  What is NOT the reference here: MathLib (restated, oracle/mathlib.h), the texture
+unit (oracle/hlsl.h) and the float evaluation of the C++ compiler (no FMA contraction, IEEE division / sqrt).
+
+usage: python oracle/build_refshaders.py [pass ...]      (needs /root/reference: this container only; oracle/_ref/ travels)"""
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("NRD_REFERENCE", "/root/reference")
+SHIM = os.path.join(ROOT, "oracle", "refshader")
+OUT = os.path.join(ROOT, "oracle", "_ref", "shaders")
+GEN = os.path.join(ROOT, "oracle", "_ref", "refshader")
+
+# shader file (without .cs.hlsl) per pass this recipe builds; the name is PipelineDesc::shaderFileName minus ".cs"
+PASSES = [
+    "REBLUR_DiffuseSpecular_PrePass", "REBLUR_DiffuseSpecular_Blur", "REBLUR_DiffuseSpecular_PostBlur",
+]
+
+ENTRY = """
+} // namespace refshader (opened by oracle/refshader/hlsl_cpp.h)
+extern "C" __attribute__((visibility("default"))) int refshader_dispatch(const void* constants, int constantsSize, const OracleTexture* textures, int texturesNum, int gridW, int gridH)
+{
+    return refshader::RefShaderDispatchC(refshader::refshader_main, GROUP_X, GROUP_Y, constants, constantsSize, textures, texturesNum, gridW, gridH);
+}
+"""
+
+FLOAT_LITERAL = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])")
+ATTRIBUTE = re.compile(r"\[\s*(?:unroll|loop|branch|flatten|fastopt|allow_uav_condition|numthreads)\s*(?:\([^\]]*\))?\s*\]")
+SEMANTIC = re.compile(r":\s*SV_\w+")
+OUT_PARAM = re.compile(r"\b(?:inout|out)\s+((?:const\s+)?[A-Za-z_]\w*)\s+(?=[A-Za-z_])")
+IN_PARAM = re.compile(r"([(,]\s*)in\s+(?=[A-Za-z_]\w*\s+[A-Za-z_])")
+
+
+def fix_hlsl(text):
+    text = ATTRIBUTE.sub("", text)
+    text = SEMANTIC.sub("", text)
+    text = OUT_PARAM.sub(r"\1& ", text)
+    text = IN_PARAM.sub(r"\1", text)
+    text = FLOAT_LITERAL.sub(r"\1f", text)
+    text = re.sub(r"\bgroupshared\b", "static", text)
+    # x.xxx on a scalar (HLSL: float3(x)) -- also harmless on a vector
+    text = re.sub(r"((?<![\w.])\d[\d.]*(?:[eE][-+]?\d+)?f)\s*\.(x{2,4})\b", r"_splat_\2(\1)", text)
+    text = re.sub(r"(?<![\w.\])])([A-Za-z_]\w*)\.(x{2,4})\b", r"_splat_\2(\1)", text)
+    return text
+
+
+def build(name, keep_source=False):
+    os.makedirs(OUT, exist_ok=True)
+    os.makedirs(GEN, exist_ok=True)
+    gen = os.path.join(GEN, "hlsl_vec_gen.h")
+    if not os.path.exists(gen) or os.path.getmtime(gen) < os.path.getmtime(os.path.join(SHIM, "gen_vec.py")):
+        with open(gen, "w") as f:
+            subprocess.run([sys.executable, os.path.join(SHIM, "gen_vec.py")], stdout=f, check=True)
+    src = os.path.join(REF, "Shaders", "Source", name + ".cs.hlsl")
+    wrapper = '#include "%s"\n%s' % (src, ENTRY)
+    cpp = subprocess.run(["gcc", "-E", "-P", "-x", "c", "-undef", "-nostdinc", "-include", os.path.join(SHIM, "nrd_macros.h"), "-I", SHIM,
+                          "-I", os.path.join(REF, "Shaders", "Include"), "-I", os.path.join(REF, "Shaders", "Resources"),
+                          "-DNRD_NORMAL_ENCODING=2", "-DNRD_ROUGHNESS_ENCODING=1", "-"], input=wrapper, capture_output=True, text=True)
+    if cpp.returncode != 0:
+        raise RuntimeError("preprocessing %s failed:\n%s" % (name, cpp.stderr[-4000:]))
+    text = fix_hlsl(cpp.stdout)
+    if keep_source:  # debugging aid only: the stream is reference text, it must stay under the git-ignored oracle/_ref/
+        with open(os.path.join(OUT, name + ".ii"), "w") as f:
+            f.write(text)
+    so = os.path.join(OUT, name + ".so")
+    cxx = subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-fvisibility=hidden", "-mavx2", "-mf16c",
+                          "-include", os.path.join(SHIM, "hlsl_cpp.h"), "-I", GEN, "-o", so, "-"], input=text, capture_output=True, text=True)
+    if cxx.returncode != 0:
+        with open("/tmp/refshader_errors.txt", "w") as f:
+            f.write(cxx.stderr)
+        raise RuntimeError("compiling %s failed (full log: /tmp/refshader_errors.txt):\n%s" % (name, cxx.stderr[:3000]))
+    return so
+
+
+def build_all(names=None, keep_source=False):
+    if not os.path.isdir(os.path.join(REF, "Shaders", "Source")):
+        return []  # the GPU box: only the prebuilt oracle/_ref/shaders/*.so exist
+    return [build(n, keep_source) for n in (names or PASSES)]
+
+
+if __name__ == "__main__":
+    keep = "--keep" in sys.argv
+    for so in build_all([a for a in sys.argv[1:] if not a.startswith("--")] or None, keep):
+        print(so)

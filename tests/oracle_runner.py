@@ -69,6 +69,26 @@ _NP = {nrd.Format.R8_UNORM: (np.uint8, 1), nrd.Format.R8_UINT: (np.uint8, 1), nr
        nrd.Format.R32_SFLOAT: (np.float32, 1), nrd.Format.R10_G10_B10_A2_UNORM: (np.uint32, 1), nrd.Format.RGBA32_SFLOAT: (np.float32, 4)}
 
 
+_REFSHADERS = {}
+
+
+def reference_shader_path(shader_file_name):
+    name = shader_file_name[:-3] if shader_file_name.endswith(".cs") else shader_file_name
+    return os.path.join(_ROOT, "oracle", "_ref", "shaders", name + ".so")
+
+
+def reference_shader_lib(shader_file_name):
+    """The reference's own shader source of one pass, compiled for the CPU by oracle/build_refshaders.py (built here when
+    /root/reference is present; on the GPU box the prebuilt oracle/_ref/ travels with the snapshot)."""
+    path = reference_shader_path(shader_file_name)
+    if path not in _REFSHADERS:
+        lib = C.CDLL(path)
+        lib.refshader_dispatch.restype = C.c_int
+        lib.refshader_dispatch.argtypes = [C.c_void_p, C.c_int, C.POINTER(OracleTexture), C.c_int, C.c_int, C.c_int]
+        _REFSHADERS[path] = lib
+    return _REFSHADERS[path]
+
+
 def alloc(fmt, w, h):
     dt, ch = _NP[nrd.Format(fmt)]
     return np.zeros((h, w, ch) if ch > 1 else (h, w), dtype=dt)
@@ -137,6 +157,51 @@ class CpuDenoiser(object):
         r = lib.oracle_dispatch(d.shaderFileName.encode(), buf, len(d.constants), texs, len(d.resources), d.gridWidth, d.gridHeight)
         if r != 0:
             raise RuntimeError("oracle_dispatch(%s) failed with %d" % (d.shaderFileName, r))
+
+    def _textures(self, d):
+        from raytracingdenoiser_b200 import harness
+        texs = (OracleTexture * len(d.resources))()
+        keep = []
+        for i, (_, rtype, index) in enumerate(d.resources):
+            arr, fmt = self.resolve(rtype, index)
+            keep.append(arr)
+            texs[i].originX = texs[i].originY = 0
+            if nrd.ResourceType(rtype).name in harness.RECT_ORIGIN_INPUTS:
+                texs[i].originX, texs[i].originY = self.rect_origin
+            texs[i].data = arr.ctypes.data
+            texs[i].height, texs[i].width = arr.shape[0], arr.shape[1]
+            texs[i].pitchBytes = arr.strides[0]
+            texs[i].format = int(fmt)
+            texs[i].firstRow = 0
+        return texs, keep
+
+    def run_reference_shader(self, d):
+        """Executes the dispatch with the REFERENCE's own shader source compiled for the CPU (oracle/build_refshaders.py ->
+        oracle/_ref/shaders/<shader>.so) instead of the oracle's restatement of it."""
+        lib = reference_shader_lib(d.shaderFileName)
+        texs, keep = self._textures(d)
+        buf = C.create_string_buffer(d.constants, (len(d.constants) + 15) // 16 * 16)
+        r = lib.refshader_dispatch(buf, len(d.constants), texs, len(d.resources), d.gridWidth, d.gridHeight)
+        if r != 0:
+            raise RuntimeError("refshader_dispatch(%s) failed with %d" % (d.shaderFileName, r))
+
+    def run_both(self, d):
+        """Runs the dispatch twice on the same state -- the oracle's pass, then the reference's own shader -- and returns
+        [(resource label, format, oracle output, reference-shader output, texture before the pass)] for every texture the pass writes.  The oracle's
+        outputs stay in place (the chain continues on the oracle's state)."""
+        outs = [(i, rtype, index) for i, (dtype, rtype, index) in enumerate(d.resources) if dtype == nrd.DescriptorType.STORAGE_TEXTURE]
+        before = {i: self.resolve(rtype, index)[0].copy() for i, rtype, index in outs}
+        self.run_dispatch(d)
+        mine = {i: self.resolve(rtype, index)[0].copy() for i, rtype, index in outs}
+        for i, rtype, index in outs:
+            self.resolve(rtype, index)[0][...] = before[i]
+        self.run_reference_shader(d)
+        res = []
+        for i, rtype, index in outs:
+            arr, fmt = self.resolve(rtype, index)
+            res.append(("%s[%d]" % (nrd.ResourceType(rtype).name, index), fmt, mine[i], arr.copy(), before[i]))
+            arr[...] = mine[i]
+        return res
 
     def denoise(self, common_settings, on_dispatch=None):
         self.rect_origin = (int(common_settings.rectOrigin[0]), int(common_settings.rectOrigin[1]))
