@@ -37,7 +37,7 @@ ENTRY = """
 } // namespace refshader (opened by oracle/refshader/hlsl_cpp.h)
 extern "C" __attribute__((visibility("default"))) int refshader_dispatch(const void* constants, int constantsSize, const OracleTexture* textures, int texturesNum, int gridW, int gridH)
 {
-    return refshader::RefShaderDispatchC(refshader::refshader_main, GROUP_X, GROUP_Y, constants, constantsSize, textures, texturesNum, gridW, gridH);
+    return refshader::RefShaderDispatchC(refshader::refshader_main, REFSHADER_NUMTHREADS_X, REFSHADER_NUMTHREADS_Y, constants, constantsSize, textures, texturesNum, gridW, gridH);
 }
 """
 
@@ -58,6 +58,8 @@ def fix_hlsl(text):
     # x.xxx on a scalar (HLSL: float3(x)) -- also harmless on a vector
     text = re.sub(r"((?<![\w.])\d[\d.]*(?:[eE][-+]?\d+)?f)\s*\.(x{2,4})\b", r"_splat_\2(\1)", text)
     text = re.sub(r"(?<![\w.\])])([A-Za-z_]\w*)\.(x{2,4})\b", r"_splat_\2(\1)", text)
+    # NAME.x where NAME may be a scalar variable (REBLUR_FAST_TYPE)
+    text = re.sub(r"(?<![\w.\])])([A-Za-z_]\w*)\.x\b(?!\s*\()", r"_comp_x(\1)", text)
     return text
 
 
@@ -75,7 +77,11 @@ def build(name, keep_source=False):
                           "-DNRD_NORMAL_ENCODING=2", "-DNRD_ROUGHNESS_ENCODING=1", "-"], input=wrapper, capture_output=True, text=True)
     if cpp.returncode != 0:
         raise RuntimeError("preprocessing %s failed:\n%s" % (name, cpp.stderr[-4000:]))
-    text = fix_hlsl(cpp.stdout)
+    # the group size is what the entry point's [numthreads( x, y, 1 )] says (macros are expanded by now)
+    m = re.search(r"\[\s*numthreads\s*\(([^,\]]+),([^,\]]+),", cpp.stdout)
+    if not m:
+        raise RuntimeError("no [numthreads] in " + name)
+    text = fix_hlsl(cpp.stdout).replace("REFSHADER_NUMTHREADS_X", "(" + m.group(1).strip() + ")").replace("REFSHADER_NUMTHREADS_Y", "(" + m.group(2).strip() + ")")
     if keep_source:  # debugging aid only: the stream is reference text, it must stay under the git-ignored oracle/_ref/
         with open(os.path.join(OUT, name + ".ii"), "w") as f:
             f.write(text)

@@ -117,6 +117,15 @@ inline uint reversebits(uint v) { uint r = 0; for (int i = 0; i < 32; i++) r |= 
     inline T##3 _splat_xxx(const T##4& a) { return a.xxx; } \
     inline T##4 _splat_xxxx(const T##4& a) { return a.xxxx; }
 REFSHADER_SPLAT(float) REFSHADER_SPLAT(int) REFSHADER_SPLAT(uint)
+// NAME.x on a scalar variable (REBLUR_FAST_TYPE is float): build_refshaders.py rewrites NAME.x into _comp_x(NAME), an lvalue
+template <class V> inline auto _comp_x(V& a) -> decltype((a.x)) { return a.x; }
+template <class V> inline auto _comp_x(const V& a) -> decltype((a.x)) { return a.x; }
+inline float& _comp_x(float& a) { return a; }
+inline const float& _comp_x(const float& a) { return a; }
+inline int& _comp_x(int& a) { return a; }
+inline const int& _comp_x(const int& a) { return a; }
+inline uint& _comp_x(uint& a) { return a; }
+inline const uint& _comp_x(const uint& a) { return a; }
 // mixed scalar arguments (clamp( x, 0, 65504.0 ) ...): everything is evaluated in float like HLSL does
 template <class A, class B> inline float clamp(float x, A a, B b) { return clamp(x, (float)a, (float)b); }
 
@@ -191,34 +200,51 @@ struct SamplerState
 struct float1
 {
     union { float x; float r; };
-    float1(float v = 0.0f) : x(v) {}
+    float1() : x(0.0f) {}
+    explicit float1(float v) : x(v) {}
     operator float() const { return x; }
 };
 template <class T> struct TexelOf;
-template <> struct TexelOf<float> { typedef float1 R; static float from(const hlsl::Tex& t, int x, int y) { return t.load(x, y).x; } static void to(hlsl::Tex& t, int x, int y, float v) { t.store(x, y, hlsl::float4(v, 0, 0, 0)); } static float cv(const hlsl::float4& v) { return v.x; } };
-template <> struct TexelOf<float2> { typedef float2 R; static float2 from(const hlsl::Tex& t, int x, int y) { hlsl::float4 v = t.load(x, y); return float2(v.x, v.y); } static void to(hlsl::Tex& t, int x, int y, const float2& v) { t.store(x, y, hlsl::float4(v.x, v.y, 0, 0)); } static float2 cv(const hlsl::float4& v) { return float2(v.x, v.y); } };
-template <> struct TexelOf<float3> { typedef float3 R; static float3 from(const hlsl::Tex& t, int x, int y) { hlsl::float4 v = t.load(x, y); return float3(v.x, v.y, v.z); } static void to(hlsl::Tex& t, int x, int y, const float3& v) { t.store(x, y, hlsl::float4(v.x, v.y, v.z, 0)); } static float3 cv(const hlsl::float4& v) { return float3(v.x, v.y, v.z); } };
-template <> struct TexelOf<float4> { typedef float4 R; static float4 from(const hlsl::Tex& t, int x, int y) { return S(t.load(x, y)); } static void to(hlsl::Tex& t, int x, int y, const float4& v) { t.store(x, y, O(v)); } static float4 cv(const hlsl::float4& v) { return S(v); } };
-template <> struct TexelOf<uint> { typedef uint R; static uint from(const hlsl::Tex& t, int x, int y) { return t.loadu(x, y); } static void to(hlsl::Tex& t, int x, int y, uint v) { t.storeu(x, y, v); } };
+struct TexelGatherFloat
+{
+    typedef float4 G;
+    static float4 gather(const hlsl::Tex& t, const float2& uv, int ch, const int2& offset) { return S(t.gather(O(uv), ch, O(offset))); }
+};
+struct TexelGatherUint
+{
+    typedef uint4 G;
+    static uint4 gather(const hlsl::Tex& t, const float2& uv, int, const int2& offset)
+    {
+        hlsl::uint4 v = t.gatheru(O(uv), O(offset));
+        return uint4(v.x, v.y, v.z, v.w);
+    }
+};
+template <> struct TexelOf<float> : TexelGatherFloat { typedef float1 R; static float from(const hlsl::Tex& t, int x, int y) { return t.load(x, y).x; } static void to(hlsl::Tex& t, int x, int y, float v) { t.store(x, y, hlsl::float4(v, 0, 0, 0)); } static float cv(const hlsl::float4& v) { return v.x; } };
+template <> struct TexelOf<float2> : TexelGatherFloat { typedef float2 R; static float2 from(const hlsl::Tex& t, int x, int y) { hlsl::float4 v = t.load(x, y); return float2(v.x, v.y); } static void to(hlsl::Tex& t, int x, int y, const float2& v) { t.store(x, y, hlsl::float4(v.x, v.y, 0, 0)); } static float2 cv(const hlsl::float4& v) { return float2(v.x, v.y); } };
+template <> struct TexelOf<float3> : TexelGatherFloat { typedef float3 R; static float3 from(const hlsl::Tex& t, int x, int y) { hlsl::float4 v = t.load(x, y); return float3(v.x, v.y, v.z); } static void to(hlsl::Tex& t, int x, int y, const float3& v) { t.store(x, y, hlsl::float4(v.x, v.y, v.z, 0)); } static float3 cv(const hlsl::float4& v) { return float3(v.x, v.y, v.z); } };
+template <> struct TexelOf<float4> : TexelGatherFloat { typedef float4 R; static float4 from(const hlsl::Tex& t, int x, int y) { return S(t.load(x, y)); } static void to(hlsl::Tex& t, int x, int y, const float4& v) { t.store(x, y, O(v)); } static float4 cv(const hlsl::float4& v) { return S(v); } };
+template <> struct TexelOf<uint> : TexelGatherUint { typedef uint R; static uint from(const hlsl::Tex& t, int x, int y) { return t.loadu(x, y); } static void to(hlsl::Tex& t, int x, int y, uint v) { t.storeu(x, y, v); } };
 
 template <class T> struct Texture2D
 {
     typedef typename TexelOf<T>::R R;
     hlsl::Tex* t = nullptr;
-    R operator[](const int2& p) const { return TexelOf<T>::from(*t, p.x, p.y); }
-    R operator[](const uint2& p) const { return TexelOf<T>::from(*t, (int)p.x, (int)p.y); }
+    R operator[](const int2& p) const { return R(TexelOf<T>::from(*t, p.x, p.y)); }
+    R operator[](const uint2& p) const { return R(TexelOf<T>::from(*t, (int)p.x, (int)p.y)); }
     template <int... I> R operator[](const Swz<int, I...>& p) const { return (*this)[int2(p)]; }
     template <int... I> R operator[](const Swz<uint, I...>& p) const { return (*this)[uint2(p)]; }
-    R Load(const int3& p) const { return TexelOf<T>::from(*t, p.x, p.y); }
-    R Load(const int3& p, const int2& offset) const { return TexelOf<T>::from(*t, p.x + offset.x, p.y + offset.y); }
-    R SampleLevel(SamplerState s, const float2& uv, float) const { return TexelOf<T>::cv(s.linear ? t->sampleLinear(O(uv)) : t->sampleNearest(O(uv))); }
+    R Load(const int3& p) const { return R(TexelOf<T>::from(*t, p.x, p.y)); }
+    R Load(const int3& p, const int2& offset) const { return R(TexelOf<T>::from(*t, p.x + offset.x, p.y + offset.y)); }
+    R SampleLevel(SamplerState s, const float2& uv, float) const { return R(TexelOf<T>::cv(s.linear ? t->sampleLinear(O(uv)) : t->sampleNearest(O(uv)))); }
     // texel offsets of a nearest / linear sample = a uv shifted by whole texels
     R SampleLevel(SamplerState s, const float2& uv, float lod, const int2& offset) const { return SampleLevel(s, uv + float2(offset) / float2((float)t->w, (float)t->h), lod); }
-    float4 GatherRed(SamplerState, const float2& uv) const { return S(t->gather(O(uv), 0)); }
-    float4 GatherRed(SamplerState, const float2& uv, const int2& offset) const { return S(t->gather(O(uv), 0, O(offset))); }
-    float4 GatherGreen(SamplerState, const float2& uv) const { return S(t->gather(O(uv), 1)); }
-    float4 GatherBlue(SamplerState, const float2& uv) const { return S(t->gather(O(uv), 2)); }
-    float4 GatherAlpha(SamplerState, const float2& uv) const { return S(t->gather(O(uv), 3)); }
+    typedef typename TexelOf<T>::G G; // float4, or uint4 for a uint texture
+    G GatherRed(SamplerState, const float2& uv) const { return TexelOf<T>::gather(*t, uv, 0, int2(0, 0)); }
+    G GatherRed(SamplerState, const float2& uv, const int2& offset) const { return TexelOf<T>::gather(*t, uv, 0, offset); }
+    G GatherRed(SamplerState, const float2& uv, const float2& offset) const { return TexelOf<T>::gather(*t, uv, 0, int2(offset)); }
+    G GatherGreen(SamplerState, const float2& uv) const { return TexelOf<T>::gather(*t, uv, 1, int2(0, 0)); }
+    G GatherBlue(SamplerState, const float2& uv) const { return TexelOf<T>::gather(*t, uv, 2, int2(0, 0)); }
+    G GatherAlpha(SamplerState, const float2& uv) const { return TexelOf<T>::gather(*t, uv, 3, int2(0, 0)); }
     void GetDimensions(uint& w, uint& h) const { w = (uint)t->w; h = (uint)t->h; }
 };
 template <class T> struct RWTexture2D
@@ -258,7 +284,8 @@ template <class T> inline hlsl::Tex** RefShaderTexPtr(Texture2D<T>* t) { return 
 template <class T> inline hlsl::Tex** RefShaderTexPtr(RWTexture2D<T>* t) { return &t->t; }
 
 // ---- thread groups -------------------------------------------------------------------------------------------------------------------
-typedef void (*RefShaderMain)(int2 threadPos, uint2 groupPos, int2 pixelPos, uint threadIndex);
+typedef void (*RefShaderMain)(int2 threadPos, uint2 groupPos, int2 pixelPos, uint threadIndex);  // NRD_CS_MAIN_ARGS (Common.hlsli)
+typedef void (*RefShaderMain3)(uint2 threadPos, uint2 groupPos, uint threadIndex);                 // the tile classifiers
 struct RefShaderGroup
 {
     static const int kMaxThreads = 1024;
@@ -267,6 +294,7 @@ struct RefShaderGroup
     bool done[kMaxThreads];
     char* stacks = nullptr;
     RefShaderMain entry = nullptr;
+    RefShaderMain3 entry3 = nullptr;
     int gx = 0, gy = 0, groupX = 0, groupY = 0, current = -1;
 };
 inline RefShaderGroup& RefShaderCurrentGroup()
@@ -278,7 +306,8 @@ inline void RefShaderFiberBody(int index)
 {
     RefShaderGroup& g = RefShaderCurrentGroup();
     const int tx = index % g.gx, ty = index / g.gx;
-    g.entry(int2(tx, ty), uint2((uint)g.groupX, (uint)g.groupY), int2(g.groupX * g.gx + tx, g.groupY * g.gy + ty), (uint)index);
+    if (g.entry) g.entry(int2(tx, ty), uint2((uint)g.groupX, (uint)g.groupY), int2(g.groupX * g.gx + tx, g.groupY * g.gy + ty), (uint)index);
+    else g.entry3(uint2((uint)tx, (uint)ty), uint2((uint)g.groupX, (uint)g.groupY), (uint)index);
     g.done[index] = true;
     swapcontext(&g.fiber[index], &g.scheduler);
 }
@@ -288,13 +317,24 @@ inline void GroupMemoryBarrierWithGroupSync()
     RefShaderGroup& g = RefShaderCurrentGroup();
     swapcontext(&g.fiber[g.current], &g.scheduler);
 }
-inline void GroupMemoryBarrier() {}
-inline void RefShaderRunGroup(RefShaderMain entry, int gx, int gy, int groupX, int groupY)
+// The SIGMA tile classifier separates its phases with GroupMemoryBarrier() only: its 8x4 group is one warp, which executes in
+// lockstep on the GPUs the shader was written for.  Fibers do not: the memory barrier is made an execution barrier as well.
+inline void GroupMemoryBarrier() { GroupMemoryBarrierWithGroupSync(); }
+// the fibers of a group run one at a time: atomics on groupshared memory are plain read-modify-writes
+template <class A, class B> inline void InterlockedAdd(A& dst, B v) { dst += (A)v; }
+template <class A, class B> inline void InterlockedAdd(A& dst, B v, A& original) { original = dst; dst += (A)v; }
+inline void InterlockedOr(uint& dst, uint v) { dst |= v; }
+inline void InterlockedAnd(uint& dst, uint v) { dst &= v; }
+inline void InterlockedMax(uint& dst, uint v) { dst = dst > v ? dst : v; }
+inline void InterlockedMin(uint& dst, uint v) { dst = dst < v ? dst : v; }
+inline void RefShaderSetEntry(RefShaderMain e) { RefShaderCurrentGroup().entry = e; RefShaderCurrentGroup().entry3 = nullptr; }
+inline void RefShaderSetEntry(RefShaderMain3 e) { RefShaderCurrentGroup().entry = nullptr; RefShaderCurrentGroup().entry3 = e; }
+inline void RefShaderRunGroup(int gx, int gy, int groupX, int groupY)
 {
     RefShaderGroup& g = RefShaderCurrentGroup();
     const int n = gx * gy;
     if (!g.stacks) g.stacks = (char*)malloc(RefShaderGroup::kStack * RefShaderGroup::kMaxThreads);
-    g.entry = entry; g.gx = gx; g.gy = gy; g.groupX = groupX; g.groupY = groupY;
+    g.gx = gx; g.gy = gy; g.groupX = groupX; g.groupY = groupY;
     for (int i = 0; i < n; i++)
     {
         g.done[i] = false;
@@ -320,7 +360,7 @@ inline void RefShaderRunGroup(RefShaderMain entry, int gx, int gy, int groupX, i
 // One dispatch: constants are copied member by member in declaration order (the reference's host code fills a C++ struct generated
 // from the same NRD_CONSTANT list, Source/InstanceImpl.h), textures are bound in declaration order (inputs, then outputs -- the
 // order of DispatchDesc::resources).  Returns 0, or a negative number when the shader's declarations do not match the dispatch.
-inline int RefShaderDispatch(RefShaderMain entry, int gx, int gy, const void* constants, int constantsSize, hlsl::Tex* tex, int texNum, int gridW, int gridH)
+template <class Entry> inline int RefShaderDispatch(Entry entry, int gx, int gy, const void* constants, int constantsSize, hlsl::Tex* tex, int texNum, int gridW, int gridH)
 {
     int offset = 0, texIndex = 0;
     for (const RefShaderSlot& s : RefShaderSlots())
@@ -339,13 +379,14 @@ inline int RefShaderDispatch(RefShaderMain entry, int gx, int gy, const void* co
                 *(hlsl::Tex**)s.ptr = &tex[texIndex++];
             }
     if (texIndex != texNum) return -4;
+    RefShaderSetEntry(entry);
     for (int y = 0; y < gridH; y++)
-        for (int x = 0; x < gridW; x++) RefShaderRunGroup(entry, gx, gy, x, y);
+        for (int x = 0; x < gridW; x++) RefShaderRunGroup(gx, gy, x, y);
     return 0;
 }
 
 // C entry used by the generated refshader_dispatch of every pass: same texture descriptors as oracle_dispatch (oracle/oracle.h)
-inline int RefShaderDispatchC(RefShaderMain entry, int gx, int gy, const void* constants, int constantsSize, const OracleTexture* textures, int texturesNum, int gridW, int gridH)
+template <class Entry> inline int RefShaderDispatchC(Entry entry, int gx, int gy, const void* constants, int constantsSize, const OracleTexture* textures, int texturesNum, int gridW, int gridH)
 {
     hlsl::Tex tex[32];
     if (texturesNum > 32) return -5;

@@ -91,7 +91,7 @@ inline float4 UintToRgba(uint p, uint rb, uint gb, uint bb, uint ab) { return S(
 
 namespace ImportanceSampling
 {
-inline float GetSpecularDominantFactor(float NoV, float roughness) { return hlsl::ImportanceSampling::GetSpecularDominantFactor(NoV, roughness); }
+inline float GetSpecularDominantFactor(float NoV, float roughness, int = 0 /* ML_SPECULAR_DOMINANT_DIRECTION_G2 */) { return hlsl::ImportanceSampling::GetSpecularDominantFactor(NoV, roughness); }
 inline float4 GetSpecularDominantDirection(float3 N, float3 V, float roughness, int = 0 /* ML_SPECULAR_DOMINANT_DIRECTION_G2: the fit the oracle restates */) { return S(hlsl::ImportanceSampling::GetSpecularDominantDirection(O(N), O(V), roughness)); }
 inline float GetSpecularLobeTanHalfAngle(float roughness, float percentOfVolume = 0.75f) { return hlsl::ImportanceSampling::GetSpecularLobeTanHalfAngle(roughness, percentOfVolume); }
 } // namespace ImportanceSampling
@@ -99,6 +99,17 @@ inline float GetSpecularLobeTanHalfAngle(float roughness, float percentOfVolume 
 namespace Color
 {
 inline float Luminance(float3 c) { return hlsl::Color::Luminance(O(c)); }
+// (restated like oracle/relax.cpp RgbToYCoCg / YCoCgToRgb)
+inline float3 RgbToYCoCg(float3 c) { return float3(dot(c, float3(0.25f, 0.5f, 0.25f)), dot(c, float3(0.5f, 0.0f, -0.5f)), dot(c, float3(-0.25f, 0.5f, -0.25f))); }
+inline float3 YCoCgToRgb(float3 c)
+{
+    float t = c.x - c.z;
+    float3 r;
+    r.y = c.x + c.z;
+    r.x = t + c.y;
+    r.z = t - c.y;
+    return max(r, float3(0.0f));
+}
 inline float Clamp(float m1, float sigma, float x) { return hlsl::Color::Clamp(m1, sigma, x); }
 inline float2 Clamp(float2 m1, float2 sigma, float2 x) { return clamp(x, m1 - sigma, m1 + sigma); }
 inline float3 Clamp(float3 m1, float3 sigma, float3 x) { return clamp(x, m1 - sigma, m1 + sigma); }
