@@ -28,10 +28,23 @@ SHIM = os.path.join(ROOT, "oracle", "refshader")
 OUT = os.path.join(ROOT, "oracle", "_ref", "shaders")
 GEN = os.path.join(ROOT, "oracle", "_ref", "refshader")
 
-# shader file (without .cs.hlsl) per pass this recipe builds; the name is PipelineDesc::shaderFileName minus ".cs"
-PASSES = [
-    "REBLUR_DiffuseSpecular_PrePass", "REBLUR_DiffuseSpecular_Blur", "REBLUR_DiffuseSpecular_PostBlur",
-]
+def pass_list():
+    """Every pass shader of the denoisers the product supports (PipelineDesc::shaderFileName minus ".cs"), from the shader
+    sources that exist.  Not built: Clear_* (trivial), *_Validation (debug overlay, needs MathLib's text renderer) and the two SIGMA
+    split-screen shaders (they initialise a float2 from a one-channel texture fetch, which this C++ shim cannot express)."""
+    out = []
+    for f in sorted(os.listdir(os.path.join(REF, "Shaders", "Source"))):
+        if not f.endswith(".cs.hlsl"):
+            continue
+        n = f[:-len(".cs.hlsl")]
+        if n.startswith("Clear_") or n.endswith("_Validation") or n.startswith("SIGMA_") and n.endswith("_SplitScreen"):
+            continue
+        if any(k in n for k in ("Occlusion", "Sh_", "DirectionalOcclusion")):  # denoisers the product does not implement
+            continue
+        if n.startswith(("REBLUR_", "RELAX_", "SIGMA_", "REFERENCE_")):
+            out.append(n)
+    return out
+
 
 ENTRY = """
 } // namespace refshader (opened by oracle/refshader/hlsl_cpp.h)
@@ -95,13 +108,37 @@ def build(name, keep_source=False):
     return so
 
 
-def build_all(names=None, keep_source=False):
+def _stamp():
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(os.listdir(SHIM)) + ["../hlsl.h", "../mathlib.h", "../oracle.h", "../build_refshaders.py"]:
+        path = os.path.join(SHIM, f)
+        if os.path.isfile(path):
+            h.update(open(path, "rb").read())
+    return h.hexdigest()
+
+
+def build_all(names=None, keep_source=False, force=False):
+    """Builds the shaders whose .so is missing or older than the shim (a stamp file records the shim's hash)."""
     if not os.path.isdir(os.path.join(REF, "Shaders", "Source")):
         return []  # the GPU box: only the prebuilt oracle/_ref/shaders/*.so exist
-    return [build(n, keep_source) for n in (names or PASSES)]
+    import concurrent.futures
+    os.makedirs(OUT, exist_ok=True)
+    stamp_path, stamp = os.path.join(OUT, "shim.stamp"), _stamp()
+    fresh = os.path.exists(stamp_path) and open(stamp_path).read() == stamp
+    names = names or pass_list()
+    todo = [n for n in names if force or not fresh or not os.path.exists(os.path.join(OUT, n + ".so"))]
+    if todo:
+        build(todo[0], keep_source)  # generates the vector header once, before the parallel part
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            for fut in [ex.submit(build, n, keep_source) for n in todo[1:]]:
+                fut.result()
+        with open(stamp_path, "w") as f:
+            f.write(stamp)
+    return [os.path.join(OUT, n + ".so") for n in names]
 
 
 if __name__ == "__main__":
-    keep = "--keep" in sys.argv
-    for so in build_all([a for a in sys.argv[1:] if not a.startswith("--")] or None, keep):
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    for so in build_all(args or None, "--keep" in sys.argv, "--force" in sys.argv or bool(args)):
         print(so)

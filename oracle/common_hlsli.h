@@ -1,4 +1,4 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h).  PARITY UNPINNED.
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h for what the parity of the oracle is pinned against).
 // Restatement of the denoiser-independent helpers of Shaders/Include/Common.hlsli and NRD.hlsli used by the SIGMA and
 // RELAX restatements (the REBLUR file carries its own copies inside its Pass struct).
 #pragma once

@@ -1,7 +1,10 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked into, imported by or called from the product library.
-// PARITY UNPINNED: the reference ships no golden vectors and its shaders cannot be executed here (HLSL, no DXC, no
-// GPU API); this file emulates the HLSL / D3D semantics the reference's shaders rely on so that they can be restated
-// line by line in C++:
+// PARITY PINNED against the reference's own shader sources compiled for the CPU (oracle/build_refshaders.py,
+// tests/test_reference_shaders.py: bit-identical but for the rounding-sensitive passes listed there); NOT pinned: MathLib (absent from the
+// reference tree, restated in mathlib.h), the texture unit (this file / hlsl.h) and GPU float behaviour.
+// The reference ships no golden vectors and no GPU API exists here; this file emulates the HLSL / D3D semantics the reference's
+// shaders rely on so that they can be restated line by line in C++ -- and so that the shader sources
+// themselves can run on the CPU (oracle/refshader/hlsl_cpp.h builds its textures on the Tex below):
 //   * tex[p] / Load out of bounds returns 0, UAV stores out of bounds are dropped
 //   * SampleLevel(gNearestClamp): texel clamp(floor(uv * size), 0, size-1)
 //   * SampleLevel(gLinearClamp): clamp-to-edge bilinear with exact float weights frac(uv * size - 0.5)

@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED at this boundary.
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED at this boundary (the one part of the oracle that the reference-shader pin of
+// tests/test_reference_shaders.py cannot reach: both sides of that comparison call these functions).
 // Restatement of the shader-side MathLib functions the reference's passes call (ml.hlsli from NVIDIA-RTX/MathLib,
 // fetched by the reference's CMakeLists.txt:120-129 with GIT_TAG main, i.e. unpinned, and absent from /root/reference).
 // Each function lists its first call site in the reference; in-tree twins (Shaders/Include/NRD.hlsli) win where they exist.

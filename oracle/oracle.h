@@ -1,6 +1,6 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.  C entry points of the CPU restatement (liboracle.so).
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
-// PARITY UNPINNED: see hlsl.h.
+// Parity: see hlsl.h (pinned against the reference's shader sources run on the CPU; MathLib restated).
 #pragma once
 #include "hlsl.h"
 

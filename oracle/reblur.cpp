@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h).  PARITY UNPINNED (no reference golden vectors exist).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h).  Every pass below is checked against the reference's own shader source of that pass,
+// compiled for the CPU (oracle/build_refshaders.py), by tests/test_reference_shaders.py; the reference ships no golden vectors.
 // CPU restatement, statement by statement, of the reference's REBLUR passes for the DIFFUSE / SPECULAR /
 // DIFFUSE_SPECULAR denoisers at the default compile-time switches (Common.hlsli:51-85, REBLUR_Config.hlsli:13-98,
 // NRD_NORMAL_ENCODING = 2, NRD_ROUGHNESS_ENCODING = 1, no REBLUR_PERFORMANCE_MODE / OCCLUSION / SH):

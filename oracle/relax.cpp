@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h).  PARITY UNPINNED (no reference golden vectors exist).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h).  Every pass below is checked against the reference's own shader source of that pass,
+// compiled for the CPU (oracle/build_refshaders.py), by tests/test_reference_shaders.py; the reference ships no golden vectors.
 // CPU restatement of the reference's RELAX_DIFFUSE_SPECULAR passes (non-SH) at the default compile-time switches:
 //   ClassifyTiles        Shaders/Source/RELAX_ClassifyTiles.cs.hlsl:18-49
 //   PrePass              Shaders/Include/RELAX_PrePass.hlsli:13-347

@@ -1,4 +1,5 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h).  PARITY UNPINNED (no reference golden vectors exist).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see hlsl.h).  Every pass below is checked against the reference's own shader source of that pass,
+// compiled for the CPU (oracle/build_refshaders.py), by tests/test_reference_shaders.py; the reference ships no golden vectors.
 // CPU restatement of the reference's SIGMA_SHADOW / SIGMA_SHADOW_TRANSLUCENCY passes at the default compile-time switches
 // (SIGMA_Config.hlsli:13-43; SIGMA_TYPE is float / float4: the signal is carried as float4 here, the scalar variant uses .x only):
 //   ClassifyTiles            Shaders/Include/SIGMA_ClassifyTiles.hlsli:10-81

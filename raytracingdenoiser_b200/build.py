@@ -123,6 +123,19 @@ def build_reference_host(force=False):
     return os.path.join(ORACLE_DIR, "_ref", "libnrd_ref.so")
 
 
+def build_reference_shaders():
+    """The reference's own pass shaders compiled for the CPU (oracle/build_refshaders.py -> oracle/_ref/shaders/*.so) -- test
+    infrastructure that pins the oracle; only buildable where the reference tree is mounted, the prebuilt files travel."""
+    if not os.path.isdir("/root/reference/Shaders/Source"):
+        return
+    sys.path.insert(0, ORACLE_DIR)
+    try:
+        import build_refshaders
+        build_refshaders.build_all()
+    finally:
+        sys.path.remove(ORACLE_DIR)
+
+
 def build_all(force=False):
     """Builds whatever is out of date.  Serialised across processes with a file lock: every rank of a torchrun job calls this."""
     import fcntl
@@ -130,7 +143,9 @@ def build_all(force=False):
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
             build_reference_host(force)
-            return build_product(force), build_oracle(force)
+            libs = build_product(force), build_oracle(force)
+            build_reference_shaders()
+            return libs
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
 
