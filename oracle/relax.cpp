@@ -90,10 +90,20 @@ struct Pass
         return sum < 0.0001f ? 0.0f : o * rcp(sum);
     }
     // :66-96
+    // RELAX_Common.hlsli:75-80.  The shader sums forward + right * x - up * y left to right; this restatement (and the kernels, whose
+    // world positions select history footprints and are pinned to it operation by operation) sums right * x - up * y first.  The two
+    // differ by one rounding, which RELAX temporal accumulation amplifies (acos of nearly parallel view vectors, the difference of the
+    // surface- and virtual-motion uv): tests/test_reference_shaders.py shows that with ORACLE_REFERENCE_ASSOCIATION (the "src" build of
+    // the oracle) every RELAX pass is bit-identical to the reference's own shader, and what the difference costs without it.
     float3 GetCurrentWorldPosFromClipSpaceXY(float2 cs, float viewZ) const
     {
+#ifdef ORACLE_REFERENCE_ASSOCIATION
+        return c.gOrthoMode == 0.0f ? float3(viewZ) * (c.gFrustumForward.xyz() + c.gFrustumRight.xyz() * float3(cs.x) - c.gFrustumUp.xyz() * float3(cs.y))
+                                    : float3(viewZ) * c.gFrustumForward.xyz() + c.gFrustumRight.xyz() * float3(cs.x) - c.gFrustumUp.xyz() * float3(cs.y);
+#else
         float3 d = c.gFrustumRight.xyz() * float3(cs.x) - c.gFrustumUp.xyz() * float3(cs.y);
         return c.gOrthoMode == 0.0f ? float3(viewZ) * (c.gFrustumForward.xyz() + d) : float3(viewZ) * c.gFrustumForward.xyz() + d;
+#endif
     }
     float3 GetCurrentWorldPosFromPixelPos(int2 p, float viewZ) const
     {
@@ -102,8 +112,13 @@ struct Pass
     }
     float3 GetPreviousWorldPosFromClipSpaceXY(float2 cs, float viewZ) const
     {
+#ifdef ORACLE_REFERENCE_ASSOCIATION
+        return c.gOrthoMode == 0.0f ? float3(viewZ) * (c.gPrevFrustumForward.xyz() + c.gPrevFrustumRight.xyz() * float3(cs.x) - c.gPrevFrustumUp.xyz() * float3(cs.y))
+                                    : float3(viewZ) * c.gPrevFrustumForward.xyz() + c.gPrevFrustumRight.xyz() * float3(cs.x) - c.gPrevFrustumUp.xyz() * float3(cs.y);
+#else
         float3 d = c.gPrevFrustumRight.xyz() * float3(cs.x) - c.gPrevFrustumUp.xyz() * float3(cs.y);
         return c.gOrthoMode == 0.0f ? float3(viewZ) * (c.gPrevFrustumForward.xyz() + d) : float3(viewZ) * c.gPrevFrustumForward.xyz() + d;
+#endif
     }
     float3 GetPreviousWorldPosFromPixelPos(int2 p, float viewZ) const
     {

@@ -21,6 +21,7 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 # the same oracle sources with FMA contraction allowed: a second, equally IEEE-legal evaluation of the same math.  Tests use the
 # pair to measure the rounding-noise floor of the (chaotic) temporal chains: how far two legal CPU evaluations drift apart.
 ORACLE_FMA_LIB = os.path.join(ORACLE_DIR, "liboracle_fma.so")  # noise-floor variant: FMA contraction allowed
+ORACLE_SRC_LIB = os.path.join(ORACLE_DIR, "liboracle_src.so")  # the reference's association order where the oracle's differs (oracle/relax.cpp)
 ORACLE_UV_LIB = os.path.join(ORACLE_DIR, "liboracle_uv.so")    # noise-floor variant: bilinear fetches one float ulp further (oracle/hlsl.h)
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -98,7 +99,7 @@ def build_oracle(force=False):
     srcs = [os.path.join(ORACLE_DIR, f) for f in sorted(os.listdir(ORACLE_DIR)) if f.endswith(".cpp")]
     deps = srcs + [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".h")]
     libs = ((ORACLE_LIB, ORACLE_FLAGS), (ORACLE_FMA_LIB, [f if f != "-ffp-contract=off" else "-ffp-contract=fast" for f in ORACLE_FLAGS]),
-            (ORACLE_UV_LIB, ORACLE_FLAGS + ["-DORACLE_NUDGE_UV"]))
+            (ORACLE_UV_LIB, ORACLE_FLAGS + ["-DORACLE_NUDGE_UV"]), (ORACLE_SRC_LIB, ORACLE_FLAGS + ["-DORACLE_REFERENCE_ASSOCIATION"]))
     if not force and all(os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps) for lib, _ in libs):
         return ORACLE_LIB
     for lib, flags in libs:

@@ -45,8 +45,9 @@ def host_threads():
 
 def oracle_lib(variant=""):
     """variant "": the oracle (no FMA contraction); "fma": the same sources compiled with contraction allowed -- a second
-    IEEE-legal evaluation; "uv": the same sources with the uv of every bilinear fetch moved by one float ulp (oracle/hlsl.h).
-    The variants are used only to measure the rounding-noise floor of the temporal passes and chains (tests/parity.py)."""
+    IEEE-legal evaluation; "uv": the same sources with the uv of every bilinear fetch moved by one float ulp (oracle/hlsl.h);
+    "src": the reference's association order in the one helper where the oracle's differs (oracle/relax.cpp, used by
+    tests/test_reference_shaders.py).  The fma / uv variants are used only to measure the rounding-noise floor of the temporal passes and chains (tests/parity.py)."""
     if variant not in _oracle:
         path = _ORACLE_PATH if not variant else _ORACLE_PATH.replace("liboracle.so", "liboracle_%s.so" % variant)
         if not os.path.exists(path):

@@ -23,6 +23,16 @@ def main():
         if missing:
             print("%s | (no compiled reference shader: %s)" % (name, ", ".join(missing)))
     print("# %d of %d (case, shader) pairs are bit-identical" % (identical, total))
+    print()
+    print("# RELAX with the oracle built in the reference's association order (liboracle_src.so, oracle/relax.cpp): the one deviation removed")
+    identical = total = 0
+    for name in sorted(n for n in t.CASES if n.startswith("relax")):
+        stats, _ = t.run_case(name, variant="src")
+        for shader, s in sorted(stats.items()):
+            total += 1
+            identical += s["min_bytes_equal"] == 1.0
+            print("%s | %s | %d | %s | %.5f | %.5f | %.1f" % (name, shader, s["outputs"], "yes" if s["min_bytes_equal"] == 1.0 else "no", s["min_fraction"], s["min_bytes_equal"], s["worst"]))
+    print("# %d of %d (case, shader) pairs are bit-identical" % (identical, total))
 
 
 if __name__ == "__main__":
