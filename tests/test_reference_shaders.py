@@ -76,11 +76,12 @@ CASES = {
 }
 
 
-def run_case(name, variant=""):
+def run_case(name, variant="", size=None):
     """variant: which build of the oracle (oracle_runner.oracle_lib).  Returns {shader: dict(outputs, min_fraction, min_bytes_equal, worst, changed)} over all dispatches of the case that have a
     compiled reference shader, and the list of dispatched shaders that have none."""
     den_name, settings_fn, common, frame_fn, frames = CASES[name]
     den = getattr(nrd.Denoiser, den_name)
+    W, H = size or (96, 64)
     sc = scene.Scene(W, H)
     cpu = orr.CpuDenoiser(den, W, H, settings=settings_fn() if settings_fn else None, common=common, variant=variant)
     stats, missing = {}, set()
@@ -136,5 +137,25 @@ def test_relax_oracle_in_reference_association_is_bit_identical(name):
     for shader, s in stats.items():
         if "TemporalAccumulation" in shader:
             assert s["min_bytes_equal"] >= 0.9995 and s["min_fraction"] == 1.0, (shader, s)
+        else:
+            assert s["min_bytes_equal"] == 1.0, (shader, s)
+
+
+def test_reblur_at_640x360_against_the_reference_shaders():
+    """The tap positions of the spatial filters are the one place where the oracle does not follow the shader's operation order
+    (it evaluates them in texel units, the shader in uv units and hands them to a nearest sampler).  At 96x64
+    both select the same texels everywhere; at larger sizes a tap within one rounding of a texel border can land on the neighbour.
+    Measured here: a few dozen texels of 230 400 per output differ at all (1080p: 300-1300 of 2.07 M) -- far inside the per-pass
+    parity gate of 99.9 %.  Passes without such taps stay bit-identical."""
+    CASES["reblur_640"] = ("REBLUR_DIFFUSE_SPECULAR", None, None, None, 2)
+    try:
+        stats, _ = run_case("reblur_640", size=(640, 360))
+    finally:
+        del CASES["reblur_640"]
+    for shader, s in stats.items():
+        if any(k in shader for k in ("PrePass", "_Blur", "PostBlur")):
+            assert s["min_fraction"] >= 0.9995, (shader, s)
+        elif "TemporalAccumulation" in shader:
+            assert s["min_fraction"] >= 0.999, (shader, s)
         else:
             assert s["min_bytes_equal"] == 1.0, (shader, s)
