@@ -108,10 +108,55 @@ def build(name, keep_source=False):
     return so
 
 
+FRONTEND_PRELUDE = """
+// tests/frontend_probe.cpp is written against include/nrd_b200_frontend.cuh; the same text is compiled here against the reference's
+// NRD.hlsli: these few names map the probe's helpers onto HLSL
+inline float3 f3(float x, float y, float z) { return float3(x, y, z); }
+inline float4 f4(float x, float y, float z, float w) { return float4(x, y, z, w); }
+inline float3 normalize3(float3 v) { return normalize(v); }
+typedef uint uint32_t;
+inline uint nrdPackR10G10B10A2(float4 p)
+{
+    uint8_t texel[4];
+    hlsl::Tex t; t.data = texel; t.w = t.h = 1; t.pitch = 4; t.fmt = hlsl::R10_G10_B10_A2_UNORM;
+    t.store(0, 0, O(p));
+    uint v;
+    memcpy(&v, texel, 4);
+    return v;
+}
+inline float4 nrdUnpackR10G10B10A2(uint v)
+{
+    uint8_t texel[4];
+    memcpy(texel, &v, 4);
+    hlsl::Tex t; t.data = texel; t.w = t.h = 1; t.pitch = 4; t.fmt = hlsl::R10_G10_B10_A2_UNORM;
+    return S(t.load(0, 0));
+}
+"""
+
+
+def build_frontend_probe():
+    """tests/frontend_probe.cpp (the probe of include/nrd_b200_frontend.cuh) compiled a second time -- against the reference's own
+    NRD.hlsli through the shim -- into oracle/_ref/shaders/frontend_probe_ref: same inputs, same columns, reference code."""
+    os.makedirs(OUT, exist_ok=True)
+    probe = open(os.path.join(ROOT, "tests", "frontend_probe.cpp")).read()
+    body = probe[probe.index("static unsigned lcg"):].replace("int main()", "int probe_main()")
+    wrapper = '#include "%s"\n%s\n%s\n}\nint main() { return refshader::probe_main(); }\n' % (os.path.join(REF, "Shaders", "Include", "NRD.hlsli"), FRONTEND_PRELUDE, body)
+    cpp = subprocess.run(["gcc", "-E", "-P", "-x", "c", "-undef", "-nostdinc", "-include", os.path.join(SHIM, "nrd_macros.h"), "-I", SHIM,
+                          "-I", os.path.join(REF, "Shaders", "Include"), "-DNRD_NORMAL_ENCODING=2", "-DNRD_ROUGHNESS_ENCODING=1", "-"], input=wrapper, capture_output=True, text=True)
+    if cpp.returncode != 0:
+        raise RuntimeError("preprocessing the front-end probe failed:\n%s" % cpp.stderr[-3000:])
+    exe = os.path.join(OUT, "frontend_probe_ref")
+    cxx = subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-w", "-ffp-contract=off", "-mavx2", "-mf16c", "-include", os.path.join(SHIM, "hlsl_cpp.h"), "-I", GEN, "-o", exe, "-"],
+                         input=fix_hlsl(cpp.stdout), capture_output=True, text=True)
+    if cxx.returncode != 0:
+        raise RuntimeError("compiling the front-end probe failed:\n%s" % cxx.stderr[:4000])
+    return exe
+
+
 def _stamp():
     import hashlib
     h = hashlib.sha1()
-    for f in sorted(os.listdir(SHIM)) + ["../hlsl.h", "../mathlib.h", "../oracle.h", "../build_refshaders.py"]:
+    for f in sorted(os.listdir(SHIM)) + ["../hlsl.h", "../mathlib.h", "../oracle.h", "../build_refshaders.py", "../../tests/frontend_probe.cpp"]:
         path = os.path.join(SHIM, f)
         if os.path.isfile(path):
             h.update(open(path, "rb").read())
@@ -133,6 +178,9 @@ def build_all(names=None, keep_source=False, force=False):
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
             for fut in [ex.submit(build, n, keep_source) for n in todo[1:]]:
                 fut.result()
+    if todo or not os.path.exists(os.path.join(OUT, "frontend_probe_ref")):
+        build_frontend_probe()
+    if todo:
         with open(stamp_path, "w") as f:
             f.write(stamp)
     return [os.path.join(OUT, n + ".so") for n in names]

@@ -77,3 +77,25 @@ def test_frontend_header_compiles_as_cuda_device_code():
         r = subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-c", cu, "-o",
                             os.path.join(tmp, "t.o")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_frontend_header_equals_the_reference_nrd_hlsli():
+    """The same probe compiled twice: against include/nrd_b200_frontend.cuh, and against the reference's OWN Shaders/Include/NRD.hlsli
+    through the C++ HLSL shim (oracle/build_refshaders.py build_frontend_probe -> oracle/_ref/shaders/frontend_probe_ref; built where
+    /root/reference is mounted, the binary travels).  Same inputs, same 50 columns: packers, unpackers, hit-distance normalisation,
+    SH / SG carriers and resolves, material factors, SIGMA penumbra / translucency.  Bit-identical except the SG direction and the
+    material factors, which agree to 2 ulp (a * rsqrt(dot) against a / length, the environment-term polynomial)."""
+    import pytest
+    exe = os.path.join(ROOT, "oracle", "_ref", "shaders", "frontend_probe_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/shaders/frontend_probe_ref is built from /root/reference (not present here)")
+    mine = _run_probe()
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    ref = np.array([[float(v) for v in line.split()] for line in out.strip().split("\n")], dtype=np.float64)
+    assert mine.shape == ref.shape == (400, 50)
+    loose = {40, 41, 42, 43, 44}
+    for c in range(50):
+        if c in loose:
+            assert np.allclose(mine[:, c], ref[:, c], rtol=5e-7, atol=1e-7), c
+        else:
+            assert np.array_equal(mine[:, c], ref[:, c]), c
