@@ -62,6 +62,9 @@ CASES = {
                                            None, None, 3),
     "reblur_checkerboard": ("REBLUR_DIFFUSE_SPECULAR", lambda: nrd.ReblurSettings(checkerboardMode=int(nrd.CheckerboardMode.BLACK)), None, _checkerboard("BLACK"), 3),
     "reblur_optional_inputs": ("REBLUR_DIFFUSE_SPECULAR", None, dict(isHistoryConfidenceAvailable=True, isDisocclusionThresholdMixAvailable=True, isBaseColorMetalnessAvailable=True), None, 3),
+    "reblur_dynamic_resolution": ("REBLUR_DIFFUSE_SPECULAR", None, None, None, 3, (160, 96)),
+    "relax_dynamic_resolution": ("RELAX_DIFFUSE_SPECULAR", None, None, None, 3, (160, 96)),
+    "sigma_dynamic_resolution": ("SIGMA_SHADOW", None, None, None, 3, (160, 96)),
     "reblur_split_screen": ("REBLUR_DIFFUSE_SPECULAR", None, dict(splitScreen=0.5), None, 2),
     "relax": ("RELAX_DIFFUSE_SPECULAR", None, None, None, 5),
     "relax_antifirefly_hitdist5x5": ("RELAX_DIFFUSE_SPECULAR", lambda: nrd.RelaxSettings(enableAntiFirefly=True, hitDistanceReconstructionMode=int(nrd.HitDistanceReconstructionMode.AREA_5X5)), None, None, 3),
@@ -79,11 +82,14 @@ CASES = {
 def run_case(name, variant="", size=None):
     """variant: which build of the oracle (oracle_runner.oracle_lib).  Returns {shader: dict(outputs, min_fraction, min_bytes_equal, worst, changed)} over all dispatches of the case that have a
     compiled reference shader, and the list of dispatched shaders that have none."""
-    den_name, settings_fn, common, frame_fn, frames = CASES[name]
+    den_name, settings_fn, common, frame_fn, frames = CASES[name][:5]
     den = getattr(nrd.Denoiser, den_name)
     W, H = size or (96, 64)
     sc = scene.Scene(W, H)
-    cpu = orr.CpuDenoiser(den, W, H, settings=settings_fn() if settings_fn else None, common=common, variant=variant)
+    RW, RH = CASES[name][5] if len(CASES[name]) > 5 else (W, H)  # dynamic resolution: the rect (W, H) lives in textures of (RW, RH)
+    if (RW, RH) != (W, H):
+        common = dict(common or {}, resourceSize=(RW, RH), resourceSizePrev=(RW, RH))
+    cpu = orr.CpuDenoiser(den, RW, RH, settings=settings_fn() if settings_fn else None, common=common, variant=variant)
     stats, missing = {}, set()
     for f in range(frames):
         fr = sc.frame(f, harness.radiance_mode(den))
@@ -123,6 +129,8 @@ def test_oracle_pass_equals_the_reference_shader(name):
             assert s["changed"] > 0.0, (shader, "the reference shader wrote nothing")
         if name == "reblur_checkerboard" and shader.endswith("_PrePass"):
             assert s["min_fraction"] >= 0.995, (shader, s)
+        elif name == "reblur_dynamic_resolution" and any(k in shader for k in ("PrePass", "_Blur", "PostBlur")):
+            assert s["min_fraction"] >= 0.9995, (shader, s)  # tap positions in uv units scaled by rect / resource: single texels (see the 640x360 test)
         elif any(k in shader for k in ROUNDING_SENSITIVE):
             assert s["min_fraction"] >= 0.997, (shader, s)
         else:
