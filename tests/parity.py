@@ -30,8 +30,11 @@ def _scene_device(width, height, device):
 
 
 class SideBySide(object):
-    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",), common=None, frame_fn=None):
-        """frame_fn(frame, f) -> frame: transformation of the scene's frame f before either executor sees it (checkerboarded inputs).
+    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",), common=None, frame_fn=None, reference_shaders=False):
+        """reference_shaders=True: the CPU side of every pass that has one is the REFERENCE's own shader source compiled for the CPU
+        (oracle/build_refshaders.py; tests/oracle_runner.py run_reference_shader) instead of the oracle's restatement -- the kernels
+        are compared with the reference's code directly, and the chain continues on the reference's state.
+        frame_fn(frame, f) -> frame: transformation of the scene's frame f before either executor sees it (checkerboarded inputs).
         noise_floor=True: the dispatches whose shader name contains one of `floor_passes` are also run, on the same re-synchronised
         inputs, by two perturbed builds of the oracle -- "fma" (FMA contraction allowed: a second IEEE-legal evaluation of the same
         expressions) and "uv" (the uv of every bilinear fetch moved by one float ulp: the sub-texel position a shader hands to the
@@ -43,6 +46,7 @@ class SideBySide(object):
         import torch
         self.denoiser, self.w, self.h, self.identifier, self.common = denoiser, width, height, identifier, common
         self.frame_fn = frame_fn
+        self.reference_shaders = reference_shaders
         self.cpu = orr.CpuDenoiser(denoiser, width, height, identifier=identifier, settings=settings, common=common)
         self.instance = self.cpu.instance
         self.floor_passes = tuple(floor_passes)
@@ -57,6 +61,13 @@ class SideBySide(object):
             self.ctx.set_user_texture(getattr(nrd.ResourceType, name), t.data_ptr(), t.stride(0) * t.element_size(), fmt)
         self.scene = scene.Scene(width, height, device=_scene_device(width, height, device))
         self.report = []
+
+    def _cpu_run(self, d):
+        import os
+        if self.reference_shaders and os.path.exists(orr.reference_shader_path(d.shaderFileName)):
+            self.cpu.run_reference_shader(d)
+        else:
+            self.cpu.run_dispatch(d)
 
     def _scene_frame(self, sc, f):
         fr = sc.frame(f, harness.radiance_mode(self.denoiser))
@@ -146,7 +157,7 @@ class SideBySide(object):
                             alt_den.resolve(rtype, index)[0][...] = self.cpu.resolve(rtype, index)[0]
                 self.ctx.execute_raw(C.byref(raw[i]))
                 self.torch.cuda.synchronize()
-                self.cpu.run_dispatch(d)
+                self._cpu_run(d)
                 if floor:
                     for alt_den in self.cpu_alt:
                         alt_den.run_dispatch(d)
@@ -173,7 +184,7 @@ class SideBySide(object):
                 self._sync_to_gpu(d)
                 self.ctx.execute_raw(C.byref(raw[i]))
                 self.torch.cuda.synchronize()
-                self.cpu.run_dispatch(d)
+                self._cpu_run(d)
                 self._compare_outputs(f, d)
             if f == 0:
                 self.cpu.set_inputs(fr, rect_origin=origin)  # the frame-0 clears also zero IN_MV (reference quirk), restore it
