@@ -1240,7 +1240,11 @@ void TemporalAccumulation(const Pass& P, Signals sg, Tex* t, int W, int H)
                         float3 xw = Geometry::RotateVector(c.gViewToWorld, xv);
                         float3 v = P.GetViewVector(xw);
                         float3 o = c.gOrthoMode == 0.0f ? float3(0.0f) : xw;
-                        x10 = o + v * float3(dot(X - o, N) / dot(N, v));
+#ifdef ORACLE_REFERENCE_ASSOCIATION
+                        x10 = o + v * float3(dot(X - o, N)) / float3(dot(N, v)); // the shader's order: ( v * a ) / b (:379, :389)
+#else
+                        x10 = o + v * float3(dot(X - o, N) / dot(N, v));         // this restatement and the kernels: v * ( a / b ) -- one rounding apart
+#endif
                         n10 = sNormalRoughness(2, 1).xyz();
                     }
                     {
@@ -1248,7 +1252,11 @@ void TemporalAccumulation(const Pass& P, Signals sg, Tex* t, int W, int H)
                         float3 xw = Geometry::RotateVector(c.gViewToWorld, xv);
                         float3 v = P.GetViewVector(xw);
                         float3 o = c.gOrthoMode == 0.0f ? float3(0.0f) : xw;
-                        x01 = o + v * float3(dot(X - o, N) / dot(N, v));
+#ifdef ORACLE_REFERENCE_ASSOCIATION
+                        x01 = o + v * float3(dot(X - o, N)) / float3(dot(N, v)); // the shader's order: ( v * a ) / b (:379, :389)
+#else
+                        x01 = o + v * float3(dot(X - o, N) / dot(N, v));         // this restatement and the kernels: v * ( a / b ) -- one rounding apart
+#endif
                         n01 = sNormalRoughness(1, 2).xyz();
                     }
                     float2 w = abs(deltaUv) + float2(1.0f / 256.0f);

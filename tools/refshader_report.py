@@ -24,9 +24,9 @@ def main():
             print("%s | (no compiled reference shader: %s)" % (name, ", ".join(missing)))
     print("# %d of %d (case, shader) pairs are bit-identical" % (identical, total))
     print()
-    print("# RELAX with the oracle built in the reference's association order (liboracle_src.so, oracle/relax.cpp): the one deviation removed")
+    print("# REBLUR and RELAX with the oracle built in the reference's association order (liboracle_src.so: oracle/reblur.cpp curvature, oracle/relax.cpp world positions)")
     identical = total = 0
-    for name in sorted(n for n in t.CASES if n.startswith("relax")):
+    for name in sorted(n for n in t.CASES if n.startswith(("relax", "reblur"))):
         stats, _ = t.run_case(name, variant="src")
         for shader, s in sorted(stats.items()):
             total += 1
