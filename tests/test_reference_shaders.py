@@ -174,7 +174,7 @@ def test_reblur_at_640x360_against_the_reference_shaders():
             assert s["min_bytes_equal"] == 1.0, (shader, s)
 
 
-@pytest.mark.parametrize("den_name,variant,gate", [("REBLUR_DIFFUSE_SPECULAR", "", 0.99), ("SIGMA_SHADOW", "", 0.99), ("RELAX_DIFFUSE_SPECULAR", "src", 0.99),
+@pytest.mark.parametrize("den_name,variant,gate", [("REBLUR_DIFFUSE_SPECULAR", "", 0.99), ("REBLUR_DIFFUSE_SPECULAR", "src", 0.99), ("SIGMA_SHADOW", "", 0.99), ("RELAX_DIFFUSE_SPECULAR", "src", 0.99),
                                                    ("RELAX_DIFFUSE_SPECULAR", "", 0.98)])
 def test_oracle_chain_against_the_reference_shader_chain(den_name, variant, gate):
     """Sequence parity on the CPU: two INDEPENDENT 12-frame runs at 320x180 -- one executes every pass with the oracle, the other with
