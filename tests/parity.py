@@ -29,9 +29,19 @@ def _scene_device(width, height, device):
     return "cuda:%d" % device if width * height > 1000000 else "cpu"
 
 
+class _NoCuda(object):
+    """Stand-in for the torch module when the harness runs on a CPU executor (tests/test_parity_harness.py)."""
+    class cuda(object):
+        @staticmethod
+        def synchronize():
+            pass
+
+
 class SideBySide(object):
-    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",), common=None, frame_fn=None, reference_shaders=False):
-        """reference_shaders=True: the CPU side of every pass that has one is the REFERENCE's own shader source compiled for the CPU
+    def __init__(self, denoiser, width, height, settings=None, device=0, identifier=0, noise_floor=False, floor_passes=("TemporalAccumulation",), common=None, frame_fn=None, reference_shaders=False, executor=None):
+        """executor: None = the CUDA executor (nrd.CudaContext); tests/test_parity_harness.py passes a CPU stand-in with the same
+        upload / download / execute_raw methods to exercise this harness without a GPU.
+        reference_shaders=True: the CPU side of every pass that has one is the REFERENCE's own shader source compiled for the CPU
         (oracle/build_refshaders.py; tests/oracle_runner.py run_reference_shader) instead of the oracle's restatement -- the kernels
         are compared with the reference's code directly, and the chain continues on the reference's state.
         frame_fn(frame, f) -> frame: transformation of the scene's frame f before either executor sees it (checkerboarded inputs).
@@ -51,6 +61,11 @@ class SideBySide(object):
         self.instance = self.cpu.instance
         self.floor_passes = tuple(floor_passes)
         self.cpu_alt = [orr.CpuDenoiser(denoiser, width, height, identifier=identifier, instance=self.instance, variant=v, common=common) for v in ("fma", "uv")] if noise_floor else []
+        self.report = []
+        if executor is not None:
+            self.ctx, self.torch, self.dev_user = executor(self), _NoCuda, {}
+            self.scene = scene.Scene(width, height, device="cpu")
+            return
         self.ctx = nrd.CudaContext(self.instance, width, height, device=device)
         self.torch = torch
         self.dev_user = {}
