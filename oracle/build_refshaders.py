@@ -30,14 +30,13 @@ GEN = os.path.join(ROOT, "oracle", "_ref", "refshader")
 
 def pass_list():
     """Every pass shader of the denoisers the product supports (PipelineDesc::shaderFileName minus ".cs"), from the shader
-    sources that exist.  Not built: Clear_* (trivial), *_Validation (debug overlay, needs MathLib's text renderer) and the two SIGMA
-    split-screen shaders (they initialise a float2 from a one-channel texture fetch, which this C++ shim cannot express)."""
+    sources that exist.  Not built: Clear_* (trivial) and *_Validation (debug overlay, needs MathLib's text renderer)."""
     out = []
     for f in sorted(os.listdir(os.path.join(REF, "Shaders", "Source"))):
         if not f.endswith(".cs.hlsl"):
             continue
         n = f[:-len(".cs.hlsl")]
-        if n.startswith("Clear_") or n.endswith("_Validation") or n.startswith("SIGMA_") and n.endswith("_SplitScreen"):
+        if n.startswith("Clear_") or n.endswith("_Validation"):
             continue
         if any(k in n for k in ("Occlusion", "Sh_", "DirectionalOcclusion")):  # denoisers the product does not implement
             continue
@@ -68,6 +67,8 @@ def fix_hlsl(text):
     text = IN_PARAM.sub(r"\1", text)
     text = FLOAT_LITERAL.sub(r"\1f", text)
     text = re.sub(r"\bgroupshared\b", "static", text)
+    # a vector initialised from a one-channel texture fetch (HLSL replicates the scalar): float2 data = gIn_Penumbra[ pixelPos ];
+    text = re.sub(r"\b(float[234])\s+(\w+)\s*=\s*(gIn_\w+\s*\[[^\]]*\])\s*;", r"\1 \2 = \1(float(\3));", text)
     # x.xxx on a scalar (HLSL: float3(x)) -- also harmless on a vector
     text = re.sub(r"((?<![\w.])\d[\d.]*(?:[eE][-+]?\d+)?f)\s*\.(x{2,4})\b", r"_splat_\2(\1)", text)
     text = re.sub(r"(?<![\w.\])])([A-Za-z_]\w*)\.(x{2,4})\b", r"_splat_\2(\1)", text)
